@@ -1,0 +1,218 @@
+// TEST INFRASTRUCTURE ONLY -- C entry points onto the oracle for ctypes (tests/, smoke(), bench.py
+// cpu_baseline / --impl reference).  Never linked into or loaded by poroelasticity_b200.
+#include "poro_oracle.hpp"
+
+#include <chrono>
+#include <cstring>
+
+using namespace orc;
+
+extern "C"
+{
+  // Unit square, refine_global(n_refine), all four sides boundary id 0.  bc_mode:
+  //   0 = "general case": u and p_face Dirichlet on every boundary face (BASELINE cfg 1-4)
+  //   1 = cantilever as shipped in BR1new: u Dirichlet on x=0, traction (0,-1) on y=1, no p Dirichlet
+  void *
+  orc_create(int element, int n_refine, double distort, std::uint64_t seed, int bc_mode)
+  {
+    Problem *P = new Problem;
+    P->mesh    = make_unit_square(n_refine, distort, seed);
+    P->dofs    = distribute_dofs(P->mesh, (Element)element);
+    P->pattern = make_sparsity_pattern(P->dofs, P->mesh.n_cells());
+    P->kcell.assign(P->mesh.n_cells(), 1.);
+    P->face_kind.assign(4 * (size_t)P->mesh.n_cells(), 0);
+    const int N = P->mesh.N;
+    for (int c = 0; c < P->mesh.n_cells(); ++c)
+      {
+        std::uint32_t ix, iy;
+        morton_decode(c, ix, iy);
+        for (int f = 0; f < 4; ++f)
+          if (P->mesh.face_bid[4 * c + f] != 255)
+            {
+              if (bc_mode == 0)
+                P->face_kind[4 * c + f] = FK_DIR_U | FK_DIR_P;
+              else
+                {
+                  if (f == 0)
+                    P->face_kind[4 * c + f] = FK_DIR_U;
+                  else if (f == 3 && (int)iy == N - 1)
+                    P->face_kind[4 * c + f] = FK_NEU_U;
+                }
+            }
+      }
+    if (bc_mode == 1)
+      {
+        P->traction[0] = 0;
+        P->traction[1] = -1;
+      }
+    return P;
+  }
+  void
+  orc_destroy(void *h)
+  {
+    delete (Problem *)h;
+  }
+  void
+  orc_set_material(void *h, double lambda, double mu, double alpha, double c0, double dt)
+  {
+    Problem *P   = (Problem *)h;
+    P->lambda    = lambda;
+    P->mu        = mu;
+    P->alpha     = alpha;
+    P->capacity  = c0;
+    P->time_step = dt;
+  }
+  void
+  orc_set_case(void *h, int id, double f_lambda, double f_mu, double f_alpha, double s_capacity, double s_alpha)
+  {
+    Problem *P       = (Problem *)h;
+    P->cs.id         = id;
+    P->cs.f_lambda   = f_lambda;
+    P->cs.f_mu       = f_mu;
+    P->cs.f_alpha    = f_alpha;
+    P->cs.s_capacity = s_capacity;
+    P->cs.s_alpha    = s_alpha;
+  }
+  void
+  orc_set_kcell(void *h, const double *k)
+  {
+    Problem *P = (Problem *)h;
+    std::copy(k, k + P->mesh.n_cells(), P->kcell.begin());
+  }
+  void
+  orc_set_traction(void *h, double tx, double ty)
+  {
+    Problem *P     = (Problem *)h;
+    P->traction[0] = tx;
+    P->traction[1] = ty;
+  }
+  void
+  orc_set_face_kind(void *h, const std::uint8_t *fk)
+  {
+    Problem *P = (Problem *)h;
+    std::copy(fk, fk + P->face_kind.size(), P->face_kind.begin());
+  }
+  // sizes: [n_cells, n_vertices, n_loc, n_u, n_pint, n_pface, n_dofs, nnz]
+  void
+  orc_sizes(void *h, std::int64_t *s)
+  {
+    Problem *P = (Problem *)h;
+    s[0]       = P->mesh.n_cells();
+    s[1]       = (std::int64_t)P->mesh.vx.size();
+    s[2]       = P->dofs.n_loc;
+    s[3]       = P->dofs.n_u;
+    s[4]       = P->dofs.n_pint;
+    s[5]       = P->dofs.n_pface;
+    s[6]       = P->dofs.n();
+    s[7]       = (std::int64_t)P->pattern.colidx.size();
+  }
+  void
+  orc_get_mesh(void *h, double *vx, double *vy, std::uint32_t *cell_vertices, std::uint8_t *face_kind)
+  {
+    Problem *P = (Problem *)h;
+    std::copy(P->mesh.vx.begin(), P->mesh.vx.end(), vx);
+    std::copy(P->mesh.vy.begin(), P->mesh.vy.end(), vy);
+    std::copy(P->mesh.cell_vertices.begin(), P->mesh.cell_vertices.end(), cell_vertices);
+    std::copy(P->face_kind.begin(), P->face_kind.end(), face_kind);
+  }
+  void
+  orc_get_dofs(void *h, std::uint32_t *cell_dofs)
+  {
+    Problem *P = (Problem *)h;
+    std::copy(P->dofs.cell_dofs.begin(), P->dofs.cell_dofs.end(), cell_dofs);
+  }
+  void
+  orc_get_pattern(void *h, std::int64_t *rowptr, std::int32_t *colidx)
+  {
+    Problem *P = (Problem *)h;
+    std::copy(P->pattern.rowptr.begin(), P->pattern.rowptr.end(), rowptr);
+    std::copy(P->pattern.colidx.begin(), P->pattern.colidx.end(), colidx);
+  }
+  // one cell: local matrix (n_loc^2, row major), local rhs, constraint flags/values per local dof
+  void
+  orc_local(void *h, int cell, double t, const double *old_solution, double *A, double *b, std::uint8_t *is_con,
+            double *g)
+  {
+    Problem            *P = (Problem *)h;
+    std::vector<double> old(old_solution, old_solution + P->dofs.n());
+    CellResult          R;
+    assemble_cell(*P, cell, t, old, R);
+    std::copy(R.A.begin(), R.A.end(), A);
+    std::copy(R.b.begin(), R.b.end(), b);
+    if (is_con)
+      for (int i = 0; i < P->dofs.n_loc; ++i)
+        {
+          const dof_t d  = P->dofs.cell_dofs[(size_t)cell * P->dofs.n_loc + i];
+          auto        it = R.con.lines.find(d);
+          is_con[i]      = it != R.con.lines.end();
+          g[i]           = is_con[i] ? it->second : 0.;
+        }
+  }
+  // local matrices of cells [first, first+n): out[n][n_loc^2]; returns seconds spent
+  double
+  orc_local_matrices(void *h, int first, int n, double t, double *out)
+  {
+    Problem            *P = (Problem *)h;
+    std::vector<double> old(P->dofs.n(), 0.);
+    CellResult          R;
+    const auto          t0 = std::chrono::steady_clock::now();
+    const size_t        nn = (size_t)P->dofs.n_loc * P->dofs.n_loc;
+    for (int c = first; c < first + n; ++c)
+      {
+        assemble_cell(*P, c, t, old, R);
+        if (out)
+          std::copy(R.A.begin(), R.A.end(), out + (size_t)(c - first) * nn);
+      }
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
+  // assemble_system(t); returns seconds spent
+  double
+  orc_assemble(void *h, double t, const double *old_solution, double *values, double *rhs)
+  {
+    Problem            *P = (Problem *)h;
+    std::vector<double> old(old_solution, old_solution + P->dofs.n()), v, r;
+    const auto          t0 = std::chrono::steady_clock::now();
+    assemble_system(*P, t, old, v, r);
+    const double dtm = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    std::copy(v.begin(), v.end(), values);
+    std::copy(r.begin(), r.end(), rhs);
+    return dtm;
+  }
+  void
+  orc_step_errors(void *h, double t, const double *solution, double *e3)
+  {
+    Problem            *P = (Problem *)h;
+    std::vector<double> s(solution, solution + P->dofs.n());
+    step_errors(*P, t, s, e3);
+  }
+  // number of steps the reference's float-accumulated loop runs:
+  //   for (n=1, time=dt; time <= t_end; time += dt, ++n)      BR1new:2181, CGQ1:2929
+  int
+  orc_count_steps(double dt, double t_end)
+  {
+    int n = 0;
+    for (double time = dt; time <= t_end; time += dt)
+      ++n;
+    return n;
+  }
+  void
+  orc_gauss_jordan(double *a, int n)
+  {
+    std::vector<double> v(a, a + (size_t)n * n);
+    gauss_jordan(v, n);
+    std::copy(v.begin(), v.end(), a);
+  }
+  void
+  orc_qgauss(int n, double *x, double *w)
+  {
+    std::vector<double> xv, wv;
+    qgauss_1d(n, xv, wv);
+    std::copy(xv.begin(), xv.end(), x);
+    std::copy(wv.begin(), wv.end(), w);
+  }
+  double
+  orc_u01(std::uint64_t seed, std::uint64_t id, std::uint64_t k)
+  {
+    return u01(seed, id, k);
+  }
+}

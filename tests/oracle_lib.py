@@ -1,0 +1,147 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle.so).  TEST INFRASTRUCTURE ONLY: imported by
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs -- never by
+the product package."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ORACLE_DIR = os.path.join(os.path.dirname(_HERE), "oracle")
+_lib = None
+
+BR1_WG, CGQ1_WG = 0, 1
+CASE_ZERO, CASE_COSCOS = 0, 1
+FK_DIR_U, FK_DIR_P, FK_NEU_U = 1, 2, 4
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _ORACLE_DIR])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        so = os.path.join(_ORACLE_DIR, "liboracle.so")
+        if not os.path.exists(so):
+            build()
+        _lib = C.CDLL(so)
+        _lib.orc_create.restype = C.c_void_p
+        _lib.orc_create.argtypes = [C.c_int, C.c_int, C.c_double, C.c_uint64, C.c_int]
+        _lib.orc_destroy.argtypes = [C.c_void_p]
+        _lib.orc_set_material.argtypes = [C.c_void_p] + [C.c_double] * 5
+        _lib.orc_set_case.argtypes = [C.c_void_p, C.c_int] + [C.c_double] * 5
+        _lib.orc_set_kcell.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.orc_set_traction.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        _lib.orc_set_face_kind.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.orc_sizes.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.orc_get_mesh.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+        _lib.orc_get_dofs.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.orc_get_pattern.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.orc_local.argtypes = [C.c_void_p, C.c_int, C.c_double] + [C.c_void_p] * 5
+        _lib.orc_local_matrices.restype = C.c_double
+        _lib.orc_local_matrices.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p]
+        _lib.orc_assemble.restype = C.c_double
+        _lib.orc_assemble.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.orc_step_errors.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+        _lib.orc_count_steps.restype = C.c_int
+        _lib.orc_count_steps.argtypes = [C.c_double, C.c_double]
+        _lib.orc_gauss_jordan.argtypes = [C.c_void_p, C.c_int]
+        _lib.orc_qgauss.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        _lib.orc_u01.restype = C.c_double
+        _lib.orc_u01.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    """One reference problem on the unit square (see oracle/oracle_capi.cpp)."""
+
+    def __init__(self, element, n_refine, distort=0.0, seed=12345, bc_mode=0):
+        self.L = lib()
+        self.h = self.L.orc_create(element, n_refine, distort, seed, bc_mode)
+        s = np.zeros(8, np.int64)
+        self.L.orc_sizes(self.h, _p(s))
+        (self.n_cells, self.n_vertices, self.n_loc, self.n_u, self.n_pint, self.n_pface, self.n_dofs,
+         self.nnz) = [int(x) for x in s]
+        self.element = element
+
+    def __del__(self):
+        try:
+            self.L.orc_destroy(self.h)
+        except Exception:
+            pass
+
+    def set_material(self, lam, mu, alpha, c0, dt):
+        self.L.orc_set_material(self.h, lam, mu, alpha, c0, dt)
+
+    def set_case(self, cid, f_lambda=1.0, f_mu=1.0, f_alpha=1.0, s_capacity=0.0, s_alpha=1.0):
+        self.L.orc_set_case(self.h, cid, f_lambda, f_mu, f_alpha, s_capacity, s_alpha)
+
+    def set_kcell(self, k):
+        k = np.ascontiguousarray(k, np.float64)
+        assert k.size == self.n_cells
+        self.L.orc_set_kcell(self.h, _p(k))
+
+    def set_traction(self, tx, ty):
+        self.L.orc_set_traction(self.h, tx, ty)
+
+    def set_face_kind(self, fk):
+        fk = np.ascontiguousarray(fk, np.uint8)
+        assert fk.size == 4 * self.n_cells
+        self.L.orc_set_face_kind(self.h, _p(fk))
+
+    def mesh(self):
+        vx = np.zeros(self.n_vertices)
+        vy = np.zeros(self.n_vertices)
+        cv = np.zeros((self.n_cells, 4), np.uint32)
+        fk = np.zeros((self.n_cells, 4), np.uint8)
+        self.L.orc_get_mesh(self.h, _p(vx), _p(vy), _p(cv), _p(fk))
+        return vx, vy, cv, fk
+
+    def cell_dofs(self):
+        cd = np.zeros((self.n_cells, self.n_loc), np.uint32)
+        self.L.orc_get_dofs(self.h, _p(cd))
+        return cd
+
+    def pattern(self):
+        rp = np.zeros(self.n_dofs + 1, np.int64)
+        ci = np.zeros(self.nnz, np.int32)
+        self.L.orc_get_pattern(self.h, _p(rp), _p(ci))
+        return rp, ci
+
+    def local(self, cell, t, old=None):
+        old = np.zeros(self.n_dofs) if old is None else np.ascontiguousarray(old, np.float64)
+        A = np.zeros((self.n_loc, self.n_loc))
+        b = np.zeros(self.n_loc)
+        ic = np.zeros(self.n_loc, np.uint8)
+        g = np.zeros(self.n_loc)
+        self.L.orc_local(self.h, cell, t, _p(old), _p(A), _p(b), _p(ic), _p(g))
+        return A, b, ic.astype(bool), g
+
+    def local_matrices(self, first, n, t=0.0, want=True):
+        out = np.zeros((n, self.n_loc, self.n_loc)) if want else None
+        sec = self.L.orc_local_matrices(self.h, first, n, t, _p(out) if want else None)
+        return out, sec
+
+    def assemble(self, t, old=None):
+        old = np.zeros(self.n_dofs) if old is None else np.ascontiguousarray(old, np.float64)
+        v = np.zeros(self.nnz)
+        r = np.zeros(self.n_dofs)
+        sec = self.L.orc_assemble(self.h, t, _p(old), _p(v), _p(r))
+        return v, r, sec
+
+    def step_errors(self, t, sol):
+        sol = np.ascontiguousarray(sol, np.float64)
+        e = np.zeros(3)
+        self.L.orc_step_errors(self.h, t, _p(sol), _p(e))
+        return e
+
+    def csr(self, values):
+        import scipy.sparse as sp
+        rp, ci = self.pattern()
+        return sp.csr_matrix((values, ci, rp), shape=(self.n_dofs, self.n_dofs))
