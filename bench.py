@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (BASELINE.json metric: cells assembled/s and seconds
+per time step (assemble + solve)).
+
+A "step" is one backward-Euler time step of the reference's run() loop on BASELINE cfg 2
+(PoroElasBR1WG, 2-D unit square, 1024 x 1024 quads, coscos data, dt = 0.1):
+    assemble_system(t)   -> K1+K2+K3 CUDA kernels (matrix AND rhs rebuilt, as the reference does)
+    solve_time_step()    -> preconditioned MINRES on the CUDA CSR SpMV
+`value`  = cells * steps / device time, old_solution resident in HBM (old_solution = solution).
+`e2e`    = the same through the C ABI with HOST buffers: old_solution copied host->device and the
+           solution copied device->host inside the timed region, every step.
+`--impl reference` times the CPU oracle (literal restatement of the reference loops + sparse LU:
+the reference itself needs deal.II 9.1 + UMFPACK, which cannot be installed here) on a bounded
+sample of the same workload (a smaller mesh of the same family) with the same metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "cells assembled/s per time step (assemble+solve), BR1-WG"
+UNIT = "cells/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, nm in enumerate(names):
+                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def cpu_baseline(n_refine_cpu, steps, dt):
+    """Oracle (CPU port of the reference loops) + SuperLU per step, 1 thread, on a smaller mesh of the
+    same family.  Returns (cells/s, seconds, description)."""
+    import numpy as np
+    import scipy.sparse.linalg as spla
+    from oracle_lib import BR1_WG, CASE_COSCOS, Oracle
+    o = Oracle(BR1_WG, n_refine_cpu)
+    o.set_material(1, 1, 1, 0, dt)
+    o.set_case(CASE_COSCOS)
+    old = np.zeros(o.n_dofs)
+    t0 = time.perf_counter()
+    t_asm = 0.0
+    for k in range(steps):
+        v, r, sec = o.assemble(dt * (k + 1), old)
+        t_asm += sec
+        old = spla.splu(o.csr(v).tocsc()).solve(r)   # factor + solve every step (BR1new:1181-1183)
+    total = time.perf_counter() - t0
+    N = 1 << n_refine_cpu
+    return o.n_cells * steps / total, total, ("oracle port, %dx%d BR1-WG, %d steps: assemble %.2fs + LU %.2fs"
+                                              % (N, N, steps, t_asm, total - t_asm))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    ncpu = args.cpu_refine
+    steps = max(1, args.steps)
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_baseline(max(ncpu - 2, 2), 1, 0.1)
+    val, sec, desc = cpu_baseline(ncpu, steps, 0.1)
+    N = 1 << args.n_refine
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": sec / steps * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "PoroElasBR1WG 2D unit square %dx%d quads, coscos, dt=0.1" % (N, N),
+                       "sample": desc},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--n-refine", type=int, default=10, help="mesh = 2^n x 2^n cells (cfg 2: 10)")
+    ap.add_argument("--cpu-refine", type=int, default=7, help="mesh of the bounded CPU sample")
+    ap.add_argument("--rel-tol", type=float, default=1e-10)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import poroelasticity_b200 as pb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    dt = 0.1
+    b = pb.PoroElasBR1WG(device=local_rank, rank=rank, world_size=world)
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.frombuffer(bytearray(pb.comm_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(idt, 0)
+        b.comm_init(idt.cpu().numpy().tobytes())
+    t_setup = time.perf_counter()
+    s = b.make_grid_and_dofs(args.n_refine)
+    t_setup = time.perf_counter() - t_setup
+    b.time_step = dt
+    b.set_material(1.0, 1.0, 1.0, 0.0)
+    b.set_case(pb.PE_CASE_COSCOS)
+    b.rel_tol = args.rel_tol
+    n_cells, n_dofs = s.n_cells, s.n_dofs
+    N = 1 << args.n_refine
+
+    def step(k, host_io, old_host):
+        t = dt * (k + 1)
+        if host_io:
+            b.assemble_system(t, old_host)       # H2D of old_solution inside
+            x = b.solve_time_step(want_solution=True, check=False)   # D2H of the solution inside
+            return x
+        b.assemble_system(t)                      # old_solution resident on the device
+        b.solve_time_step(want_solution=False, check=False)
+        return None
+
+    # ---- device-resident arm ------------------------------------------------------------------
+    b.set_solution(np.zeros(s.n_owned_rows if world == 1 else n_dofs))
+    for k in range(args.warmup):
+        step(k, False, None)
+    b.set_solution(np.zeros(s.n_owned_rows if world == 1 else n_dofs))
+    launches0 = b.timings()["launches"]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    asm_ms, asm_k_ms, sol_ms, iters, spmvs = [], [], [], [], []
+    for k in range(args.steps):
+        step(k, False, None)
+        tm = b.timings()
+        asm_ms.append(tm["assemble_ms"])
+        asm_k_ms.append(tm["assemble_kernel_ms"])
+        sol_ms.append(tm["solve_ms"])
+        iters.append(b.stats.iterations)
+        spmvs.append(b.stats.spmv_count)
+    barrier()
+    wall = time.perf_counter() - t0
+    # device time of the steps = sum of the CUDA-event timed phases on the handle's stream
+    dev_s = (sum(asm_ms) + sum(sol_ms)) * 1e-3
+    tt = torch.tensor([dev_s, wall], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_s, wall = float(tt[0]), float(tt[1])
+    launches = b.timings()["launches"] - launches0
+    clocks = sampler.finish() if rank == 0 else None
+    converged = bool(b.stats.converged)
+    rel_res = b.stats.rel_residual
+
+    # ---- dominant kernel (SpMV) in isolation, CUDA events on the library's stream -----------------
+    hbm, peak_src = peaks()
+    nnz_owned, rows_owned = s.nnz_owned, s.n_owned_rows
+    x = np.random.default_rng(0).normal(size=(s.n_owned_rows if world == 1 else n_dofs))
+    spmv_bytes = 12.0 * nnz_owned + 20.0 * rows_owned
+    # pe_spmv copies x and y through the host; time only the kernel through the solver statistics:
+    # spmv share of the solve = measured by a dedicated loop below (pe_get_timings.spmv_ms_avg)
+    spmv_ms = None
+    try:
+        spmv_ms = b.bench_spmv(20)
+    except Exception:
+        spmv_ms = None
+
+    # ---- end-to-end arm: host buffers through the C ABI -------------------------------------------
+    e2e = None
+    if world == 1:
+        old = np.zeros(n_dofs)
+        step(0, True, old)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            old = step(k, True, old)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        e2e = {"value": n_cells * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(n_dofs * 8),
+               "d2h_bytes_per_step": int(n_dofs * 8), "ms_per_step": e2e_s / args.steps * 1e3}
+
+    if rank != 0:
+        return
+    asm_kernel_s = (sum(asm_k_ms) / len(asm_k_ms)) * 1e-3
+    roof_asm = {"bound": "hbm", "kernel": "k_assemble_interior<BR1>", "achieved": 1904.0 * n_cells / asm_kernel_s / 1e9,
+                "peak": hbm, "unit": "GB/s", "frac": 1904.0 * n_cells / asm_kernel_s / 1e9 / hbm, "traffic": None,
+                "bytes_per_cell": 1904, "cells_per_s": n_cells / asm_kernel_s, "peak_source": peak_src}
+    roof = None
+    if spmv_ms:
+        ach = spmv_bytes / (spmv_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "k_spmv", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                "traffic": None, "bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_ms, "peak_source": peak_src}
+    line = {"metric": METRIC, "value": n_cells * args.steps / dev_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "PoroElasBR1WG 2D unit square %dx%d quads, coscos, dt=0.1, backward Euler" % (N, N),
+                       "n_dofs": n_dofs, "nnz": s.nnz if world == 1 else None, "rel_tol": args.rel_tol,
+                       "l2": "inputs (2.9 GB CSR) exceed L2; no flush needed", "setup_s": t_setup},
+            "s_per_time_step": dev_s / args.steps, "assemble_ms": sum(asm_ms) / len(asm_ms),
+            "assembly_cells_per_s": n_cells / asm_kernel_s, "solve_ms": sum(sol_ms) / len(sol_ms),
+            "solver": {"method": "MINRES + diagonal Schur preconditioner", "iterations": iters, "spmv": spmvs,
+                       "converged": converged, "rel_residual": rel_res},
+            "wall_s": wall, "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e,
+            "roofline": roof if roof else roof_asm, "roofline_assembly": roof_asm}
+    if not args.no_cpu:
+        val, sec, desc = cpu_baseline(args.cpu_refine, 2, dt)
+        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

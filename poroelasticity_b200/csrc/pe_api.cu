@@ -1,0 +1,1118 @@
+// C ABI of libporoelas_b200.so (include/poroelas_b200.h).  Host logic only: argument checking,
+// device residency of the mesh / DoF / CSR arrays, kernel launches, timing.  No CPU compute path:
+// every entry point that produces numbers launches the CUDA kernels or fails.
+#include "pe_internal.h"
+#include "pe_kernels.h"
+#include "pe_solver.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <exception>
+
+using namespace pe;
+
+namespace pe
+{
+  // pe_comm.cu
+  int  comm_init(pe_handle *h, const uint8_t id[128]);
+  void comm_destroy(pe_handle *h);
+  int  comm_setup_halo(pe_handle *h);
+  void comm_halo_exchange(void *ctx, double *x);
+  void comm_allreduce(void *ctx, double *v, int n);
+  int  comm_unique_id(uint8_t id[128]);
+} // namespace pe
+
+namespace
+{
+  int
+  fail(pe_handle *h, const int code, const std::string &msg)
+  {
+    if (h)
+      h->err = msg;
+    return code;
+  }
+  int
+  cuda_fail(pe_handle *h, const cudaError_t e, const char *where)
+  {
+    return fail(h, PE_ERR_CUDA, std::string(where) + ": " + cudaGetErrorString(e));
+  }
+#define PE_CUDA(call)                                 \
+  do                                                  \
+    {                                                 \
+      const cudaError_t e_ = (call);                  \
+      if (e_ != cudaSuccess)                          \
+        return cuda_fail(h, e_, #call);               \
+    }                                                 \
+  while (0)
+
+  template <class T>
+  cudaError_t
+  upload(DevBuf<T> &d, const T *src, const size_t n, cudaStream_t s)
+  {
+    cudaError_t e = d.alloc(n);
+    if (e != cudaSuccess || n == 0)
+      return e;
+    return cudaMemcpyAsync(d.p, src, n * sizeof(T), cudaMemcpyHostToDevice, s);
+  }
+
+  DevParams
+  make_params(const pe_handle *h, const double t, const double dt)
+  {
+    DevParams P;
+    P.lambda      = h->lambda;
+    P.mu          = h->mu;
+    P.alpha       = h->alpha;
+    P.c0          = h->c0;
+    P.dt          = dt;
+    P.traction[0] = h->mesh.traction[0];
+    P.traction[1] = h->mesh.traction[1];
+    P.case_id     = h->case_id == PE_CASE_COSCOS ? 1 : 0;
+    const double *q = h->case_params;
+    const double  st = std::sin(M_PI / 2. * t), ct = std::cos(M_PI / 2. * t);
+    P.f_coef = M_PI * (q[0] + 2. * q[1] - q[2]) * st;
+    P.s_coef = M_PI / 2. * ct * (q[3] + q[4]) + 2. * M_PI * M_PI * st;
+    P.u_coef = st / (2. * M_PI);
+    P.p_coef = st;
+    return P;
+  }
+
+  // upload everything the kernels need; (re)build the scatter offsets and the boundary-cell list
+  int
+  ensure_device(pe_handle *h)
+  {
+    if (h->device_ready)
+      return PE_OK;
+    if (h->device < 0)
+      return fail(h, PE_ERR_NO_DEVICE, "handle was created with PE_CFG_HOST_SETUP_ONLY: no hot path without a GPU");
+    if (!h->have_mesh || !h->have_dofs || !h->have_pattern)
+      return fail(h, PE_ERR_ARG, "mesh, dofs and sparsity pattern must be set before the hot path runs");
+    cudaStream_t     s     = h->stream;
+    const int        n_loc = h->dofs.n_loc;
+    const Partition &pt    = h->part;
+    const int64_t    n_asm = (int64_t)pt.asm_cells.size();
+    h->n_asm               = n_asm;
+    h->L                   = pt.n_owned;
+    h->H                   = (int64_t)pt.ghost_cols.size();
+    h->nnz                 = (int64_t)h->pat.colidx.size();
+
+    PE_CUDA(upload(h->d_vx, h->mesh.x.data(), h->mesh.x.size(), s));
+    PE_CUDA(upload(h->d_vy, h->mesh.y.data(), h->mesh.y.size(), s));
+
+    // global -> local column map for the dofs this rank can see
+    auto to_local = [&](const uint32_t g) -> int32_t {
+      const int64_t l = pt.global_to_owned(g);
+      if (l >= 0)
+        return (int32_t)l;
+      const auto it = std::lower_bound(pt.ghost_cols.begin(), pt.ghost_cols.end(), g);
+      if (it == pt.ghost_cols.end() || *it != g)
+        return -1;
+      return (int32_t)(h->L + (it - pt.ghost_cols.begin()));
+    };
+
+    // SoA copies of the per-cell arrays for the cells this rank assembles
+    std::vector<uint32_t> cv((size_t)4 * n_asm), flags((size_t)n_asm, 0);
+    std::vector<int32_t>  cd((size_t)n_loc * n_asm), bnd;
+    // CGQ1: mesh-wide displacement constraints (interpolate_boundary_values over the whole
+    // DoFHandler inside the cell loop, CGQ1:1673-1679): flag every vertex of a DIR_U face
+    std::vector<uint8_t> vflag;
+    if (h->dofs.element == PE_CGQ1_WG)
+      {
+        vflag.assign((size_t)h->mesh.n_vertices, 0);
+        for (int64_t c = 0; c < h->mesh.n_cells; ++c)
+          for (int f = 0; f < 4; ++f)
+            if (h->mesh.face_kinds[4 * c + f] & PE_FACE_DIR_U)
+              for (int v = 0; v < 2; ++v)
+                vflag[h->mesh.cell_vertices[4 * c + kFaceVertex[f][v]]] = 1;
+      }
+    for (int64_t a = 0; a < n_asm; ++a)
+      {
+        const int64_t c = pt.asm_cells[a];
+        for (int v = 0; v < 4; ++v)
+          cv[(size_t)v * n_asm + a] = h->mesh.cell_vertices[4 * c + v];
+        for (int i = 0; i < n_loc; ++i)
+          {
+            const int32_t l = to_local(h->dofs.cell_dofs[(size_t)c * n_loc + i]);
+            if (l < 0)
+              return fail(h, PE_ERR_PATTERN, "a dof of an assembled cell is neither owned nor in the halo");
+            cd[(size_t)i * n_asm + a] = l;
+          }
+        uint32_t fl = 0;
+        for (int f = 0; f < 4; ++f)
+          fl |= (uint32_t)(h->mesh.face_kinds[4 * c + f] & 7) << (3 * f);
+        if (!vflag.empty())
+          for (int v = 0; v < 4; ++v)
+            if (vflag[h->mesh.cell_vertices[4 * c + v]])
+              fl |= 1u << (12 + v);
+        flags[a] = fl;
+        if (fl)
+          bnd.push_back((int32_t)a);
+      }
+    h->n_bnd = (int64_t)bnd.size();
+    PE_CUDA(upload(h->d_cv, cv.data(), cv.size(), s));
+    PE_CUDA(upload(h->d_flags, flags.data(), flags.size(), s));
+    PE_CUDA(upload(h->d_cdofs, cd.data(), cd.size(), s));
+    PE_CUDA(upload(h->d_bnd_list, bnd.data(), bnd.size(), s));
+
+    // CSR with local column numbering
+    PE_CUDA(upload(h->d_rowptr, h->pat.rowptr.data(), h->pat.rowptr.size(), s));
+    if (pt.world == 1)
+      PE_CUDA(upload(h->d_colidx, h->pat.colidx.data(), h->pat.colidx.size(), s));
+    else
+      {
+        std::vector<int32_t> lc(h->pat.colidx.size());
+        for (size_t k = 0; k < lc.size(); ++k)
+          lc[k] = to_local((uint32_t)h->pat.colidx[k]);
+        PE_CUDA(upload(h->d_colidx, lc.data(), lc.size(), s));
+      }
+    PE_CUDA(h->d_values.alloc((size_t)h->nnz));
+    PE_CUDA(h->d_rhs.alloc((size_t)(h->L + h->H)));
+    PE_CUDA(h->d_sol.alloc((size_t)(h->L + h->H)));
+    PE_CUDA(cudaMemsetAsync(h->d_sol.p, 0, sizeof(double) * (size_t)(h->L + h->H), s));
+    PE_CUDA(h->d_err.alloc(1));
+    PE_CUDA(cudaMemsetAsync(h->d_err.p, 0, sizeof(int), s));
+
+    // permeability
+    if (h->k_lognormal)
+      {
+        PE_CUDA(h->d_k.alloc((size_t)n_asm));
+        DevBuf<int64_t> ids;
+        PE_CUDA(upload(ids, pt.asm_cells.data(), pt.asm_cells.size(), s));
+        PE_CUDA(launch_lognormal(n_asm, ids.p, 0, h->k_sigma, h->k_seed, h->d_k.p, s));
+        ++h->launches;
+        PE_CUDA(cudaStreamSynchronize(s));
+      }
+    else if (!h->k_cell.empty())
+      {
+        std::vector<double> k((size_t)n_asm);
+        for (int64_t a = 0; a < n_asm; ++a)
+          k[a] = h->k_cell[pt.asm_cells[a]];
+        PE_CUDA(upload(h->d_k, k.data(), k.size(), s));
+      }
+    else
+      h->d_k.release();
+
+    // scatter offsets
+    PE_CUDA(h->d_off.alloc((size_t)n_loc * n_loc * n_asm));
+    PE_CUDA(launch_scatter_offsets(n_loc, n_asm, h->L, h->d_cdofs.p, h->d_rowptr.p, h->d_colidx.p, h->d_off.p,
+                                   h->d_err.p, s));
+    ++h->launches;
+    int err = 0;
+    PE_CUDA(cudaMemcpyAsync(&err, h->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PE_CUDA(cudaStreamSynchronize(s));
+    if (err == 1)
+      return fail(h, PE_ERR_PATTERN, "an entry of a local matrix is not in the sparsity pattern");
+    if (err == 2)
+      return fail(h, PE_ERR_PATTERN, "a CSR row is longer than 256 entries (scatter offsets are 8 bit)");
+    if (pt.world > 1)
+      {
+        const int rc = comm_setup_halo(h);
+        if (rc != PE_OK)
+          return rc;
+      }
+    h->device_ready = true;
+    h->matrix_valid = false;
+    return PE_OK;
+  }
+
+  AsmArgs
+  make_args(pe_handle *h, const bool do_matrix)
+  {
+    AsmArgs a{};
+    a.n_asm     = h->n_asm;
+    a.n_bnd     = h->n_bnd;
+    a.L         = h->L;
+    a.vx        = h->d_vx.p;
+    a.vy        = h->d_vy.p;
+    a.kcell     = h->d_k.p;
+    a.k_scalar  = h->k_scalar;
+    a.sol       = h->d_sol.p;
+    a.cv        = h->d_cv.p;
+    a.flags     = h->d_flags.p;
+    a.cdofs     = h->d_cdofs.p;
+    a.bnd_list  = h->d_bnd_list.p;
+    a.rowptr    = h->d_rowptr.p;
+    a.off       = h->d_off.p;
+    a.values    = h->d_values.p;
+    a.rhs       = h->d_rhs.p;
+    a.do_matrix = do_matrix ? 1 : 0;
+    return a;
+  }
+
+  // host vector in global block order -> device vector in local numbering (owned + halo)
+  int
+  upload_global_vector(pe_handle *h, const double *src, double *dst_dev)
+  {
+    const Partition &pt = h->part;
+    if (pt.world == 1)
+      {
+        PE_CUDA(cudaMemcpyAsync(dst_dev, src, sizeof(double) * (size_t)h->L, cudaMemcpyHostToDevice, h->stream));
+        return PE_OK;
+      }
+    std::vector<double> tmp((size_t)(h->L + h->H));
+    for (int b = 0; b < 3; ++b)
+      std::copy(src + pt.row_begin[b], src + pt.row_end[b], tmp.begin() + pt.local_off[b]);
+    for (int64_t k = 0; k < h->H; ++k)
+      tmp[(size_t)(h->L + k)] = src[pt.ghost_cols[k]];
+    PE_CUDA(cudaMemcpyAsync(dst_dev, tmp.data(), sizeof(double) * tmp.size(), cudaMemcpyHostToDevice, h->stream));
+    PE_CUDA(cudaStreamSynchronize(h->stream));
+    return PE_OK;
+  }
+
+  int
+  assemble_impl(pe_handle *h, const double t, const double dt, const double *old_solution, const bool do_matrix)
+  {
+    if (h->cfg.element != PE_BR1_WG && h->cfg.element != PE_CGQ1_WG)
+      return fail(h, PE_ERR_ARG, "assemble_system: element not implemented yet");
+    int rc = ensure_device(h);
+    if (rc != PE_OK)
+      return rc;
+    if (!do_matrix && !h->matrix_valid)
+      return fail(h, PE_ERR_ARG, "pe_assemble_rhs_only needs a previous pe_assemble_system");
+    cudaStream_t s = h->stream;
+    PE_CUDA(cudaEventRecord(h->ev[0], s));
+    if (old_solution)
+      {
+        rc = upload_global_vector(h, old_solution, h->d_sol.p);
+        if (rc != PE_OK)
+          return rc;
+      }
+    else if (h->part.world > 1)
+      comm_halo_exchange(h, h->d_sol.p);
+    // system_matrix = 0; system_rhs = 0                                    BR1new:687-688
+    if (do_matrix)
+      PE_CUDA(cudaMemsetAsync(h->d_values.p, 0, sizeof(double) * (size_t)h->nnz, s));
+    PE_CUDA(cudaMemsetAsync(h->d_rhs.p, 0, sizeof(double) * (size_t)(h->L + h->H), s));
+    const DevParams P = make_params(h, t, dt);
+    const AsmArgs   a = make_args(h, do_matrix);
+    PE_CUDA(cudaEventRecord(h->ev[1], s));
+    int nl = 0;
+    PE_CUDA(launch_assemble(h->cfg.element, a, P, s, &nl));
+    h->launches += nl;
+    PE_CUDA(cudaEventRecord(h->ev[2], s));
+    PE_CUDA(cudaEventSynchronize(h->ev[2]));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev[0], h->ev[2]);
+    h->assemble_ms = ms;
+    cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]);
+    h->assemble_kernel_ms = ms;
+    h->last_dt            = dt;
+    if (do_matrix)
+      h->matrix_valid = true;
+    return PE_OK;
+  }
+
+  SolverCtx
+  make_solver_ctx(pe_handle *h)
+  {
+    SolverCtx c;
+    c.L          = h->L;
+    c.H          = h->H;
+    c.n_pos      = h->part.local_off[1]; // owned u rows come first
+    c.pint_begin = h->part.local_off[1];
+    c.pint_end   = h->part.local_off[2];
+    c.rowptr     = h->d_rowptr.p;
+    c.colidx     = h->d_colidx.p;
+    c.values     = h->d_values.p;
+    c.stream     = h->stream;
+    if (h->part.world > 1)
+      {
+        c.halo      = comm_halo_exchange;
+        c.allreduce = comm_allreduce;
+        c.halo_ctx  = h;
+      }
+    return c;
+  }
+} // namespace
+
+extern "C"
+{
+  const char *
+  pe_version(void)
+  {
+    return "poroelas_b200 0.1 (sm_100a)";
+  }
+
+  int
+  pe_create(pe_handle **out, const pe_config *cfg)
+  {
+    if (!out || !cfg)
+      return PE_ERR_ARG;
+    *out = nullptr;
+    if (cfg->element < 0 || cfg->element > 2 || (cfg->dim != 2 && cfg->dim != 0))
+      return PE_ERR_ARG;
+    const bool  host_only = (cfg->flags & PE_CFG_HOST_SETUP_ONLY) != 0;
+    int         n_dev     = 0;
+    cudaError_t e         = host_only ? cudaSuccess : cudaGetDeviceCount(&n_dev);
+    if (!host_only && (e != cudaSuccess || n_dev == 0))
+      return PE_ERR_NO_DEVICE;
+    pe_handle *h = nullptr;
+    try
+      {
+        h = new pe_handle;
+      }
+    catch (...)
+      {
+        return PE_ERR_ALLOC;
+      }
+    h->cfg = *cfg;
+    if (h->cfg.world_size <= 0)
+      {
+        h->cfg.world_size = 1;
+        h->cfg.rank       = 0;
+      }
+    h->part.rank  = h->cfg.rank;
+    h->part.world = h->cfg.world_size;
+    if (host_only)
+      {
+        h->device = -1;
+        *out      = h;
+        return PE_OK;
+      }
+    if (cfg->device >= 0)
+      {
+        if (cfg->device >= n_dev || cudaSetDevice(cfg->device) != cudaSuccess)
+          {
+            delete h;
+            return PE_ERR_NO_DEVICE;
+          }
+        h->device = cfg->device;
+      }
+    else
+      cudaGetDevice(&h->device);
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
+      {
+        delete h;
+        return PE_ERR_CUDA;
+      }
+    for (auto &ev : h->ev)
+      cudaEventCreate(&ev);
+    cudaMallocHost((void **)&h->h_scal, 64 * sizeof(double));
+    *out = h;
+    return PE_OK;
+  }
+
+  int
+  pe_destroy(pe_handle *h)
+  {
+    if (!h)
+      return PE_OK;
+    if (h->device < 0)
+      {
+        delete h;
+        return PE_OK;
+      }
+    cudaSetDevice(h->device);
+    comm_destroy(h);
+    if (h->stream)
+      cudaStreamSynchronize(h->stream);
+    for (auto &ev : h->ev)
+      if (ev)
+        cudaEventDestroy(ev);
+    if (h->h_scal)
+      cudaFreeHost(h->h_scal);
+    if (h->stream)
+      cudaStreamDestroy(h->stream);
+    delete h;
+    return PE_OK;
+  }
+
+  const char *
+  pe_last_error(const pe_handle *h)
+  {
+    return h ? h->err.c_str() : "null handle";
+  }
+
+#define PE_TRY try {
+#define PE_CATCH                                                     \
+  }                                                                  \
+  catch (const std::bad_alloc &)                                     \
+  {                                                                  \
+    return fail(h, PE_ERR_ALLOC, "out of host memory");              \
+  }                                                                  \
+  catch (const std::exception &ex)                                   \
+  {                                                                  \
+    return fail(h, PE_ERR_ARG, ex.what());                           \
+  }
+
+  int
+  pe_make_unit_square(pe_handle *h, int n_refine, double distort, uint64_t seed, int boundary_kinds)
+  {
+    if (!h)
+      return PE_ERR_ARG;
+    PE_TRY
+    make_unit_square(h->mesh, n_refine, distort, seed, boundary_kinds);
+    h->have_mesh = true;
+    h->have_dofs = h->have_pattern = h->device_ready = false;
+    return PE_OK;
+    PE_CATCH
+  }
+
+  int
+  pe_set_mesh(pe_handle *h, int64_t n_vertices, const double *x, const double *y, int64_t xy_stride,
+              int64_t n_cells, const uint32_t *cell_vertices)
+  {
+    if (!h || !x || !y || !cell_vertices || n_vertices <= 0 || n_cells <= 0 || xy_stride < 1)
+      return fail(h, PE_ERR_ARG, "pe_set_mesh: bad argument");
+    PE_TRY
+    HostMesh &m  = h->mesh;
+    m.n_refine   = -1;
+    m.n_vertices = n_vertices;
+    m.n_cells    = n_cells;
+    m.x.resize((size_t)n_vertices);
+    m.y.resize((size_t)n_vertices);
+    for (int64_t i = 0; i < n_vertices; ++i)
+      {
+        m.x[i] = x[i * xy_stride];
+        m.y[i] = y[i * xy_stride];
+      }
+    m.cell_vertices.assign(cell_vertices, cell_vertices + 4 * (size_t)n_cells);
+    for (const uint32_t v : m.cell_vertices)
+      if ((int64_t)v >= n_vertices)
+        return fail(h, PE_ERR_ARG, "pe_set_mesh: vertex index out of range");
+    m.face_kinds.assign(4 * (size_t)n_cells, 0);
+    h->have_mesh = true;
+    h->have_dofs = h->have_pattern = h->device_ready = false;
+    return PE_OK;
+    PE_CATCH
+  }
+
+  int
+  pe_distribute_dofs(pe_handle *h)
+  {
+    if (!h || !h->have_mesh)
+      return fail(h, PE_ERR_ARG, "pe_distribute_dofs: set the mesh first");
+    PE_TRY
+    distribute_dofs(h->mesh, h->cfg.element, h->dofs, h->part);
+    h->have_dofs    = true;
+    h->have_pattern = h->device_ready = false;
+    return PE_OK;
+    PE_CATCH
+  }
+
+  int
+  pe_set_dofs(pe_handle *h, int64_t n_u, int64_t n_pint, int64_t n_pface, const uint32_t *cell_dofs)
+  {
+    if (!h || !h->have_mesh || !cell_dofs)
+      return fail(h, PE_ERR_ARG, "pe_set_dofs: bad argument");
+    if (h->part.world != 1)
+      return fail(h, PE_ERR_ARG, "pe_set_dofs: user numbering is supported on one GPU only");
+    PE_TRY
+    HostDofs &d = h->dofs;
+    d.element   = h->cfg.element;
+    d.n_loc     = element_n_loc(h->cfg.element);
+    d.n_u       = n_u;
+    d.n_pint    = n_pint;
+    d.n_pface   = n_pface;
+    d.cell_dofs.assign(cell_dofs, cell_dofs + (size_t)h->mesh.n_cells * d.n_loc);
+    for (const uint32_t g : d.cell_dofs)
+      if ((int64_t)g >= d.n())
+        return fail(h, PE_ERR_ARG, "pe_set_dofs: dof index out of range");
+    Partition &pt = h->part;
+    pt.cell_begin = 0;
+    pt.cell_end   = h->mesh.n_cells;
+    pt.n_owned    = d.n();
+    const int64_t st[4] = {0, n_u, n_u + n_pint, d.n()};
+    for (int b = 0; b < 3; ++b)
+      {
+        pt.row_begin[b] = st[b];
+        pt.row_end[b]   = st[b + 1];
+        pt.local_off[b] = st[b];
+      }
+    pt.all_row_begin.assign(pt.row_begin, pt.row_begin + 3);
+    pt.all_row_end.assign(pt.row_end, pt.row_end + 3);
+    h->have_dofs    = true;
+    h->have_pattern = h->device_ready = false;
+    return PE_OK;
+    PE_CATCH
+  }
+
+  int
+  pe_make_sparsity_pattern(pe_handle *h)
+  {
+    if (!h || !h->have_dofs)
+      return fail(h, PE_ERR_ARG, "pe_make_sparsity_pattern: distribute dofs first");
+    PE_TRY
+    make_sparsity_pattern(h->mesh, h->dofs, h->part, h->pat);
+    h->have_pattern = true;
+    h->device_ready = false;
+    return PE_OK;
+    PE_CATCH
+  }
+
+  int
+  pe_set_pattern(pe_handle *h, const int64_t *rowptr, const int32_t *colidx)
+  {
+    if (!h || !h->have_dofs || !rowptr || !colidx)
+      return fail(h, PE_ERR_ARG, "pe_set_pattern: bad argument");
+    if (h->part.world != 1)
+      return fail(h, PE_ERR_ARG, "pe_set_pattern: supported on one GPU only");
+    PE_TRY
+    const int64_t n = h->dofs.n();
+    if (rowptr[0] != 0)
+      return fail(h, PE_ERR_ARG, "pe_set_pattern: rowptr[0] != 0");
+    for (int64_t r = 0; r < n; ++r)
+      {
+        if (rowptr[r + 1] < rowptr[r])
+          return fail(h, PE_ERR_ARG, "pe_set_pattern: rowptr not monotone");
+        for (int64_t k = rowptr[r] + 1; k < rowptr[r + 1]; ++k)
+          if (colidx[k] <= colidx[k - 1])
+            return fail(h, PE_ERR_ARG, "pe_set_pattern: columns of a row must be strictly ascending");
+      }
+    h->pat.rowptr.assign(rowptr, rowptr + n + 1);
+    h->pat.colidx.assign(colidx, colidx + rowptr[n]);
+    Partition &pt = h->part;
+    pt.asm_cells.resize((size_t)h->mesh.n_cells);
+    for (int64_t c = 0; c < h->mesh.n_cells; ++c)
+      pt.asm_cells[c] = c;
+    pt.n_ghost_cells = 0;
+    pt.ghost_cols.clear();
+    h->have_pattern = true;
+    h->device_ready = false;
+    return PE_OK;
+    PE_CATCH
+  }
+
+  int
+  pe_get_sizes(const pe_handle *h, pe_sizes *s)
+  {
+    if (!h || !s)
+      return PE_ERR_ARG;
+    std::memset(s, 0, sizeof(*s));
+    s->n_cells    = h->mesh.n_cells;
+    s->n_vertices = h->mesh.n_vertices;
+    s->n_loc      = element_n_loc(h->cfg.element);
+    if (h->have_dofs)
+      {
+        s->n_u          = h->dofs.n_u;
+        s->n_pint       = h->dofs.n_pint;
+        s->n_pface      = h->dofs.n_pface;
+        s->n_dofs       = h->dofs.n();
+        s->cell_begin   = h->part.cell_begin;
+        s->cell_end     = h->part.cell_end;
+        s->n_owned_rows = h->part.n_owned;
+      }
+    if (h->have_pattern)
+      {
+        s->nnz_owned     = (int64_t)h->pat.colidx.size();
+        s->nnz           = s->nnz_owned; // global count only known on one GPU
+        s->n_ghost_cells = h->part.n_ghost_cells;
+      }
+    return PE_OK;
+  }
+
+  int
+  pe_get_mesh(const pe_handle *h, double *x, double *y, uint32_t *cell_vertices, uint8_t *face_kinds)
+  {
+    if (!h || !h->have_mesh)
+      return PE_ERR_ARG;
+    if (x)
+      std::copy(h->mesh.x.begin(), h->mesh.x.end(), x);
+    if (y)
+      std::copy(h->mesh.y.begin(), h->mesh.y.end(), y);
+    if (cell_vertices)
+      std::copy(h->mesh.cell_vertices.begin(), h->mesh.cell_vertices.end(), cell_vertices);
+    if (face_kinds)
+      std::copy(h->mesh.face_kinds.begin(), h->mesh.face_kinds.end(), face_kinds);
+    return PE_OK;
+  }
+
+  int
+  pe_get_dofs(const pe_handle *h, uint32_t *cell_dofs)
+  {
+    if (!h || !h->have_dofs || !cell_dofs)
+      return PE_ERR_ARG;
+    std::copy(h->dofs.cell_dofs.begin(), h->dofs.cell_dofs.end(), cell_dofs);
+    return PE_OK;
+  }
+
+  int
+  pe_get_pattern(const pe_handle *h, int64_t *rowptr, int32_t *colidx)
+  {
+    if (!h || !h->have_pattern)
+      return PE_ERR_ARG;
+    if (rowptr)
+      std::copy(h->pat.rowptr.begin(), h->pat.rowptr.end(), rowptr);
+    if (colidx)
+      std::copy(h->pat.colidx.begin(), h->pat.colidx.end(), colidx);
+    return PE_OK;
+  }
+
+  int
+  pe_get_dealii_block_order(const pe_handle *hc, int64_t *perm)
+  {
+    pe_handle *h = const_cast<pe_handle *>(hc);
+    if (!h || !h->have_pattern || !perm || h->part.world != 1)
+      return fail(h, PE_ERR_ARG, "pe_get_dealii_block_order: needs a pattern on one GPU");
+    PE_TRY
+    std::vector<int64_t> p;
+    dealii_block_order(h->dofs, h->pat, p);
+    std::copy(p.begin(), p.end(), perm);
+    return PE_OK;
+    PE_CATCH
+  }
+
+  int
+  pe_set_material(pe_handle *h, double lambda, double mu, double alpha, double c0, double k_scalar,
+                  const double *k_cell)
+  {
+    if (!h)
+      return PE_ERR_ARG;
+    PE_TRY
+    h->lambda      = lambda;
+    h->mu          = mu;
+    h->alpha       = alpha;
+    h->c0          = c0;
+    h->k_scalar    = k_scalar;
+    h->k_lognormal = false;
+    if (k_cell)
+      {
+        if (!h->have_mesh)
+          return fail(h, PE_ERR_ARG, "pe_set_material: per-cell K needs the mesh first");
+        h->k_cell.assign(k_cell, k_cell + h->mesh.n_cells);
+      }
+    else
+      h->k_cell.clear();
+    if (h->device_ready)
+      {
+        // refresh the device copy of K only
+        if (!h->k_cell.empty())
+          {
+            std::vector<double> k((size_t)h->n_asm);
+            for (int64_t a = 0; a < h->n_asm; ++a)
+              k[a] = h->k_cell[h->part.asm_cells[a]];
+            PE_CUDA(upload(h->d_k, k.data(), k.size(), h->stream));
+            PE_CUDA(cudaStreamSynchronize(h->stream));
+          }
+        else
+          h->d_k.release();
+      }
+    return PE_OK;
+    PE_CATCH
+  }
+
+  int
+  pe_set_lognormal_k(pe_handle *h, double sigma, uint64_t seed)
+  {
+    if (!h)
+      return PE_ERR_ARG;
+    h->k_lognormal  = true;
+    h->k_sigma      = sigma;
+    h->k_seed       = seed;
+    h->device_ready = false;
+    return PE_OK;
+  }
+
+  int
+  pe_set_case(pe_handle *h, int case_id, const double *params)
+  {
+    if (!h || case_id < 0 || case_id > 2)
+      return fail(h, PE_ERR_ARG, "pe_set_case: unknown case");
+    h->case_id = case_id;
+    const double def[5] = {1., 1., 1., 0., 1.};
+    std::copy(params ? params : def, (params ? params : def) + 5, h->case_params);
+    return PE_OK;
+  }
+
+  int
+  pe_set_boundary(pe_handle *h, int64_t n_bfaces, const uint32_t *cell, const uint8_t *face, const uint8_t *kinds,
+                  const double traction[2])
+  {
+    if (!h || !h->have_mesh || (n_bfaces > 0 && (!cell || !face || !kinds)))
+      return fail(h, PE_ERR_ARG, "pe_set_boundary: bad argument");
+    std::fill(h->mesh.face_kinds.begin(), h->mesh.face_kinds.end(), 0);
+    for (int64_t k = 0; k < n_bfaces; ++k)
+      {
+        if ((int64_t)cell[k] >= h->mesh.n_cells || face[k] > 3)
+          return fail(h, PE_ERR_ARG, "pe_set_boundary: cell/face out of range");
+        h->mesh.face_kinds[4 * (size_t)cell[k] + face[k]] = kinds[k] & 7;
+      }
+    h->mesh.traction[0] = traction ? traction[0] : 0.;
+    h->mesh.traction[1] = traction ? traction[1] : 0.;
+    h->device_ready     = false;
+    return PE_OK;
+  }
+
+  int
+  pe_assemble_system(pe_handle *h, double t, double time_step, const double *old_solution)
+  {
+    if (!h)
+      return PE_ERR_ARG;
+    PE_TRY
+    return assemble_impl(h, t, time_step, old_solution, true);
+    PE_CATCH
+  }
+
+  int
+  pe_assemble_rhs_only(pe_handle *h, double t, double time_step, const double *old_solution)
+  {
+    if (!h)
+      return PE_ERR_ARG;
+    PE_TRY
+    return assemble_impl(h, t, time_step, old_solution, false);
+    PE_CATCH
+  }
+
+  int
+  pe_get_matrix(const pe_handle *hc, double *values)
+  {
+    pe_handle *h = const_cast<pe_handle *>(hc);
+    if (!h || !values || !h->device_ready || !h->matrix_valid)
+      return fail(h, PE_ERR_ARG, "pe_get_matrix: nothing assembled");
+    PE_CUDA(cudaMemcpyAsync(values, h->d_values.p, sizeof(double) * (size_t)h->nnz, cudaMemcpyDeviceToHost, h->stream));
+    PE_CUDA(cudaStreamSynchronize(h->stream));
+    return PE_OK;
+  }
+
+  int
+  pe_get_rhs(const pe_handle *hc, double *rhs)
+  {
+    pe_handle *h = const_cast<pe_handle *>(hc);
+    if (!h || !rhs || !h->device_ready)
+      return fail(h, PE_ERR_ARG, "pe_get_rhs: nothing assembled");
+    PE_CUDA(cudaMemcpyAsync(rhs, h->d_rhs.p, sizeof(double) * (size_t)h->L, cudaMemcpyDeviceToHost, h->stream));
+    PE_CUDA(cudaStreamSynchronize(h->stream));
+    return PE_OK;
+  }
+
+  int
+  pe_get_solution(const pe_handle *hc, double *solution)
+  {
+    pe_handle *h = const_cast<pe_handle *>(hc);
+    if (!h || !solution || !h->device_ready)
+      return fail(h, PE_ERR_ARG, "pe_get_solution: no device state");
+    PE_CUDA(cudaMemcpyAsync(solution, h->d_sol.p, sizeof(double) * (size_t)h->L, cudaMemcpyDeviceToHost, h->stream));
+    PE_CUDA(cudaStreamSynchronize(h->stream));
+    return PE_OK;
+  }
+
+  int
+  pe_set_solution(pe_handle *h, const double *solution)
+  {
+    if (!h || !solution)
+      return PE_ERR_ARG;
+    PE_TRY
+    const int rc = ensure_device(h);
+    if (rc != PE_OK)
+      return rc;
+    const int r2 = upload_global_vector(h, solution, h->d_sol.p);
+    if (r2 != PE_OK)
+      return r2;
+    PE_CUDA(cudaStreamSynchronize(h->stream));
+    return PE_OK;
+    PE_CATCH
+  }
+
+  int
+  pe_spmv(pe_handle *h, const double *x, double *y)
+  {
+    if (!h || !x || !y || !h->device_ready || !h->matrix_valid)
+      return fail(h, PE_ERR_ARG, "pe_spmv: assemble first");
+    PE_TRY
+    const size_t n = (size_t)(h->L + h->H);
+    for (int k = 0; k < 2; ++k)
+      if (h->d_w[k].n < n)
+        PE_CUDA(h->d_w[k].alloc(n));
+    const int rc = upload_global_vector(h, x, h->d_w[0].p);
+    if (rc != PE_OK)
+      return rc;
+    SolverCtx c = make_solver_ctx(h);
+    c.n_pos     = c.L; // plain A x
+    spmv_signed(c, h->d_w[0].p, h->d_w[1].p, nullptr);
+    ++h->launches;
+    PE_CUDA(cudaGetLastError());
+    PE_CUDA(cudaMemcpyAsync(y, h->d_w[1].p, sizeof(double) * (size_t)h->L, cudaMemcpyDeviceToHost, h->stream));
+    PE_CUDA(cudaStreamSynchronize(h->stream));
+    return PE_OK;
+    PE_CATCH
+  }
+
+  int
+  pe_bench_spmv(pe_handle *h, int repeats, double *ms_per_launch)
+  {
+    if (!h || repeats <= 0 || !ms_per_launch || !h->device_ready || !h->matrix_valid)
+      return fail(h, PE_ERR_ARG, "pe_bench_spmv: assemble first");
+    PE_TRY
+    const size_t n = (size_t)(h->L + h->H);
+    for (int k = 0; k < 2; ++k)
+      if (h->d_w[k].n < n)
+        PE_CUDA(h->d_w[k].alloc(n));
+    SolverCtx c = make_solver_ctx(h);
+    PE_CUDA(cudaMemcpyAsync(h->d_w[0].p, h->d_rhs.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
+    for (int k = 0; k < 3; ++k)
+      spmv_signed(c, h->d_w[0].p, h->d_w[1].p, nullptr);
+    PE_CUDA(cudaEventRecord(h->ev[5], h->stream));
+    for (int k = 0; k < repeats; ++k)
+      spmv_signed(c, h->d_w[0].p, h->d_w[1].p, nullptr);
+    PE_CUDA(cudaEventRecord(h->ev[6], h->stream));
+    PE_CUDA(cudaEventSynchronize(h->ev[6]));
+    h->launches += repeats + 3;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev[5], h->ev[6]);
+    *ms_per_launch = ms / repeats;
+    h->spmv_ms_avg = *ms_per_launch;
+    return PE_OK;
+    PE_CATCH
+  }
+
+  int
+  pe_solve_time_step(pe_handle *h, double rel_tol, int max_iterations, double *solution, pe_solve_stats *stats)
+  {
+    if (!h || !h->device_ready || !h->matrix_valid)
+      return fail(h, PE_ERR_ARG, "pe_solve_time_step: assemble first");
+    PE_TRY
+    pe_solve_stats local{};
+    if (!stats)
+      stats = &local;
+    std::memset(stats, 0, sizeof(*stats));
+    const size_t n = (size_t)(h->L + h->H);
+    for (int k = 0; k < 9; ++k)
+      if (h->d_w[k].n < n)
+        PE_CUDA(h->d_w[k].alloc(n));
+    if (h->d_pinv.n < n)
+      PE_CUDA(h->d_pinv.alloc(n));
+    if (h->d_scal.n < 64)
+      PE_CUDA(h->d_scal.alloc(64));
+    cudaStream_t s = h->stream;
+    SolverCtx    c = make_solver_ctx(h);
+    PE_CUDA(cudaEventRecord(h->ev[3], s));
+    int rc;
+    // initial guess: the previous solution (old_solution), already in d_sol
+    if (h->cfg.element == PE_WG_Q2RT2)
+      {
+        double *work[3] = {h->d_w[0].p, h->d_w[1].p, h->d_w[2].p};
+        PE_CUDA(cudaMemsetAsync(h->d_sol.p, 0, sizeof(double) * n, s)); // deal.II: solution starts at 0
+        rc = cg_solve(c, h->d_rhs.p, h->d_sol.p, work, h->d_scal.p, h->h_scal, rel_tol, max_iterations, stats);
+      }
+    else
+      {
+        if (build_preconditioner(c, h->d_w[7].p, h->d_pinv.p) != 0)
+          return cuda_fail(h, cudaGetLastError(), "build_preconditioner");
+        double *work[7] = {h->d_w[0].p, h->d_w[1].p, h->d_w[2].p, h->d_w[3].p, h->d_w[4].p, h->d_w[5].p, h->d_w[6].p};
+        rc = minres_solve(c, h->d_rhs.p, h->d_sol.p, h->d_pinv.p, work, (MinresState *)h->d_scal.p, h->h_scal,
+                          rel_tol, max_iterations, stats);
+      }
+    PE_CUDA(cudaEventRecord(h->ev[4], s));
+    PE_CUDA(cudaEventSynchronize(h->ev[4]));
+    if (rc != 0)
+      return cuda_fail(h, cudaGetLastError(), "krylov solve");
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]);
+    h->solve_ms    = ms;
+    stats->seconds = ms * 1e-3;
+    h->launches += (int64_t)stats->iterations * 7 + stats->spmv_count + 8;
+    if (solution)
+      {
+        PE_CUDA(cudaMemcpyAsync(solution, h->d_sol.p, sizeof(double) * (size_t)h->L, cudaMemcpyDeviceToHost, s));
+        PE_CUDA(cudaStreamSynchronize(s));
+      }
+    if (!stats->converged)
+      return fail(h, PE_ERR_NOT_CONVERGED, "Krylov solver did not reach the requested residual");
+    return PE_OK;
+    PE_CATCH
+  }
+
+  int
+  pe_local_matrices(pe_handle *h, int64_t first_cell, int64_t n, double t, double time_step,
+                    const double *old_solution, double *out, double *rhs_out)
+  {
+    if (!h || !h->have_mesh || !out || n <= 0 || first_cell < 0 || first_cell + n > h->mesh.n_cells)
+      return fail(h, PE_ERR_ARG, "pe_local_matrices: bad argument");
+    if (h->cfg.element != PE_BR1_WG && h->cfg.element != PE_CGQ1_WG)
+      return fail(h, PE_ERR_ARG, "pe_local_matrices: element not implemented yet");
+    if (h->part.world != 1)
+      return fail(h, PE_ERR_ARG, "pe_local_matrices: one GPU only");
+    if (h->device < 0)
+      return fail(h, PE_ERR_NO_DEVICE, "no hot path without a GPU");
+    PE_TRY
+    cudaStream_t s     = h->stream;
+    const int    n_loc = element_n_loc(h->cfg.element);
+    const size_t nn    = (size_t)n_loc * n_loc;
+    // stand-alone path: only the mesh and K are needed
+    DevBuf<double>   vx, vy, kc, o, ro, sol;
+    DevBuf<uint32_t> cv;
+    DevBuf<int32_t>  cd;
+    PE_CUDA(upload(vx, h->mesh.x.data(), h->mesh.x.size(), s));
+    PE_CUDA(upload(vy, h->mesh.y.data(), h->mesh.y.size(), s));
+    std::vector<uint32_t> cvh((size_t)4 * n);
+    for (int64_t c = 0; c < n; ++c)
+      for (int v = 0; v < 4; ++v)
+        cvh[(size_t)v * n + c] = h->mesh.cell_vertices[4 * (first_cell + c) + v];
+    PE_CUDA(upload(cv, cvh.data(), cvh.size(), s));
+    AsmArgs a{};
+    a.n_asm    = n;
+    a.vx       = vx.p;
+    a.vy       = vy.p;
+    a.cv       = cv.p;
+    a.k_scalar = h->k_scalar;
+    if (h->k_lognormal)
+      {
+        PE_CUDA(kc.alloc((size_t)n));
+        PE_CUDA(launch_lognormal(n, nullptr, first_cell, h->k_sigma, h->k_seed, kc.p, s));
+        ++h->launches;
+        a.kcell = kc.p;
+      }
+    else if (!h->k_cell.empty())
+      {
+        PE_CUDA(upload(kc, h->k_cell.data() + first_cell, (size_t)n, s));
+        a.kcell = kc.p;
+      }
+    if (old_solution)
+      {
+        if (!h->have_dofs)
+          return fail(h, PE_ERR_ARG, "pe_local_matrices: old_solution needs dofs");
+        std::vector<int32_t> cdh((size_t)n_loc * n);
+        for (int64_t c = 0; c < n; ++c)
+          for (int i = 0; i < n_loc; ++i)
+            cdh[(size_t)i * n + c] = (int32_t)h->dofs.cell_dofs[(size_t)(first_cell + c) * n_loc + i];
+        PE_CUDA(upload(cd, cdh.data(), cdh.size(), s));
+        PE_CUDA(upload(sol, old_solution, (size_t)h->dofs.n(), s));
+        a.cdofs = cd.p;
+        a.sol   = sol.p;
+      }
+    PE_CUDA(o.alloc(nn * (size_t)n));
+    if (rhs_out)
+      PE_CUDA(ro.alloc((size_t)n_loc * n));
+    const DevParams P = make_params(h, t, time_step);
+    PE_CUDA(launch_local_matrices(h->cfg.element, a, P, 0, n, o.p, rhs_out ? ro.p : nullptr, s));
+    ++h->launches;
+    std::vector<double> tmp(nn * (size_t)n);
+    PE_CUDA(cudaMemcpyAsync(tmp.data(), o.p, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, s));
+    PE_CUDA(cudaStreamSynchronize(s));
+    for (int64_t c = 0; c < n; ++c)
+      for (size_t e = 0; e < nn; ++e)
+        out[(size_t)c * nn + e] = tmp[e * (size_t)n + c];
+    if (rhs_out)
+      {
+        std::vector<double> tr((size_t)n_loc * n);
+        PE_CUDA(cudaMemcpyAsync(tr.data(), ro.p, sizeof(double) * tr.size(), cudaMemcpyDeviceToHost, s));
+        PE_CUDA(cudaStreamSynchronize(s));
+        for (int64_t c = 0; c < n; ++c)
+          for (int i = 0; i < n_loc; ++i)
+            rhs_out[(size_t)c * n_loc + i] = tr[(size_t)i * n + c];
+      }
+    return PE_OK;
+    PE_CATCH
+  }
+
+  int
+  pe_local_matrices_bench(pe_handle *h, double t, double time_step, int64_t chunk_cells, int repeats,
+                          double *checksum, double *seconds)
+  {
+    if (!h || !h->have_mesh || chunk_cells <= 0 || repeats <= 0)
+      return fail(h, PE_ERR_ARG, "pe_local_matrices_bench: bad argument");
+    if (h->cfg.element != PE_BR1_WG && h->cfg.element != PE_CGQ1_WG)
+      return fail(h, PE_ERR_ARG, "pe_local_matrices_bench: element not implemented yet");
+    if (h->device < 0)
+      return fail(h, PE_ERR_NO_DEVICE, "no hot path without a GPU");
+    PE_TRY
+    cudaStream_t  s     = h->stream;
+    const int     n_loc = element_n_loc(h->cfg.element);
+    const size_t  nn    = (size_t)n_loc * n_loc;
+    const int64_t nc    = h->mesh.n_cells;
+    chunk_cells         = std::min(chunk_cells, nc);
+    DevBuf<double>   vx, vy, kc, o, sum;
+    DevBuf<uint32_t> cv;
+    PE_CUDA(upload(vx, h->mesh.x.data(), h->mesh.x.size(), s));
+    PE_CUDA(upload(vy, h->mesh.y.data(), h->mesh.y.size(), s));
+    {
+      std::vector<uint32_t> cvh((size_t)4 * nc);
+      for (int64_t c = 0; c < nc; ++c)
+        for (int v = 0; v < 4; ++v)
+          cvh[(size_t)v * nc + c] = h->mesh.cell_vertices[4 * c + v];
+      PE_CUDA(upload(cv, cvh.data(), cvh.size(), s));
+      PE_CUDA(cudaStreamSynchronize(s));
+    }
+    AsmArgs a{};
+    a.n_asm    = nc;
+    a.vx       = vx.p;
+    a.vy       = vy.p;
+    a.cv       = cv.p;
+    a.k_scalar = h->k_scalar;
+    if (h->k_lognormal)
+      {
+        PE_CUDA(kc.alloc((size_t)nc));
+        PE_CUDA(launch_lognormal(nc, nullptr, 0, h->k_sigma, h->k_seed, kc.p, s));
+        a.kcell = kc.p;
+      }
+    else if (!h->k_cell.empty())
+      {
+        PE_CUDA(upload(kc, h->k_cell.data(), (size_t)nc, s));
+        a.kcell = kc.p;
+      }
+    PE_CUDA(o.alloc(nn * (size_t)chunk_cells));
+    PE_CUDA(sum.alloc(1));
+    const DevParams P = make_params(h, t, time_step);
+    double          total_ms = 0., cs = 0.;
+    for (int rep = 0; rep <= repeats; ++rep) // rep 0 = warm-up + checksum
+      {
+        PE_CUDA(cudaEventRecord(h->ev[5], s));
+        for (int64_t first = 0; first < nc; first += chunk_cells)
+          {
+            const int64_t n = std::min(chunk_cells, nc - first);
+            PE_CUDA(launch_local_matrices(h->cfg.element, a, P, first, n, o.p, nullptr, s));
+            ++h->launches;
+            if (rep == 0)
+              {
+                PE_CUDA(launch_sum(o.p, nn * (size_t)n, sum.p, s));
+                double part = 0.;
+                PE_CUDA(cudaMemcpyAsync(&part, sum.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+                PE_CUDA(cudaStreamSynchronize(s));
+                cs += part;
+              }
+          }
+        PE_CUDA(cudaEventRecord(h->ev[6], s));
+        PE_CUDA(cudaEventSynchronize(h->ev[6]));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev[5], h->ev[6]);
+        if (rep > 0)
+          total_ms += ms;
+      }
+    if (checksum)
+      *checksum = cs;
+    if (seconds)
+      *seconds = total_ms * 1e-3 / repeats;
+    return PE_OK;
+    PE_CATCH
+  }
+
+  int
+  pe_step_errors(pe_handle *h, double, double *)
+  {
+    return fail(h, PE_ERR_ARG, "pe_step_errors: not implemented yet");
+  }
+
+  int
+  pe_comm_unique_id(uint8_t id[128])
+  {
+    return comm_unique_id(id);
+  }
+
+  int
+  pe_comm_init(pe_handle *h, const uint8_t id[128])
+  {
+    if (!h || !id)
+      return PE_ERR_ARG;
+    return comm_init(h, id);
+  }
+
+  int
+  pe_get_timings(const pe_handle *h, double *assemble_ms, double *assemble_kernel_ms, double *solve_ms,
+                 double *spmv_ms_avg, int64_t *launches)
+  {
+    if (!h)
+      return PE_ERR_ARG;
+    if (assemble_ms)
+      *assemble_ms = h->assemble_ms;
+    if (assemble_kernel_ms)
+      *assemble_kernel_ms = h->assemble_kernel_ms;
+    if (solve_ms)
+      *solve_ms = h->solve_ms;
+    if (spmv_ms_avg)
+      *spmv_ms_avg = h->spmv_ms_avg;
+    if (launches)
+      *launches = h->launches;
+    return PE_OK;
+  }
+}

@@ -1,0 +1,577 @@
+// Device-side cell kernel math (FP64, sm_100a): one thread builds the whole local matrix and local
+// right-hand side of one cell in registers and hands every entry to an "emit" functor.
+//
+// Replaces the cell loop body of assemble_system:
+//   BR1-WG  : PoroElasBR1WG_new.cc:794-961   (A1-A6 of SURVEY.md 8(a))
+//   CGQ1-WG : PoroElasCGQ1_WG.cc:1168-1453
+// in lean form: for RT0 the weak-gradient right-hand side F is the
+// constant matrix F_int = (+1,-1,+1,-1), F_face = diag(-1,+1,-1,+1) on ANY quadrilateral, so the
+// Darcy block is dt k F M^{-1} F^T with M the RT0 Gram matrix; the strain block is assembled from
+// the three gradient-moment matrices of the 8 scalar shape functions.
+#pragma once
+#include <cstdint>
+
+namespace pe
+{
+  struct DevParams
+  {
+    double lambda, mu, alpha, c0, dt;
+    double traction[2];
+    int    case_id;
+    // time-dependent factors of the "coscos" case, evaluated on the host once per assemble:
+    double f_coef; // pi (f_lambda + 2 f_mu - f_alpha) sin(pi t/2)              BR1new:409-412
+    double s_coef; // (pi/2) cos(pi t/2)(s_capacity + s_alpha) + 2 pi^2 sin(pi t/2)  BR1new:376-378
+    double u_coef; // sin(pi t/2) / (2 pi)                                      BR1new:207-208
+    double p_coef; // sin(pi t/2)                                               BR1new:209-210
+  };
+
+  // QGauss<1>(3) on [0,1] (deal.II quadrature_lib.cc): 0.5 -+ sqrt(3/5)/2, 0.5
+  __device__ constexpr double kGx[3] = {0.11270166537925831148, 0.5, 0.88729833462074168852};
+  __device__ constexpr double kGw[3] = {5. / 18., 8. / 18., 5. / 18.};
+
+  template <int EL>
+  struct Elem;
+  template <>
+  struct Elem<0> // BR1-WG: (v0x v0y .. v3x v3y | b0 pf0 | b1 pf1 | b2 pf2 | b3 pf3 | pint)
+  {
+    static constexpr int NL = 17, NS = 8, NU = 12, PINT = 16;
+    __host__ __device__ static constexpr int
+    pface(int f)
+    {
+      return 9 + 2 * f;
+    }
+    __host__ __device__ static constexpr int
+    bubble(int f)
+    {
+      return 8 + 2 * f;
+    }
+  };
+  template <>
+  struct Elem<1> // CGQ1-WG: (v0x .. v3y | pf0 pf1 pf2 pf3 | pint)
+  {
+    static constexpr int NL = 13, NS = 4, NU = 8, PINT = 12;
+    __host__ __device__ static constexpr int
+    pface(int f)
+    {
+      return 8 + f;
+    }
+    __host__ __device__ static constexpr int
+    bubble(int)
+    {
+      return -1;
+    }
+  };
+
+  struct Geom
+  {
+    double x0, y0;                     // vertex 0
+    double a1x, a1y, a2x, a2y, a3x, a3y; // x(xi,eta) = x0 + a1 xi + a2 eta + a3 xi eta
+    __device__ __forceinline__ void
+    set(const double vx[4], const double vy[4])
+    {
+      x0  = vx[0];
+      y0  = vy[0];
+      a1x = vx[1] - vx[0];
+      a1y = vy[1] - vy[0];
+      a2x = vx[2] - vx[0];
+      a2y = vy[2] - vy[0];
+      a3x = (vx[0] - vx[1]) - (vx[2] - vx[3]);
+      a3y = (vy[0] - vy[1]) - (vy[2] - vy[3]);
+    }
+    __device__ __forceinline__ void
+    jac(const double xi, const double eta, double &j00, double &j01, double &j10, double &j11) const
+    {
+      j00 = a1x + a3x * eta;
+      j01 = a2x + a3x * xi;
+      j10 = a1y + a3y * eta;
+      j11 = a2y + a3y * xi;
+    }
+    __device__ __forceinline__ void
+    point(const double xi, const double eta, double &px, double &py) const
+    {
+      px = x0 + a1x * xi + (a2x + a3x * xi) * eta;
+      py = y0 + a1y * xi + (a2y + a3y * xi) * eta;
+    }
+  };
+
+  // reference gradients of the scalar shape functions (Q1 nodal 0..3, BR bubbles 4..7) times the
+  // adjugate of J:  nx = s_xi J11 - s_eta J10,  ny = -s_xi J01 + s_eta J00   (grad = n / det J)
+  template <int NS>
+  __device__ __forceinline__ void
+  shape_grads(const double xi, const double eta, const double j00, const double j01, const double j10,
+              const double j11, double nx[NS], double ny[NS])
+  {
+    const double mxi = 1. - xi, meta = 1. - eta;
+    double       sx[NS], se[NS];
+    sx[0] = -meta;
+    se[0] = -mxi;
+    sx[1] = meta;
+    se[1] = -xi;
+    sx[2] = -eta;
+    se[2] = mxi;
+    sx[3] = eta;
+    se[3] = xi;
+    if (NS == 8)
+      {
+        const double bx = 4. * xi * mxi, dbx = 4. * (1. - 2. * xi);
+        const double by = 4. * eta * meta, dby = 4. * (1. - 2. * eta);
+        sx[4] = -by;
+        se[4] = mxi * dby;
+        sx[5] = by;
+        se[5] = xi * dby;
+        sx[6] = dbx * meta;
+        se[6] = -bx;
+        sx[7] = dbx * eta;
+        se[7] = bx;
+      }
+#pragma unroll
+    for (int a = 0; a < NS; ++a)
+      {
+        nx[a] = sx[a] * j11 - se[a] * j10;
+        ny[a] = se[a] * j00 - sx[a] * j01;
+      }
+  }
+
+  template <int NS>
+  __device__ __forceinline__ void
+  shape_values(const double xi, const double eta, double s[NS])
+  {
+    const double mxi = 1. - xi, meta = 1. - eta;
+    s[0] = mxi * meta;
+    s[1] = xi * meta;
+    s[2] = mxi * eta;
+    s[3] = xi * eta;
+    if (NS == 8)
+      {
+        const double bx = 4. * xi * mxi, by = 4. * eta * meta;
+        s[4] = mxi * by;
+        s[5] = xi * by;
+        s[6] = bx * meta;
+        s[7] = bx * eta;
+      }
+  }
+
+  // displacement component carried by scalar shape a: vertex shapes carry both, bubbles 4,5 -> x,
+  // bubbles 6,7 -> y.  Local dof index of (shape a, component c):
+  template <int EL>
+  __host__ __device__ constexpr int
+  udof(int a, int c)
+  {
+    return a < 4 ? 2 * a + c : Elem<EL>::bubble(a - 4);
+  }
+
+  // inverse of a symmetric positive definite 4x4 (RT0 Gram matrix; FullMatrix::gauss_jordan at
+  // BR1new:826).  m: 10 unique entries in row-major upper order 00 01 02 03 11 12 13 22 23 33.
+  __device__ __forceinline__ void
+  spd4_inverse(const double m[10], double g[10])
+  {
+    // Cholesky-free: block 2x2 inversion  M = [A B; B^T D]
+    const double a00 = m[0], a01 = m[1], a11 = m[4];
+    const double b00 = m[2], b01 = m[3], b10 = m[5], b11 = m[6];
+    const double d00 = m[7], d01 = m[8], d11 = m[9];
+    const double ida = 1. / (a00 * a11 - a01 * a01);
+    const double i00 = a11 * ida, i01 = -a01 * ida, i11 = a00 * ida; // A^{-1}
+    // T = A^{-1} B  (2x2)
+    const double t00 = i00 * b00 + i01 * b10, t01 = i00 * b01 + i01 * b11;
+    const double t10 = i01 * b00 + i11 * b10, t11 = i01 * b01 + i11 * b11;
+    // S = D - B^T T (symmetric)
+    const double s00 = d00 - (b00 * t00 + b10 * t10);
+    const double s01 = d01 - (b00 * t01 + b10 * t11);
+    const double s11 = d11 - (b01 * t01 + b11 * t11);
+    const double ids = 1. / (s00 * s11 - s01 * s01);
+    const double q00 = s11 * ids, q01 = -s01 * ids, q11 = s00 * ids; // S^{-1}
+    // lower-right = S^{-1}; upper-right = -T S^{-1}; upper-left = A^{-1} + T S^{-1} T^T
+    const double u00 = t00 * q00 + t01 * q01, u01 = t00 * q01 + t01 * q11; // T S^{-1}
+    const double u10 = t10 * q00 + t11 * q01, u11 = t10 * q01 + t11 * q11;
+    g[7] = q00;
+    g[8] = q01;
+    g[9] = q11;
+    g[2] = -u00;
+    g[3] = -u01;
+    g[5] = -u10;
+    g[6] = -u11;
+    g[0] = i00 + (u00 * t00 + u01 * t01);
+    g[1] = i01 + (u00 * t10 + u01 * t11);
+    g[4] = i11 + (u10 * t10 + u11 * t11);
+  }
+  __host__ __device__ constexpr int
+  sym4(int i, int j)
+  {
+    // index into the 10-entry upper-triangular storage
+    return i <= j ? (i == 0 ? j : i == 1 ? 3 + j : i == 2 ? 5 + j : 9) : sym4(j, i);
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // The cell kernel.  `old` = old_solution restricted to the cell (FESystem order).  Emit must
+  // provide  void mat(int i, int j, double v)  and  void rhs(int i, double v); every (i,j) pair
+  // of the NL x NL matrix is emitted exactly once (structural zeros included) with compile-time
+  // constant indices after unrolling.
+  // ---------------------------------------------------------------------------------------------
+  template <int EL, class Emit>
+  __device__ __forceinline__ void
+  cell_kernel(const Geom &G, const double kperm, const DevParams &P, const double *old, Emit &E)
+  {
+    using EE         = Elem<EL>;
+    constexpr int NS = EE::NS, NL = EE::NL, PI = EE::PINT;
+
+    // ---- quadrature sweep: gradient moments, divergence moments, RT0 Gram, load vector ----
+    double pxx[NS][NS], pyy[NS][NS], pxy[NS][NS]; // only the needed entries are ever touched
+    double dx[NS], dy[NS];                        // sum_q w_hat nx_a , ny_a  (= int d/dx s_a)
+    double bfx[NS], bfy[NS];                      // int f_x s_a , int f_y s_a
+    double m[10];                                 // RT0 Gram (unscaled by K)
+    double W = 0., bs = 0.;                       // sum JxW ; int s
+#pragma unroll
+    for (int a = 0; a < NS; ++a)
+      {
+        dx[a] = dy[a] = bfx[a] = bfy[a] = 0.;
+#pragma unroll
+        for (int b = 0; b < NS; ++b)
+          pxx[a][b] = pyy[a][b] = pxy[a][b] = 0.;
+      }
+#pragma unroll
+    for (int k = 0; k < 10; ++k)
+      m[k] = 0.;
+
+#pragma unroll
+    for (int qy = 0; qy < 3; ++qy)
+#pragma unroll
+      for (int qx = 0; qx < 3; ++qx)
+        {
+          const double xi = kGx[qx], eta = kGx[qy], wh = kGw[qx] * kGw[qy];
+          double       j00, j01, j10, j11;
+          G.jac(xi, eta, j00, j01, j10, j11);
+          const double det = j00 * j11 - j01 * j10;
+          const double r   = wh / det;
+          const double jxw = wh * det;
+          W += jxw;
+          double nx[NS], ny[NS];
+          shape_grads<NS>(xi, eta, j00, j01, j10, j11, nx, ny);
+#pragma unroll
+          for (int a = 0; a < NS; ++a)
+            {
+              dx[a] += wh * nx[a];
+              dy[a] += wh * ny[a];
+            }
+#pragma unroll
+          for (int a = 0; a < NS; ++a)
+            {
+              const double rx = r * nx[a], ry = r * ny[a];
+#pragma unroll
+              for (int b = 0; b < NS; ++b)
+                {
+                  // which moments does the strain block need for the pair (a,b)?  vertex shapes
+                  // carry both components; bubbles 4,5 only x; bubbles 6,7 only y.
+                  const bool ax = a < 6, ay = a < 4 || a >= 6, bx = b < 6, by = b < 4 || b >= 6;
+                  const bool same = (ax && bx) || (ay && by);
+                  if (same && b >= a)
+                    {
+                      pxx[a][b] += rx * nx[b];
+                      pyy[a][b] += ry * ny[b];
+                    }
+                  if (ay && bx) // A[(a,y),(b,x)] = mu int d_x s_a d_y s_b  (a carries y, b carries x)
+                    pxy[a][b] += rx * ny[b];
+                }
+            }
+          // RT0 Gram: w_k = J w_hat_k / det;  (w_k . w_l) JxW = r (J w_hat_k).(J w_hat_l)
+          {
+            const double c00 = j00 * j00 + j10 * j10, c01 = j00 * j01 + j10 * j11, c11 = j01 * j01 + j11 * j11;
+            const double mxi = 1. - xi, meta = 1. - eta;
+            const double rc00 = r * c00, rc01 = r * c01, rc11 = r * c11;
+            m[0] += rc00 * (mxi * mxi);
+            m[1] += rc00 * (mxi * xi);
+            m[4] += rc00 * (xi * xi);
+            m[2] += rc01 * (mxi * meta);
+            m[3] += rc01 * (mxi * eta);
+            m[5] += rc01 * (xi * meta);
+            m[6] += rc01 * (xi * eta);
+            m[7] += rc11 * (meta * meta);
+            m[8] += rc11 * (meta * eta);
+            m[9] += rc11 * (eta * eta);
+          }
+          if (P.case_id == 1)
+            {
+              double px, py, sx, cx, sy, cy;
+              G.point(xi, eta, px, py);
+              sincospi(px, &sx, &cx);
+              sincospi(py, &sy, &cy);
+              const double fx = P.f_coef * sx * cy * jxw, fy = P.f_coef * cx * sy * jxw;
+              bs += cx * cy * jxw;
+              double s[NS];
+              shape_values<NS>(xi, eta, s);
+#pragma unroll
+              for (int a = 0; a < NS; ++a)
+                {
+                  if (a < 6)
+                    bfx[a] += fx * s[a];
+                  if (a < 4 || a >= 6)
+                    bfy[a] += fy * s[a];
+                }
+            }
+        }
+
+    // cell->measure(): shoelace on vertices 0,1,3,2                          BR1new:867
+    const double area = 0.5 * ((G.a1x + G.a1x + G.a3x) * (G.a2y + G.a2y + G.a3y) -
+                               (G.a2x + G.a2x + G.a3x) * (G.a1y + G.a1y + G.a3y)) *
+                        0.5;
+    const double inv_area = 1. / area;
+
+    // ---- divergence vector of the u-dofs --------------------------------------------------------
+    // BR1: cell-averaged divergence (BR1new:867-876).  CGQ1: divergence at the 1-point rule
+    // times JxW_1 (CGQ1:1341-1358): n(center) / det_c * det_c.
+    double dv[EE::NU]; // BR1: dbar_i ; CGQ1: div_i(center)
+    double wq;         // weight the lambda / coupling terms are integrated with
+    double c0_weight;  // what multiplies c0 on the diagonal of p_int
+    if (EL == 0)
+      {
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+          {
+            dv[2 * a]     = dx[a] * inv_area;
+            dv[2 * a + 1] = dy[a] * inv_area;
+          }
+        dv[8]     = dx[4 % NS] * inv_area;
+        dv[9]     = dx[5 % NS] * inv_area;
+        dv[10]    = dy[6 % NS] * inv_area;
+        dv[11]    = dy[7 % NS] * inv_area;
+        wq        = W;
+        c0_weight = W;
+      }
+    else
+      {
+        double j00, j01, j10, j11, nx[NS], ny[NS];
+        G.jac(.5, .5, j00, j01, j10, j11);
+        const double detc = j00 * j11 - j01 * j10;
+        shape_grads<NS>(.5, .5, j00, j01, j10, j11, nx, ny);
+        const double id = 1. / detc;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+          {
+            dv[2 * a]     = nx[a] * id;
+            dv[2 * a + 1] = ny[a] * id;
+          }
+        wq        = detc;     // JxW of QGauss(1)
+        c0_weight = W + detc; // the storage term is integrated twice: CGQ1:1335 and :1352
+      }
+
+    // ---- strain + lambda block:  A[(a,c),(b,d)] = mu[d_cd (Pxx+Pyy)_ab + P^{dc}_ab] + lambda dv dv wq
+    // local u index -> position in dv: BR1: vertex dofs 0..7, bubbles 8..11
+    auto dvi = [&](int a, int c) -> double { return a < 4 ? dv[2 * a + c] : dv[(8 + (a - 4)) % EE::NU]; };
+#pragma unroll
+    for (int a = 0; a < NS; ++a)
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+        {
+          if (a >= 4 && c != (a - 4) / 2)
+            continue;
+          const int i = udof<EL>(a, c);
+#pragma unroll
+          for (int b = 0; b < NS; ++b)
+#pragma unroll
+            for (int d = 0; d < 2; ++d)
+              {
+                if (b >= 4 && d != (b - 4) / 2)
+                  continue;
+                const int j = udof<EL>(b, d);
+                double    v;
+                if (c == d)
+                  {
+                    const double xx = (b >= a) ? pxx[a][b] : pxx[b][a];
+                    const double yy = (b >= a) ? pyy[a][b] : pyy[b][a];
+                    v               = (c == 0) ? (xx + xx + yy) : (xx + yy + yy);
+                  }
+                else if (c == 1) // (a,y),(b,x): int d_x s_a d_y s_b
+                  v = pxy[a][b];
+                else             // (a,x),(b,y): int d_y s_a d_x s_b = the transposed entry
+                  v = pxy[b][a];
+                E.mat(i, j, P.mu * v + P.lambda * dvi(a, c) * dvi(b, d) * wq);
+              }
+          // coupling with p_int                                        BR1new:915,917 / CGQ1:1351,1354
+          E.mat(i, PI, -P.alpha * dvi(a, c) * wq);
+          E.mat(PI, i, P.alpha * dvi(a, c) * wq);
+#pragma unroll
+          for (int f = 0; f < 4; ++f)
+            {
+              E.mat(i, EE::pface(f), 0.);
+              E.mat(EE::pface(f), i, 0.);
+            }
+        }
+
+    // ---- Darcy block  dt k F M^{-1} F^T on (p_int, p_face 0..3)           BR1new:811-863,879-901
+    {
+      double g[10];
+      spd4_inverse(m, g);
+      const double sc    = P.dt * kperm;
+      const double sg[4] = {-1., 1., -1., 1.}; // F_face = diag(sg); F_int = -sg
+      double       rowsum[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        {
+          double s = 0.;
+#pragma unroll
+          for (int l = 0; l < 4; ++l)
+            s += -sg[l] * g[sym4(k, l)];
+          rowsum[k] = s; // (M^{-1} F_int^T)_k
+        }
+      double sii = 0.;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        sii += -sg[k] * rowsum[k];
+      E.mat(PI, PI, P.c0 * c0_weight + sc * sii);
+#pragma unroll
+      for (int f = 0; f < 4; ++f)
+        {
+          const double v = sc * sg[f] * rowsum[f];
+          E.mat(PI, EE::pface(f), v);
+          E.mat(EE::pface(f), PI, v);
+#pragma unroll
+          for (int f2 = 0; f2 < 4; ++f2)
+            E.mat(EE::pface(f), EE::pface(f2), sc * sg[f] * sg[f2] * g[sym4(f, f2)]);
+        }
+    }
+
+    // ---- right-hand side                                                  BR1new:928-961 / CGQ1:1381-1453
+    {
+      double div_old = 0.; // BR1: average divergence of u_old ; CGQ1: divergence at the cell centre
+#pragma unroll
+      for (int a = 0; a < NS; ++a)
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+          {
+            if (a >= 4 && c != (a - 4) / 2)
+              continue;
+            const int i = udof<EL>(a, c);
+            div_old += old[i] * dvi(a, c);
+            E.rhs(i, c == 0 ? bfx[a] : bfy[a]);
+          }
+      const double pold = old[PI];
+      E.rhs(PI, P.c0 * pold * W + P.dt * P.s_coef * bs + P.alpha * div_old * wq);
+#pragma unroll
+      for (int f = 0; f < 4; ++f)
+        E.rhs(EE::pface(f), 0.);
+    }
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // Boundary data of one cell (BR1new:963-1165, CGQ1:1563-1720): traction contribution to the local
+  // rhs and the per-cell Dirichlet constraint lines (is_con / g per local dof).
+  // flags: bits 3f..3f+2 = PE_FACE_* kinds of face f; bits 12..15 = vertex v carries a mesh-wide
+  // displacement constraint (CGQ1's interpolate_boundary_values over the whole DoFHandler).
+  // ---------------------------------------------------------------------------------------------
+  __device__ __forceinline__ void
+  exact_u(const DevParams &P, const double x, const double y, double &ux, double &uy)
+  {
+    if (P.case_id == 1)
+      {
+        double sx, cx, sy, cy;
+        sincospi(x, &sx, &cx);
+        sincospi(y, &sy, &cy);
+        ux = P.u_coef * sx * cy;
+        uy = P.u_coef * cx * sy;
+      }
+    else
+      ux = uy = 0.;
+  }
+  __device__ __forceinline__ double
+  exact_p(const DevParams &P, const double x, const double y)
+  {
+    if (P.case_id == 1)
+      {
+        double sx, cx, sy, cy;
+        sincospi(x, &sx, &cx);
+        sincospi(y, &sy, &cy);
+        return P.p_coef * cx * cy;
+      }
+    return 0.;
+  }
+
+  template <int EL>
+  __device__ inline void
+  cell_boundary(const Geom &G, const double vx[4], const double vy[4], const uint32_t flags, const DevParams &P,
+                double *b, bool *is_con, double *g)
+  {
+    using EE = Elem<EL>;
+    const int fv[4][2] = {{0, 2}, {1, 3}, {0, 1}, {2, 3}};
+    for (int i = 0; i < EE::NL; ++i)
+      {
+        is_con[i] = false;
+        g[i]      = 0.;
+      }
+    for (int f = 0; f < 4; ++f)
+      {
+        const uint32_t kind = (flags >> (3 * f)) & 7u;
+        if (kind == 0)
+          continue;
+        const int    v0 = fv[f][0], v1 = fv[f][1];
+        const double tx = vx[v1] - vx[v0], ty = vy[v1] - vy[v0];
+        const double len = sqrt(tx * tx + ty * ty);
+        if (kind & 4u) // traction: b_i += int_f t_N . phi_i                   BR1new:981-988
+          {
+            // Q1 traces integrate to len/2 each; the bubble 4t(1-t) e_{f/2} integrates to 2/3 len
+            for (int c = 0; c < 2; ++c)
+              {
+                b[2 * v0 + c] += P.traction[c] * (0.5 * len);
+                b[2 * v1 + c] += P.traction[c] * (0.5 * len);
+              }
+            if (EL == 0)
+              b[EE::bubble(f)] += P.traction[f / 2] * (2. / 3. * len);
+          }
+        if (kind & 2u) // p_face <- p(face midpoint)                           BR1new:1063-1070
+          {
+            const double mx = 0.5 * (vx[v0] + vx[v1]), my = 0.5 * (vy[v0] + vy[v1]);
+            is_con[EE::pface(f)] = true;
+            g[EE::pface(f)]      = exact_p(P, mx, my);
+          }
+        if (kind & 1u) // u Dirichlet                                          BR1new:1109-1159
+          {
+            double vv[4];
+            exact_u(P, vx[v0], vy[v0], vv[0], vv[1]);
+            exact_u(P, vx[v1], vy[v1], vv[2], vv[3]);
+            is_con[2 * v0] = is_con[2 * v0 + 1] = is_con[2 * v1] = is_con[2 * v1 + 1] = true;
+            g[2 * v0]     = vv[0];
+            g[2 * v0 + 1] = vv[1];
+            g[2 * v1]     = vv[2];
+            g[2 * v1 + 1] = vv[3];
+            if (EL == 0)
+              {
+                // outward normal at face quadrature point 0: sgn * row nb of J^{-1}, normalised
+                const int    nb = f < 2 ? 0 : 1;
+                const double sg = (f % 2 == 0) ? -1. : 1.;
+                const double t0 = kGx[0];
+                const double xi = f == 0 ? 0. : f == 1 ? 1. : t0, eta = f == 2 ? 0. : f == 3 ? 1. : t0;
+                double       j00, j01, j10, j11;
+                G.jac(xi, eta, j00, j01, j10, j11);
+                // rows of adj(J): row0 = (j11, -j01), row1 = (-j10, j00); det > 0 drops out
+                double nx = sg * (nb == 0 ? j11 : -j10), ny = sg * (nb == 0 ? -j01 : j00);
+                const double nl = sqrt(nx * nx + ny * ny);
+                nx /= nl;
+                ny /= nl;
+                double res_flux = 0., bubble_flux = 0.;
+                for (int q = 0; q < 3; ++q)
+                  {
+                    const double t  = kGx[q], w = kGw[q] * len;
+                    const double qx = vx[v0] + t * tx, qy = vy[v0] + t * ty;
+                    double       ux, uy;
+                    exact_u(P, qx, qy, ux, uy);
+                    ux -= vv[0] * (1. - t) + vv[2] * t;
+                    uy -= vv[1] * (1. - t) + vv[3] * t;
+                    const double bub = 4. * t * (1. - t);
+                    bubble_flux += (f / 2 == 0 ? nx : ny) * bub * w;
+                    res_flux += (ux * nx + uy * ny) * w;
+                  }
+                is_con[EE::bubble(f)] = true;
+                g[EE::bubble(f)]      = res_flux / bubble_flux;
+              }
+          }
+      }
+    if (EL == 1) // mesh-wide vertex constraints                              CGQ1:1673-1679
+      for (int v = 0; v < 4; ++v)
+        if ((flags >> (12 + v)) & 1u)
+          {
+            double ux, uy;
+            exact_u(P, vx[v], vy[v], ux, uy);
+            is_con[2 * v] = is_con[2 * v + 1] = true;
+            g[2 * v]     = ux;
+            g[2 * v + 1] = uy;
+          }
+  }
+} // namespace pe

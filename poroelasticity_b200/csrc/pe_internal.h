@@ -1,0 +1,127 @@
+// Internal state behind pe_handle.  Device memory layout (HBM), all structure-of-arrays so that a
+// warp of 32 consecutive cells reads/writes 32 consecutive words:
+//   vx, vy          double [n_vertices]
+//   cell_vertices   uint32 [4][n_asm]          asm cells = owned cells then ghost cells
+//   cell_dofs       int32  [n_loc][n_asm]      LOCAL numbering: < L owned row, >= L halo column
+//   kcell           double [n_asm]
+//   cell_flags      uint32 [n_asm]             3 bits of PE_FACE_* per face + CGQ1 vertex mask
+//   rowptr          int64  [L+1]   colidx int32 [nnz] (local numbering)   values double [nnz]
+//   scatter_off     uint8  [n_loc*n_loc][n_asm]  position of entry (i,j) inside CSR row of dof i
+//   rhs, sol, ...   double [L (+H)]
+#pragma once
+#include "../../include/poroelas_b200.h"
+#include "pe_cell.cuh"
+#include "pe_host.h"
+
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+struct ncclComm;
+
+namespace pe
+{
+  template <class T>
+  struct DevBuf
+  {
+    T     *p = nullptr;
+    size_t n = 0;
+    ~DevBuf() { release(); }
+    DevBuf()                = default;
+    DevBuf(const DevBuf &)  = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n)
+    {
+      o.p = nullptr;
+      o.n = 0;
+    }
+    DevBuf &
+    operator=(DevBuf &&o) noexcept
+    {
+      if (this != &o)
+        {
+          release();
+          p   = o.p;
+          n   = o.n;
+          o.p = nullptr;
+          o.n = 0;
+        }
+      return *this;
+    }
+    void
+    release()
+    {
+      if (p)
+        cudaFree(p);
+      p = nullptr;
+      n = 0;
+    }
+    cudaError_t
+    alloc(const size_t count)
+    {
+      release();
+      n = count;
+      if (count == 0)
+        return cudaSuccess;
+      return cudaMalloc((void **)&p, count * sizeof(T));
+    }
+  };
+
+  struct HaloPeer
+  {
+    int                  rank = -1;
+    std::vector<int32_t> send_rows; // local owned rows this peer needs from us
+    int64_t              recv_off = 0, recv_cnt = 0; // slice of our halo [L + recv_off, ...)
+    DevBuf<int32_t>      d_send_rows;
+    DevBuf<double>       d_send_buf;
+  };
+} // namespace pe
+
+struct pe_handle
+{
+  pe_config    cfg{};
+  std::string  err;
+  int          device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t  ev[8]  = {};
+
+  // ---- host side
+  pe::HostMesh    mesh;
+  pe::HostDofs    dofs;
+  pe::Partition   part;
+  pe::HostPattern pat;
+  bool            have_mesh = false, have_dofs = false, have_pattern = false, device_ready = false;
+  bool            matrix_valid = false;
+  double          lambda = 1., mu = 1., alpha = 1., c0 = 0., k_scalar = 1.;
+  std::vector<double> k_cell; // empty = scalar
+  bool            k_lognormal = false;
+  double          k_sigma = 0.;
+  uint64_t        k_seed = 0;
+  int             case_id = 0;
+  double          case_params[5] = {1., 1., 1., 0., 1.};
+  double          last_dt = 0.;
+
+  // ---- device side
+  int64_t n_asm = 0, n_bnd = 0, L = 0, H = 0, nnz = 0;
+  pe::DevBuf<double>   d_vx, d_vy, d_k, d_values, d_rhs, d_sol;
+  pe::DevBuf<uint32_t> d_cv, d_flags;
+  pe::DevBuf<int32_t>  d_cdofs, d_colidx, d_bnd_list;
+  pe::DevBuf<int64_t>  d_rowptr;
+  pe::DevBuf<uint8_t>  d_off;
+  pe::DevBuf<int>      d_err;
+  // solver work vectors (each L+H long so that any of them can be the SpMV input)
+  pe::DevBuf<double> d_w[10];
+  pe::DevBuf<double> d_pinv;   // block-Jacobi preconditioner (inverse diagonal)
+  pe::DevBuf<double> d_scal;   // small scalar scratch (dots)
+  double            *h_scal = nullptr; // pinned
+
+  // multi-GPU
+  ncclComm                 *comm = nullptr;
+  std::vector<pe::HaloPeer> peers;
+  cudaStream_t              comm_stream = nullptr;
+
+  // timings
+  double  assemble_ms = 0., assemble_kernel_ms = 0., solve_ms = 0., spmv_ms_avg = 0.;
+  int64_t launches = 0;
+};

@@ -1,0 +1,35 @@
+// Solver interface between pe_api.cu and pe_solver.cu.
+#pragma once
+#include "../../include/poroelas_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace pe
+{
+  struct MinresState;
+  struct SolverCtx
+  {
+    int64_t        L = 0, H = 0;    // owned rows, halo columns
+    int64_t        n_pos = 0;       // rows [0,n_pos) keep their sign, rows >= n_pos are negated (p rows)
+    int64_t        pint_begin = 0, pint_end = 0; // local row range of the interior pressures
+    const int64_t *rowptr = nullptr;
+    const int32_t *colidx = nullptr;
+    const double  *values = nullptr;
+    const uint8_t *col_is_u = nullptr; // per local column (L+H): 1 if displacement dof (multi-GPU only)
+    cudaStream_t   stream = nullptr;
+    // multi-GPU hooks (null on one GPU): fill x[L..L+H) from the owners; sum n doubles over ranks
+    void (*halo)(void *ctx, double *x)               = nullptr;
+    void (*allreduce)(void *ctx, double *v, int n)   = nullptr;
+    void *halo_ctx                                   = nullptr;
+  };
+
+  void   spmv_signed(const SolverCtx &c, const double *x, double *y, double *dot);
+  int    build_preconditioner(const SolverCtx &c, double *diag_full, double *pinv);
+  int    minres_solve(const SolverCtx &c, const double *b, double *x, const double *pinv, double *work[7],
+                      MinresState *st, double *h_pinned, double rel_tol, int max_it, pe_solve_stats *stats);
+  int    cg_solve(const SolverCtx &c, const double *b, double *x, double *work[3], void *st_dev, double *h_pinned,
+                  double rel_tol, int max_it, pe_solve_stats *stats);
+  size_t minres_state_bytes();
+} // namespace pe

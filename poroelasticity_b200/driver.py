@@ -1,0 +1,268 @@
+"""Host-side mirror of the reference's classes for the hot path, on top of the C ABI.
+
+The reference programs are one class per file with the private members make_grid_and_dofs() /
+setup_system(), assemble_system(t), solve_time_step() / solve() and run()
+(PoroElasBR1WG_new.cc:62-137, PoroElasCGQ1_WG.cc, EltStiffMat.cc).  The same names are kept here
+so that the parity tests read like the reference; the C++ twin lives in host/.  Nothing in this
+module computes: every method forwards to libporoelas_b200.so.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _capi as capi
+from ._capi import (PE_BR1_WG, PE_CGQ1_WG, PE_WG_Q2RT2, PE_CASE_ZERO, PE_CASE_COSCOS, PE_FACE_DIR_U,
+                    PE_FACE_DIR_P, PE_FACE_NEU_U, PoroElasError, pe_config, pe_sizes, pe_solve_stats, ptr)
+
+
+class BiotSystem:
+    """One reference program instance bound to one GPU."""
+
+    element = PE_BR1_WG
+
+    def __init__(self, element=None, device=-1, rank=0, world_size=1, host_setup_only=False):
+        self.L = capi.load()
+        if element is not None:
+            self.element = element
+        cfg = pe_config(self.element, 2, device, rank, world_size, 1 if host_setup_only else 0)
+        h = C.c_void_p()
+        rc = self.L.pe_create(C.byref(h), C.byref(cfg))
+        if rc != 0:
+            raise PoroElasError(rc, "pe_create failed (no CUDA device? this library has no CPU path)")
+        self.h = h
+        self.rank, self.world_size = rank, world_size
+        # constructor init-list of the reference's "general case" (BR1new:532-539)
+        self.lam, self.mu, self.alpha, self.capacity = 1.0, 1.0, 1.0, 0.0
+        self.time_step = 1.0 / 16
+        self.total_time = 1.0
+        self.stats = pe_solve_stats()
+        self.rel_tol, self.max_iterations = 1e-10, 200000
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pe_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise PoroElasError(rc, self.L.pe_last_error(self.h).decode())
+
+    # ---- make_grid_and_dofs()  BR1new:580-681 / CGQ1:883-1027
+    def make_grid_and_dofs(self, n_refine, distort=0.0, seed=12345,
+                           boundary_kinds=PE_FACE_DIR_U | PE_FACE_DIR_P, pattern=True):
+        self._ck(self.L.pe_make_unit_square(self.h, n_refine, distort, seed, boundary_kinds))
+        self._ck(self.L.pe_distribute_dofs(self.h))
+        if pattern:
+            self._ck(self.L.pe_make_sparsity_pattern(self.h))
+        return self.sizes()
+
+    def make_grid(self, n_refine, distort=0.0, seed=12345, boundary_kinds=0):
+        self._ck(self.L.pe_make_unit_square(self.h, n_refine, distort, seed, boundary_kinds))
+
+    def set_mesh(self, x, y, cell_vertices):
+        x = np.ascontiguousarray(x, np.float64)
+        y = np.ascontiguousarray(y, np.float64)
+        cv = np.ascontiguousarray(cell_vertices, np.uint32)
+        self._ck(self.L.pe_set_mesh(self.h, x.size, ptr(x), ptr(y), 1, cv.shape[0], ptr(cv)))
+
+    def distribute_dofs(self):
+        self._ck(self.L.pe_distribute_dofs(self.h))
+
+    def set_dofs(self, n_u, n_pint, n_pface, cell_dofs):
+        cd = np.ascontiguousarray(cell_dofs, np.uint32)
+        self._ck(self.L.pe_set_dofs(self.h, n_u, n_pint, n_pface, ptr(cd)))
+
+    def make_sparsity_pattern(self):
+        self._ck(self.L.pe_make_sparsity_pattern(self.h))
+
+    def set_pattern(self, rowptr, colidx):
+        rp = np.ascontiguousarray(rowptr, np.int64)
+        ci = np.ascontiguousarray(colidx, np.int32)
+        self._ck(self.L.pe_set_pattern(self.h, ptr(rp), ptr(ci)))
+
+    def sizes(self):
+        s = pe_sizes()
+        self._ck(self.L.pe_get_sizes(self.h, C.byref(s)))
+        return s
+
+    def mesh(self):
+        s = self.sizes()
+        x = np.zeros(s.n_vertices)
+        y = np.zeros(s.n_vertices)
+        cv = np.zeros((s.n_cells, 4), np.uint32)
+        fk = np.zeros((s.n_cells, 4), np.uint8)
+        self._ck(self.L.pe_get_mesh(self.h, ptr(x), ptr(y), ptr(cv), ptr(fk)))
+        return x, y, cv, fk
+
+    def cell_dofs(self):
+        s = self.sizes()
+        cd = np.zeros((s.n_cells, s.n_loc), np.uint32)
+        self._ck(self.L.pe_get_dofs(self.h, ptr(cd)))
+        return cd
+
+    def pattern(self):
+        s = self.sizes()
+        rp = np.zeros(s.n_owned_rows + 1, np.int64)
+        ci = np.zeros(s.nnz_owned, np.int32)
+        self._ck(self.L.pe_get_pattern(self.h, ptr(rp), ptr(ci)))
+        return rp, ci
+
+    def dealii_block_order(self):
+        s = self.sizes()
+        p = np.zeros(s.nnz, np.int64)
+        self._ck(self.L.pe_get_dealii_block_order(self.h, ptr(p)))
+        return p
+
+    # ---- problem data
+    def set_material(self, lam=None, mu=None, alpha=None, capacity=None, k_scalar=1.0, k_cell=None):
+        self.lam = self.lam if lam is None else lam
+        self.mu = self.mu if mu is None else mu
+        self.alpha = self.alpha if alpha is None else alpha
+        self.capacity = self.capacity if capacity is None else capacity
+        kc = None if k_cell is None else np.ascontiguousarray(k_cell, np.float64)
+        self._ck(self.L.pe_set_material(self.h, self.lam, self.mu, self.alpha, self.capacity, k_scalar, ptr(kc)))
+
+    def set_lognormal_k(self, sigma, seed):
+        self._ck(self.L.pe_set_lognormal_k(self.h, sigma, seed))
+
+    def set_case(self, case_id, params=None):
+        p = None if params is None else np.ascontiguousarray(params, np.float64)
+        self._ck(self.L.pe_set_case(self.h, case_id, ptr(p)))
+
+    def set_boundary(self, cells, faces, kinds, traction=(0.0, 0.0)):
+        c = np.ascontiguousarray(cells, np.uint32)
+        f = np.ascontiguousarray(faces, np.uint8)
+        k = np.ascontiguousarray(kinds, np.uint8)
+        t = np.ascontiguousarray(traction, np.float64)
+        self._ck(self.L.pe_set_boundary(self.h, c.size, ptr(c), ptr(f), ptr(k), ptr(t)))
+
+    def set_face_kinds(self, face_kinds, traction=(0.0, 0.0)):
+        fk = np.asarray(face_kinds, np.uint8).reshape(-1, 4)
+        cells, faces = np.nonzero(fk)
+        self.set_boundary(cells, faces, fk[cells, faces], traction)
+
+    # ---- hot path
+    def assemble_system(self, t, old_solution=None, time_step=None):
+        dt = self.time_step if time_step is None else time_step
+        o = None if old_solution is None else np.ascontiguousarray(old_solution, np.float64)
+        self._ck(self.L.pe_assemble_system(self.h, t, dt, ptr(o)))
+
+    def assemble_rhs_only(self, t, old_solution=None, time_step=None):
+        dt = self.time_step if time_step is None else time_step
+        o = None if old_solution is None else np.ascontiguousarray(old_solution, np.float64)
+        self._ck(self.L.pe_assemble_rhs_only(self.h, t, dt, ptr(o)))
+
+    def system_matrix(self):
+        v = np.zeros(self.sizes().nnz_owned)
+        self._ck(self.L.pe_get_matrix(self.h, ptr(v)))
+        return v
+
+    def system_rhs(self):
+        r = np.zeros(self.sizes().n_owned_rows)
+        self._ck(self.L.pe_get_rhs(self.h, ptr(r)))
+        return r
+
+    def solve_time_step(self, want_solution=True, check=True):
+        n = self.sizes().n_owned_rows
+        sol = np.zeros(n) if want_solution else None
+        rc = self.L.pe_solve_time_step(self.h, self.rel_tol, self.max_iterations, ptr(sol), C.byref(self.stats))
+        if rc != 0 and (check or rc != capi.PE_ERR_NOT_CONVERGED):
+            self._ck(rc)
+        return sol
+
+    def solution(self):
+        s = np.zeros(self.sizes().n_owned_rows)
+        self._ck(self.L.pe_get_solution(self.h, ptr(s)))
+        return s
+
+    def set_solution(self, sol):
+        s = np.ascontiguousarray(sol, np.float64)
+        self._ck(self.L.pe_set_solution(self.h, ptr(s)))
+
+    def spmv(self, x):
+        x = np.ascontiguousarray(x, np.float64)
+        y = np.zeros(self.sizes().n_owned_rows)
+        self._ck(self.L.pe_spmv(self.h, ptr(x), ptr(y)))
+        return y
+
+    def bench_spmv(self, repeats=20):
+        ms = C.c_double()
+        self._ck(self.L.pe_bench_spmv(self.h, repeats, C.byref(ms)))
+        return ms.value
+
+    def local_matrices(self, first, n, t=0.0, old_solution=None, time_step=None, want_rhs=False):
+        dt = self.time_step if time_step is None else time_step
+        nl = self.sizes().n_loc
+        out = np.zeros((n, nl, nl))
+        rhs = np.zeros((n, nl)) if want_rhs else None
+        o = None if old_solution is None else np.ascontiguousarray(old_solution, np.float64)
+        self._ck(self.L.pe_local_matrices(self.h, first, n, t, dt, ptr(o), ptr(out), ptr(rhs)))
+        return (out, rhs) if want_rhs else out
+
+    def local_matrices_bench(self, chunk_cells, repeats=1, t=0.0, time_step=None):
+        dt = self.time_step if time_step is None else time_step
+        cs, sec = C.c_double(), C.c_double()
+        self._ck(self.L.pe_local_matrices_bench(self.h, t, dt, chunk_cells, repeats, C.byref(cs), C.byref(sec)))
+        return cs.value, sec.value
+
+    def step_errors(self, t):
+        e = np.zeros(3)
+        self._ck(self.L.pe_step_errors(self.h, t, ptr(e)))
+        return e
+
+    def timings(self):
+        a, k, s, m = C.c_double(), C.c_double(), C.c_double(), C.c_double()
+        n = C.c_int64()
+        self._ck(self.L.pe_get_timings(self.h, C.byref(a), C.byref(k), C.byref(s), C.byref(m), C.byref(n)))
+        return {"assemble_ms": a.value, "assemble_kernel_ms": k.value, "solve_ms": s.value,
+                "spmv_ms_avg": m.value, "launches": n.value}
+
+    def comm_init(self, unique_id_bytes):
+        b = np.frombuffer(bytes(unique_id_bytes), np.uint8).copy()
+        self._ck(self.L.pe_comm_init(self.h, ptr(b)))
+
+    # ---- run(): the time loop  BR1new:2156-2243 / CGQ1:2908-2992
+    def run(self, n_refine, t_end=1.0, verbose=False, errors=False):
+        self.make_grid_and_dofs(n_refine)
+        self.set_material()
+        step, time = 1, self.time_step
+        hist = []
+        while time <= t_end:  # float-accumulated loop bound, as in the reference (BR1new:2181)
+            if verbose:
+                print("Time step %d at t=%g time_step %g" % (step, time, self.time_step))
+            self.assemble_system(time)  # old_solution = previous solution, on the device
+            self.solve_time_step(want_solution=False)
+            hist.append((time, self.stats.iterations, self.stats.rel_residual))
+            time += self.time_step
+            step += 1
+        return hist
+
+
+def comm_unique_id():
+    L = capi.load()
+    b = np.zeros(128, np.uint8)
+    rc = L.pe_comm_unique_id(ptr(b))
+    if rc != 0:
+        raise PoroElasError(rc, "ncclGetUniqueId failed")
+    return b.tobytes()
+
+
+class PoroElasBR1WG(BiotSystem):
+    """PoroElasBR1WG<2> of PoroElasBR1WG_new.cc."""
+    element = PE_BR1_WG
+
+
+class PoroElas_CGQ1_WG(BiotSystem):
+    """PoroElas_CGQ1_WG<2> of PoroElasCGQ1_WG.cc (2-D general case)."""
+    element = PE_CGQ1_WG
+
+    def __init__(self, **kw):
+        super().__init__(**kw)
+        self.time_step = 1.0 / 1024  # CGQ1:825

@@ -1,0 +1,162 @@
+"""Parity of the CUDA hot path (through the C ABI) against the CPU oracle on the same inputs.
+Tolerances (BASELINE north_star): matrix and rhs 1e-12 relative (measured against the largest entry
+of the same object, entries that cancel to ~0 cannot be compared entry-relative), per-step solution
+1e-8 relative L2."""
+import numpy as np
+import pytest
+
+import poroelasticity_b200 as pb
+from oracle_lib import BR1_WG, CGQ1_WG, CASE_COSCOS, CASE_ZERO, Oracle
+
+pytestmark = pytest.mark.gpu
+
+TOL_MAT = 1e-12
+TOL_SOL = 1e-8
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def make_pair(el, nref, distort=0.0, bc_mode=0, lam=1.0, mu=1.0, alpha=1.0, c0=0.0, dt=0.1, case=CASE_COSCOS,
+              kcell=None):
+    o = Oracle(el, nref, distort=distort, bc_mode=bc_mode)
+    o.set_material(lam, mu, alpha, c0, dt)
+    o.set_case(case)
+    b = pb.BiotSystem(element=el)
+    b.make_grid_and_dofs(nref, distort=distort)
+    b.time_step = dt
+    if bc_mode == 1:
+        b.set_face_kinds(o.mesh()[3], traction=(0.0, -1.0))
+    if kcell is not None:
+        o.set_kcell(kcell)
+    b.set_material(lam, mu, alpha, c0, 1.0, kcell)
+    b.set_case(case)
+    return o, b
+
+
+@pytest.mark.parametrize("el", [BR1_WG, CGQ1_WG])
+@pytest.mark.parametrize("distort", [0.0, 0.2])
+def test_local_matrices(el, distort):
+    rng = np.random.default_rng(0)
+    o, b = make_pair(el, 3, distort=distort, lam=3.0, mu=0.7, alpha=0.93, c0=0.1, dt=0.05,
+                     kcell=np.exp(rng.normal(size=64)))
+    old = rng.normal(size=o.n_dofs)
+    A_ref = np.zeros((o.n_cells, o.n_loc, o.n_loc))
+    b_ref = np.zeros((o.n_cells, o.n_loc))
+    for c in range(o.n_cells):
+        A_ref[c], b_ref[c], _, _ = o.local(c, 0.37, old)
+    A, r = b.local_matrices(0, o.n_cells, t=0.37, old_solution=old, want_rhs=True)
+    assert rel(A, A_ref) < TOL_MAT
+    for c in range(o.n_cells):
+        assert np.abs(A[c] - A_ref[c]).max() <= TOL_MAT * np.abs(A_ref[c]).max()
+    assert rel(r, b_ref) < TOL_MAT
+
+
+@pytest.mark.parametrize("el", [BR1_WG, CGQ1_WG])
+@pytest.mark.parametrize("nref,distort,bc_mode", [(0, 0.0, 0), (1, 0.0, 0), (3, 0.0, 0), (4, 0.2, 0), (3, 0.0, 1), (4, 0.15, 1)])
+def test_assembled_system(el, nref, distort, bc_mode):
+    rng = np.random.default_rng(1)
+    case = CASE_COSCOS if bc_mode == 0 else CASE_ZERO
+    o, b = make_pair(el, nref, distort=distort, bc_mode=bc_mode, lam=2.0, mu=0.8, alpha=0.9, c0=0.05, dt=0.1, case=case)
+    old = rng.normal(size=o.n_dofs)
+    v_ref, r_ref, _ = o.assemble(0.3, old)
+    b.assemble_system(0.3, old)
+    v, r = b.system_matrix(), b.system_rhs()
+    assert rel(v, v_ref) < TOL_MAT
+    assert rel(r, r_ref) < TOL_MAT
+    # structure: the same entries are (non)zero up to rounding noise
+    assert np.array_equal(np.abs(v) > 1e-9 * np.abs(v_ref).max(), np.abs(v_ref) > 1e-9 * np.abs(v_ref).max())
+    # right-hand-side-only reassembly keeps the matrix and reproduces the rhs
+    b.assemble_rhs_only(0.3, old)
+    assert np.array_equal(b.system_matrix(), v)
+    assert rel(b.system_rhs(), r_ref) < TOL_MAT
+
+
+def test_assembly_is_deterministic_up_to_atomics_order():
+    o, b = make_pair(BR1_WG, 4)
+    b.assemble_system(0.5)
+    v1 = b.system_matrix()
+    b.assemble_system(0.5)
+    assert rel(b.system_matrix(), v1) < 1e-14
+
+
+def test_lognormal_k_field_matches_generator():
+    """cfg 4: K = exp(sigma Z) from the shared counter generator, device vs numpy."""
+    from oracle_lib import lib
+    L = lib()
+    n = 256
+    u1 = np.array([L.orc_u01(12345, c, 0) for c in range(n)])
+    u2 = np.array([L.orc_u01(12345, c, 1) for c in range(n)])
+    k = np.exp(2.0 * np.sqrt(-2 * np.log(u1)) * np.cos(2 * np.pi * u2))
+    o = Oracle(BR1_WG, 4)
+    o.set_material(1e6, 1, 1, 1e-6, 0.1)
+    o.set_kcell(k)
+    b = pb.BiotSystem(element=BR1_WG)
+    b.make_grid_and_dofs(4)
+    b.time_step = 0.1
+    b.set_material(1e6, 1, 1, 1e-6)
+    b.set_lognormal_k(2.0, 12345)
+    A = b.local_matrices(0, n)
+    A_ref, _ = o.local_matrices(0, n)
+    assert rel(A, A_ref) < 1e-11
+
+
+@pytest.mark.parametrize("el", [BR1_WG, CGQ1_WG])
+def test_spmv(el):
+    rng = np.random.default_rng(2)
+    o, b = make_pair(el, 4, distort=0.1)
+    b.assemble_system(0.2)
+    A = o.csr(b.system_matrix())
+    x = rng.normal(size=o.n_dofs)
+    y = b.spmv(x)
+    assert rel(y, A @ x) < 1e-13
+
+
+@pytest.mark.parametrize("el,nref", [(BR1_WG, 3), (BR1_WG, 5), (CGQ1_WG, 3), (CGQ1_WG, 5)])
+def test_solve_time_steps_match_direct_solver(el, nref):
+    """Three backward-Euler steps: Krylov solution of the CUDA system vs sparse LU (SuperLU stands in
+    for UMFPACK, BR1new:1181-1183) of the oracle's system, 1e-8 relative L2 on u and on p."""
+    import scipy.sparse.linalg as spla
+    dt = 0.1
+    o, b = make_pair(el, nref, dt=dt)
+    b.rel_tol = 1e-12
+    old = np.zeros(o.n_dofs)
+    t = dt
+    for step in range(3):
+        v_ref, r_ref, _ = o.assemble(t, old)
+        x_ref = spla.splu(o.csr(v_ref).tocsc()).solve(r_ref)
+        b.assemble_system(t)            # old_solution = previous device solution
+        x = b.solve_time_step()
+        assert b.stats.converged
+        nu = o.n_u
+        assert np.linalg.norm(x[:nu] - x_ref[:nu]) <= TOL_SOL * np.linalg.norm(x_ref[:nu])
+        assert np.linalg.norm(x[nu:] - x_ref[nu:]) <= TOL_SOL * np.linalg.norm(x_ref[nu:])
+        old = x_ref
+        t += dt
+
+
+def test_full_size_properties_n1024():
+    """BASELINE cfg 2 size (1024 x 1024 BR1-WG): size-independent properties of the assembled system.
+    A_uu symmetric, pressure block symmetric, coupling blocks anti-symmetric, WG rows of interior
+    faces sum to zero, checksum of the local-matrix kernel equals the per-cell closed form."""
+    b = pb.PoroElasBR1WG()
+    s = b.make_grid_and_dofs(10)
+    assert (s.n_dofs, s.nnz) == (7348226, 231800836)
+    b.time_step = 0.1
+    b.set_material(1.0, 1.0, 1.0, 0.0)
+    b.set_case(pb.PE_CASE_COSCOS)
+    b.assemble_system(0.1)
+    rng = np.random.default_rng(3)
+    x = rng.normal(size=s.n_dofs)
+    y = rng.normal(size=s.n_dofs)
+    Ax, Ay = b.spmv(x), b.spmv(y)
+    D = np.ones(s.n_dofs)
+    D[s.n_u:] = -1.0
+    # D A is symmetric:  y^T D A x == x^T D A y
+    lhs, rhs = y @ (D * Ax), x @ (D * Ay)
+    assert abs(lhs - rhs) <= 1e-10 * max(abs(lhs), abs(rhs), 1.0)
+    # every local matrix on the uniform mesh is the same: checksum = n_cells * sum(A_cell)
+    cs, _ = b.local_matrices_bench(1 << 18, repeats=1, t=0.1)
+    one = b.local_matrices(0, 1, t=0.1)[0].sum()
+    assert cs == pytest.approx(one * s.n_cells, rel=1e-10)
