@@ -261,7 +261,7 @@ def main():
                        "l2": "inputs (2.9 GB CSR) exceed L2; no flush needed", "setup_s": t_setup},
             "s_per_time_step": dev_s / args.steps, "assemble_ms": sum(asm_ms) / len(asm_ms),
             "assembly_cells_per_s": n_cells / asm_kernel_s, "solve_ms": sum(sol_ms) / len(sol_ms),
-            "solver": {"method": "MINRES + diagonal Schur preconditioner", "iterations": iters, "spmv": spmvs,
+            "solver": {"method": "MINRES + block preconditioner (bubble Jacobi x Q1 V-cycle; p_int elimination + face V-cycle)", "iterations": iters, "spmv": spmvs,
                        "converged": converged, "rel_residual": rel_res},
             "wall_s": wall, "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e,
             "roofline": roof if roof else roof_asm, "roofline_assembly": roof_asm}

@@ -158,6 +158,11 @@ int pe_get_rhs(const pe_handle *h, double *rhs);
  * solution may be NULL (result stays on the device as the next old_solution). */
 int pe_solve_time_step(pe_handle *h, double rel_tol, int max_iterations, double *solution,
                        pe_solve_stats *stats);
+/* preconditioner of the Krylov solve: use_multigrid = 1: block preconditioner with
+ * auxiliary-space V-cycles (pe_precond.cu), 2: additive Jacobi + V-cycles, 0: diagonal only (meshes made
+ * by pe_make_unit_square); theta scales the diagonal part, omega / nu = Jacobi damping / sweeps.
+ * Defaults 1, 1.0, 0.8, 2. */
+int pe_set_solver_options(pe_handle *h, int use_multigrid, double theta, double omega, int nu);
 int pe_get_solution(const pe_handle *h, double *solution);
 int pe_set_solution(pe_handle *h, const double *solution);
 

@@ -3,6 +3,8 @@
 // every entry point that produces numbers launches the CUDA kernels or fails.
 #include "pe_internal.h"
 #include "pe_kernels.h"
+#include "pe_mg.h"
+#include "pe_precond.h"
 #include "pe_solver.h"
 
 #include <algorithm>
@@ -88,6 +90,10 @@ namespace
       return fail(h, PE_ERR_NO_DEVICE, "handle was created with PE_CFG_HOST_SETUP_ONLY: no hot path without a GPU");
     if (!h->have_mesh || !h->have_dofs || !h->have_pattern)
       return fail(h, PE_ERR_ARG, "mesh, dofs and sparsity pattern must be set before the hot path runs");
+    delete h->mg;
+    h->mg                  = nullptr;
+    delete h->bp;
+    h->bp                  = nullptr;
     cudaStream_t     s     = h->stream;
     const int        n_loc = h->dofs.n_loc;
     const Partition &pt    = h->part;
@@ -166,6 +172,12 @@ namespace
           lc[k] = to_local((uint32_t)h->pat.colidx[k]);
         PE_CUDA(upload(h->d_colidx, lc.data(), lc.size(), s));
       }
+    {
+      std::vector<int32_t> blk;
+      build_row_blocks(h->L, h->pat.rowptr.data(), blk);
+      h->n_rowblk = (int64_t)blk.size() - 1;
+      PE_CUDA(upload(h->d_rowblk, blk.data(), blk.size(), s));
+    }
     PE_CUDA(h->d_values.alloc((size_t)h->nnz));
     PE_CUDA(h->d_rhs.alloc((size_t)(h->L + h->H)));
     PE_CUDA(h->d_sol.alloc((size_t)(h->L + h->H)));
@@ -316,6 +328,11 @@ namespace
     c.colidx     = h->d_colidx.p;
     c.values     = h->d_values.p;
     c.stream     = h->stream;
+    if (h->spmv_kernel == 1)
+      {
+        c.rowblk   = h->d_rowblk.p;
+        c.n_rowblk = h->n_rowblk;
+      }
     if (h->part.world > 1)
       {
         c.halo      = comm_halo_exchange;
@@ -407,6 +424,10 @@ extern "C"
     comm_destroy(h);
     if (h->stream)
       cudaStreamSynchronize(h->stream);
+    delete h->mg;
+    h->mg = nullptr;
+    delete h->bp;
+    h->bp = nullptr;
     for (auto &ev : h->ev)
       if (ev)
         cudaEventDestroy(ev);
@@ -829,6 +850,19 @@ extern "C"
   }
 
   int
+  pe_set_solver_options(pe_handle *h, int use_multigrid, double theta, double omega, int nu)
+  {
+    if (!h || theta <= 0. || omega <= 0. || nu < 1)
+      return fail(h, PE_ERR_ARG, "pe_set_solver_options: bad argument");
+    h->use_mg      = use_multigrid & 3;
+    h->spmv_kernel = (use_multigrid & 16) ? 0 : 1; // bit 4: fall back to the warp-per-row SpMV (A/B measurements)
+    h->mg_theta = theta;
+    h->mg_omega = omega;
+    h->mg_nu    = nu;
+    return PE_OK;
+  }
+
+  int
   pe_bench_spmv(pe_handle *h, int repeats, double *ms_per_launch)
   {
     if (!h || repeats <= 0 || !ms_per_launch || !h->device_ready || !h->matrix_valid)
@@ -889,6 +923,55 @@ extern "C"
       {
         if (build_preconditioner(c, h->d_w[7].p, h->d_pinv.p) != 0)
           return cuda_fail(h, cudaGetLastError(), "build_preconditioner");
+        // multigrid part: hierarchy topology once per mesh, operators re-discretised every solve
+        if (h->use_mg && h->part.world == 1)
+          {
+            if (!h->mg)
+              {
+                h->mg = new MgHierarchy;
+                const int mrc = mg_build_topology(*h->mg, h->mesh, h->dofs, s);
+                if (mrc < 0)
+                  return cuda_fail(h, cudaGetLastError(), "mg_build_topology");
+              }
+            if (h->mg->ready)
+              {
+                h->mg->omega = h->mg_omega;
+                h->mg->nu    = h->mg_nu;
+                // reaction coefficient of the pressure auxiliary operator: c0 + alpha^2/(lambda+2mu)
+                const double gamma = h->c0 + h->alpha * h->alpha / (h->lambda + 2. * h->mu);
+                if (mg_assemble(*h->mg, h->d_k.p, h->k_scalar, h->lambda, h->mu, h->last_dt, gamma, s, &h->launches) != 0)
+                  return cuda_fail(h, cudaGetLastError(), "mg_assemble");
+                if (h->use_mg == 2)
+                  {
+                    // additive variant: theta D^{-1} + Pi V Pi^T on both blocks
+                    if (h->mg_theta != 1.0)
+                      scale_vector(c, h->d_pinv.p, h->mg_theta);
+                    c.precond_add = [](void *ctx, const double *r, double *z) {
+                      pe_handle *hh = (pe_handle *)ctx;
+                      mg_apply_add(*hh->mg, r, z, hh->stream, &hh->launches);
+                    };
+                  }
+                else
+                  {
+                    if (!h->bp)
+                      {
+                        h->bp = new BlockPrecond;
+                        if (precond_build_structure(*h->bp, h->mesh, h->dofs, h->pat, s) < 0)
+                          return cuda_fail(h, cudaGetLastError(), "precond_build_structure");
+                      }
+                    if (h->bp->ready)
+                      {
+                        if (precond_update(*h->bp, h->d_values.p, h->d_w[7].p, gamma, s, &h->launches) != 0)
+                          return cuda_fail(h, cudaGetLastError(), "precond_update");
+                        c.precond_apply = [](void *ctx, const double *r, double *z) {
+                          pe_handle *hh = (pe_handle *)ctx;
+                          precond_apply(*hh->bp, *hh->mg, hh->d_pinv.p, r, z, hh->stream, &hh->launches);
+                        };
+                      }
+                  }
+                c.precond_ctx = h;
+              }
+          }
         double *work[7] = {h->d_w[0].p, h->d_w[1].p, h->d_w[2].p, h->d_w[3].p, h->d_w[4].p, h->d_w[5].p, h->d_w[6].p};
         rc = minres_solve(c, h->d_rhs.p, h->d_sol.p, h->d_pinv.p, work, (MinresState *)h->d_scal.p, h->h_scal,
                           rel_tol, max_iterations, stats);

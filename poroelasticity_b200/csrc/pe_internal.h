@@ -19,6 +19,7 @@
 #include <vector>
 
 struct ncclComm;
+namespace pe { struct MgHierarchy; struct BlockPrecond; }
 
 namespace pe
 {
@@ -106,7 +107,9 @@ struct pe_handle
   int64_t n_asm = 0, n_bnd = 0, L = 0, H = 0, nnz = 0;
   pe::DevBuf<double>   d_vx, d_vy, d_k, d_values, d_rhs, d_sol;
   pe::DevBuf<uint32_t> d_cv, d_flags;
-  pe::DevBuf<int32_t>  d_cdofs, d_colidx, d_bnd_list;
+  pe::DevBuf<int32_t>  d_cdofs, d_colidx, d_bnd_list, d_rowblk;
+  int64_t              n_rowblk = 0;
+  int                  spmv_kernel = 1; // 1 = stream, 0 = warp per row
   pe::DevBuf<int64_t>  d_rowptr;
   pe::DevBuf<uint8_t>  d_off;
   pe::DevBuf<int>      d_err;
@@ -115,6 +118,14 @@ struct pe_handle
   pe::DevBuf<double> d_pinv;   // block-Jacobi preconditioner (inverse diagonal)
   pe::DevBuf<double> d_scal;   // small scalar scratch (dots)
   double            *h_scal = nullptr; // pinned
+
+  // auxiliary-space multigrid preconditioner (pe_mg.cu); null = diagonal preconditioner only
+  pe::MgHierarchy *mg = nullptr;
+  pe::BlockPrecond *bp = nullptr;
+  int              use_mg = 1;
+  double           mg_theta = 1.0, mg_omega = 0.6;
+  int              mg_nu = 1;
+  double           precond_ms = 0.;
 
   // multi-GPU
   ncclComm                 *comm = nullptr;

@@ -1,0 +1,604 @@
+// Auxiliary-space geometric multigrid preconditioner for the Biot system (new work: the reference
+// factorises with UMFPACK every step, PoroElasBR1WG_new.cc:1177-1187; BASELINE north_star asks for a
+// preconditioned Krylov solver).
+//
+//   P^{-1} = theta D^{-1}                       (diagonal part: bubbles, p_int/p_face oscillations)
+//          + Pi_u V_u Pi_u^T                    (vector Q1 elasticity V-cycle on the vertex grids)
+//          + Pi_p V_p Pi_p^T                    (scalar Q1 reaction-diffusion V-cycle)
+//
+// Pi_u injects a Q1 displacement into the vertex dofs of the BR1 / CGQ1 space (Q1 is a subspace);
+// Pi_p maps a Q1 pressure to (p_int = mean of the 4 cell vertices, p_face = mean of the 2 face
+// vertices).  The Q1 operators live on the nested vertex grids of refine_global
+// ((2^l+1)^2 vertices, lexicographic) as 9-point block stencils in SoA layout -- no index arrays,
+// fully coalesced -- and are re-discretised on every level from the level's own vertex coordinates
+// and the cell permeabilities averaged over children (Morton order makes children contiguous).
+// Smoother: damped (block-)Jacobi; V(2,2); R = P^T (bilinear): V_u, V_p are symmetric positive
+// definite, so MINRES stays applicable.
+#include "pe_internal.h"
+#include "pe_mg.h"
+
+#include <algorithm>
+#include <cmath>
+
+namespace pe
+{
+  namespace
+  {
+    __device__ __forceinline__ uint32_t
+    part1by1(uint32_t x)
+    {
+      x &= 0x0000ffffu;
+      x = (x ^ (x << 8)) & 0x00ff00ffu;
+      x = (x ^ (x << 4)) & 0x0f0f0f0fu;
+      x = (x ^ (x << 2)) & 0x33333333u;
+      x = (x ^ (x << 1)) & 0x55555555u;
+      return x;
+    }
+    __device__ __forceinline__ uint32_t
+    morton(const int ix, const int iy)
+    {
+      return part1by1((uint32_t)ix) | (part1by1((uint32_t)iy) << 1);
+    }
+
+    // ---- stencil assembly: one thread per vertex, contributions of the <= 4 adjacent cells ---------
+    // NC = 2: mu (d_cd grad N_a . grad N_b + d_d N_a d_c N_b) + lambda dbar dbar |E|   (vertex block
+    //         of the BR1 operator, BR1new:904-925)
+    // NC = 1: dtk grad N_a . grad N_b + gamma N_a N_b
+    template <int NC>
+    __global__ void
+    k_mg_assemble(const int N, const double *__restrict__ vx, const double *__restrict__ vy,
+                  const double *__restrict__ kc, const double k_scalar, const uint8_t *__restrict__ mask,
+                  const double c_a /* mu | dt */, const double c_b /* lambda | gamma */, double *__restrict__ st,
+                  double *__restrict__ dinv)
+    {
+      const int V = N + 1, nv = V * V;
+      const int v = blockIdx.x * blockDim.x + threadIdx.x;
+      if (v >= nv)
+        return;
+      const int i = v % V, j = v / V;
+      double    acc[9][NC * NC];
+#pragma unroll
+      for (int k = 0; k < 9; ++k)
+#pragma unroll
+        for (int e = 0; e < NC * NC; ++e)
+          acc[k][e] = 0.;
+      const bool self_masked = mask && mask[v];
+      if (!self_masked)
+        for (int cj = j - 1; cj <= j; ++cj)
+          for (int ci = i - 1; ci <= i; ++ci)
+            {
+              if (ci < 0 || cj < 0 || ci >= N || cj >= N)
+                continue;
+              const int a  = (i - ci) + 2 * (j - cj);
+              double    px[4], py[4];
+#pragma unroll
+              for (int b = 0; b < 4; ++b)
+                {
+                  const int w = (cj + (b >> 1)) * V + ci + (b & 1);
+                  px[b]       = vx[w];
+                  py[b]       = vy[w];
+                }
+              Geom G;
+              G.set(px, py);
+              const double kperm = kc ? kc[morton(ci, cj)] : k_scalar;
+              double       gxx[4] = {0, 0, 0, 0}, gyy[4] = {0, 0, 0, 0}, gxy[4] = {0, 0, 0, 0}, gyx[4] = {0, 0, 0, 0};
+              double       mass[4] = {0, 0, 0, 0}, dxs[4] = {0, 0, 0, 0}, dys[4] = {0, 0, 0, 0}, W = 0.;
+              const double gp[2] = {0.21132486540518711775, 0.78867513459481288225};
+#pragma unroll
+              for (int qy = 0; qy < 2; ++qy)
+#pragma unroll
+                for (int qx = 0; qx < 2; ++qx)
+                  {
+                    const double xi = gp[qx], eta = gp[qy];
+                    double       j00, j01, j10, j11, nx[4], ny[4];
+                    G.jac(xi, eta, j00, j01, j10, j11);
+                    const double det = j00 * j11 - j01 * j10;
+                    const double r   = 0.25 / det;
+                    shape_grads<4>(xi, eta, j00, j01, j10, j11, nx, ny);
+                    W += 0.25 * det;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                      {
+                        gxx[b] += r * nx[a] * nx[b];
+                        gyy[b] += r * ny[a] * ny[b];
+                        gxy[b] += r * nx[a] * ny[b];
+                        gyx[b] += r * ny[a] * nx[b];
+                        dxs[b] += 0.25 * nx[b];
+                        dys[b] += 0.25 * ny[b];
+                      }
+                    if (NC == 1)
+                      {
+                        double s[4];
+                        shape_values<4>(xi, eta, s);
+#pragma unroll
+                        for (int b = 0; b < 4; ++b)
+                          mass[b] += 0.25 * det * s[a] * s[b];
+                      }
+                  }
+#pragma unroll
+              for (int b = 0; b < 4; ++b)
+                {
+                  const int wi = ci + (b & 1), wj = cj + (b >> 1);
+                  const int w  = wj * V + wi;
+                  if (b != a && mask && mask[w])
+                    continue; // Dirichlet neighbour: column eliminated
+                  const int k = (wj - j + 1) * 3 + (wi - i + 1);
+                  if (NC == 2)
+                    {
+                      const double iw = 1. / W; // dbar = int d/dx N / |E|, times |E| once: dxs dxs / W
+                      acc[k][0] += c_a * (2. * gxx[b] + gyy[b]) + c_b * dxs[a] * dxs[b] * iw;
+                      acc[k][3 % (NC * NC)] += c_a * (gxx[b] + 2. * gyy[b]) + c_b * dys[a] * dys[b] * iw;
+                      // (a,x),(b,y): mu d_y N_a d_x N_b ; (a,y),(b,x): mu d_x N_a d_y N_b
+                      acc[k][1 % (NC * NC)] += c_a * gyx[b] + c_b * dxs[a] * dys[b] * iw;
+                      acc[k][2 % (NC * NC)] += c_a * gxy[b] + c_b * dys[a] * dxs[b] * iw;
+                    }
+                  else
+                    acc[k][0] += c_a * kperm * (gxx[b] + gyy[b]) + c_b * mass[b];
+                }
+            }
+      if (self_masked)
+        {
+          acc[4][0] = 1.;
+          if (NC == 2)
+            acc[4][3 % (NC * NC)] = 1.;
+        }
+#pragma unroll
+      for (int k = 0; k < 9; ++k)
+#pragma unroll
+        for (int e = 0; e < NC * NC; ++e)
+          st[(size_t)(k * NC * NC + e) * nv + v] = acc[k][e];
+      if (NC == 1)
+        dinv[v] = acc[4][0] != 0. ? 1. / acc[4][0] : 0.;
+      else
+        {
+          const double a00 = acc[4][0], a01 = acc[4][1 % (NC * NC)], a10 = acc[4][2 % (NC * NC)], a11 = acc[4][3 % (NC * NC)];
+          const double d   = a00 * a11 - a01 * a10;
+          const double id  = d != 0. ? 1. / d : 0.;
+          dinv[v]                  = a11 * id;
+          dinv[(size_t)nv + v]     = -a01 * id;
+          dinv[(size_t)2 * nv + v] = -a10 * id;
+          dinv[(size_t)3 * nv + v] = a00 * id;
+        }
+    }
+
+    // (A x)[v] for the 9-point block stencil; x is [NC][nv]
+    template <int NC>
+    __device__ __forceinline__ void
+    stencil_row(const int N, const int v, const double *__restrict__ st, const double *__restrict__ x, double out[NC])
+    {
+      const int V = N + 1, nv = V * V;
+      const int i = v % V, j = v / V;
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+        out[c] = 0.;
+#pragma unroll
+      for (int dj = -1; dj <= 1; ++dj)
+#pragma unroll
+        for (int di = -1; di <= 1; ++di)
+          {
+            const int wi = i + di, wj = j + dj;
+            if (wi < 0 || wj < 0 || wi > N || wj > N)
+              continue;
+            const int w = wj * V + wi, k = (dj + 1) * 3 + (di + 1);
+            double    xv[NC];
+#pragma unroll
+            for (int d = 0; d < NC; ++d)
+              xv[d] = x[(size_t)d * nv + w];
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+#pragma unroll
+              for (int d = 0; d < NC; ++d)
+                out[c] += st[(size_t)(k * NC * NC + c * NC + d) * nv + v] * xv[d];
+          }
+    }
+
+    // xo = xi + omega Dinv (b - A xi)     (xi == nullptr: xo = omega Dinv b)
+    template <int NC>
+    __global__ void
+    k_mg_jacobi(const int N, const double *__restrict__ st, const double *__restrict__ dinv,
+                const double *__restrict__ b, const double *__restrict__ xi, double *__restrict__ xo, const double omega)
+    {
+      const int nv = (N + 1) * (N + 1);
+      const int v  = blockIdx.x * blockDim.x + threadIdx.x;
+      if (v >= nv)
+        return;
+      double r[NC];
+      if (xi)
+        {
+          stencil_row<NC>(N, v, st, xi, r);
+#pragma unroll
+          for (int c = 0; c < NC; ++c)
+            r[c] = b[(size_t)c * nv + v] - r[c];
+        }
+      else
+        {
+#pragma unroll
+          for (int c = 0; c < NC; ++c)
+            r[c] = b[(size_t)c * nv + v];
+        }
+      if (NC == 1)
+        xo[v] = (xi ? xi[v] : 0.) + omega * dinv[v] * r[0];
+      else
+        {
+          const double d00 = dinv[v], d01 = dinv[(size_t)nv + v], d10 = dinv[(size_t)2 * nv + v], d11 = dinv[(size_t)3 * nv + v];
+          xo[v]              = (xi ? xi[v] : 0.) + omega * (d00 * r[0] + d01 * r[NC - 1]);
+          xo[(size_t)nv + v] = (xi ? xi[(size_t)nv + v] : 0.) + omega * (d10 * r[0] + d11 * r[NC - 1]);
+        }
+    }
+
+    // r = b - A x
+    template <int NC>
+    __global__ void
+    k_mg_residual(const int N, const double *__restrict__ st, const double *__restrict__ b,
+                  const double *__restrict__ x, double *__restrict__ r)
+    {
+      const int nv = (N + 1) * (N + 1);
+      const int v  = blockIdx.x * blockDim.x + threadIdx.x;
+      if (v >= nv)
+        return;
+      double ax[NC];
+      stencil_row<NC>(N, v, st, x, ax);
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+        r[(size_t)c * nv + v] = b[(size_t)c * nv + v] - ax[c];
+    }
+
+    // coarse b = P^T r   (full weighting), one thread per COARSE vertex
+    template <int NC>
+    __global__ void
+    k_mg_restrict(const int Nf, const double *__restrict__ r, double *__restrict__ bc,
+                  const uint8_t *__restrict__ mask_c)
+    {
+      const int Nc = Nf / 2, Vc = Nc + 1, nvc = Vc * Vc, Vf = Nf + 1, nvf = Vf * Vf;
+      const int vc = blockIdx.x * blockDim.x + threadIdx.x;
+      if (vc >= nvc)
+        return;
+      const int I = vc % Vc, J = vc / Vc;
+      double    s[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+        s[c] = 0.;
+      if (!(mask_c && mask_c[vc]))
+        for (int dj = -1; dj <= 1; ++dj)
+          for (int di = -1; di <= 1; ++di)
+            {
+              const int fi = 2 * I + di, fj = 2 * J + dj;
+              if (fi < 0 || fj < 0 || fi > Nf || fj > Nf)
+                continue;
+              const double w  = (di == 0 ? 1. : .5) * (dj == 0 ? 1. : .5);
+              const int    vf = fj * Vf + fi;
+#pragma unroll
+              for (int c = 0; c < NC; ++c)
+                s[c] += w * r[(size_t)c * nvf + vf];
+            }
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+        bc[(size_t)c * nvc + vc] = s[c];
+    }
+
+    // xf += P xc   (bilinear), one thread per FINE vertex
+    template <int NC>
+    __global__ void
+    k_mg_prolong_add(const int Nf, const double *__restrict__ xc, double *__restrict__ xf,
+                     const uint8_t *__restrict__ mask_f)
+    {
+      const int Nc = Nf / 2, Vc = Nc + 1, nvc = Vc * Vc, Vf = Nf + 1, nvf = Vf * Vf;
+      const int vf = blockIdx.x * blockDim.x + threadIdx.x;
+      if (vf >= nvf)
+        return;
+      if (mask_f && mask_f[vf])
+        return;
+      const int i = vf % Vf, j = vf / Vf;
+      const int I0 = i >> 1, J0 = j >> 1, I1 = (i + 1) >> 1, J1 = (j + 1) >> 1;
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+        {
+          const double *q = xc + (size_t)c * nvc;
+          xf[(size_t)c * nvf + vf] +=
+            0.25 * (q[J0 * Vc + I0] + q[J0 * Vc + I1] + q[J1 * Vc + I0] + q[J1 * Vc + I1]);
+        }
+    }
+
+    // ---- maps between the Biot vector and the vertex grids ------------------------------------------
+    // b_u[v] = r[vdof[v] + c]   (Pi_u^T: Q1 is the vertex-dof subspace); masked vertices get 0
+    __global__ void
+    k_mg_gather_u(const int nv, const int32_t *__restrict__ vdof, const uint8_t *__restrict__ mask,
+                  const double *__restrict__ r, double *__restrict__ bu)
+    {
+      const int v = blockIdx.x * blockDim.x + threadIdx.x;
+      if (v >= nv)
+        return;
+      const bool m       = mask && mask[v];
+      const int  d       = vdof[v];
+      bu[v]              = m ? 0. : r[d];
+      bu[(size_t)nv + v] = m ? 0. : r[d + 1];
+    }
+    __global__ void
+    k_mg_scatter_u(const int nv, const int32_t *__restrict__ vdof, const uint8_t *__restrict__ mask,
+                   const double *__restrict__ xu, double *__restrict__ z)
+    {
+      const int v = blockIdx.x * blockDim.x + threadIdx.x;
+      if (v >= nv || (mask && mask[v]))
+        return;
+      const int d = vdof[v];
+      z[d] += xu[v];
+      z[d + 1] += xu[(size_t)nv + v];
+    }
+    // Pi_p^T r: b_p[v] = 1/4 sum_{cells at v} r_int + 1/2 sum_{edges at v} r_face
+    __global__ void
+    k_mg_gather_p(const int N, const int32_t *__restrict__ pint_dof /* [N*N] by (cj*N+ci) */,
+                  const int32_t *__restrict__ hedge /* [(N+1)*N]: edge (i,j)-(i+1,j) at j*N+i */,
+                  const int32_t *__restrict__ vedge /* [N*(N+1)]: edge (i,j)-(i,j+1) at j*(N+1)+i */,
+                  const uint8_t *__restrict__ mask, const double *__restrict__ r, double *__restrict__ bp)
+    {
+      const int V = N + 1, nv = V * V;
+      const int v = blockIdx.x * blockDim.x + threadIdx.x;
+      if (v >= nv)
+        return;
+      if (mask && mask[v])
+        {
+          bp[v] = 0.;
+          return;
+        }
+      const int i = v % V, j = v / V;
+      double    s = 0.;
+      for (int cj = j - 1; cj <= j; ++cj)
+        for (int ci = i - 1; ci <= i; ++ci)
+          if (ci >= 0 && cj >= 0 && ci < N && cj < N)
+            s += 0.25 * r[pint_dof[cj * N + ci]];
+      if (i > 0)
+        s += 0.5 * r[hedge[j * N + i - 1]];
+      if (i < N)
+        s += 0.5 * r[hedge[j * N + i]];
+      if (j > 0)
+        s += 0.5 * r[vedge[(j - 1) * V + i]];
+      if (j < N)
+        s += 0.5 * r[vedge[j * V + i]];
+      bp[v] = s;
+    }
+    // z += Pi_p x_p : cells, horizontal edges, vertical edges in one launch
+    __global__ void
+    k_mg_scatter_p(const int N, const int32_t *__restrict__ pint_dof, const int32_t *__restrict__ hedge,
+                   const int32_t *__restrict__ vedge, const double *__restrict__ xp, double *__restrict__ z)
+    {
+      const int V = N + 1;
+      const int t = blockIdx.x * blockDim.x + threadIdx.x;
+      const int n_c = N * N, n_h = V * N, n_v = N * V;
+      if (t < n_c)
+        {
+          const int ci = t % N, cj = t / N;
+          const int v0 = cj * V + ci;
+          z[pint_dof[t]] += 0.25 * (xp[v0] + xp[v0 + 1] + xp[v0 + V] + xp[v0 + V + 1]);
+        }
+      else if (t < n_c + n_h)
+        {
+          const int e = t - n_c, i = e % N, j = e / N;
+          z[hedge[e]] += 0.5 * (xp[j * V + i] + xp[j * V + i + 1]);
+        }
+      else if (t < n_c + n_h + n_v)
+        {
+          const int e = t - n_c - n_h, i = e % V, j = e / V;
+          z[vedge[e]] += 0.5 * (xp[j * V + i] + xp[(j + 1) * V + i]);
+        }
+    }
+    // coarse arrays by injection / averaging
+    __global__ void
+    k_mg_coarsen_geometry(const int Nc, const double *__restrict__ xf, const double *__restrict__ yf,
+                          const uint8_t *__restrict__ mu_f, const uint8_t *__restrict__ mp_f, double *__restrict__ xc,
+                          double *__restrict__ yc, uint8_t *__restrict__ mu_c, uint8_t *__restrict__ mp_c)
+    {
+      const int Vc = Nc + 1, Vf = 2 * Nc + 1;
+      const int v  = blockIdx.x * blockDim.x + threadIdx.x;
+      if (v >= Vc * Vc)
+        return;
+      const int I = v % Vc, J = v / Vc, f = (2 * J) * Vf + 2 * I;
+      xc[v]   = xf[f];
+      yc[v]   = yf[f];
+      mu_c[v] = mu_f[f];
+      mp_c[v] = mp_f[f];
+    }
+    __global__ void
+    k_mg_coarsen_k(const int n_coarse_cells, const double *__restrict__ kf, double *__restrict__ kcoarse)
+    {
+      const int c = blockIdx.x * blockDim.x + threadIdx.x;
+      if (c >= n_coarse_cells)
+        return;
+      // children of Morton cell c are 4c..4c+3; harmonic-arithmetic compromise: geometric mean
+      const double a = kf[4 * c], b = kf[4 * c + 1], d = kf[4 * c + 2], e = kf[4 * c + 3];
+      kcoarse[c]     = exp(0.25 * (log(a) + log(b) + log(d) + log(e)));
+    }
+
+    inline unsigned
+    g1(const int n)
+    {
+      return (unsigned)((n + 127) / 128);
+    }
+  } // namespace
+
+  // -------------------------------------------------------------------------------------------------
+  MgHierarchy::~MgHierarchy() = default;
+
+  int
+  mg_build_topology(MgHierarchy &mg, const HostMesh &mesh, const HostDofs &dofs, cudaStream_t s)
+  {
+    mg.ready = false;
+    if (mesh.n_refine < 1 || (dofs.element != 0 && dofs.element != 1))
+      return 1; // no hierarchy available: caller falls back to the diagonal preconditioner
+    const int N = 1 << mesh.n_refine, V = N + 1, n_loc = dofs.n_loc;
+    mg.N0       = N;
+    // level arrays
+    int nl = 0;
+    for (int n = N; n >= 2; n /= 2)
+      ++nl;
+    mg.lv.clear();
+    mg.lv.resize((size_t)nl);
+    // dof maps on the fine vertex grid
+    std::vector<int32_t> vdof((size_t)V * V, -1), pint((size_t)N * N), hedge((size_t)V * N), vedge((size_t)N * V);
+    std::vector<uint8_t> mask_u((size_t)V * V, 0), mask_p((size_t)V * V, 0);
+    const int pf0 = dofs.element == 0 ? 9 : 8, pfs = dofs.element == 0 ? 2 : 1;
+    for (int64_t c = 0; c < mesh.n_cells; ++c)
+      {
+        const uint32_t *cv = &mesh.cell_vertices[4 * (size_t)c];
+        const uint32_t *cd = &dofs.cell_dofs[(size_t)c * n_loc];
+        const int       ci = (int)(cv[0] % V), cj = (int)(cv[0] / V);
+        for (int v = 0; v < 4; ++v)
+          vdof[cv[v]] = (int32_t)cd[2 * v];
+        pint[(size_t)cj * N + ci]        = (int32_t)cd[n_loc - 1];
+        vedge[(size_t)cj * V + ci]       = (int32_t)cd[pf0 + 0 * pfs]; // face 0: x = left, vertical edge
+        vedge[(size_t)cj * V + ci + 1]   = (int32_t)cd[pf0 + 1 * pfs];
+        hedge[(size_t)cj * N + ci]       = (int32_t)cd[pf0 + 2 * pfs]; // face 2: bottom, horizontal edge
+        hedge[(size_t)(cj + 1) * N + ci] = (int32_t)cd[pf0 + 3 * pfs];
+        for (int f = 0; f < 4; ++f)
+          {
+            const uint8_t k = mesh.face_kinds[4 * (size_t)c + f];
+            for (int e = 0; e < 2; ++e)
+              {
+                const uint32_t w = cv[kFaceVertex[f][e]];
+                if (k & PE_FACE_DIR_U)
+                  mask_u[w] = 1;
+                if (k & PE_FACE_DIR_P)
+                  mask_p[w] = 1;
+              }
+          }
+      }
+    auto up = [&](auto &dev, const auto &host) -> bool {
+      if (dev.alloc(host.size()) != cudaSuccess)
+        return false;
+      return cudaMemcpyAsync(dev.p, host.data(), host.size() * sizeof(host[0]), cudaMemcpyHostToDevice, s) == cudaSuccess;
+    };
+    if (!up(mg.vdof, vdof) || !up(mg.pint, pint) || !up(mg.hedge, hedge) || !up(mg.vedge, vedge))
+      return -1;
+    MgLevel &l0 = mg.lv[0];
+    l0.N        = N;
+    if (!up(l0.x, mesh.x) || !up(l0.y, mesh.y) || !up(l0.mask_u, mask_u) || !up(l0.mask_p, mask_p))
+      return -1;
+    cudaStreamSynchronize(s);
+    for (int l = 0; l < nl; ++l)
+      {
+        MgLevel &L = mg.lv[(size_t)l];
+        L.N        = N >> l;
+        const size_t nv = (size_t)(L.N + 1) * (L.N + 1);
+        if (l > 0)
+          {
+            if (L.x.alloc(nv) || L.y.alloc(nv) || L.mask_u.alloc(nv) || L.mask_p.alloc(nv))
+              return -1;
+            MgLevel &F = mg.lv[(size_t)l - 1];
+            k_mg_coarsen_geometry<<<g1((int)nv), 128, 0, s>>>(L.N, F.x.p, F.y.p, F.mask_u.p, F.mask_p.p, L.x.p, L.y.p,
+                                                               L.mask_u.p, L.mask_p.p);
+          }
+        if (L.kc.alloc((size_t)L.N * L.N) || L.st_u.alloc(36 * nv) || L.st_p.alloc(9 * nv) || L.dinv_u.alloc(4 * nv) ||
+            L.dinv_p.alloc(nv))
+          return -1;
+        for (int k = 0; k < 3; ++k)
+          if (L.wu[k].alloc(2 * nv) || L.wp[k].alloc(nv))
+            return -1;
+        if (L.bu.alloc(2 * nv) || L.bp.alloc(nv))
+          return -1;
+      }
+    if (cudaStreamSynchronize(s) != cudaSuccess)
+      return -1;
+    mg.ready = true;
+    return 0;
+  }
+
+  // (re)discretise all levels from the current material data: called once per solve (the reference
+  // refactorises every step; the "cached" mode of SURVEY 8(f).1 would skip this)
+  int
+  mg_assemble(MgHierarchy &mg, const double *kcell_fine /* Morton, may be null */, const double k_scalar,
+              const double lambda, const double mu, const double dt, const double gamma, cudaStream_t s, int64_t *launches)
+  {
+    for (size_t l = 0; l < mg.lv.size(); ++l)
+      {
+        MgLevel  &L  = mg.lv[l];
+        const int nv = (L.N + 1) * (L.N + 1);
+        const double *kc = nullptr;
+        if (kcell_fine)
+          {
+            if (l == 0)
+              kc = kcell_fine;
+            else
+              {
+                const double *kf = l == 1 ? kcell_fine : mg.lv[l - 1].kc.p;
+                k_mg_coarsen_k<<<g1(L.N * L.N), 128, 0, s>>>(L.N * L.N, kf, L.kc.p);
+                ++*launches;
+                kc = L.kc.p;
+              }
+          }
+        k_mg_assemble<2><<<g1(nv), 128, 0, s>>>(L.N, L.x.p, L.y.p, nullptr, 1., L.mask_u.p, mu, lambda, L.st_u.p, L.dinv_u.p);
+        k_mg_assemble<1><<<g1(nv), 128, 0, s>>>(L.N, L.x.p, L.y.p, kc, k_scalar, L.mask_p.p, dt, gamma, L.st_p.p, L.dinv_p.p);
+        *launches += 2;
+      }
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  }
+
+  template <int NC>
+  static void
+  vcycle(MgHierarchy &mg, const size_t l, const double omega, const int nu, cudaStream_t s, int64_t *launches)
+  {
+    MgLevel      &L    = mg.lv[l];
+    const int     nv   = (L.N + 1) * (L.N + 1);
+    const double *st   = NC == 2 ? L.st_u.p : L.st_p.p;
+    const double *dinv = NC == 2 ? L.dinv_u.p : L.dinv_p.p;
+    double       *b    = NC == 2 ? L.bu.p : L.bp.p;
+    double       *x0   = NC == 2 ? L.wu[0].p : L.wp[0].p;
+    double       *x1   = NC == 2 ? L.wu[1].p : L.wp[1].p;
+    const bool    last = l + 1 == mg.lv.size();
+    const int     pre  = last ? 24 : nu;
+    // pre-smoothing from x = 0
+    k_mg_jacobi<NC><<<g1(nv), 128, 0, s>>>(L.N, st, dinv, b, nullptr, x0, omega);
+    ++*launches;
+    for (int k = 1; k < pre; ++k)
+      {
+        k_mg_jacobi<NC><<<g1(nv), 128, 0, s>>>(L.N, st, dinv, b, x0, x1, omega);
+        ++*launches;
+        std::swap(x0, x1);
+      }
+    if (!last)
+      {
+        MgLevel  &C   = mg.lv[l + 1];
+        const int nvc = (C.N + 1) * (C.N + 1);
+        k_mg_residual<NC><<<g1(nv), 128, 0, s>>>(L.N, st, b, x0, x1);
+        k_mg_restrict<NC><<<g1(nvc), 128, 0, s>>>(L.N, x1, NC == 2 ? C.bu.p : C.bp.p, NC == 2 ? C.mask_u.p : C.mask_p.p);
+        *launches += 2;
+        vcycle<NC>(mg, l + 1, omega, nu, s, launches);
+        k_mg_prolong_add<NC><<<g1(nv), 128, 0, s>>>(L.N, NC == 2 ? C.wu[2].p : C.wp[2].p, x0,
+                                                     NC == 2 ? L.mask_u.p : L.mask_p.p);
+        ++*launches;
+        for (int k = 0; k < nu; ++k)
+          {
+            k_mg_jacobi<NC><<<g1(nv), 128, 0, s>>>(L.N, st, dinv, b, x0, x1, omega);
+            ++*launches;
+            std::swap(x0, x1);
+          }
+      }
+    // result of this level -> w[2]
+    double *out = NC == 2 ? L.wu[2].p : L.wp[2].p;
+    cudaMemcpyAsync(out, x0, sizeof(double) * (size_t)NC * nv, cudaMemcpyDeviceToDevice, s);
+  }
+
+  void
+  mg_vcycle(MgHierarchy &mg, const int nc, cudaStream_t s, int64_t *launches)
+  {
+    if (nc == 2)
+      vcycle<2>(mg, 0, mg.omega, mg.nu, s, launches);
+    else
+      vcycle<1>(mg, 0, mg.omega, mg.nu, s, launches);
+  }
+
+  // z += Pi_u V_u Pi_u^T r + Pi_p V_p Pi_p^T r
+  void
+  mg_apply_add(MgHierarchy &mg, const double *r, double *z, cudaStream_t s, int64_t *launches)
+  {
+    MgLevel  &L  = mg.lv[0];
+    const int N  = L.N, nv = (N + 1) * (N + 1);
+    k_mg_gather_u<<<g1(nv), 128, 0, s>>>(nv, mg.vdof.p, L.mask_u.p, r, L.bu.p);
+    k_mg_gather_p<<<g1(nv), 128, 0, s>>>(N, mg.pint.p, mg.hedge.p, mg.vedge.p, L.mask_p.p, r, L.bp.p);
+    *launches += 2;
+    vcycle<2>(mg, 0, mg.omega, mg.nu, s, launches);
+    vcycle<1>(mg, 0, mg.omega, mg.nu, s, launches);
+    k_mg_scatter_u<<<g1(nv), 128, 0, s>>>(nv, mg.vdof.p, L.mask_u.p, L.wu[2].p, z);
+    const int np = N * N + 2 * N * (N + 1);
+    k_mg_scatter_p<<<g1(np), 128, 0, s>>>(N, mg.pint.p, mg.hedge.p, mg.vedge.p, L.wp[2].p, z);
+    *launches += 2;
+  }
+} // namespace pe

@@ -1,0 +1,33 @@
+// Auxiliary-space geometric multigrid (pe_mg.cu).
+#pragma once
+#include "pe_host.h"
+#include "pe_internal.h"
+
+#include <vector>
+
+namespace pe
+{
+  struct MgLevel
+  {
+    int             N = 0; // cells per side on this level
+    DevBuf<double>  x, y, kc, st_u, st_p, dinv_u, dinv_p, wu[3], wp[3], bu, bp;
+    DevBuf<uint8_t> mask_u, mask_p;
+  };
+  struct MgHierarchy
+  {
+    bool                 ready = false;
+    int                  N0    = 0;
+    std::vector<MgLevel> lv;
+    DevBuf<int32_t>      vdof, pint, hedge, vedge;
+    double               omega = 0.6, theta = 1.0;
+    int                  nu    = 1;
+    ~MgHierarchy();
+  };
+  // 0 = built, 1 = no hierarchy for this mesh (fallback: diagonal preconditioner), -1 = CUDA error
+  int  mg_build_topology(MgHierarchy &mg, const HostMesh &mesh, const HostDofs &dofs, cudaStream_t s);
+  int  mg_assemble(MgHierarchy &mg, const double *kcell_fine, double k_scalar, double lambda, double mu, double dt,
+                   double gamma, cudaStream_t s, int64_t *launches);
+  // V-cycle on level-0 right-hand side lv[0].bu (nc = 2) / lv[0].bp (nc = 1); result in lv[0].wu[2] / wp[2]
+  void mg_vcycle(MgHierarchy &mg, int nc, cudaStream_t s, int64_t *launches);
+  void mg_apply_add(MgHierarchy &mg, const double *r, double *z, cudaStream_t s, int64_t *launches);
+} // namespace pe

@@ -1,0 +1,356 @@
+// Block preconditioner of the MINRES solve (new work, see pe_mg.cu for the multigrid part):
+//
+//   P = diag(P_u, P_p),  both symmetric positive definite.
+//
+//   P_u^{-1}: symmetric multiplicative two-space method on A_uu, spaces = {face bubbles} + {vertex
+//             dofs = Q1}: bubble Jacobi -> Q1 V-cycle on the updated residual -> bubble Jacobi.
+//             (CGQ1 has no bubbles: P_u^{-1} is the V-cycle alone.)
+//   P_p^{-1}: exact block elimination of the interior pressures (their block is diagonal) from
+//             S^ = c0 M + dt S + gamma M_int, gamma = alpha^2/(lambda+2 mu):
+//               F = S^_ff - S^_fi D_i^{-1} S^_if  on the face pressures,
+//               F^{-1} ~ D_F^{-1} + Pi_f V_p Pi_f^T   (scalar Q1 reaction-diffusion V-cycle),
+//             then back-substitution for p_int.
+// Measured on the oracle's matrices (scripts/precond_study.py): kappa(P_u^{-1} A_uu) ~ 3.2,
+// kappa(P_F^{-1} F) ~ 3.0, S^ vs the exact Schur complement 1.12; MINRES needs ~3x fewer iterations
+// than with the additive Jacobi + V-cycle preconditioner.
+//
+// The sub-blocks of the system matrix that the method multiplies with (A_bu, A_vb, S_if, S_fi) are
+// index lists into the assembled CSR values, built once per mesh on the host.
+#include "pe_internal.h"
+#include "pe_mg.h"
+#include "pe_precond.h"
+
+#include <algorithm>
+
+namespace pe
+{
+  namespace
+  {
+    enum
+    {
+      CLS_VERTEX = 0,
+      CLS_BUBBLE = 1,
+      CLS_PINT   = 2,
+      CLS_PFACE  = 3
+    };
+
+    // out[row] = a[row] + m[row] * (b[row] - sum_k values[src[k]] x[col[k]])   (null a -> 0, null m -> 1,
+    // null b -> 0 and the sign of the sum flips to +)
+    template <int TPR>
+    __global__ void
+    k_sub_spmv(const int n_rows, const int32_t *__restrict__ rows, const int32_t *__restrict__ rp,
+               const int32_t *__restrict__ col, const uint32_t *__restrict__ src, const double *__restrict__ values,
+               const double *x, const double *a, const double *__restrict__ m, const double *b, double *out)
+    {
+      const int t   = blockIdx.x * blockDim.x + threadIdx.x;
+      const int r   = t / TPR, sub = t % TPR;
+      double    s   = 0.;
+      int       row = 0;
+      if (r < n_rows)
+        {
+          row = rows[r];
+          for (int k = rp[r] + sub; k < rp[r + 1]; k += TPR)
+            s += values[src[k]] * x[col[k]];
+        }
+#pragma unroll
+      for (int o = TPR / 2; o > 0; o >>= 1)
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (r < n_rows && sub == 0)
+        {
+          double v = b ? b[row] - s : s;
+          if (m)
+            v *= m[row];
+          if (a)
+            v += a[row];
+          out[row] = v;
+        }
+    }
+
+    // t = [bubble: pinv r, other u: 0]; z = pinv r on Dirichlet-masked / all u dofs as default
+    __global__ void
+    k_pre_u(const int64_t n_u, const uint8_t *__restrict__ cls, const double *__restrict__ pinv,
+            const double *__restrict__ r, double *__restrict__ t, double *__restrict__ z)
+    {
+      const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      if (i >= n_u)
+        return;
+      const double j = pinv[i] * r[i];
+      z[i]           = j; // overwritten for free vertex dofs and for bubbles later
+      t[i]           = cls[i] == CLS_BUBBLE ? j : 0.;
+    }
+    // b_u[v] = r[d] - t2[d]
+    __global__ void
+    k_gather_u2(const int nv, const int32_t *__restrict__ vdof, const uint8_t *__restrict__ mask,
+                const double *__restrict__ r, const double *__restrict__ t2, double *__restrict__ bu)
+    {
+      const int v = blockIdx.x * blockDim.x + threadIdx.x;
+      if (v >= nv)
+        return;
+      const bool m       = mask && mask[v];
+      const int  d       = vdof[v];
+      bu[v]              = m ? 0. : r[d] - (t2 ? t2[d] : 0.);
+      bu[(size_t)nv + v] = m ? 0. : r[d + 1] - (t2 ? t2[d + 1] : 0.);
+    }
+    // z[d] = t[d] = x_v on free vertex dofs
+    __global__ void
+    k_scatter_u2(const int nv, const int32_t *__restrict__ vdof, const uint8_t *__restrict__ mask,
+                 const double *__restrict__ xu, double *__restrict__ z, double *__restrict__ t)
+    {
+      const int v = blockIdx.x * blockDim.x + threadIdx.x;
+      if (v >= nv || (mask && mask[v]))
+        return;
+      const int    d  = vdof[v];
+      const double a0 = xu[v], a1 = xu[(size_t)nv + v];
+      z[d]     = a0;
+      z[d + 1] = a1;
+      t[d]     = a0;
+      t[d + 1] = a1;
+    }
+    // pressure diagonals: dinv_i = 1/(|A_ii| + gamma area_i)
+    __global__ void
+    k_pint_dinv(const int n, const int32_t *__restrict__ rows, const double *__restrict__ diag,
+                const double *__restrict__ area, const double gamma, double *__restrict__ dinv)
+    {
+      const int r = blockIdx.x * blockDim.x + threadIdx.x;
+      if (r >= n)
+        return;
+      const int    row = rows[r];
+      const double d   = fabs(diag[row]) + gamma * area[r];
+      dinv[row]        = d != 0. ? 1. / d : 1.;
+    }
+    // dinvF[f] = 1/(A_ff - sum_i A_fi^2 dinv_i)
+    __global__ void
+    k_face_dinv(const int n, const int32_t *__restrict__ rows, const int32_t *__restrict__ rp,
+                const int32_t *__restrict__ col, const uint32_t *__restrict__ src, const double *__restrict__ values,
+                const double *__restrict__ diag, double *__restrict__ dinv)
+    {
+      const int r = blockIdx.x * blockDim.x + threadIdx.x;
+      if (r >= n)
+        return;
+      const int row = rows[r];
+      double    d   = fabs(diag[row]);
+      for (int k = rp[r]; k < rp[r + 1]; ++k)
+        {
+          const double v = values[src[k]];
+          d -= v * v * dinv[col[k]];
+        }
+      dinv[row] = d > 0. ? 1. / d : 1.;
+    }
+    // t_i = dinv_i r_i on interior pressures (others untouched)
+    __global__ void
+    k_pre_p(const int n, const int32_t *__restrict__ rows, const double *__restrict__ dinv,
+            const double *__restrict__ r, double *__restrict__ t)
+    {
+      const int k = blockIdx.x * blockDim.x + threadIdx.x;
+      if (k >= n)
+        return;
+      const int row = rows[k];
+      t[row]        = dinv[row] * r[row];
+    }
+    // b_p[v] = 1/2 sum_{edges at v} rf[edge]
+    __global__ void
+    k_gather_f(const int N, const int32_t *__restrict__ hedge, const int32_t *__restrict__ vedge,
+               const uint8_t *__restrict__ mask, const double *__restrict__ rf, double *__restrict__ bp)
+    {
+      const int V = N + 1, nv = V * V;
+      const int v = blockIdx.x * blockDim.x + threadIdx.x;
+      if (v >= nv)
+        return;
+      if (mask && mask[v])
+        {
+          bp[v] = 0.;
+          return;
+        }
+      const int i = v % V, j = v / V;
+      double    s = 0.;
+      if (i > 0)
+        s += rf[hedge[j * N + i - 1]];
+      if (i < N)
+        s += rf[hedge[j * N + i]];
+      if (j > 0)
+        s += rf[vedge[(j - 1) * V + i]];
+      if (j < N)
+        s += rf[vedge[j * V + i]];
+      bp[v] = 0.5 * s;
+    }
+    // z_f = dinvF rf + 1/2 (x_a + x_b)
+    __global__ void
+    k_scatter_f(const int N, const int32_t *__restrict__ hedge, const int32_t *__restrict__ vedge,
+                const double *__restrict__ xp, const double *__restrict__ dinv, const double *__restrict__ rf,
+                double *__restrict__ z)
+    {
+      const int V = N + 1;
+      const int t = blockIdx.x * blockDim.x + threadIdx.x;
+      const int n_h = V * N, n_v = N * V;
+      int       d;
+      double    c;
+      if (t < n_h)
+        {
+          const int i = t % N, j = t / N;
+          d           = hedge[t];
+          c           = 0.5 * (xp[j * V + i] + xp[j * V + i + 1]);
+        }
+      else if (t < n_h + n_v)
+        {
+          const int e = t - n_h, i = e % V, j = e / V;
+          d           = vedge[e];
+          c           = 0.5 * (xp[j * V + i] + xp[(j + 1) * V + i]);
+        }
+      else
+        return;
+      z[d] = dinv[d] * rf[d] + c;
+    }
+
+    inline unsigned
+    gb(const int64_t n, const int b = 128)
+    {
+      return (unsigned)std::max<int64_t>(1, (n + b - 1) / b);
+    }
+  } // namespace
+
+  BlockPrecond::~BlockPrecond() = default;
+
+  // ---- once per mesh: dof classes and the sub-block index lists ------------------------------------
+  int
+  precond_build_structure(BlockPrecond &bp, const HostMesh &mesh, const HostDofs &d, const HostPattern &pat,
+                          cudaStream_t s)
+  {
+    bp.ready        = false;
+    const int n_loc = d.n_loc;
+    const int64_t n = d.n();
+    if ((int64_t)pat.colidx.size() > 0xffffffffll)
+      return 1;
+    std::vector<uint8_t> cls((size_t)n, CLS_VERTEX);
+    std::vector<double>  area_of_pint;
+    std::vector<int32_t> pint_rows;
+    for (int64_t c = 0; c < mesh.n_cells; ++c)
+      {
+        const uint32_t *cd = &d.cell_dofs[(size_t)c * n_loc];
+        for (int i = 8; i < n_loc - 1; ++i)
+          cls[cd[i]] = (d.element == 0 && ((i - 8) % 2 == 0)) ? CLS_BUBBLE : CLS_PFACE;
+        cls[cd[n_loc - 1]] = CLS_PINT;
+      }
+    // p_int rows with their cell areas (shoelace on vertices 0,1,3,2)
+    pint_rows.resize((size_t)mesh.n_cells);
+    area_of_pint.resize((size_t)mesh.n_cells);
+    for (int64_t c = 0; c < mesh.n_cells; ++c)
+      {
+        const uint32_t *cv = &mesh.cell_vertices[4 * (size_t)c];
+        const double    x0 = mesh.x[cv[0]], y0 = mesh.y[cv[0]], x1 = mesh.x[cv[1]], y1 = mesh.y[cv[1]];
+        const double    x2 = mesh.x[cv[2]], y2 = mesh.y[cv[2]], x3 = mesh.x[cv[3]], y3 = mesh.y[cv[3]];
+        pint_rows[c]       = (int32_t)d.cell_dofs[(size_t)c * n_loc + n_loc - 1];
+        area_of_pint[c]    = 0.5 * ((x3 - x0) * (y2 - y1) - (x2 - x1) * (y3 - y0));
+      }
+    auto build = [&](const int row_cls, const int col_mask, SubCsr &out) -> bool {
+      std::vector<int32_t>  rows, rp(1, 0), col;
+      std::vector<uint32_t> src;
+      for (int64_t r = 0; r < n; ++r)
+        {
+          if (cls[r] != row_cls)
+            continue;
+          rows.push_back((int32_t)r);
+          for (int64_t k = pat.rowptr[r]; k < pat.rowptr[r + 1]; ++k)
+            {
+              const int32_t cc = pat.colidx[k];
+              if ((col_mask >> cls[cc]) & 1)
+                {
+                  col.push_back(cc);
+                  src.push_back((uint32_t)k);
+                }
+            }
+          rp.push_back((int32_t)col.size());
+        }
+      out.n_rows = (int)rows.size();
+      auto up    = [&](auto &dev, const auto &host) -> bool {
+        if (dev.alloc(host.size()) != cudaSuccess)
+          return false;
+        if (host.empty())
+          return true;
+        return cudaMemcpyAsync(dev.p, host.data(), host.size() * sizeof(host[0]), cudaMemcpyHostToDevice, s) ==
+               cudaSuccess;
+      };
+      const bool ok = up(out.rows, rows) && up(out.rp, rp) && up(out.col, col) && up(out.src, src);
+      cudaStreamSynchronize(s);
+      return ok;
+    };
+    bp.has_bubbles = d.element == 0;
+    if (bp.has_bubbles)
+      if (!build(CLS_BUBBLE, (1 << CLS_VERTEX) | (1 << CLS_BUBBLE), bp.Abu) ||
+          !build(CLS_VERTEX, 1 << CLS_BUBBLE, bp.Avb))
+        return -1;
+    if (!build(CLS_PINT, 1 << CLS_PFACE, bp.Sif) || !build(CLS_PFACE, 1 << CLS_PINT, bp.Sfi))
+      return -1;
+    if (bp.cls.alloc(cls.size()) != cudaSuccess || bp.pint_rows.alloc(pint_rows.size()) != cudaSuccess ||
+        bp.pint_area.alloc(area_of_pint.size()) != cudaSuccess)
+      return -1;
+    cudaMemcpyAsync(bp.cls.p, cls.data(), cls.size(), cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(bp.pint_rows.p, pint_rows.data(), pint_rows.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(bp.pint_area.p, area_of_pint.data(), area_of_pint.size() * sizeof(double), cudaMemcpyHostToDevice, s);
+    if (bp.t.alloc((size_t)n) != cudaSuccess || bp.t2.alloc((size_t)n) != cudaSuccess || bp.dinv.alloc((size_t)n) != cudaSuccess)
+      return -1;
+    cudaMemsetAsync(bp.t.p, 0, sizeof(double) * (size_t)n, s);
+    cudaMemsetAsync(bp.t2.p, 0, sizeof(double) * (size_t)n, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess)
+      return -1;
+    bp.n_u   = d.n_u;
+    bp.n     = n;
+    bp.ready = true;
+    return 0;
+  }
+
+  // ---- once per solve: the pressure diagonals from the freshly assembled values ---------------------
+  int
+  precond_update(BlockPrecond &bp, const double *values, const double *diag, const double gamma, cudaStream_t s,
+                 int64_t *launches)
+  {
+    bp.values = values;
+    k_pint_dinv<<<gb(bp.Sif.n_rows), 128, 0, s>>>(bp.Sif.n_rows, bp.pint_rows.p, diag, bp.pint_area.p, gamma, bp.dinv.p);
+    k_face_dinv<<<gb(bp.Sfi.n_rows), 128, 0, s>>>(bp.Sfi.n_rows, bp.Sfi.rows.p, bp.Sfi.rp.p, bp.Sfi.col.p, bp.Sfi.src.p,
+                                                   values, diag, bp.dinv.p);
+    *launches += 2;
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  }
+
+  // ---- z = P^{-1} r ---------------------------------------------------------------------------------
+  void
+  precond_apply(BlockPrecond &bp, MgHierarchy &mg, const double *pinv, const double *r, double *z, cudaStream_t s,
+                int64_t *launches)
+  {
+    MgLevel  &L0 = mg.lv[0];
+    const int N  = L0.N, nv = (N + 1) * (N + 1);
+    // ----- displacement block
+    k_pre_u<<<gb(bp.n_u, 256), 256, 0, s>>>(bp.n_u, bp.cls.p, pinv, r, bp.t.p, z);
+    ++*launches;
+    if (bp.has_bubbles)
+      {
+        k_sub_spmv<4><<<gb((int64_t)bp.Avb.n_rows * 4), 128, 0, s>>>(bp.Avb.n_rows, bp.Avb.rows.p, bp.Avb.rp.p, bp.Avb.col.p,
+                                                                      bp.Avb.src.p, bp.values, bp.t.p, nullptr, nullptr,
+                                                                      nullptr, bp.t2.p);
+        ++*launches;
+      }
+    k_gather_u2<<<gb(nv), 128, 0, s>>>(nv, mg.vdof.p, L0.mask_u.p, r, bp.has_bubbles ? bp.t2.p : nullptr, L0.bu.p);
+    mg_vcycle(mg, 2, s, launches);
+    k_scatter_u2<<<gb(nv), 128, 0, s>>>(nv, mg.vdof.p, L0.mask_u.p, L0.wu[2].p, z, bp.t.p);
+    *launches += 2;
+    if (bp.has_bubbles)
+      {
+        // z_b = y1 + pinv_b (r_b - A_bb y1 - A_bv x_v),  t = (x_v, y1)
+        k_sub_spmv<8><<<gb((int64_t)bp.Abu.n_rows * 8), 128, 0, s>>>(bp.Abu.n_rows, bp.Abu.rows.p, bp.Abu.rp.p, bp.Abu.col.p,
+                                                                      bp.Abu.src.p, bp.values, bp.t.p, bp.t.p, pinv, r, z);
+        ++*launches;
+      }
+    // ----- pressure block
+    k_pre_p<<<gb(bp.Sif.n_rows), 128, 0, s>>>(bp.Sif.n_rows, bp.pint_rows.p, bp.dinv.p, r, bp.t.p);
+    // rf' = r_f - S_fi t_i   -> t2 (face entries)
+    k_sub_spmv<1><<<gb(bp.Sfi.n_rows), 128, 0, s>>>(bp.Sfi.n_rows, bp.Sfi.rows.p, bp.Sfi.rp.p, bp.Sfi.col.p, bp.Sfi.src.p,
+                                                     bp.values, bp.t.p, nullptr, nullptr, r, bp.t2.p);
+    k_gather_f<<<gb(nv), 128, 0, s>>>(N, mg.hedge.p, mg.vedge.p, L0.mask_p.p, bp.t2.p, L0.bp.p);
+    *launches += 3;
+    mg_vcycle(mg, 1, s, launches);
+    k_scatter_f<<<gb(2 * (int64_t)N * (N + 1)), 128, 0, s>>>(N, mg.hedge.p, mg.vedge.p, L0.wp[2].p, bp.dinv.p, bp.t2.p, z);
+    // z_i = dinv_i (r_i - S_if z_f)
+    k_sub_spmv<4><<<gb((int64_t)bp.Sif.n_rows * 4), 128, 0, s>>>(bp.Sif.n_rows, bp.Sif.rows.p, bp.Sif.rp.p, bp.Sif.col.p,
+                                                                  bp.Sif.src.p, bp.values, z, nullptr, bp.dinv.p, r, z);
+    *launches += 2;
+  }
+} // namespace pe

@@ -1,0 +1,32 @@
+// Block preconditioner (pe_precond.cu).
+#pragma once
+#include "pe_host.h"
+#include "pe_internal.h"
+#include "pe_mg.h"
+
+namespace pe
+{
+  struct SubCsr
+  {
+    int              n_rows = 0;
+    DevBuf<int32_t>  rows, rp, col;
+    DevBuf<uint32_t> src; // index into the assembled CSR values
+  };
+  struct BlockPrecond
+  {
+    bool            ready = false, has_bubbles = false;
+    int64_t         n_u = 0, n = 0;
+    SubCsr          Abu, Avb, Sif, Sfi;
+    DevBuf<uint8_t> cls;
+    DevBuf<int32_t> pint_rows;
+    DevBuf<double>  pint_area, t, t2, dinv;
+    const double   *values = nullptr;
+    ~BlockPrecond();
+  };
+  int  precond_build_structure(BlockPrecond &bp, const HostMesh &mesh, const HostDofs &d, const HostPattern &pat,
+                               cudaStream_t s);
+  int  precond_update(BlockPrecond &bp, const double *values, const double *diag, double gamma, cudaStream_t s,
+                      int64_t *launches);
+  void precond_apply(BlockPrecond &bp, MgHierarchy &mg, const double *pinv, const double *r, double *z, cudaStream_t s,
+                     int64_t *launches);
+} // namespace pe

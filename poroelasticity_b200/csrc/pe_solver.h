@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <vector>
 
 namespace pe
 {
@@ -17,15 +18,24 @@ namespace pe
     const int64_t *rowptr = nullptr;
     const int32_t *colidx = nullptr;
     const double  *values = nullptr;
+    const int32_t *rowblk = nullptr; // row runs of the stream SpMV (n_rowblk + 1 entries), null = warp-per-row
+    int64_t        n_rowblk = 0;
     const uint8_t *col_is_u = nullptr; // per local column (L+H): 1 if displacement dof (multi-GPU only)
     cudaStream_t   stream = nullptr;
     // multi-GPU hooks (null on one GPU): fill x[L..L+H) from the owners; sum n doubles over ranks
     void (*halo)(void *ctx, double *x)               = nullptr;
     void (*allreduce)(void *ctx, double *v, int n)   = nullptr;
     void *halo_ctx                                   = nullptr;
+    // optional additive part of the preconditioner: z += M_aux^{-1} r  (multigrid, pe_mg.cu)
+    void (*precond_add)(void *ctx, const double *r, double *z) = nullptr;
+    void *precond_ctx                                          = nullptr;
+    // full replacement of the diagonal preconditioner: z = P^{-1} r  (pe_precond.cu)
+    void (*precond_apply)(void *ctx, const double *r, double *z) = nullptr;
   };
 
+  void   build_row_blocks(int64_t n_rows, const int64_t *rowptr, std::vector<int32_t> &blk);
   void   spmv_signed(const SolverCtx &c, const double *x, double *y, double *dot);
+  void   scale_vector(const SolverCtx &c, double *x, double a);
   int    build_preconditioner(const SolverCtx &c, double *diag_full, double *pinv);
   int    minres_solve(const SolverCtx &c, const double *b, double *x, const double *pinv, double *work[7],
                       MinresState *st, double *h_pinned, double rel_tol, int max_it, pe_solve_stats *stats);

@@ -177,6 +177,9 @@ class BiotSystem:
             self._ck(rc)
         return sol
 
+    def set_solver_options(self, use_multigrid=1, theta=1.0, omega=0.8, nu=2):
+        self._ck(self.L.pe_set_solver_options(self.h, use_multigrid, theta, omega, nu))
+
     def solution(self):
         s = np.zeros(self.sizes().n_owned_rows)
         self._ck(self.L.pe_get_solution(self.h, ptr(s)))
