@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <climits>
 #include <exception>
 
 using namespace pe;
@@ -156,6 +157,11 @@ namespace
           bnd.push_back((int32_t)a);
       }
     h->n_bnd = (int64_t)bnd.size();
+    // boundary cells per colour (bnd is ascending in asm index, asm order is colour-major)
+    h->bnd_color_begin.assign((size_t)pt.n_colors + 1, 0);
+    for (int col = 0; col <= pt.n_colors; ++col)
+      h->bnd_color_begin[col] =
+        std::lower_bound(bnd.begin(), bnd.end(), (int32_t)(col < pt.n_colors ? pt.color_begin[col] : n_asm)) - bnd.begin();
     PE_CUDA(upload(h->d_cv, cv.data(), cv.size(), s));
     PE_CUDA(upload(h->d_flags, flags.data(), flags.size(), s));
     PE_CUDA(upload(h->d_cdofs, cd.data(), cd.size(), s));
@@ -204,11 +210,40 @@ namespace
       }
     else
       h->d_k.release();
+    // the same field in cell (Morton) order for the multigrid levels
+    h->d_k_morton.release();
+    if (pt.world == 1 && (h->k_lognormal || !h->k_cell.empty()))
+      {
+        if (h->k_lognormal)
+          {
+            PE_CUDA(h->d_k_morton.alloc((size_t)h->mesh.n_cells));
+            PE_CUDA(launch_lognormal(h->mesh.n_cells, nullptr, 0, h->k_sigma, h->k_seed, h->d_k_morton.p, s));
+            ++h->launches;
+          }
+        else
+          PE_CUDA(upload(h->d_k_morton, h->k_cell.data(), h->k_cell.size(), s));
+      }
 
     // scatter offsets
-    PE_CUDA(h->d_off.alloc((size_t)n_loc * n_loc * n_asm));
-    PE_CUDA(launch_scatter_offsets(n_loc, n_asm, h->L, h->d_cdofs.p, h->d_rowptr.p, h->d_colidx.p, h->d_off.p,
-                                   h->d_err.p, s));
+    PE_CUDA(h->d_off.alloc((size_t)scatter_table_words(n_loc) * 4 * n_asm));
+    PE_CUDA(cudaMemsetAsync(h->d_off.p, 0, (size_t)scatter_table_words(n_loc) * 4 * n_asm, s));
+    PE_CUDA(h->d_rhs_first.alloc((size_t)n_asm));
+    {
+      // cells adjacent to each owned row, as asm indices
+      std::vector<int32_t> pos((size_t)h->mesh.n_cells, -1);
+      for (int64_t a = 0; a < n_asm; ++a)
+        pos[pt.asm_cells[a]] = (int32_t)a;
+      std::vector<int32_t> rc(pt.adj.size());
+      for (size_t k = 0; k < rc.size(); ++k)
+        rc[k] = pos[pt.adj[k]];
+      DevBuf<int64_t> d_rcp;
+      DevBuf<int32_t> d_rci;
+      PE_CUDA(upload(d_rcp, pt.adj_ptr.data(), pt.adj_ptr.size(), s));
+      PE_CUDA(upload(d_rci, rc.data(), rc.size(), s));
+      PE_CUDA(launch_scatter_offsets(n_loc, n_asm, h->L, h->d_cdofs.p, h->d_rowptr.p, h->d_colidx.p, d_rcp.p, d_rci.p,
+                                     h->d_off.p, h->d_rhs_first.p, h->d_err.p, s));
+      PE_CUDA(cudaStreamSynchronize(s));
+    }
     ++h->launches;
     int err = 0;
     PE_CUDA(cudaMemcpyAsync(&err, h->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -216,7 +251,40 @@ namespace
     if (err == 1)
       return fail(h, PE_ERR_PATTERN, "an entry of a local matrix is not in the sparsity pattern");
     if (err == 2)
-      return fail(h, PE_ERR_PATTERN, "a CSR row is longer than 256 entries (scatter offsets are 8 bit)");
+      return fail(h, PE_ERR_PATTERN, "a CSR row is longer than 128 entries (scatter offsets are 7 bit)");
+    // chunks for the atomics mode: rows first touched by asm cells [c0, c1) are contiguous per block
+    h->chunk_cell_begin.clear();
+    h->chunk_zero.clear();
+    if (pt.scatter_mode == 0)
+      {
+        std::vector<int32_t> pos((size_t)h->mesh.n_cells, -1);
+        for (int64_t a = 0; a < n_asm; ++a)
+          pos[pt.asm_cells[a]] = (int32_t)a;
+        // first asm cell touching each owned row (ascending inside each block)
+        std::vector<int32_t> owner((size_t)h->L);
+        for (int64_t l = 0; l < h->L; ++l)
+          {
+            int32_t mn = INT32_MAX;
+            for (int64_t k = pt.adj_ptr[l]; k < pt.adj_ptr[l + 1]; ++k)
+              mn = std::min(mn, pos[pt.adj[k]]);
+            owner[l] = mn;
+          }
+        const int64_t blk_end[3] = {pt.local_off[1], pt.local_off[2], h->L};
+        for (int64_t c0 = 0; c0 < n_asm; c0 += h->chunk_cells)
+          {
+            const int64_t c1 = std::min(n_asm, c0 + h->chunk_cells);
+            h->chunk_cell_begin.push_back(c0);
+            for (int b = 0; b < 3; ++b)
+              {
+                auto          bb = owner.begin() + pt.local_off[b], be = owner.begin() + blk_end[b];
+                const int64_t ra = std::lower_bound(bb, be, (int32_t)c0) - owner.begin();
+                const int64_t rb = std::lower_bound(bb, be, (int32_t)c1) - owner.begin();
+                h->chunk_zero.push_back(h->pat.rowptr[ra]);
+                h->chunk_zero.push_back(h->pat.rowptr[rb]);
+              }
+          }
+        h->chunk_cell_begin.push_back(n_asm);
+      }
     if (pt.world > 1)
       {
         const int rc = comm_setup_halo(h);
@@ -246,9 +314,11 @@ namespace
     a.bnd_list  = h->d_bnd_list.p;
     a.rowptr    = h->d_rowptr.p;
     a.off       = h->d_off.p;
+    a.rhs_first = h->d_rhs_first.p;
     a.values    = h->d_values.p;
     a.rhs       = h->d_rhs.p;
     a.do_matrix = do_matrix ? 1 : 0;
+    a.atomic_mode = h->part.scatter_mode == 0 ? 1 : 0;
     return a;
   }
 
@@ -292,15 +362,20 @@ namespace
       }
     else if (h->part.world > 1)
       comm_halo_exchange(h, h->d_sol.p);
-    // system_matrix = 0; system_rhs = 0                                    BR1new:687-688
-    if (do_matrix)
-      PE_CUDA(cudaMemsetAsync(h->d_values.p, 0, sizeof(double) * (size_t)h->nnz, s));
-    PE_CUDA(cudaMemsetAsync(h->d_rhs.p, 0, sizeof(double) * (size_t)(h->L + h->H), s));
+    // system_matrix = 0; system_rhs = 0 (BR1new:687-688).  In the colour-ordered mode it is implicit:
+    // the first writer of every entry stores instead of adding (pe_assemble.cu)
+    if (h->part.scatter_mode == 0)
+      PE_CUDA(cudaMemsetAsync(h->d_rhs.p, 0, sizeof(double) * (size_t)(h->L + h->H), s));
     const DevParams P = make_params(h, t, dt);
     const AsmArgs   a = make_args(h, do_matrix);
     PE_CUDA(cudaEventRecord(h->ev[1], s));
     int nl = 0;
-    PE_CUDA(launch_assemble(h->cfg.element, a, P, s, &nl));
+    if (h->part.scatter_mode == 0 && do_matrix)
+      PE_CUDA(launch_assemble_chunked(h->cfg.element, a, P, (int)h->chunk_cell_begin.size() - 1,
+                                      h->chunk_cell_begin.data(), h->chunk_zero.data(), s, &nl));
+    else
+      PE_CUDA(launch_assemble(h->cfg.element, a, P, h->part.n_colors, h->part.color_begin.data(),
+                              h->bnd_color_begin.data(), s, &nl));
     h->launches += nl;
     PE_CUDA(cudaEventRecord(h->ev[2], s));
     PE_CUDA(cudaEventSynchronize(h->ev[2]));
@@ -584,10 +659,8 @@ extern "C"
     h->pat.rowptr.assign(rowptr, rowptr + n + 1);
     h->pat.colidx.assign(colidx, colidx + rowptr[n]);
     Partition &pt = h->part;
-    pt.asm_cells.resize((size_t)h->mesh.n_cells);
-    for (int64_t c = 0; c < h->mesh.n_cells; ++c)
-      pt.asm_cells[c] = c;
-    pt.n_ghost_cells = 0;
+    build_row_adjacency(h->mesh, h->dofs, pt);
+    color_asm_cells(h->mesh, h->dofs, pt);
     pt.ghost_cols.clear();
     h->have_pattern = true;
     h->device_ready = false;
@@ -704,10 +777,15 @@ extern "C"
             for (int64_t a = 0; a < h->n_asm; ++a)
               k[a] = h->k_cell[h->part.asm_cells[a]];
             PE_CUDA(upload(h->d_k, k.data(), k.size(), h->stream));
+            if (h->part.world == 1)
+              PE_CUDA(upload(h->d_k_morton, h->k_cell.data(), h->k_cell.size(), h->stream));
             PE_CUDA(cudaStreamSynchronize(h->stream));
           }
         else
-          h->d_k.release();
+          {
+            h->d_k.release();
+            h->d_k_morton.release();
+          }
       }
     return PE_OK;
     PE_CATCH
@@ -855,6 +933,12 @@ extern "C"
     if (!h || theta <= 0. || omega <= 0. || nu < 1)
       return fail(h, PE_ERR_ARG, "pe_set_solver_options: bad argument");
     h->use_mg      = use_multigrid & 3;
+    // bit 5: colour-ordered first-writer scatter (deterministic) instead of pre-zero + RED atomics;
+    // takes effect at the next pe_make_sparsity_pattern / pe_set_pattern
+    h->part.scatter_mode = (use_multigrid & 32) ? 1 : 0;
+    // bits 8..: chunk size of the atomics mode in units of 4096 cells (0 = default 32768)
+    if ((use_multigrid >> 8) > 0)
+      h->chunk_cells = (int64_t)(use_multigrid >> 8) * 4096;
     h->spmv_kernel = (use_multigrid & 16) ? 0 : 1; // bit 4: fall back to the warp-per-row SpMV (A/B measurements)
     h->mg_theta = theta;
     h->mg_omega = omega;
@@ -939,7 +1023,7 @@ extern "C"
                 h->mg->nu    = h->mg_nu;
                 // reaction coefficient of the pressure auxiliary operator: c0 + alpha^2/(lambda+2mu)
                 const double gamma = h->c0 + h->alpha * h->alpha / (h->lambda + 2. * h->mu);
-                if (mg_assemble(*h->mg, h->d_k.p, h->k_scalar, h->lambda, h->mu, h->last_dt, gamma, s, &h->launches) != 0)
+                if (mg_assemble(*h->mg, h->d_k_morton.p, h->k_scalar, h->lambda, h->mu, h->last_dt, gamma, s, &h->launches) != 0)
                   return cuda_fail(h, cudaGetLastError(), "mg_assemble");
                 if (h->use_mg == 2)
                   {

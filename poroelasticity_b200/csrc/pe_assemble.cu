@@ -6,15 +6,24 @@
 #include "pe_internal.h"
 #include "pe_kernels.h"
 
+#include <algorithm>
+
 namespace pe
 {
   // ---------------------------------------------------------------------------------------------
-  // setup kernel: position of entry (i,j) of every cell inside the CSR row of dof i
+  // setup kernel: for every assembled cell a and local pair (i,j): the position of the entry inside
+  // the CSR row of dof i (7 bits) and whether a is the FIRST cell, in launch order, that
+  // contributes to that entry (bit 7).  First writers store, later ones add: no memset of the
+  // matrix, no atomics, and a fixed summation order (bitwise reproducible assembly).
+  // The assembled cells are ordered colour-major, so "first" = smallest asm index among the cells
+  // that contain both dofs.  row_cells = cells adjacent to every owned row (asm indices).
   // ---------------------------------------------------------------------------------------------
   __global__ void
   k_scatter_offsets(const int n_loc, const int64_t n_asm, const int64_t L, const int32_t *__restrict__ cdofs,
                     const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
-                    uint8_t *__restrict__ off, int *__restrict__ err)
+                    const int64_t *__restrict__ rc_ptr, const int32_t *__restrict__ rc_idx,
+                    const uint16_t *__restrict__ slot /* [n_loc*n_loc] */, uint8_t *__restrict__ off /* [4*words][n_asm] */,
+                    uint32_t *__restrict__ rhs_first, int *__restrict__ err)
   {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_asm * n_loc)
@@ -25,15 +34,27 @@ namespace pe
     if (r >= L)
       {
         for (int j = 0; j < n_loc; ++j)
-          off[((size_t)i * n_loc + j) * n_asm + c] = 0;
+          {
+            const int sl = slot[i * n_loc + j];
+            off[((size_t)(sl >> 2) * n_asm + c) * 4 + (sl & 3)] = 0;
+          }
         return;
       }
     const int64_t b = rowptr[r], e = rowptr[r + 1];
-    if (e - b > 256)
+    if (e - b > 128)
       {
         atomicExch(err, 2);
         return;
       }
+    const int64_t cb = rc_ptr[r], ce = rc_ptr[r + 1];
+    // rhs: first cell touching the row
+    {
+      int64_t first = c;
+      for (int64_t k = cb; k < ce; ++k)
+        first = min(first, (int64_t)rc_idx[k]);
+      if (first == c)
+        atomicOr(rhs_first + c, 1u << i);
+    }
     for (int j = 0; j < n_loc; ++j)
       {
         const int32_t col = cdofs[(size_t)j * n_asm + c];
@@ -51,31 +72,60 @@ namespace pe
             atomicExch(err, 1);
             lo = b;
           }
-        off[((size_t)i * n_loc + j) * n_asm + c] = (uint8_t)(lo - b);
+        // smallest asm index among the cells of this row that also contain `col`
+        int64_t first = c;
+        for (int64_t k = cb; k < ce; ++k)
+          {
+            const int64_t o = rc_idx[k];
+            if (o >= first)
+              continue;
+            bool has = false;
+            for (int jj = 0; jj < n_loc; ++jj)
+              has |= cdofs[(size_t)jj * n_asm + o] == col;
+            if (has)
+              first = o;
+          }
+        const int sl = slot[i * n_loc + j];
+        off[((size_t)(sl >> 2) * n_asm + c) * 4 + (sl & 3)] = (uint8_t)((lo - b) | (first == c ? 128 : 0));
       }
   }
 
   // ---------------------------------------------------------------------------------------------
   // emit functors
   // ---------------------------------------------------------------------------------------------
-  template <int NL, bool MAT>
-  struct ScatterEmit // straight into the CSR values with FP64 RED atomics
+  template <int EL, int NL, bool MAT, bool ATOMIC>
+  struct ColorEmit // first writer stores; later colours add with RED (no return value -> no load latency
+                   // in the dependency chain; uncontended and ordered by the colour launches -> deterministic)
   {
-    double        *values, *rhsp;
-    const uint8_t *off; // + c
-    size_t         n_asm;
+    double         *values, *rhsp;
+    const uint32_t *soff; // shared memory: word w of this thread at soff[w * 128]; words relative to the sweep
+    int             word0; // first word of the sweep
+    uint32_t        rhs_first;
     int64_t        rs[NL]; // CSR row start of local dof i, -1 if the row is not owned
     int32_t        row[NL];
     __device__ __forceinline__ void
     mat(const int i, const int j, const double v)
     {
-      if (MAT && v != 0. && rs[i] >= 0)
-        atomicAdd(values + rs[i] + off[(size_t)(i * NL + j) * n_asm], v);
+      if (!MAT || rs[i] < 0)
+        return;
+      if (ATOMIC && v == 0.)
+        return; // pre-zeroed matrix: structural zeros need no traffic
+      const int      sl = SlotMap<EL>::slot(i, j);
+      const uint32_t o  = (soff[((sl >> 2) - word0) * 128] >> ((sl & 3) * 8)) & 255u;
+      double        *p  = values + rs[i] + (o & 127u);
+      if (!ATOMIC && (o & 128u))
+        *p = v;
+      else if (v != 0.)
+        atomicAdd(p, v); // RED: fire-and-forget
     }
     __device__ __forceinline__ void
     rhs(const int i, const double v)
     {
-      if (v != 0. && rs[i] >= 0)
+      if (rs[i] < 0)
+        return;
+      if (!ATOMIC && ((rhs_first >> i) & 1u))
+        rhsp[row[i]] = v;
+      else if (v != 0.)
         atomicAdd(rhsp + row[i], v);
     }
   };
@@ -135,15 +185,15 @@ namespace pe
   }
 
   // ---------------------------------------------------------------------------------------------
-  // interior cells (no boundary face, no constrained dof): K1 + K2
+  // interior cells (no boundary face, no constrained dof): K1 + K2, one launch per colour and sweep
   // ---------------------------------------------------------------------------------------------
-  template <int EL, bool MAT>
-  __global__ void __launch_bounds__(128)
-  k_assemble_interior(const AsmArgs a, const DevParams P)
+  template <int EL, int SW, bool MAT, bool ATOMIC>
+  __device__ __forceinline__ void
+  assemble_interior_body(const AsmArgs &a, const DevParams &P)
   {
     constexpr int NL = Elem<EL>::NL;
-    const int64_t c  = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= a.n_asm)
+    const int64_t c  = a.a_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.a_end)
       return;
     if (a.flags[c] != 0u)
       return; // handled by k_assemble_boundary
@@ -152,18 +202,60 @@ namespace pe
     load_cell<EL>(a, c, vx, vy, idx, old);
     Geom G;
     G.set(vx, vy);
-    ScatterEmit<NL, MAT> E;
-    E.values = a.values;
-    E.rhsp   = a.rhs;
-    E.off    = a.off + c;
-    E.n_asm  = (size_t)a.n_asm;
+    // stage this sweep's scatter-offset words through shared memory: independent coalesced loads
+    constexpr int SWI = SW == 1 ? 0 : SW == 2 ? 1 : 2;
+    constexpr int W0 = SlotMap<EL>::word_begin(SWI), W1 = SlotMap<EL>::word_begin(SWI + 1);
+    __shared__ uint32_t soff[(MAT ? W1 - W0 : 1) * 128];
+    if (MAT)
+      {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(a.off) + (size_t)W0 * a.n_asm + c;
+#pragma unroll
+        for (int w = 0; w < W1 - W0; ++w)
+          soff[w * 128 + threadIdx.x] = __ldg(src + (size_t)w * a.n_asm);
+      }
+    ColorEmit<EL, NL, MAT, ATOMIC> E;
+    E.values    = a.values;
+    E.rhsp      = a.rhs;
+    E.soff      = soff + threadIdx.x;
+    E.word0     = W0;
+    E.rhs_first = a.rhs_first[c];
 #pragma unroll
     for (int i = 0; i < NL; ++i)
       {
         E.row[i] = idx[i];
         E.rs[i]  = idx[i] < a.L ? __ldg(a.rowptr + idx[i]) : -1;
       }
-    cell_kernel<EL>(G, a.kcell ? a.kcell[c] : a.k_scalar, P, old, E);
+    cell_kernel<EL, SW>(G, a.kcell ? a.kcell[c] : a.k_scalar, P, old, E);
+  }
+  template <int EL, int SW, bool MAT, bool ATOMIC>
+  __global__ void __launch_bounds__(128)
+  k_assemble_interior(const AsmArgs a, const DevParams P)
+  {
+    assemble_interior_body<EL, SW, MAT, ATOMIC>(a, P);
+  }
+  // the three sweeps of one chunk of cells in ONE launch (blockIdx.y = sweep)
+  template <int EL>
+  __global__ void __launch_bounds__(128)
+  k_assemble_interior3(const AsmArgs a, const DevParams P)
+  {
+    if (blockIdx.y == 0)
+      assemble_interior_body<EL, 1, true, true>(a, P);
+    else if (blockIdx.y == 1)
+      assemble_interior_body<EL, 2, true, true>(a, P);
+    else
+      assemble_interior_body<EL, 4, true, true>(a, P);
+  }
+  // zero up to three ranges of the CSR values (the rows first touched by a chunk of cells)
+  __global__ void
+  k_zero_ranges(double *__restrict__ v, const int64_t b0, const int64_t e0, const int64_t b1, const int64_t e1,
+                const int64_t b2, const int64_t e2)
+  {
+    const int64_t n0 = e0 - b0, n1 = e1 - b1, n2 = e2 - b2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n0 + n1 + n2; i += (int64_t)gridDim.x * blockDim.x)
+      {
+        const int64_t k = i < n0 ? b0 + i : (i < n0 + n1 ? b1 + (i - n0) : b2 + (i - n0 - n1));
+        v[k]            = 0.;
+      }
   }
 
   // ---------------------------------------------------------------------------------------------
@@ -172,14 +264,15 @@ namespace pe
   // 8(a) row A8):
   //   unconstrained row r:  Mat(r,c) += A(r,c) for unconstrained c;  rhs(r) += b(r) - sum_c A(r,c) g_c
   //   constrained dof c  :  d = |A(c,c)| != 0 ? |A(c,c)| : mean_i |A(i,i)| ;  Mat(c,c) += d ; rhs(c) += d g_c
+  // Entries dropped by the elimination still have to be written (as zeros) by their first writer.
   // ---------------------------------------------------------------------------------------------
   template <int EL>
   __global__ void __launch_bounds__(64)
   k_assemble_boundary(const AsmArgs a, const DevParams P)
   {
     constexpr int NL = Elem<EL>::NL;
-    const int64_t t  = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.n_bnd)
+    const int64_t t  = a.bnd_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.bnd_end)
       return;
     const int64_t c = a.bnd_list[t];
     double        vx[4], vy[4], old[NL];
@@ -190,53 +283,74 @@ namespace pe
     double        A[NL * NL], b[NL], g[NL];
     bool          con[NL];
     LocalEmit<NL> E{A, b};
-    cell_kernel<EL>(G, a.kcell ? a.kcell[c] : a.k_scalar, P, old, E);
+    cell_kernel<EL, 7>(G, a.kcell ? a.kcell[c] : a.k_scalar, P, old, E);
     cell_boundary<EL>(G, vx, vy, a.flags[c], P, b, con, g);
 
-    bool   any = false;
     double avg = 0.;
     for (int i = 0; i < NL; ++i)
-      {
-        any |= con[i];
-        avg += fabs(A[i * NL + i]);
-      }
+      avg += fabs(A[i * NL + i]);
     avg /= (double)NL;
+    const uint32_t rf = a.rhs_first[c];
     for (int i = 0; i < NL; ++i)
       {
         if (idx[i] >= a.L)
           continue; // row owned by another rank
-        const int64_t  rs = a.rowptr[idx[i]];
-        const uint8_t *o  = a.off + (size_t)(i * NL) * a.n_asm + c;
+        const int64_t rs = a.rowptr[idx[i]];
+        auto          o  = [&](const int j) -> uint32_t {
+          const int sl = SlotMap<EL>::slot(i, j);
+          return a.off[((size_t)(sl >> 2) * a.n_asm + c) * 4 + (sl & 3)];
+        };
+        double         val;
         if (con[i])
           {
             const double d = fabs(A[i * NL + i]) != 0. ? fabs(A[i * NL + i]) : avg;
+            val            = d * g[i];
             if (a.do_matrix)
-              atomicAdd(a.values + rs + o[(size_t)i * a.n_asm], d);
-            atomicAdd(a.rhs + idx[i], d * g[i]);
-            continue;
+              for (int j = 0; j < NL; ++j)
+                {
+                  const uint32_t ob = o(j);
+                  double        *p  = a.values + rs + (ob & 127u);
+                  const double   v  = j == i ? d : 0.;
+                  if (!a.atomic_mode && (ob & 128u))
+                    *p = v;
+                  else if (v != 0.)
+                    atomicAdd(p, v);
+                }
           }
-        double val = b[i];
-        for (int j = 0; j < NL; ++j)
+        else
           {
-            const double v = A[i * NL + j];
-            if (con[j])
+            val = b[i];
+            for (int j = 0; j < NL; ++j)
               {
-                if (g[j] != 0.)
-                  val -= v * g[j];
+                double v = A[i * NL + j];
+                if (con[j])
+                  {
+                    if (g[j] != 0.)
+                      val -= v * g[j];
+                    v = 0.;
+                  }
+                if (a.do_matrix)
+                  {
+                    const uint32_t ob = o(j);
+                    double        *p  = a.values + rs + (ob & 127u);
+                    if (!a.atomic_mode && (ob & 128u))
+                      *p = v;
+                    else if (v != 0.)
+                      atomicAdd(p, v);
+                  }
               }
-            else if (a.do_matrix && v != 0.)
-              atomicAdd(a.values + rs + o[(size_t)j * a.n_asm], v);
           }
-        if (val != 0.)
+        if (!a.atomic_mode && ((rf >> i) & 1u))
+          a.rhs[idx[i]] = val;
+        else if (val != 0.)
           atomicAdd(a.rhs + idx[i], val);
       }
-    (void)any;
   }
 
   // ---------------------------------------------------------------------------------------------
   // local matrices only (BASELINE cfg 5 and the parity hook pe_local_matrices)
   // ---------------------------------------------------------------------------------------------
-  template <int EL>
+  template <int EL, int SW>
   __global__ void __launch_bounds__(128)
   k_local_matrices(const AsmArgs a, const DevParams P, const int64_t first, const int64_t n, double *out,
                    double *rhs_out)
@@ -260,7 +374,7 @@ namespace pe
     Geom G;
     G.set(vx, vy);
     SoaEmit<NL> E{out + t, rhs_out ? rhs_out + t : nullptr, (size_t)n};
-    cell_kernel<EL>(G, a.kcell ? a.kcell[c] : a.k_scalar, P, old, E);
+    cell_kernel<EL, SW>(G, a.kcell ? a.kcell[c] : a.k_scalar, P, old, E);
   }
 
   // K = exp(sigma Z), Z by Box-Muller from the counter generator keyed on (seed, global cell id)
@@ -324,31 +438,112 @@ namespace pe
 
   cudaError_t
   launch_scatter_offsets(const int n_loc, const int64_t n_asm, const int64_t L, const int32_t *cdofs,
-                         const int64_t *rowptr, const int32_t *colidx, uint8_t *off, int *err, cudaStream_t s)
+                         const int64_t *rowptr, const int32_t *colidx, const int64_t *rc_ptr, const int32_t *rc_idx,
+                         uint8_t *off, uint32_t *rhs_first, int *err, cudaStream_t s)
   {
     const int64_t n = n_asm * n_loc;
     if (n == 0)
       return cudaSuccess;
-    k_scatter_offsets<<<grid_for(n, 256), 256, 0, s>>>(n_loc, n_asm, L, cdofs, rowptr, colidx, off, err);
-    return cudaGetLastError();
+    uint16_t slot_h[17 * 17];
+    for (int i = 0; i < n_loc; ++i)
+      for (int j = 0; j < n_loc; ++j)
+        slot_h[i * n_loc + j] = (uint16_t)(n_loc == 17 ? SlotMap<0>::slot(i, j) : SlotMap<1>::slot(i, j));
+    uint16_t *slot_d = nullptr;
+    cudaError_t     e      = cudaMalloc((void **)&slot_d, sizeof(uint16_t) * n_loc * n_loc);
+    if (e != cudaSuccess)
+      return e;
+    cudaMemcpyAsync(slot_d, slot_h, sizeof(uint16_t) * n_loc * n_loc, cudaMemcpyHostToDevice, s);
+    cudaMemsetAsync(rhs_first, 0, sizeof(uint32_t) * (size_t)n_asm, s);
+    k_scatter_offsets<<<grid_for(n, 256), 256, 0, s>>>(n_loc, n_asm, L, cdofs, rowptr, colidx, rc_ptr, rc_idx, slot_d, off,
+                                                        rhs_first, err);
+    e = cudaGetLastError();
+    cudaStreamSynchronize(s);
+    cudaFree(slot_d);
+    return e;
   }
 
-  cudaError_t
-  launch_assemble(const int element, const AsmArgs &a, const DevParams &P, cudaStream_t s, int *n_launches)
+  int
+  scatter_table_words(const int n_loc)
   {
-    if (a.n_asm > 0)
+    return n_loc == 17 ? SlotMap<0>::word_begin(3) : SlotMap<1>::word_begin(3);
+  }
+
+  template <int EL>
+  static void
+  launch_color(AsmArgs a, const DevParams &P, cudaStream_t s, int *n_launches)
+  {
+    const int64_t n = a.a_end - a.a_begin;
+    if (n > 0)
       {
-        const unsigned g = grid_for(a.n_asm, 128);
-        if (element == 0 && a.do_matrix)
-          k_assemble_interior<0, true><<<g, 128, 0, s>>>(a, P);
-        else if (element == 0)
-          k_assemble_interior<0, false><<<g, 128, 0, s>>>(a, P);
+        const unsigned g = grid_for(n, 128);
+        if (a.do_matrix && a.atomic_mode)
+          {
+            k_assemble_interior<EL, 1, true, true><<<g, 128, 0, s>>>(a, P);
+            k_assemble_interior<EL, 2, true, true><<<g, 128, 0, s>>>(a, P);
+            k_assemble_interior<EL, 4, true, true><<<g, 128, 0, s>>>(a, P);
+            *n_launches += 3;
+          }
         else if (a.do_matrix)
-          k_assemble_interior<1, true><<<g, 128, 0, s>>>(a, P);
+          {
+            k_assemble_interior<EL, 1, true, false><<<g, 128, 0, s>>>(a, P);
+            k_assemble_interior<EL, 2, true, false><<<g, 128, 0, s>>>(a, P);
+            k_assemble_interior<EL, 4, true, false><<<g, 128, 0, s>>>(a, P);
+            *n_launches += 3;
+          }
+        else if (a.atomic_mode)
+          {
+            k_assemble_interior<EL, 4, false, true><<<g, 128, 0, s>>>(a, P);
+            *n_launches += 1;
+          }
         else
-          k_assemble_interior<1, false><<<g, 128, 0, s>>>(a, P);
+          {
+            k_assemble_interior<EL, 4, false, false><<<g, 128, 0, s>>>(a, P);
+            *n_launches += 1;
+          }
+      }
+    if (a.bnd_end > a.bnd_begin)
+      {
+        k_assemble_boundary<EL><<<grid_for(a.bnd_end - a.bnd_begin, 64), 64, 0, s>>>(a, P);
         ++*n_launches;
       }
+  }
+
+  // atomics mode: chunks of cells in deal.II (Morton) order; the CSR rows first touched by a chunk are
+  // zeroed right before the chunk is assembled, so that the zeros are still in L2 when the REDs
+  // arrive (no DRAM fetch) and every value line is written back once.
+  cudaError_t
+  launch_assemble_chunked(const int element, const AsmArgs &a0, const DevParams &P, const int n_chunks,
+                          const int64_t *chunk_cell_begin, const int64_t *chunk_zero /* [n_chunks][6] */,
+                          cudaStream_t s, int *n_launches)
+  {
+    for (int ch = 0; ch < n_chunks; ++ch)
+      {
+        AsmArgs a = a0;
+        a.a_begin = chunk_cell_begin[ch];
+        a.a_end   = chunk_cell_begin[ch + 1];
+        const int64_t *z = chunk_zero + 6 * ch;
+        const int64_t  nz = (z[1] - z[0]) + (z[3] - z[2]) + (z[5] - z[4]);
+        if (nz > 0)
+          {
+            k_zero_ranges<<<(unsigned)std::min<int64_t>((nz + 255) / 256, 148 * 16), 256, 0, s>>>(a.values, z[0], z[1], z[2],
+                                                                                                  z[3], z[4], z[5]);
+            ++*n_launches;
+          }
+        const int64_t n = a.a_end - a.a_begin;
+        if (n > 0)
+          {
+            const dim3 g(grid_for(n, 128), 3);
+            if (element == 0)
+              k_assemble_interior3<0><<<g, 128, 0, s>>>(a, P);
+            else
+              k_assemble_interior3<1><<<g, 128, 0, s>>>(a, P);
+            ++*n_launches;
+          }
+      }
+    // boundary cells last (their rows are all zeroed by now)
+    AsmArgs a   = a0;
+    a.bnd_begin = 0;
+    a.bnd_end   = a0.n_bnd;
     if (a.n_bnd > 0)
       {
         if (element == 0)
@@ -360,16 +555,45 @@ namespace pe
     return cudaGetLastError();
   }
 
+  // one pass per colour (cells of a colour share no owned row); colours in ascending order
+  cudaError_t
+  launch_assemble(const int element, const AsmArgs &a0, const DevParams &P, const int n_colors,
+                  const int64_t *color_begin, const int64_t *bnd_color_begin, cudaStream_t s, int *n_launches)
+  {
+    for (int col = 0; col < n_colors; ++col)
+      {
+        AsmArgs a   = a0;
+        a.a_begin   = color_begin[col];
+        a.a_end     = color_begin[col + 1];
+        a.bnd_begin = bnd_color_begin[col];
+        a.bnd_end   = bnd_color_begin[col + 1];
+        if (element == 0)
+          launch_color<0>(a, P, s, n_launches);
+        else
+          launch_color<1>(a, P, s, n_launches);
+      }
+    return cudaGetLastError();
+  }
+
   cudaError_t
   launch_local_matrices(const int element, const AsmArgs &a, const DevParams &P, const int64_t first,
                         const int64_t n, double *out, double *rhs_out, cudaStream_t s)
   {
     if (n == 0)
       return cudaSuccess;
+    const unsigned g = grid_for(n, 128);
     if (element == 0)
-      k_local_matrices<0><<<grid_for(n, 128), 128, 0, s>>>(a, P, first, n, out, rhs_out);
+      {
+        k_local_matrices<0, 1><<<g, 128, 0, s>>>(a, P, first, n, out, rhs_out);
+        k_local_matrices<0, 2><<<g, 128, 0, s>>>(a, P, first, n, out, rhs_out);
+        k_local_matrices<0, 4><<<g, 128, 0, s>>>(a, P, first, n, out, rhs_out);
+      }
     else
-      k_local_matrices<1><<<grid_for(n, 128), 128, 0, s>>>(a, P, first, n, out, rhs_out);
+      {
+        k_local_matrices<1, 1><<<g, 128, 0, s>>>(a, P, first, n, out, rhs_out);
+        k_local_matrices<1, 2><<<g, 128, 0, s>>>(a, P, first, n, out, rhs_out);
+        k_local_matrices<1, 4><<<g, 128, 0, s>>>(a, P, first, n, out, rhs_out);
+      }
     return cudaGetLastError();
   }
 

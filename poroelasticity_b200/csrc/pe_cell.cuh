@@ -62,6 +62,75 @@ namespace pe
     }
   };
 
+  // ---------------------------------------------------------------------------------------------
+  // Scatter-offset table layout.  Entry (i,j) of the local matrix owns one byte (position inside the
+  // CSR row of dof i + first-writer flag).  Bytes are grouped by the sweep that emits the entry
+  // (see cell_kernel) and packed four to a 32-bit word, words stored [word][cell]: a kernel stages
+  // exactly the words of its sweep through shared memory with independent coalesced loads --
+  // one memory round trip instead of one per entry.
+  // ---------------------------------------------------------------------------------------------
+  template <int EL>
+  struct SlotMap
+  {
+    using EE                  = Elem<EL>;
+    static constexpr int NL   = EE::NL;
+    static constexpr int NCX  = EL == 0 ? 6 : 4;  // displacement dofs per component
+    static constexpr int NU   = EE::NU;
+    // 0: x-displacement dof, 1: y-displacement dof, 2: p_face, 3: p_int
+    __host__ __device__ static constexpr int
+    kind(int i)
+    {
+      return i < 8 ? (i & 1) : (i == EE::PINT ? 3 : ((EL == 0 && ((i - 8) & 1) == 0) ? ((i - 8) / 2 < 2 ? 0 : 1) : 2));
+    }
+    __host__ __device__ static constexpr int
+    ci(int i) // index among the dofs of its own component (vertices 0..3, bubbles 4,5)
+    {
+      return i < 8 ? (i >> 1) : 4 + (((i - 8) / 2) & 1);
+    }
+    __host__ __device__ static constexpr int
+    ui(int i) // index among all displacement dofs
+    {
+      return i < 8 ? i : 8 + (i - 8) / 2;
+    }
+    __host__ __device__ static constexpr int
+    p5(int i) // index in the pressure block: p_int 0, p_face f -> 1 + f
+    {
+      return i == EE::PINT ? 0 : 1 + (EL == 0 ? (i - 9) / 2 : i - 8);
+    }
+    static constexpr int NX = NCX * NCX + 2 * NU + 8 * NU; // entries emitted by sweep X
+    static constexpr int NQ = 2 * NCX * NCX;
+    static constexpr int NY = NCX * NCX + 25;
+    static constexpr int WX = (NX + 3) / 4, WQ = (NQ + 3) / 4, WY = (NY + 3) / 4;
+    __host__ __device__ static constexpr int
+    word_begin(int sw)
+    {
+      return sw == 0 ? 0 : sw == 1 ? WX : sw == 2 ? WX + WQ : WX + WQ + WY;
+    }
+    // byte slot of entry (i,j): sweep-major, word aligned per sweep
+    __host__ __device__ static constexpr int
+    slot(int i, int j)
+    {
+      const int ki = kind(i), kj = kind(j);
+      if (ki == 0 && kj == 0)
+        return ci(i) * NCX + ci(j);
+      if (ki <= 1 && kj == 3)
+        return NCX * NCX + ui(i);
+      if (ki == 3 && kj <= 1)
+        return NCX * NCX + NU + ui(j);
+      if (ki <= 1 && kj == 2)
+        return NCX * NCX + 2 * NU + ui(i) * 4 + (p5(j) - 1);
+      if (ki == 2 && kj <= 1)
+        return NCX * NCX + 6 * NU + (p5(i) - 1) * NU + ui(j);
+      if (ki == 1 && kj == 0)
+        return 4 * WX + ci(i) * NCX + ci(j);
+      if (ki == 0 && kj == 1)
+        return 4 * WX + NCX * NCX + ci(i) * NCX + ci(j);
+      if (ki == 1 && kj == 1)
+        return 4 * (WX + WQ) + ci(i) * NCX + ci(j);
+      return 4 * (WX + WQ) + NCX * NCX + p5(i) * 5 + p5(j);
+    }
+  };
+
   struct Geom
   {
     double x0, y0;                     // vertex 0
@@ -206,135 +275,214 @@ namespace pe
   // provide  void mat(int i, int j, double v)  and  void rhs(int i, double v); every (i,j) pair
   // of the NL x NL matrix is emitted exactly once (structural zeros included) with compile-time
   // constant indices after unrolling.
+  //
+  // Three quadrature sweeps keep the live accumulators of one thread within the register file (a
+  // single sweep needs ~150 FP64 accumulators and spills):
+  //   sweep X: A[(a,x),(b,x)] = mu int (2 dx s_a dx s_b + dy s_a dy s_b)  + int d/dx, d/dy s_a, |E|
+  //   sweep Y: A[(a,y),(b,y)] = mu int (dx s_a dx s_b + 2 dy s_a dy s_b)  + RT0 Gram + load vector
+  //   sweep Q: A[(a,y),(b,x)] = mu int dx s_a dy s_b   (and its transpose)
   // ---------------------------------------------------------------------------------------------
-  template <int EL, class Emit>
+  template <int NS>
+  struct QPoint
+  {
+    double r, jxw, wh, xi, eta, j00, j01, j10, j11;
+    double nx[NS], ny[NS];
+  };
+  // QGauss<2>(3) in deal.II's tensor order (x fastest), in constant memory: the quadrature loop is
+  // a real loop (9 trips) so that its body stays resident in the instruction cache -- the fully
+  // unrolled version is ~160 KB of straight-line SASS and is instruction-fetch bound.
+  __constant__ double kQxi[9]  = {0.11270166537925831148, 0.5, 0.88729833462074168852, 0.11270166537925831148, 0.5,
+                                  0.88729833462074168852, 0.11270166537925831148, 0.5, 0.88729833462074168852};
+  __constant__ double kQeta[9] = {0.11270166537925831148, 0.11270166537925831148, 0.11270166537925831148, 0.5, 0.5, 0.5,
+                                  0.88729833462074168852, 0.88729833462074168852, 0.88729833462074168852};
+  __constant__ double kQw[9]   = {25. / 324., 40. / 324., 25. / 324., 40. / 324., 64. / 324., 40. / 324.,
+                                  25. / 324., 40. / 324., 25. / 324.};
+  template <int NS>
+  __device__ __forceinline__ void
+  eval_qpoint(const Geom &G, const int qi, QPoint<NS> &q)
+  {
+    q.xi  = kQxi[qi];
+    q.eta = kQeta[qi];
+    q.wh  = kQw[qi];
+    G.jac(q.xi, q.eta, q.j00, q.j01, q.j10, q.j11);
+    const double det = q.j00 * q.j11 - q.j01 * q.j10;
+    q.r              = q.wh / det;
+    q.jxw            = q.wh * det;
+    shape_grads<NS>(q.xi, q.eta, q.j00, q.j01, q.j10, q.j11, q.nx, q.ny);
+  }
+  // scalar shapes that carry an x (y) displacement component: vertices 0..3 and bubbles 4,5 (6,7)
+  template <int NS>
+  __host__ __device__ constexpr int
+  xcar(int k)
+  {
+    return k; // 0..5
+  }
+  template <int NS>
+  __host__ __device__ constexpr int
+  ycar(int k)
+  {
+    return k < 4 ? k : k + 2; // 0..3, 6, 7
+  }
+
+  // SW selects which sweeps this instantiation runs (bit 0: X, bit 1: Q, bit 2: Y + Darcy + rhs).
+  // The assembly launches one kernel per sweep: the entry sets are disjoint, the geometry is
+  // recomputed (cheap) and every kernel stays within ~130 registers.  SW = 7 is the all-in-one
+  // version used for boundary cells.
+  template <int EL, int SW, class Emit>
   __device__ __forceinline__ void
   cell_kernel(const Geom &G, const double kperm, const DevParams &P, const double *old, Emit &E)
   {
     using EE         = Elem<EL>;
-    constexpr int NS = EE::NS, NL = EE::NL, PI = EE::PINT;
+    constexpr int NS = EE::NS, PI = EE::PINT;
+    constexpr int NC = NS == 8 ? 6 : 4; // carriers per component
+    constexpr bool SX = (SW & 1) != 0, SQ = (SW & 2) != 0, SY = (SW & 4) != 0;
 
-    // ---- quadrature sweep: gradient moments, divergence moments, RT0 Gram, load vector ----
-    double pxx[NS][NS], pyy[NS][NS], pxy[NS][NS]; // only the needed entries are ever touched
-    double dx[NS], dy[NS];                        // sum_q w_hat nx_a , ny_a  (= int d/dx s_a)
-    double bfx[NS], bfy[NS];                      // int f_x s_a , int f_y s_a
-    double m[10];                                 // RT0 Gram (unscaled by K)
-    double W = 0., bs = 0.;                       // sum JxW ; int s
+    // ---- divergence moments int d/dx s_a, int d/dy s_a and |E| (needed by every sweep) -------------
+    double dx[NS], dy[NS], W = 0.;
+    double axx[SX ? NC : 1][SX ? NC : 1], q_yx[SQ ? NC : 1][SQ ? NC : 1], ayy[SY ? NC : 1][SY ? NC : 1];
+    double m[10], bs = 0.;
+    double bfx[SY ? NS : 1], bfy[SY ? NS : 1];
 #pragma unroll
     for (int a = 0; a < NS; ++a)
+      dx[a] = dy[a] = 0.;
+    if (SX)
       {
-        dx[a] = dy[a] = bfx[a] = bfy[a] = 0.;
 #pragma unroll
-        for (int b = 0; b < NS; ++b)
-          pxx[a][b] = pyy[a][b] = pxy[a][b] = 0.;
+        for (int a = 0; a < NC; ++a)
+#pragma unroll
+          for (int b = 0; b < NC; ++b)
+            axx[a % (SX ? NC : 1)][b % (SX ? NC : 1)] = 0.;
       }
+    if (SQ)
+      {
 #pragma unroll
-    for (int k = 0; k < 10; ++k)
-      m[k] = 0.;
+        for (int a = 0; a < NC; ++a)
+#pragma unroll
+          for (int b = 0; b < NC; ++b)
+            q_yx[a % (SQ ? NC : 1)][b % (SQ ? NC : 1)] = 0.;
+      }
+    if (SY)
+      {
+#pragma unroll
+        for (int a = 0; a < NC; ++a)
+#pragma unroll
+          for (int b = 0; b < NC; ++b)
+            ayy[a % (SY ? NC : 1)][b % (SY ? NC : 1)] = 0.;
+#pragma unroll
+        for (int a = 0; a < NS; ++a)
+          bfx[a % (SY ? NS : 1)] = bfy[a % (SY ? NS : 1)] = 0.;
+#pragma unroll
+        for (int k = 0; k < 10; ++k)
+          m[k] = 0.;
+      }
 
-#pragma unroll
-    for (int qy = 0; qy < 3; ++qy)
-#pragma unroll
-      for (int qx = 0; qx < 3; ++qx)
+#pragma unroll 1
+    for (int qi = 0; qi < 9; ++qi)
         {
-          const double xi = kGx[qx], eta = kGx[qy], wh = kGw[qx] * kGw[qy];
-          double       j00, j01, j10, j11;
-          G.jac(xi, eta, j00, j01, j10, j11);
-          const double det = j00 * j11 - j01 * j10;
-          const double r   = wh / det;
-          const double jxw = wh * det;
-          W += jxw;
-          double nx[NS], ny[NS];
-          shape_grads<NS>(xi, eta, j00, j01, j10, j11, nx, ny);
+          QPoint<NS> q;
+          eval_qpoint<NS>(G, qi, q);
+          W += q.jxw;
 #pragma unroll
           for (int a = 0; a < NS; ++a)
             {
-              dx[a] += wh * nx[a];
-              dy[a] += wh * ny[a];
+              dx[a] += q.wh * q.nx[a];
+              dy[a] += q.wh * q.ny[a];
             }
-#pragma unroll
-          for (int a = 0; a < NS; ++a)
+          if (SX)
             {
-              const double rx = r * nx[a], ry = r * ny[a];
 #pragma unroll
-              for (int b = 0; b < NS; ++b)
+              for (int ka = 0; ka < NC; ++ka)
                 {
-                  // which moments does the strain block need for the pair (a,b)?  vertex shapes
-                  // carry both components; bubbles 4,5 only x; bubbles 6,7 only y.
-                  const bool ax = a < 6, ay = a < 4 || a >= 6, bx = b < 6, by = b < 4 || b >= 6;
-                  const bool same = (ax && bx) || (ay && by);
-                  if (same && b >= a)
-                    {
-                      pxx[a][b] += rx * nx[b];
-                      pyy[a][b] += ry * ny[b];
-                    }
-                  if (ay && bx) // A[(a,y),(b,x)] = mu int d_x s_a d_y s_b  (a carries y, b carries x)
-                    pxy[a][b] += rx * ny[b];
+                  const int    a  = xcar<NS>(ka);
+                  const double rx = 2. * q.r * q.nx[a], ry = q.r * q.ny[a];
+#pragma unroll
+                  for (int kb = ka; kb < NC; ++kb)
+                    axx[ka % (SX ? NC : 1)][kb % (SX ? NC : 1)] += rx * q.nx[xcar<NS>(kb)] + ry * q.ny[xcar<NS>(kb)];
                 }
             }
-          // RT0 Gram: w_k = J w_hat_k / det;  (w_k . w_l) JxW = r (J w_hat_k).(J w_hat_l)
-          {
-            const double c00 = j00 * j00 + j10 * j10, c01 = j00 * j01 + j10 * j11, c11 = j01 * j01 + j11 * j11;
-            const double mxi = 1. - xi, meta = 1. - eta;
-            const double rc00 = r * c00, rc01 = r * c01, rc11 = r * c11;
-            m[0] += rc00 * (mxi * mxi);
-            m[1] += rc00 * (mxi * xi);
-            m[4] += rc00 * (xi * xi);
-            m[2] += rc01 * (mxi * meta);
-            m[3] += rc01 * (mxi * eta);
-            m[5] += rc01 * (xi * meta);
-            m[6] += rc01 * (xi * eta);
-            m[7] += rc11 * (meta * meta);
-            m[8] += rc11 * (meta * eta);
-            m[9] += rc11 * (eta * eta);
-          }
-          if (P.case_id == 1)
+          if (SQ)
             {
-              double px, py, sx, cx, sy, cy;
-              G.point(xi, eta, px, py);
-              sincospi(px, &sx, &cx);
-              sincospi(py, &sy, &cy);
-              const double fx = P.f_coef * sx * cy * jxw, fy = P.f_coef * cx * sy * jxw;
-              bs += cx * cy * jxw;
-              double s[NS];
-              shape_values<NS>(xi, eta, s);
 #pragma unroll
-              for (int a = 0; a < NS; ++a)
+              for (int ka = 0; ka < NC; ++ka)
                 {
-                  if (a < 6)
-                    bfx[a] += fx * s[a];
-                  if (a < 4 || a >= 6)
-                    bfy[a] += fy * s[a];
+                  const double rx = q.r * q.nx[ycar<NS>(ka)];
+#pragma unroll
+                  for (int kb = 0; kb < NC; ++kb)
+                    q_yx[ka % (SQ ? NC : 1)][kb % (SQ ? NC : 1)] += rx * q.ny[xcar<NS>(kb)];
+                }
+            }
+          if (SY)
+            {
+#pragma unroll
+              for (int ka = 0; ka < NC; ++ka)
+                {
+                  const int    a  = ycar<NS>(ka);
+                  const double rx = q.r * q.nx[a], ry = 2. * q.r * q.ny[a];
+#pragma unroll
+                  for (int kb = ka; kb < NC; ++kb)
+                    ayy[ka % (SY ? NC : 1)][kb % (SY ? NC : 1)] += rx * q.nx[ycar<NS>(kb)] + ry * q.ny[ycar<NS>(kb)];
+                }
+              // RT0 Gram: w_k = J w_hat_k / det;  (w_k . w_l) JxW = r (J w_hat_k).(J w_hat_l)
+              {
+                const double c00 = q.j00 * q.j00 + q.j10 * q.j10, c01 = q.j00 * q.j01 + q.j10 * q.j11,
+                             c11 = q.j01 * q.j01 + q.j11 * q.j11;
+                const double mxi = 1. - q.xi, meta = 1. - q.eta;
+                const double rc00 = q.r * c00, rc01 = q.r * c01, rc11 = q.r * c11;
+                m[0] += rc00 * (mxi * mxi);
+                m[1] += rc00 * (mxi * q.xi);
+                m[4] += rc00 * (q.xi * q.xi);
+                m[2] += rc01 * (mxi * meta);
+                m[3] += rc01 * (mxi * q.eta);
+                m[5] += rc01 * (q.xi * meta);
+                m[6] += rc01 * (q.xi * q.eta);
+                m[7] += rc11 * (meta * meta);
+                m[8] += rc11 * (meta * q.eta);
+                m[9] += rc11 * (q.eta * q.eta);
+              }
+              if (P.case_id == 1)
+                {
+                  double px, py, sx, cx, sy, cy;
+                  G.point(q.xi, q.eta, px, py);
+                  sincospi(px, &sx, &cx);
+                  sincospi(py, &sy, &cy);
+                  const double fx = P.f_coef * sx * cy * q.jxw, fy = P.f_coef * cx * sy * q.jxw;
+                  bs += cx * cy * q.jxw;
+                  double s[NS];
+                  shape_values<NS>(q.xi, q.eta, s);
+#pragma unroll
+                  for (int a = 0; a < NS; ++a)
+                    {
+                      if (a < 6)
+                        bfx[a % (SY ? NS : 1)] += fx * s[a];
+                      if (a < 4 || a >= 6)
+                        bfy[a % (SY ? NS : 1)] += fy * s[a];
+                    }
                 }
             }
         }
 
-    // cell->measure(): shoelace on vertices 0,1,3,2                          BR1new:867
-    const double area = 0.5 * ((G.a1x + G.a1x + G.a3x) * (G.a2y + G.a2y + G.a3y) -
-                               (G.a2x + G.a2x + G.a3x) * (G.a1y + G.a1y + G.a3y)) *
-                        0.5;
-    const double inv_area = 1. / area;
-
-    // ---- divergence vector of the u-dofs --------------------------------------------------------
-    // BR1: cell-averaged divergence (BR1new:867-876).  CGQ1: divergence at the 1-point rule
-    // times JxW_1 (CGQ1:1341-1358): n(center) / det_c * det_c.
-    double dv[EE::NU]; // BR1: dbar_i ; CGQ1: div_i(center)
-    double wq;         // weight the lambda / coupling terms are integrated with
-    double c0_weight;  // what multiplies c0 on the diagonal of p_int
+    // ---- divergence vector of the u-dofs.  BR1: cell-averaged divergence (BR1new:867-876);
+    // CGQ1: divergence at the 1-point rule (CGQ1:1341-1358)
+    double dv[EE::NU];
+    double wq, c0_weight;
     if (EL == 0)
       {
+        // cell->measure(): shoelace on vertices 0,1,3,2 = det J at the cell centre    BR1new:867
+        const double area = 0.25 * ((G.a1x + G.a1x + G.a3x) * (G.a2y + G.a2y + G.a3y) -
+                                    (G.a2x + G.a2x + G.a3x) * (G.a1y + G.a1y + G.a3y));
+        const double ia   = 1. / area;
 #pragma unroll
         for (int a = 0; a < 4; ++a)
           {
-            dv[2 * a]     = dx[a] * inv_area;
-            dv[2 * a + 1] = dy[a] * inv_area;
+            dv[2 * a]     = dx[a] * ia;
+            dv[2 * a + 1] = dy[a] * ia;
           }
-        dv[8]     = dx[4 % NS] * inv_area;
-        dv[9]     = dx[5 % NS] * inv_area;
-        dv[10]    = dy[6 % NS] * inv_area;
-        dv[11]    = dy[7 % NS] * inv_area;
-        wq        = W;
-        c0_weight = W;
+        dv[8 % EE::NU]  = dx[4 % NS] * ia;
+        dv[9 % EE::NU]  = dx[5 % NS] * ia;
+        dv[10 % EE::NU] = dy[6 % NS] * ia;
+        dv[11 % EE::NU] = dy[7 % NS] * ia;
+        wq              = W;
+        c0_weight       = W;
       }
     else
       {
@@ -350,105 +498,117 @@ namespace pe
             dv[2 * a + 1] = ny[a] * id;
           }
         wq        = detc;     // JxW of QGauss(1)
-        c0_weight = W + detc; // the storage term is integrated twice: CGQ1:1335 and :1352
+        c0_weight = W + detc; // storage term integrated twice: CGQ1:1335 and :1352
       }
+    const double lw = P.lambda * wq;
+    auto dvx = [&](int a) -> double { return a < 4 ? dv[2 * a] : dv[(8 + a - 4) % EE::NU]; };
+    auto dvy = [&](int a) -> double { return a < 4 ? dv[2 * a + 1] : dv[(8 + a - 4) % EE::NU]; };
 
-    // ---- strain + lambda block:  A[(a,c),(b,d)] = mu[d_cd (Pxx+Pyy)_ab + P^{dc}_ab] + lambda dv dv wq
-    // local u index -> position in dv: BR1: vertex dofs 0..7, bubbles 8..11
-    auto dvi = [&](int a, int c) -> double { return a < 4 ? dv[2 * a + c] : dv[(8 + (a - 4)) % EE::NU]; };
+    if (SX)
+      {
 #pragma unroll
-    for (int a = 0; a < NS; ++a)
+        for (int ka = 0; ka < NC; ++ka)
 #pragma unroll
-      for (int c = 0; c < 2; ++c)
-        {
-          if (a >= 4 && c != (a - 4) / 2)
-            continue;
-          const int i = udof<EL>(a, c);
+          for (int kb = 0; kb < NC; ++kb)
+            {
+              const int    a = xcar<NS>(ka), b = xcar<NS>(kb);
+              const double v = kb >= ka ? axx[ka % (SX ? NC : 1)][kb % (SX ? NC : 1)] : axx[kb % (SX ? NC : 1)][ka % (SX ? NC : 1)];
+              E.mat(udof<EL>(a, 0), udof<EL>(b, 0), P.mu * v + lw * dvx(a) * dvx(b));
+            }
+        // coupling with p_int (BR1new:915,917 / CGQ1:1351,1354), structural zeros u <-> p_face
+        const double aw = P.alpha * wq;
 #pragma unroll
-          for (int b = 0; b < NS; ++b)
+        for (int i = 0; i < EE::NU; ++i)
+          {
+            const int li = (EL == 0 && i >= 8) ? EE::bubble(i - 8) : i;
+            E.mat(li, PI, -aw * dv[i]);
+            E.mat(PI, li, aw * dv[i]);
 #pragma unroll
-            for (int d = 0; d < 2; ++d)
+            for (int f = 0; f < 4; ++f)
               {
-                if (b >= 4 && d != (b - 4) / 2)
-                  continue;
-                const int j = udof<EL>(b, d);
-                double    v;
-                if (c == d)
-                  {
-                    const double xx = (b >= a) ? pxx[a][b] : pxx[b][a];
-                    const double yy = (b >= a) ? pyy[a][b] : pyy[b][a];
-                    v               = (c == 0) ? (xx + xx + yy) : (xx + yy + yy);
-                  }
-                else if (c == 1) // (a,y),(b,x): int d_x s_a d_y s_b
-                  v = pxy[a][b];
-                else             // (a,x),(b,y): int d_y s_a d_x s_b = the transposed entry
-                  v = pxy[b][a];
-                E.mat(i, j, P.mu * v + P.lambda * dvi(a, c) * dvi(b, d) * wq);
+                E.mat(li, EE::pface(f), 0.);
+                E.mat(EE::pface(f), li, 0.);
               }
-          // coupling with p_int                                        BR1new:915,917 / CGQ1:1351,1354
-          E.mat(i, PI, -P.alpha * dvi(a, c) * wq);
-          E.mat(PI, i, P.alpha * dvi(a, c) * wq);
+          }
+      }
+    if (SQ)
+      {
+#pragma unroll
+        for (int ka = 0; ka < NC; ++ka)
+#pragma unroll
+          for (int kb = 0; kb < NC; ++kb)
+            {
+              const int    a = ycar<NS>(ka), b = xcar<NS>(kb);
+              const int    i = udof<EL>(a, 1), j = udof<EL>(b, 0);
+              const double v = P.mu * q_yx[ka % (SQ ? NC : 1)][kb % (SQ ? NC : 1)] + lw * dvy(a) * dvx(b);
+              E.mat(i, j, v); // (a,y),(b,x)
+              E.mat(j, i, v); // the u block is symmetric
+            }
+      }
+    if (SY)
+      {
+#pragma unroll
+        for (int ka = 0; ka < NC; ++ka)
+#pragma unroll
+          for (int kb = 0; kb < NC; ++kb)
+            {
+              const int    a = ycar<NS>(ka), b = ycar<NS>(kb);
+              const double v = kb >= ka ? ayy[ka % (SY ? NC : 1)][kb % (SY ? NC : 1)] : ayy[kb % (SY ? NC : 1)][ka % (SY ? NC : 1)];
+              E.mat(udof<EL>(a, 1), udof<EL>(b, 1), P.mu * v + lw * dvy(a) * dvy(b));
+            }
+        // ---- Darcy block  dt k F M^{-1} F^T on (p_int, p_face 0..3)           BR1new:811-863,879-901
+        {
+          double g[10];
+          spd4_inverse(m, g);
+          const double sc    = P.dt * kperm;
+          const double sg[4] = {-1., 1., -1., 1.}; // F_face = diag(sg); F_int = -sg
+          double       rowsum[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            {
+              double s = 0.;
+#pragma unroll
+              for (int l = 0; l < 4; ++l)
+                s += -sg[l] * g[sym4(k, l)];
+              rowsum[k] = s; // (M^{-1} F_int^T)_k
+            }
+          double sii = 0.;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            sii += -sg[k] * rowsum[k];
+          E.mat(PI, PI, P.c0 * c0_weight + sc * sii);
 #pragma unroll
           for (int f = 0; f < 4; ++f)
             {
-              E.mat(i, EE::pface(f), 0.);
-              E.mat(EE::pface(f), i, 0.);
+              const double v = sc * sg[f] * rowsum[f];
+              E.mat(PI, EE::pface(f), v);
+              E.mat(EE::pface(f), PI, v);
+#pragma unroll
+              for (int f2 = 0; f2 < 4; ++f2)
+                E.mat(EE::pface(f), EE::pface(f2), sc * sg[f] * sg[f2] * g[sym4(f, f2)]);
             }
         }
-
-    // ---- Darcy block  dt k F M^{-1} F^T on (p_int, p_face 0..3)           BR1new:811-863,879-901
-    {
-      double g[10];
-      spd4_inverse(m, g);
-      const double sc    = P.dt * kperm;
-      const double sg[4] = {-1., 1., -1., 1.}; // F_face = diag(sg); F_int = -sg
-      double       rowsum[4];
+        // ---- right-hand side                                                BR1new:928-961 / CGQ1:1381-1453
+        double div_old = 0.; // BR1: average divergence of u_old ; CGQ1: divergence at the cell centre
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        {
-          double s = 0.;
-#pragma unroll
-          for (int l = 0; l < 4; ++l)
-            s += -sg[l] * g[sym4(k, l)];
-          rowsum[k] = s; // (M^{-1} F_int^T)_k
-        }
-      double sii = 0.;
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        sii += -sg[k] * rowsum[k];
-      E.mat(PI, PI, P.c0 * c0_weight + sc * sii);
-#pragma unroll
-      for (int f = 0; f < 4; ++f)
-        {
-          const double v = sc * sg[f] * rowsum[f];
-          E.mat(PI, EE::pface(f), v);
-          E.mat(EE::pface(f), PI, v);
-#pragma unroll
-          for (int f2 = 0; f2 < 4; ++f2)
-            E.mat(EE::pface(f), EE::pface(f2), sc * sg[f] * sg[f2] * g[sym4(f, f2)]);
-        }
-    }
-
-    // ---- right-hand side                                                  BR1new:928-961 / CGQ1:1381-1453
-    {
-      double div_old = 0.; // BR1: average divergence of u_old ; CGQ1: divergence at the cell centre
-#pragma unroll
-      for (int a = 0; a < NS; ++a)
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
+        for (int i = 0; i < EE::NU; ++i)
           {
-            if (a >= 4 && c != (a - 4) / 2)
-              continue;
-            const int i = udof<EL>(a, c);
-            div_old += old[i] * dvi(a, c);
-            E.rhs(i, c == 0 ? bfx[a] : bfy[a]);
+            const int li = (EL == 0 && i >= 8) ? EE::bubble(i - 8) : i;
+            div_old += old[li] * dv[i];
           }
-      const double pold = old[PI];
-      E.rhs(PI, P.c0 * pold * W + P.dt * P.s_coef * bs + P.alpha * div_old * wq);
 #pragma unroll
-      for (int f = 0; f < 4; ++f)
-        E.rhs(EE::pface(f), 0.);
-    }
+        for (int a = 0; a < NS; ++a)
+          {
+            if (a < 6)
+              E.rhs(udof<EL>(a, 0), bfx[a % (SY ? NS : 1)]);
+            if (a < 4 || a >= 6)
+              E.rhs(udof<EL>(a, 1), bfy[a % (SY ? NS : 1)]);
+          }
+        E.rhs(PI, P.c0 * old[PI] * W + P.dt * P.s_coef * bs + P.alpha * div_old * wq);
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+          E.rhs(EE::pface(f), 0.);
+      }
   }
 
   // ---------------------------------------------------------------------------------------------

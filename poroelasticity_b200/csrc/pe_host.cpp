@@ -285,12 +285,12 @@ namespace pe
   } // namespace
 
   void
-  make_sparsity_pattern(const HostMesh &m, const HostDofs &d, Partition &part, HostPattern &p)
+  build_row_adjacency(const HostMesh &m, const HostDofs &d, Partition &part)
   {
     const int     n_loc = d.n_loc;
     const int64_t nc = m.n_cells, L = part.n_owned;
-    // owned-row -> cells adjacency (CSR), cells ascending
-    std::vector<int64_t> adj_ptr((size_t)L + 1, 0);
+    std::vector<int64_t> &adj_ptr = part.adj_ptr, &adj = part.adj;
+    adj_ptr.assign((size_t)L + 1, 0);
     for (int64_t c = part.cell_begin; c < nc; ++c) // owners are first touchers: no cell < cell_begin
       for (int i = 0; i < n_loc; ++i)
         {
@@ -300,7 +300,7 @@ namespace pe
         }
     for (int64_t l = 0; l < L; ++l)
       adj_ptr[l + 1] += adj_ptr[l];
-    std::vector<int64_t> adj((size_t)adj_ptr[L]);
+    adj.resize((size_t)adj_ptr[L]);
     {
       std::vector<int64_t> fill(adj_ptr.begin(), adj_ptr.end() - 1);
       for (int64_t c = part.cell_begin; c < nc; ++c)
@@ -312,19 +312,91 @@ namespace pe
           }
     }
     // ghost cells: cells >= cell_end adjacent to an owned row
-    {
-      std::vector<int64_t> g;
-      for (int64_t k = 0; k < (int64_t)adj.size(); ++k)
-        if (adj[k] >= part.cell_end)
-          g.push_back(adj[k]);
-      std::sort(g.begin(), g.end());
-      g.erase(std::unique(g.begin(), g.end()), g.end());
-      part.asm_cells.resize((size_t)(part.cell_end - part.cell_begin));
-      for (int64_t c = part.cell_begin; c < part.cell_end; ++c)
-        part.asm_cells[c - part.cell_begin] = c;
-      part.n_ghost_cells = (int64_t)g.size();
-      part.asm_cells.insert(part.asm_cells.end(), g.begin(), g.end());
-    }
+    std::vector<int64_t> g;
+    for (int64_t k = 0; k < (int64_t)adj.size(); ++k)
+      if (adj[k] >= part.cell_end)
+        g.push_back(adj[k]);
+    std::sort(g.begin(), g.end());
+    g.erase(std::unique(g.begin(), g.end()), g.end());
+    part.asm_cells.resize((size_t)(part.cell_end - part.cell_begin));
+    for (int64_t c = part.cell_begin; c < part.cell_end; ++c)
+      part.asm_cells[c - part.cell_begin] = c;
+    part.n_ghost_cells = (int64_t)g.size();
+    part.asm_cells.insert(part.asm_cells.end(), g.begin(), g.end());
+  }
+
+  void
+  color_asm_cells(const HostMesh &m, const HostDofs &d, Partition &part)
+  {
+    const int64_t    na = (int64_t)part.asm_cells.size();
+    std::vector<int> color((size_t)na, 0);
+    int              n_colors = 1;
+    if (part.scatter_mode == 0)
+      {
+        // atomics: one "colour", cells stay in deal.II (Morton) order
+      }
+    else if (m.n_refine >= 0)
+      {
+        // refine_global meshes: the two low bits of the Morton index are (ix & 1, iy & 1)
+        n_colors = 4;
+        for (int64_t a = 0; a < na; ++a)
+          color[a] = (int)(part.asm_cells[a] & 3);
+      }
+    else
+      {
+        // greedy colouring of the "shares an owned row" graph
+        std::vector<int32_t> pos((size_t)m.n_cells, -1);
+        for (int64_t a = 0; a < na; ++a)
+          pos[part.asm_cells[a]] = (int32_t)a;
+        std::fill(color.begin(), color.end(), -1);
+        for (int64_t a = 0; a < na; ++a)
+          {
+            uint64_t       used = 0;
+            const int64_t  c    = part.asm_cells[a];
+            for (int i = 0; i < d.n_loc; ++i)
+              {
+                const int64_t l = part.global_to_owned(d.cell_dofs[(size_t)c * d.n_loc + i]);
+                if (l < 0)
+                  continue;
+                for (int64_t k = part.adj_ptr[l]; k < part.adj_ptr[l + 1]; ++k)
+                  {
+                    const int32_t o = pos[part.adj[k]];
+                    if (o >= 0 && color[o] >= 0)
+                      used |= uint64_t(1) << color[o];
+                  }
+              }
+            int col = 0;
+            while ((used >> col) & 1)
+              ++col;
+            color[a] = col;
+            n_colors = std::max(n_colors, col + 1);
+          }
+      }
+    std::vector<int64_t> order((size_t)na);
+    for (int64_t a = 0; a < na; ++a)
+      order[a] = a;
+    std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return color[x] < color[y]; });
+    std::vector<int64_t> sorted((size_t)na);
+    part.n_colors = n_colors;
+    part.color_begin.assign((size_t)n_colors + 1, 0);
+    for (int64_t k = 0; k < na; ++k)
+      {
+        sorted[k] = part.asm_cells[order[k]];
+        ++part.color_begin[(size_t)color[order[k]] + 1];
+      }
+    for (int c = 0; c < n_colors; ++c)
+      part.color_begin[c + 1] += part.color_begin[c];
+    part.asm_cells.swap(sorted);
+  }
+
+  void
+  make_sparsity_pattern(const HostMesh &m, const HostDofs &d, Partition &part, HostPattern &p)
+  {
+    const int     n_loc = d.n_loc;
+    const int64_t L = part.n_owned;
+    build_row_adjacency(m, d, part);
+    color_asm_cells(m, d, part);
+    const std::vector<int64_t> &adj_ptr = part.adj_ptr, &adj = part.adj;
     // row lengths, then fill
     p.rowptr.assign((size_t)L + 1, 0);
     auto row_union = [&](const int64_t l, uint32_t *buf) -> int {

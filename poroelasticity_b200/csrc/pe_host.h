@@ -42,6 +42,12 @@ namespace pe
     std::vector<uint32_t> ghost_cols;  // sorted global dof ids of the halo columns (H of them)
     std::vector<int64_t>  asm_cells;   // owned cells then ghost cells (global cell ids)
     int64_t n_ghost_cells = 0;
+    // cells adjacent to every owned row (global cell ids, ascending): CSR over the owned rows
+    std::vector<int64_t> adj_ptr, adj;
+    // asm_cells is ordered colour-major: cells of one colour share no owned row
+    int                  scatter_mode = 0; // 0 = pre-zeroed matrix + RED atomics, 1 = colour-ordered first-writer stores
+    int                  n_colors = 0;
+    std::vector<int64_t> color_begin; // n_colors + 1 offsets into asm_cells
     // owned-row ranges of every rank (filled on every rank; used to route halo exchange)
     std::vector<int64_t> all_row_begin, all_row_end; // [world][3]
 
@@ -77,6 +83,11 @@ namespace pe
   void make_sparsity_pattern(const HostMesh &m, const HostDofs &d, Partition &part, HostPattern &p);
   // after pe_set_pattern: ghost cells / halo columns from a user pattern
   void finish_partition(const HostDofs &d, Partition &part, const HostPattern &p);
+  // owned-row -> cells adjacency (fills part.adj_ptr / part.adj / asm_cells / ghost cells)
+  void build_row_adjacency(const HostMesh &m, const HostDofs &d, Partition &part);
+  // colour the assembled cells (structured meshes: 4 colours from the Morton index; otherwise greedy)
+  // and sort asm_cells colour-major
+  void color_asm_cells(const HostMesh &m, const HostDofs &d, Partition &part);
   // permutation from deal.II BlockSparsityPattern storage order to CSR order
   void dealii_block_order(const HostDofs &d, const HostPattern &p, std::vector<int64_t> &perm);
 

@@ -106,7 +106,12 @@ struct pe_handle
   // ---- device side
   int64_t n_asm = 0, n_bnd = 0, L = 0, H = 0, nnz = 0;
   pe::DevBuf<double>   d_vx, d_vy, d_k, d_values, d_rhs, d_sol;
-  pe::DevBuf<uint32_t> d_cv, d_flags;
+  pe::DevBuf<uint32_t> d_cv, d_flags, d_rhs_first;
+  pe::DevBuf<double>   d_k_morton; // per-cell K in cell (Morton) order for the multigrid levels
+  std::vector<int64_t> bnd_color_begin;
+  // atomics mode: chunks of asm cells and the value ranges (3 per chunk) zeroed before each chunk
+  std::vector<int64_t> chunk_cell_begin, chunk_zero;
+  int64_t              chunk_cells = 32768;
   pe::DevBuf<int32_t>  d_cdofs, d_colidx, d_bnd_list, d_rowblk;
   int64_t              n_rowblk = 0;
   int                  spmv_kernel = 1; // 1 = stream, 0 = warp per row

@@ -11,6 +11,8 @@ namespace pe
   struct AsmArgs
   {
     int64_t         n_asm, n_bnd, L;
+    int64_t         a_begin, a_end, bnd_begin, bnd_end; // ranges of this launch (one colour)
+    const uint32_t *rhs_first;                          // bit i: this cell is the first writer of rhs row i
     const double   *vx, *vy, *kcell, *sol;
     double          k_scalar;
     const uint32_t *cv, *flags;
@@ -19,12 +21,18 @@ namespace pe
     const uint8_t  *off;
     double         *values, *rhs;
     int             do_matrix;
+    int             atomic_mode; // 1: matrix pre-zeroed, every contribution is a RED (cells in Morton order)
   };
 
   cudaError_t launch_scatter_offsets(int n_loc, int64_t n_asm, int64_t L, const int32_t *cdofs,
-                                     const int64_t *rowptr, const int32_t *colidx, uint8_t *off, int *err,
-                                     cudaStream_t s);
-  cudaError_t launch_assemble(int element, const AsmArgs &a, const DevParams &P, cudaStream_t s, int *n_launches);
+                                     const int64_t *rowptr, const int32_t *colidx, const int64_t *rc_ptr,
+                                     const int32_t *rc_idx, uint8_t *off, uint32_t *rhs_first, int *err, cudaStream_t s);
+  int         scatter_table_words(int n_loc); // 32-bit words per cell of the scatter-offset table
+  cudaError_t launch_assemble(int element, const AsmArgs &a, const DevParams &P, int n_colors, const int64_t *color_begin,
+                              const int64_t *bnd_color_begin, cudaStream_t s, int *n_launches);
+  cudaError_t launch_assemble_chunked(int element, const AsmArgs &a, const DevParams &P, int n_chunks,
+                                      const int64_t *chunk_cell_begin, const int64_t *chunk_zero, cudaStream_t s,
+                                      int *n_launches);
   cudaError_t launch_local_matrices(int element, const AsmArgs &a, const DevParams &P, int64_t first, int64_t n,
                                     double *out, double *rhs_out, cudaStream_t s);
   cudaError_t launch_lognormal(int64_t n, const int64_t *cell_ids, int64_t first, double sigma, uint64_t seed,

@@ -160,3 +160,51 @@ def test_full_size_properties_n1024():
     cs, _ = b.local_matrices_bench(1 << 18, repeats=1, t=0.1)
     one = b.local_matrices(0, 1, t=0.1)[0].sum()
     assert cs == pytest.approx(one * s.n_cells, rel=1e-10)
+
+
+@pytest.mark.parametrize("el", [BR1_WG, CGQ1_WG])
+def test_user_supplied_mesh_path(el):
+    """pe_set_mesh / pe_set_dofs / pe_set_pattern (what a deal.II host hands over): greedy colouring
+    instead of the Morton colours, no multigrid hierarchy (diagonal preconditioner fallback)."""
+    import scipy.sparse.linalg as spla
+    o = Oracle(el, 3, distort=0.15)
+    o.set_material(1.5, 0.9, 0.8, 0.02, 0.1)
+    o.set_case(CASE_COSCOS)
+    vx, vy, cv, fk = o.mesh()
+    b = pb.BiotSystem(element=el)
+    b.set_mesh(vx, vy, cv)
+    b.set_dofs(o.n_u, o.n_pint, o.n_pface, o.cell_dofs())
+    b.set_pattern(*o.pattern())
+    b.set_face_kinds(fk)
+    b.time_step = 0.1
+    b.set_material(1.5, 0.9, 0.8, 0.02)
+    b.set_case(pb.PE_CASE_COSCOS)
+    rng = np.random.default_rng(5)
+    old = rng.normal(size=o.n_dofs)
+    v_ref, r_ref, _ = o.assemble(0.4, old)
+    b.assemble_system(0.4, old)
+    assert rel(b.system_matrix(), v_ref) < TOL_MAT
+    assert rel(b.system_rhs(), r_ref) < TOL_MAT
+    b.rel_tol = 1e-12
+    x = b.solve_time_step()
+    x_ref = spla.splu(o.csr(v_ref).tocsc()).solve(r_ref)
+    assert np.linalg.norm(x - x_ref) <= TOL_SOL * np.linalg.norm(x_ref)
+
+
+def test_assembly_is_bitwise_reproducible():
+    """Colour-ordered first-writer scatter: no atomics, fixed summation order."""
+    o = Oracle(BR1_WG, 5, distort=0.1)
+    o.set_material(1, 1, 1, 0.01, 0.1)
+    o.set_case(CASE_COSCOS)
+    b = pb.BiotSystem(element=BR1_WG)
+    b.set_solver_options(1 | 32)         # bit 5: colour-ordered scatter (takes effect at pattern build)
+    b.make_grid_and_dofs(5, distort=0.1)
+    b.time_step = 0.1
+    b.set_material(1, 1, 1, 0.01)
+    b.set_case(pb.PE_CASE_COSCOS)
+    b.assemble_system(0.5)
+    v1, r1 = b.system_matrix(), b.system_rhs()
+    b.assemble_system(0.5)
+    assert np.array_equal(b.system_matrix(), v1) and np.array_equal(b.system_rhs(), r1)
+    v_ref, r_ref, _ = o.assemble(0.5)
+    assert rel(v1, v_ref) < TOL_MAT and rel(r1, r_ref) < TOL_MAT
