@@ -60,6 +60,20 @@ namespace
     return cudaMemcpyAsync(d.p, src, n * sizeof(T), cudaMemcpyHostToDevice, s);
   }
 
+  // global dof id -> local id on this rank: owned rows first, then the halo columns; -1 = not visible
+  int32_t
+  global_to_local(const pe_handle *h, const uint32_t g)
+  {
+    const Partition &pt = h->part;
+    const int64_t    l  = pt.global_to_owned(g);
+    if (l >= 0)
+      return (int32_t)l;
+    const auto it = std::lower_bound(pt.ghost_cols.begin(), pt.ghost_cols.end(), g);
+    if (it == pt.ghost_cols.end() || *it != g)
+      return -1;
+    return (int32_t)(pt.n_owned + (it - pt.ghost_cols.begin()));
+  }
+
   DevParams
   make_params(const pe_handle *h, const double t, const double dt)
   {
@@ -108,15 +122,7 @@ namespace
     PE_CUDA(upload(h->d_vy, h->mesh.y.data(), h->mesh.y.size(), s));
 
     // global -> local column map for the dofs this rank can see
-    auto to_local = [&](const uint32_t g) -> int32_t {
-      const int64_t l = pt.global_to_owned(g);
-      if (l >= 0)
-        return (int32_t)l;
-      const auto it = std::lower_bound(pt.ghost_cols.begin(), pt.ghost_cols.end(), g);
-      if (it == pt.ghost_cols.end() || *it != g)
-        return -1;
-      return (int32_t)(h->L + (it - pt.ghost_cols.begin()));
-    };
+    auto to_local = [h](const uint32_t g) -> int32_t { return global_to_local(h, g); };
 
     // SoA copies of the per-cell arrays for the cells this rank assembles
     std::vector<uint32_t> cv((size_t)4 * n_asm), flags((size_t)n_asm, 0);
@@ -212,7 +218,7 @@ namespace
       h->d_k.release();
     // the same field in cell (Morton) order for the multigrid levels
     h->d_k_morton.release();
-    if (pt.world == 1 && (h->k_lognormal || !h->k_cell.empty()))
+    if (h->k_lognormal || !h->k_cell.empty())
       {
         if (h->k_lognormal)
           {
@@ -777,8 +783,7 @@ extern "C"
             for (int64_t a = 0; a < h->n_asm; ++a)
               k[a] = h->k_cell[h->part.asm_cells[a]];
             PE_CUDA(upload(h->d_k, k.data(), k.size(), h->stream));
-            if (h->part.world == 1)
-              PE_CUDA(upload(h->d_k_morton, h->k_cell.data(), h->k_cell.size(), h->stream));
+            PE_CUDA(upload(h->d_k_morton, h->k_cell.data(), h->k_cell.size(), h->stream));
             PE_CUDA(cudaStreamSynchronize(h->stream));
           }
         else
@@ -1008,12 +1013,13 @@ extern "C"
         if (build_preconditioner(c, h->d_w[7].p, h->d_pinv.p) != 0)
           return cuda_fail(h, cudaGetLastError(), "build_preconditioner");
         // multigrid part: hierarchy topology once per mesh, operators re-discretised every solve
-        if (h->use_mg && h->part.world == 1)
+        if (h->use_mg)
           {
             if (!h->mg)
               {
                 h->mg = new MgHierarchy;
-                const int mrc = mg_build_topology(*h->mg, h->mesh, h->dofs, s);
+                const int mrc = mg_build_topology(*h->mg, h->mesh, h->dofs,
+                                                  [h](uint32_t g) { return global_to_local(h, g); }, s);
                 if (mrc < 0)
                   return cuda_fail(h, cudaGetLastError(), "mg_build_topology");
               }
@@ -1025,7 +1031,7 @@ extern "C"
                 const double gamma = h->c0 + h->alpha * h->alpha / (h->lambda + 2. * h->mu);
                 if (mg_assemble(*h->mg, h->d_k_morton.p, h->k_scalar, h->lambda, h->mu, h->last_dt, gamma, s, &h->launches) != 0)
                   return cuda_fail(h, cudaGetLastError(), "mg_assemble");
-                if (h->use_mg == 2)
+                if (h->use_mg == 2 && h->part.world == 1)
                   {
                     // additive variant: theta D^{-1} + Pi V Pi^T on both blocks
                     if (h->mg_theta != 1.0)
@@ -1040,8 +1046,15 @@ extern "C"
                     if (!h->bp)
                       {
                         h->bp = new BlockPrecond;
-                        if (precond_build_structure(*h->bp, h->mesh, h->dofs, h->pat, s) < 0)
+                        if (precond_build_structure(*h->bp, h->mesh, h->dofs, h->pat, h->part,
+                                                    [h](uint32_t g) { return global_to_local(h, g); }, s) < 0)
                           return cuda_fail(h, cudaGetLastError(), "precond_build_structure");
+                        if (h->part.world > 1)
+                          {
+                            h->bp->halo      = comm_halo_exchange;
+                            h->bp->allreduce = comm_allreduce;
+                            h->bp->comm_ctx  = h;
+                          }
                       }
                     if (h->bp->ready)
                       {

@@ -58,16 +58,11 @@ namespace pe
     for (int j = 0; j < n_loc; ++j)
       {
         const int32_t col = cdofs[(size_t)j * n_asm + c];
-        int64_t       lo = b, hi = e;
-        while (lo < hi)
-          {
-            const int64_t mid = (lo + hi) >> 1;
-            if (colidx[mid] < col)
-              lo = mid + 1;
-            else
-              hi = mid;
-          }
-        if (lo >= e || colidx[lo] != col)
+        // linear search: with local column numbering (multi-GPU) a row is not sorted
+        int64_t lo = b;
+        while (lo < e && colidx[lo] != col)
+          ++lo;
+        if (lo >= e)
           {
             atomicExch(err, 1);
             lo = b;

@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <functional>
 
 namespace pe
 {
@@ -419,7 +420,8 @@ namespace pe
   MgHierarchy::~MgHierarchy() = default;
 
   int
-  mg_build_topology(MgHierarchy &mg, const HostMesh &mesh, const HostDofs &dofs, cudaStream_t s)
+  mg_build_topology(MgHierarchy &mg, const HostMesh &mesh, const HostDofs &dofs,
+                    const std::function<int32_t(uint32_t)> &to_local, cudaStream_t s)
   {
     mg.ready = false;
     if (mesh.n_refine < 1 || (dofs.element != 0 && dofs.element != 1))
@@ -442,12 +444,12 @@ namespace pe
         const uint32_t *cd = &dofs.cell_dofs[(size_t)c * n_loc];
         const int       ci = (int)(cv[0] % V), cj = (int)(cv[0] / V);
         for (int v = 0; v < 4; ++v)
-          vdof[cv[v]] = (int32_t)cd[2 * v];
-        pint[(size_t)cj * N + ci]        = (int32_t)cd[n_loc - 1];
-        vedge[(size_t)cj * V + ci]       = (int32_t)cd[pf0 + 0 * pfs]; // face 0: x = left, vertical edge
-        vedge[(size_t)cj * V + ci + 1]   = (int32_t)cd[pf0 + 1 * pfs];
-        hedge[(size_t)cj * N + ci]       = (int32_t)cd[pf0 + 2 * pfs]; // face 2: bottom, horizontal edge
-        hedge[(size_t)(cj + 1) * N + ci] = (int32_t)cd[pf0 + 3 * pfs];
+          vdof[cv[v]] = to_local(cd[2 * v]);
+        pint[(size_t)cj * N + ci]        = to_local(cd[n_loc - 1]);
+        vedge[(size_t)cj * V + ci]       = to_local(cd[pf0 + 0 * pfs]); // face 0: x = left, vertical edge
+        vedge[(size_t)cj * V + ci + 1]   = to_local(cd[pf0 + 1 * pfs]);
+        hedge[(size_t)cj * N + ci]       = to_local(cd[pf0 + 2 * pfs]); // face 2: bottom, horizontal edge
+        hedge[(size_t)(cj + 1) * N + ci] = to_local(cd[pf0 + 3 * pfs]);
         for (int f = 0; f < 4; ++f)
           {
             const uint8_t k = mesh.face_kinds[4 * (size_t)c + f];

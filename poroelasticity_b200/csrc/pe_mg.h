@@ -3,6 +3,7 @@
 #include "pe_host.h"
 #include "pe_internal.h"
 
+#include <functional>
 #include <vector>
 
 namespace pe
@@ -24,7 +25,9 @@ namespace pe
     ~MgHierarchy();
   };
   // 0 = built, 1 = no hierarchy for this mesh (fallback: diagonal preconditioner), -1 = CUDA error
-  int  mg_build_topology(MgHierarchy &mg, const HostMesh &mesh, const HostDofs &dofs, cudaStream_t s);
+  // to_local: global dof id -> local id on this rank (owned < L <= halo) or -1 if not visible
+  int  mg_build_topology(MgHierarchy &mg, const HostMesh &mesh, const HostDofs &dofs,
+                         const std::function<int32_t(uint32_t)> &to_local, cudaStream_t s);
   int  mg_assemble(MgHierarchy &mg, const double *kcell_fine, double k_scalar, double lambda, double mu, double dt,
                    double gamma, cudaStream_t s, int64_t *launches);
   // V-cycle on level-0 right-hand side lv[0].bu (nc = 2) / lv[0].bp (nc = 1); result in lv[0].wu[2] / wp[2]

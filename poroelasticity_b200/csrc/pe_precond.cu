@@ -21,6 +21,7 @@
 #include "pe_precond.h"
 
 #include <algorithm>
+#include <functional>
 
 namespace pe
 {
@@ -80,14 +81,14 @@ namespace pe
     }
     // b_u[v] = r[d] - t2[d]
     __global__ void
-    k_gather_u2(const int nv, const int32_t *__restrict__ vdof, const uint8_t *__restrict__ mask,
+    k_gather_u2(const int nv, const int64_t L, const int32_t *__restrict__ vdof, const uint8_t *__restrict__ mask,
                 const double *__restrict__ r, const double *__restrict__ t2, double *__restrict__ bu)
     {
       const int v = blockIdx.x * blockDim.x + threadIdx.x;
       if (v >= nv)
         return;
-      const bool m       = mask && mask[v];
       const int  d       = vdof[v];
+      const bool m       = (mask && mask[v]) || d < 0 || d >= L; // only the owner contributes (all-reduced)
       bu[v]              = m ? 0. : r[d] - (t2 ? t2[d] : 0.);
       bu[(size_t)nv + v] = m ? 0. : r[d + 1] - (t2 ? t2[d + 1] : 0.);
     }
@@ -99,7 +100,9 @@ namespace pe
       const int v = blockIdx.x * blockDim.x + threadIdx.x;
       if (v >= nv || (mask && mask[v]))
         return;
-      const int    d  = vdof[v];
+      const int d = vdof[v];
+      if (d < 0)
+        return; // vertex not visible from this rank
       const double a0 = xu[v], a1 = xu[(size_t)nv + v];
       z[d]     = a0;
       z[d + 1] = a1;
@@ -148,8 +151,13 @@ namespace pe
       t[row]        = dinv[row] * r[row];
     }
     // b_p[v] = 1/2 sum_{edges at v} rf[edge]
+    __device__ __forceinline__ double
+    owned_val(const double *__restrict__ x, const int d, const int64_t L)
+    {
+      return (d >= 0 && d < L) ? x[d] : 0.;
+    }
     __global__ void
-    k_gather_f(const int N, const int32_t *__restrict__ hedge, const int32_t *__restrict__ vedge,
+    k_gather_f(const int N, const int64_t L, const int32_t *__restrict__ hedge, const int32_t *__restrict__ vedge,
                const uint8_t *__restrict__ mask, const double *__restrict__ rf, double *__restrict__ bp)
     {
       const int V = N + 1, nv = V * V;
@@ -164,18 +172,18 @@ namespace pe
       const int i = v % V, j = v / V;
       double    s = 0.;
       if (i > 0)
-        s += rf[hedge[j * N + i - 1]];
+        s += owned_val(rf, hedge[j * N + i - 1], L);
       if (i < N)
-        s += rf[hedge[j * N + i]];
+        s += owned_val(rf, hedge[j * N + i], L);
       if (j > 0)
-        s += rf[vedge[(j - 1) * V + i]];
+        s += owned_val(rf, vedge[(j - 1) * V + i], L);
       if (j < N)
-        s += rf[vedge[j * V + i]];
+        s += owned_val(rf, vedge[j * V + i], L);
       bp[v] = 0.5 * s;
     }
     // z_f = dinvF rf + 1/2 (x_a + x_b)
     __global__ void
-    k_scatter_f(const int N, const int32_t *__restrict__ hedge, const int32_t *__restrict__ vedge,
+    k_scatter_f(const int N, const int64_t L, const int32_t *__restrict__ hedge, const int32_t *__restrict__ vedge,
                 const double *__restrict__ xp, const double *__restrict__ dinv, const double *__restrict__ rf,
                 double *__restrict__ z)
     {
@@ -198,6 +206,8 @@ namespace pe
         }
       else
         return;
+      if (d < 0 || d >= L)
+        return; // owned faces only; halo faces arrive by halo exchange
       z[d] = dinv[d] * rf[d] + c;
     }
 
@@ -211,48 +221,52 @@ namespace pe
   BlockPrecond::~BlockPrecond() = default;
 
   // ---- once per mesh: dof classes and the sub-block index lists ------------------------------------
+  // Local numbering: owned rows [0, L), halo columns [L, L+H).  pat holds the owned rows with GLOBAL
+  // column ids; to_local maps them.
   int
   precond_build_structure(BlockPrecond &bp, const HostMesh &mesh, const HostDofs &d, const HostPattern &pat,
-                          cudaStream_t s)
+                          const Partition &part, const std::function<int32_t(uint32_t)> &to_local, cudaStream_t s)
   {
     bp.ready        = false;
-    const int n_loc = d.n_loc;
-    const int64_t n = d.n();
+    const int     n_loc = d.n_loc;
+    const int64_t L = part.n_owned, LH = L + (int64_t)part.ghost_cols.size();
     if ((int64_t)pat.colidx.size() > 0xffffffffll)
       return 1;
-    std::vector<uint8_t> cls((size_t)n, CLS_VERTEX);
+    std::vector<uint8_t> cls((size_t)LH, CLS_VERTEX);
     std::vector<double>  area_of_pint;
     std::vector<int32_t> pint_rows;
     for (int64_t c = 0; c < mesh.n_cells; ++c)
       {
         const uint32_t *cd = &d.cell_dofs[(size_t)c * n_loc];
-        for (int i = 8; i < n_loc - 1; ++i)
-          cls[cd[i]] = (d.element == 0 && ((i - 8) % 2 == 0)) ? CLS_BUBBLE : CLS_PFACE;
-        cls[cd[n_loc - 1]] = CLS_PINT;
+        for (int i = 8; i < n_loc; ++i)
+          {
+            const int32_t l = to_local(cd[i]);
+            if (l < 0)
+              continue;
+            cls[l] = i == n_loc - 1 ? CLS_PINT : ((d.element == 0 && ((i - 8) % 2 == 0)) ? CLS_BUBBLE : CLS_PFACE);
+          }
       }
-    // p_int rows with their cell areas (shoelace on vertices 0,1,3,2)
-    pint_rows.resize((size_t)mesh.n_cells);
-    area_of_pint.resize((size_t)mesh.n_cells);
-    for (int64_t c = 0; c < mesh.n_cells; ++c)
+    // owned p_int rows with their cell areas (shoelace on vertices 0,1,3,2)
+    for (int64_t c = part.cell_begin; c < part.cell_end; ++c)
       {
         const uint32_t *cv = &mesh.cell_vertices[4 * (size_t)c];
         const double    x0 = mesh.x[cv[0]], y0 = mesh.y[cv[0]], x1 = mesh.x[cv[1]], y1 = mesh.y[cv[1]];
         const double    x2 = mesh.x[cv[2]], y2 = mesh.y[cv[2]], x3 = mesh.x[cv[3]], y3 = mesh.y[cv[3]];
-        pint_rows[c]       = (int32_t)d.cell_dofs[(size_t)c * n_loc + n_loc - 1];
-        area_of_pint[c]    = 0.5 * ((x3 - x0) * (y2 - y1) - (x2 - x1) * (y3 - y0));
+        pint_rows.push_back(to_local(d.cell_dofs[(size_t)c * n_loc + n_loc - 1]));
+        area_of_pint.push_back(0.5 * ((x3 - x0) * (y2 - y1) - (x2 - x1) * (y3 - y0)));
       }
     auto build = [&](const int row_cls, const int col_mask, SubCsr &out) -> bool {
       std::vector<int32_t>  rows, rp(1, 0), col;
       std::vector<uint32_t> src;
-      for (int64_t r = 0; r < n; ++r)
+      for (int64_t r = 0; r < L; ++r)
         {
           if (cls[r] != row_cls)
             continue;
           rows.push_back((int32_t)r);
           for (int64_t k = pat.rowptr[r]; k < pat.rowptr[r + 1]; ++k)
             {
-              const int32_t cc = pat.colidx[k];
-              if ((col_mask >> cls[cc]) & 1)
+              const int32_t cc = to_local((uint32_t)pat.colidx[k]);
+              if (cc >= 0 && ((col_mask >> cls[cc]) & 1))
                 {
                   col.push_back(cc);
                   src.push_back((uint32_t)k);
@@ -286,15 +300,17 @@ namespace pe
     cudaMemcpyAsync(bp.cls.p, cls.data(), cls.size(), cudaMemcpyHostToDevice, s);
     cudaMemcpyAsync(bp.pint_rows.p, pint_rows.data(), pint_rows.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s);
     cudaMemcpyAsync(bp.pint_area.p, area_of_pint.data(), area_of_pint.size() * sizeof(double), cudaMemcpyHostToDevice, s);
-    if (bp.t.alloc((size_t)n) != cudaSuccess || bp.t2.alloc((size_t)n) != cudaSuccess || bp.dinv.alloc((size_t)n) != cudaSuccess)
+    if (bp.t.alloc((size_t)LH) != cudaSuccess || bp.t2.alloc((size_t)LH) != cudaSuccess || bp.dinv.alloc((size_t)LH) != cudaSuccess)
       return -1;
-    cudaMemsetAsync(bp.t.p, 0, sizeof(double) * (size_t)n, s);
-    cudaMemsetAsync(bp.t2.p, 0, sizeof(double) * (size_t)n, s);
+    cudaMemsetAsync(bp.t.p, 0, sizeof(double) * (size_t)LH, s);
+    cudaMemsetAsync(bp.t2.p, 0, sizeof(double) * (size_t)LH, s);
+    cudaMemsetAsync(bp.dinv.p, 0, sizeof(double) * (size_t)LH, s);
     if (cudaStreamSynchronize(s) != cudaSuccess)
       return -1;
-    bp.n_u   = d.n_u;
-    bp.n     = n;
-    bp.ready = true;
+    bp.n_u     = part.local_off[1]; // owned displacement rows come first
+    bp.n       = L;
+    bp.n_pint  = (int)pint_rows.size();
+    bp.ready   = true;
     return 0;
   }
 
@@ -304,7 +320,9 @@ namespace pe
                  int64_t *launches)
   {
     bp.values = values;
-    k_pint_dinv<<<gb(bp.Sif.n_rows), 128, 0, s>>>(bp.Sif.n_rows, bp.pint_rows.p, diag, bp.pint_area.p, gamma, bp.dinv.p);
+    k_pint_dinv<<<gb(bp.n_pint), 128, 0, s>>>(bp.n_pint, bp.pint_rows.p, diag, bp.pint_area.p, gamma, bp.dinv.p);
+    if (bp.halo)
+      bp.halo(bp.comm_ctx, bp.dinv.p); // D_i of the neighbours' interior pressures
     k_face_dinv<<<gb(bp.Sfi.n_rows), 128, 0, s>>>(bp.Sfi.n_rows, bp.Sfi.rows.p, bp.Sfi.rp.p, bp.Sfi.col.p, bp.Sfi.src.p,
                                                    values, diag, bp.dinv.p);
     *launches += 2;
@@ -312,15 +330,21 @@ namespace pe
   }
 
   // ---- z = P^{-1} r ---------------------------------------------------------------------------------
+  // Multi-GPU: sub-block products need the neighbours' entries (halo exchange of t and z); the two
+  // V-cycles run replicated on every rank on the all-reduced vertex-grid right-hand sides.
   void
   precond_apply(BlockPrecond &bp, MgHierarchy &mg, const double *pinv, const double *r, double *z, cudaStream_t s,
                 int64_t *launches)
   {
-    MgLevel  &L0 = mg.lv[0];
-    const int N  = L0.N, nv = (N + 1) * (N + 1);
-    // ----- displacement block
+    MgLevel      &L0 = mg.lv[0];
+    const int     N  = L0.N, nv = (N + 1) * (N + 1);
+    const int64_t L  = bp.n;
+    // local Jacobi parts:  u: z = pinv r, t = y1 on bubbles;  p_int: t_i = dinv_i r_i
     k_pre_u<<<gb(bp.n_u, 256), 256, 0, s>>>(bp.n_u, bp.cls.p, pinv, r, bp.t.p, z);
-    ++*launches;
+    k_pre_p<<<gb(bp.n_pint), 128, 0, s>>>(bp.n_pint, bp.pint_rows.p, bp.dinv.p, r, bp.t.p);
+    *launches += 2;
+    if (bp.halo)
+      bp.halo(bp.comm_ctx, bp.t.p);
     if (bp.has_bubbles)
       {
         k_sub_spmv<4><<<gb((int64_t)bp.Avb.n_rows * 4), 128, 0, s>>>(bp.Avb.n_rows, bp.Avb.rows.p, bp.Avb.rp.p, bp.Avb.col.p,
@@ -328,9 +352,21 @@ namespace pe
                                                                       nullptr, bp.t2.p);
         ++*launches;
       }
-    k_gather_u2<<<gb(nv), 128, 0, s>>>(nv, mg.vdof.p, L0.mask_u.p, r, bp.has_bubbles ? bp.t2.p : nullptr, L0.bu.p);
+    // rf' = r_f - S_fi t_i   -> t2 (face entries)
+    k_sub_spmv<1><<<gb(bp.Sfi.n_rows), 128, 0, s>>>(bp.Sfi.n_rows, bp.Sfi.rows.p, bp.Sfi.rp.p, bp.Sfi.col.p, bp.Sfi.src.p,
+                                                     bp.values, bp.t.p, nullptr, nullptr, r, bp.t2.p);
+    k_gather_u2<<<gb(nv), 128, 0, s>>>(nv, L, mg.vdof.p, L0.mask_u.p, r, bp.has_bubbles ? bp.t2.p : nullptr, L0.bu.p);
+    k_gather_f<<<gb(nv), 128, 0, s>>>(N, L, mg.hedge.p, mg.vedge.p, L0.mask_p.p, bp.t2.p, L0.bp.p);
+    *launches += 3;
+    if (bp.allreduce)
+      {
+        bp.allreduce(bp.comm_ctx, L0.bu.p, 2 * nv);
+        bp.allreduce(bp.comm_ctx, L0.bp.p, nv);
+      }
     mg_vcycle(mg, 2, s, launches);
+    mg_vcycle(mg, 1, s, launches);
     k_scatter_u2<<<gb(nv), 128, 0, s>>>(nv, mg.vdof.p, L0.mask_u.p, L0.wu[2].p, z, bp.t.p);
+    k_scatter_f<<<gb(2 * (int64_t)N * (N + 1)), 128, 0, s>>>(N, L, mg.hedge.p, mg.vedge.p, L0.wp[2].p, bp.dinv.p, bp.t2.p, z);
     *launches += 2;
     if (bp.has_bubbles)
       {
@@ -339,18 +375,11 @@ namespace pe
                                                                       bp.Abu.src.p, bp.values, bp.t.p, bp.t.p, pinv, r, z);
         ++*launches;
       }
-    // ----- pressure block
-    k_pre_p<<<gb(bp.Sif.n_rows), 128, 0, s>>>(bp.Sif.n_rows, bp.pint_rows.p, bp.dinv.p, r, bp.t.p);
-    // rf' = r_f - S_fi t_i   -> t2 (face entries)
-    k_sub_spmv<1><<<gb(bp.Sfi.n_rows), 128, 0, s>>>(bp.Sfi.n_rows, bp.Sfi.rows.p, bp.Sfi.rp.p, bp.Sfi.col.p, bp.Sfi.src.p,
-                                                     bp.values, bp.t.p, nullptr, nullptr, r, bp.t2.p);
-    k_gather_f<<<gb(nv), 128, 0, s>>>(N, mg.hedge.p, mg.vedge.p, L0.mask_p.p, bp.t2.p, L0.bp.p);
-    *launches += 3;
-    mg_vcycle(mg, 1, s, launches);
-    k_scatter_f<<<gb(2 * (int64_t)N * (N + 1)), 128, 0, s>>>(N, mg.hedge.p, mg.vedge.p, L0.wp[2].p, bp.dinv.p, bp.t2.p, z);
+    if (bp.halo)
+      bp.halo(bp.comm_ctx, z); // face pressures of the neighbours
     // z_i = dinv_i (r_i - S_if z_f)
     k_sub_spmv<4><<<gb((int64_t)bp.Sif.n_rows * 4), 128, 0, s>>>(bp.Sif.n_rows, bp.Sif.rows.p, bp.Sif.rp.p, bp.Sif.col.p,
                                                                   bp.Sif.src.p, bp.values, z, nullptr, bp.dinv.p, r, z);
-    *launches += 2;
+    ++*launches;
   }
 } // namespace pe

@@ -4,6 +4,8 @@
 #include "pe_internal.h"
 #include "pe_mg.h"
 
+#include <functional>
+
 namespace pe
 {
   struct SubCsr
@@ -15,7 +17,12 @@ namespace pe
   struct BlockPrecond
   {
     bool            ready = false, has_bubbles = false;
-    int64_t         n_u = 0, n = 0;
+    int64_t         n_u = 0, n = 0; // owned displacement rows, owned rows
+    int             n_pint = 0;
+    // multi-GPU hooks (null on one GPU)
+    void (*halo)(void *ctx, double *x)             = nullptr;
+    void (*allreduce)(void *ctx, double *v, int n) = nullptr;
+    void *comm_ctx                                 = nullptr;
     SubCsr          Abu, Avb, Sif, Sfi;
     DevBuf<uint8_t> cls;
     DevBuf<int32_t> pint_rows;
@@ -24,7 +31,7 @@ namespace pe
     ~BlockPrecond();
   };
   int  precond_build_structure(BlockPrecond &bp, const HostMesh &mesh, const HostDofs &d, const HostPattern &pat,
-                               cudaStream_t s);
+                               const Partition &part, const std::function<int32_t(uint32_t)> &to_local, cudaStream_t s);
   int  precond_update(BlockPrecond &bp, const double *values, const double *diag, double gamma, cudaStream_t s,
                       int64_t *launches);
   void precond_apply(BlockPrecond &bp, MgHierarchy &mg, const double *pinv, const double *r, double *z, cudaStream_t s,
