@@ -153,6 +153,13 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    verbose = os.environ.get("PE_BENCH_VERBOSE") == "1"
+
+    def say(msg):
+        if verbose:
+            print("[rank %d %.1fs] %s" % (rank, time.perf_counter() - t_start, msg), file=sys.stderr, flush=True)
+
+    t_start = time.perf_counter()
     dt = 0.1
     b = pb.PoroElasBR1WG(device=local_rank, rank=rank, world_size=world)
     if world > 1:
@@ -164,6 +171,7 @@ def main():
     t_setup = time.perf_counter()
     s = b.make_grid_and_dofs(args.n_refine)
     t_setup = time.perf_counter() - t_setup
+    say("setup done: owned rows %d nnz %d ghost cells %d" % (s.n_owned_rows, s.nnz_owned, s.n_ghost_cells))
     b.time_step = dt
     b.set_material(1.0, 1.0, 1.0, 0.0)
     b.set_case(pb.PE_CASE_COSCOS)
@@ -183,8 +191,10 @@ def main():
 
     # ---- device-resident arm ------------------------------------------------------------------
     b.set_solution(np.zeros(s.n_owned_rows if world == 1 else n_dofs))
+    say("device state ready")
     for k in range(args.warmup):
         step(k, False, None)
+        say("warmup step %d: %d iterations" % (k, b.stats.iterations))
     b.set_solution(np.zeros(s.n_owned_rows if world == 1 else n_dofs))
     launches0 = b.timings()["launches"]
     sampler = ClockSampler(local_rank)
@@ -203,6 +213,7 @@ def main():
         iters.append(b.stats.iterations)
         spmvs.append(b.stats.spmv_count)
     barrier()
+    say("timed steps done")
     wall = time.perf_counter() - t0
     # device time of the steps = sum of the CUDA-event timed phases on the handle's stream
     dev_s = (sum(asm_ms) + sum(sol_ms)) * 1e-3
@@ -242,6 +253,12 @@ def main():
         e2e = {"value": n_cells * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(n_dofs * 8),
                "d2h_bytes_per_step": int(n_dofs * 8), "ms_per_step": e2e_s / args.steps * 1e3}
 
+    # orderly shutdown on every rank (the library's NCCL communicator, then torch's)
+    stats_launches = int(launches)
+    b.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     asm_kernel_s = (sum(asm_k_ms) / len(asm_k_ms)) * 1e-3
@@ -269,8 +286,6 @@ def main():
         val, sec, desc = cpu_baseline(args.cpu_refine, 2, dt)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc}
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -1,0 +1,174 @@
+// Host-side C++ mirror of the reference's classes for the hot path, on top of the C ABI
+// (include/poroelas_b200.h).  Same member names as PoroElasBR1WG / PoroElas_CGQ1_WG
+// (PoroElasBR1WG_new.cc:62-137): make_grid_and_dofs(), assemble_system(t), solve_time_step(), run(),
+// same stdout lines (BR1new:599-610, 2183-2185).  No numerics live here.
+#pragma once
+#include "../include/poroelas_b200.h"
+
+#include <cstdio>
+#include <iostream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace poroelas
+{
+  template <int dim>
+  class BiotProgram
+  {
+  public:
+    BiotProgram(const pe_element element, const double total_time_, const double time_step_, const double lambda_,
+                const double mu_, const double alpha_, const double capacity_)
+      : total_time(total_time_)
+      , time_step(time_step_)
+      , number_timestep((unsigned int)(total_time_ / time_step_))
+      , timestep_number(1)
+      , lambda(lambda_)
+      , mu(mu_)
+      , alpha(alpha_)
+      , capacity(capacity_)
+    {
+      static_assert(dim == 2, "3-D is SURVEY 8(f) 'next'");
+      pe_config cfg{};
+      cfg.element    = element;
+      cfg.dim        = dim;
+      cfg.device     = -1;
+      cfg.world_size = 1;
+      check(pe_create(&h, &cfg), "pe_create");
+    }
+    ~BiotProgram() { pe_destroy(h); }
+    BiotProgram(const BiotProgram &) = delete;
+
+    // problem variants the reference selects by commenting blocks in and out
+    int    refinement    = 5;
+    int    case_id       = PE_CASE_COSCOS;
+    int    boundary_kinds = PE_FACE_DIR_U | PE_FACE_DIR_P;
+    double k_scalar      = 1.0;
+    double rel_tol       = 1e-10;
+    int    max_iterations = 100000;
+    bool   cantilever    = false; // BR1new as shipped: u = 0 on x = 0, traction (0,-1) on y = 1, K = 1e-7
+
+    void
+    run()
+    {
+      std::cout << "Solving problem in " << dim << " space dimensions." << std::endl;
+      make_grid_and_dofs();
+      // old_solution = 0 (BR1new:2163): the device solution starts at zero
+      for (timestep_number = 1, time = time_step; time <= total_time; time += time_step, ++timestep_number)
+        {
+          std::cout << "Time step " << timestep_number << " at t=" << time << " time_step " << time_step << std::endl;
+          assemble_system(time);
+          solve_time_step();
+          // old_solution = solution (BR1new:2241): stays on the device
+        }
+    }
+
+    const pe_solve_stats &last_solve() const { return stats; }
+    pe_handle            *handle() { return h; }
+    std::vector<double>
+    solution() const
+    {
+      pe_sizes s;
+      pe_get_sizes(h, &s);
+      std::vector<double> x((size_t)s.n_owned_rows);
+      pe_get_solution(h, x.data());
+      return x;
+    }
+
+  protected:
+    void
+    make_grid_and_dofs()
+    {
+      check(pe_make_unit_square(h, refinement, 0., 0, cantilever ? 0 : boundary_kinds), "pe_make_unit_square");
+      check(pe_distribute_dofs(h), "pe_distribute_dofs");
+      check(pe_make_sparsity_pattern(h), "pe_make_sparsity_pattern");
+      pe_sizes s;
+      pe_get_sizes(h, &s);
+      std::cout << "Number of active cells: " << s.n_cells << std::endl
+                << "Number of degrees of freedom: " << s.n_dofs << " (" << s.n_u << '+' << s.n_pint << '+' << s.n_pface
+                << ')' << std::endl
+                << std::endl;
+      std::cout << "   Number of rt degrees of freedom: " << s.n_pface << std::endl;
+      if (cantilever)
+        {
+          // set_boundary_id loop of BR1new:652-666 + the Neumann block BR1new:964-990
+          std::vector<uint8_t> fk(4 * (size_t)s.n_cells);
+          pe_get_mesh(h, nullptr, nullptr, nullptr, nullptr);
+          std::vector<uint32_t> cells;
+          std::vector<uint8_t>  faces, kinds;
+          const int64_t         N = int64_t(1) << refinement;
+          for (int64_t c = 0; c < s.n_cells; ++c)
+            {
+              int64_t ix = 0, iy = 0;
+              for (int b = 0; b < 16; ++b)
+                {
+                  ix |= ((c >> (2 * b)) & 1) << b;
+                  iy |= ((c >> (2 * b + 1)) & 1) << b;
+                }
+              if (ix == 0)
+                {
+                  cells.push_back((uint32_t)c);
+                  faces.push_back(0);
+                  kinds.push_back(PE_FACE_DIR_U);
+                }
+              if (iy == N - 1)
+                {
+                  cells.push_back((uint32_t)c);
+                  faces.push_back(3);
+                  kinds.push_back(PE_FACE_NEU_U);
+                }
+            }
+          const double traction[2] = {0., -1.};
+          check(pe_set_boundary(h, (int64_t)cells.size(), cells.data(), faces.data(), kinds.data(), traction),
+                "pe_set_boundary");
+        }
+      check(pe_set_material(h, lambda, mu, alpha, capacity, k_scalar, nullptr), "pe_set_material");
+      check(pe_set_case(h, case_id, nullptr), "pe_set_case");
+    }
+    void
+    assemble_system(const double t)
+    {
+      check(pe_assemble_system(h, t, time_step, nullptr), "pe_assemble_system");
+    }
+    void
+    solve_time_step()
+    {
+      check(pe_solve_time_step(h, rel_tol, max_iterations, nullptr, &stats), "pe_solve_time_step");
+    }
+    void
+    check(const int rc, const char *what) const
+    {
+      if (rc != PE_OK)
+        throw std::runtime_error(std::string(what) + ": " + (h ? pe_last_error(h) : "no handle"));
+    }
+
+    pe_handle     *h = nullptr;
+    pe_solve_stats stats{};
+    double         total_time, time = 0., time_step;
+    unsigned int   number_timestep, timestep_number;
+    const double   lambda, mu, alpha, capacity;
+  };
+
+  // PoroElasBR1WG<2>: "general case" constructor block BR1new:532-539
+  template <int dim>
+  struct PoroElasBR1WG : BiotProgram<dim>
+  {
+    PoroElasBR1WG()
+      : BiotProgram<dim>(PE_BR1_WG, 1.0, 1. / 16, 1., 1., 1.0, 0.0)
+    {}
+    PoroElasBR1WG(double T, double dt, double lambda, double mu, double alpha, double c0)
+      : BiotProgram<dim>(PE_BR1_WG, T, dt, lambda, mu, alpha, c0)
+    {}
+  };
+  // PoroElas_CGQ1_WG<2>: "general case" constructor block CGQ1:824-831
+  template <int dim>
+  struct PoroElas_CGQ1_WG : BiotProgram<dim>
+  {
+    PoroElas_CGQ1_WG()
+      : BiotProgram<dim>(PE_CGQ1_WG, 1.0, 1. / 1024, 1., 1., 1.0, 0.0)
+    {}
+    PoroElas_CGQ1_WG(double T, double dt, double lambda, double mu, double alpha, double c0)
+      : BiotProgram<dim>(PE_CGQ1_WG, T, dt, lambda, mu, alpha, c0)
+    {}
+  };
+} // namespace poroelas

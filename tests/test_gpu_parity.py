@@ -208,3 +208,17 @@ def test_assembly_is_bitwise_reproducible():
     assert np.array_equal(b.system_matrix(), v1) and np.array_equal(b.system_rhs(), r1)
     v_ref, r_ref, _ = o.assemble(0.5)
     assert rel(v1, v_ref) < TOL_MAT and rel(r1, r_ref) < TOL_MAT
+
+
+def test_cpp_host_driver_runs():
+    """host/poroelas_br1wg: the C++ twin of the reference's main() on top of the C ABI."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "host", "poroelas_br1wg")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(root, "host")])
+    out = subprocess.run([exe, "4", "0.25"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "Number of degrees of freedom: 1986 (1186+256+544)" in out.stdout
+    assert out.stdout.count("Time step") == 4
