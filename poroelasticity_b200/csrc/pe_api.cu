@@ -999,6 +999,31 @@ extern "C"
       PE_CUDA(h->d_scal.alloc(64));
     cudaStream_t s = h->stream;
     SolverCtx    c = make_solver_ctx(h);
+    // once per mesh (not timed as part of the solve): multigrid topology, sub-block index lists
+    if (h->cfg.element != PE_WG_Q2RT2 && h->use_mg)
+      {
+        if (!h->mg)
+          {
+            h->mg = new MgHierarchy;
+            const int mrc = mg_build_topology(*h->mg, h->mesh, h->dofs,
+                                              [h](uint32_t g) { return global_to_local(h, g); }, s);
+            if (mrc < 0)
+              return cuda_fail(h, cudaGetLastError(), "mg_build_topology");
+          }
+        if (h->mg->ready && !(h->use_mg == 2 && h->part.world == 1) && !h->bp)
+          {
+            h->bp = new BlockPrecond;
+            if (precond_build_structure(*h->bp, h->mesh, h->dofs, h->pat, h->part,
+                                        [h](uint32_t g) { return global_to_local(h, g); }, s) < 0)
+              return cuda_fail(h, cudaGetLastError(), "precond_build_structure");
+            if (h->part.world > 1)
+              {
+                h->bp->halo      = comm_halo_exchange;
+                h->bp->allreduce = comm_allreduce;
+                h->bp->comm_ctx  = h;
+              }
+          }
+      }
     PE_CUDA(cudaEventRecord(h->ev[3], s));
     int rc;
     // initial guess: the previous solution (old_solution), already in d_sol

@@ -227,6 +227,47 @@ namespace pe
         }
     }
 
+    // coarsest level (<= 1024 vertices): `sweeps` damped Jacobi sweeps from x = 0 in ONE single-CTA launch
+    // (ping-pong in shared memory); replaces 24 tiny launches per V-cycle.
+    template <int NC>
+    __global__ void __launch_bounds__(1024)
+    k_mg_coarse(const int N, const double *__restrict__ st, const double *__restrict__ dinv,
+                const double *__restrict__ b, double *__restrict__ xo, const double omega, const int sweeps)
+    {
+      extern __shared__ double sm[]; // 2 * NC * nv
+      const int nv = (N + 1) * (N + 1);
+      double   *x0 = sm, *x1 = sm + NC * nv;
+      for (int v = threadIdx.x; v < NC * nv; v += blockDim.x)
+        x0[v] = 0.;
+      __syncthreads();
+      for (int it = 0; it < sweeps; ++it)
+        {
+          for (int v = threadIdx.x; v < nv; v += blockDim.x)
+            {
+              double r[NC];
+              stencil_row<NC>(N, v, st, x0, r);
+#pragma unroll
+              for (int c = 0; c < NC; ++c)
+                r[c] = b[(size_t)c * nv + v] - r[c];
+              if (NC == 1)
+                x1[v] = x0[v] + omega * dinv[v] * r[0];
+              else
+                {
+                  const double d00 = dinv[v], d01 = dinv[(size_t)nv + v], d10 = dinv[(size_t)2 * nv + v],
+                               d11 = dinv[(size_t)3 * nv + v];
+                  x1[v]      = x0[v] + omega * (d00 * r[0] + d01 * r[NC - 1]);
+                  x1[nv + v] = x0[nv + v] + omega * (d10 * r[0] + d11 * r[NC - 1]);
+                }
+            }
+          __syncthreads();
+          double *t = x0;
+          x0        = x1;
+          x1        = t;
+        }
+      for (int v = threadIdx.x; v < NC * nv; v += blockDim.x)
+        xo[v] = x0[v];
+    }
+
     // r = b - A x
     template <int NC>
     __global__ void
@@ -545,7 +586,16 @@ namespace pe
     double       *x0   = NC == 2 ? L.wu[0].p : L.wp[0].p;
     double       *x1   = NC == 2 ? L.wu[1].p : L.wp[1].p;
     const bool    last = l + 1 == mg.lv.size();
-    const int     pre  = last ? 24 : nu;
+    if (last)
+      {
+        // coarse solve: 24 Jacobi sweeps in one launch, result straight into w[2]
+        const int threads = std::min(1024, ((nv + 31) / 32) * 32);
+        k_mg_coarse<NC><<<1, threads, sizeof(double) * 2 * NC * nv, s>>>(L.N, st, dinv, b, NC == 2 ? L.wu[2].p : L.wp[2].p,
+                                                                         omega, 24);
+        ++*launches;
+        return;
+      }
+    const int     pre  = nu;
     // pre-smoothing from x = 0
     k_mg_jacobi<NC><<<g1(nv), 128, 0, s>>>(L.N, st, dinv, b, nullptr, x0, omega);
     ++*launches;

@@ -91,9 +91,26 @@ namespace pe
       {
         const double  *v = values + k0;
         const int32_t *c = colidx + k0;
-#pragma unroll 4
-        for (int i = threadIdx.x; i < n; i += 256)
-          prod[i] = v[i] * __ldg(x + c[i]);
+        // all column loads first, then all gathers: kStreamNnz/256 = 16 independent chains per thread
+        constexpr int PER = kStreamNnz / 256;
+        int32_t       cc[PER];
+        double        vv[PER];
+#pragma unroll
+        for (int u = 0; u < PER; ++u)
+          {
+            const int i = threadIdx.x + u * 256;
+            cc[u]       = i < n ? __ldg(c + i) : -1;
+          }
+#pragma unroll
+        for (int u = 0; u < PER; ++u)
+          {
+            const int i = threadIdx.x + u * 256;
+            vv[u]       = i < n ? __ldcs(v + i) : 0.; // streamed once: evict-first
+          }
+#pragma unroll
+        for (int u = 0; u < PER; ++u)
+          if (cc[u] >= 0)
+            prod[threadIdx.x + u * 256] = vv[u] * __ldg(x + cc[u]);
         __syncthreads();
         for (int r = r0 + threadIdx.x; r < r1; r += 256)
           {

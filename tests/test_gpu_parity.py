@@ -220,5 +220,5 @@ def test_cpp_host_driver_runs():
         subprocess.check_call(["make", "-s", "-C", os.path.join(root, "host")])
     out = subprocess.run([exe, "4", "0.25"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert "Number of degrees of freedom: 1986 (1186+256+544)" in out.stdout
+    assert "Number of degrees of freedom: 1922 (1122+256+544)" in out.stdout
     assert out.stdout.count("Time step") == 4
