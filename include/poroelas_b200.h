@@ -161,7 +161,9 @@ int pe_solve_time_step(pe_handle *h, double rel_tol, int max_iterations, double 
 /* preconditioner of the Krylov solve: use_multigrid = 1: block preconditioner with
  * auxiliary-space V-cycles (pe_precond.cu), 2: additive Jacobi + V-cycles, 0: diagonal only (meshes made
  * by pe_make_unit_square); theta scales the diagonal part, omega / nu = Jacobi damping / sweeps.
- * Defaults 1, 1.0, 0.8, 2. */
+ * Defaults 1, 1.0, 0.6, 2.  Higher bits of use_multigrid: 16 = warp-per-row SpMV, 32 = colour-ordered
+ * deterministic scatter (applies at the next pattern build), 64 = no CUDA graphs, bits 8.. = assembly
+ * chunk size in units of 4096 cells. */
 int pe_set_solver_options(pe_handle *h, int use_multigrid, double theta, double omega, int nu);
 int pe_get_solution(const pe_handle *h, double *solution);
 int pe_set_solution(pe_handle *h, const double *solution);

@@ -409,6 +409,8 @@ namespace
     c.colidx     = h->d_colidx.p;
     c.values     = h->d_values.p;
     c.stream     = h->stream;
+    c.launch_counter = &h->launches;
+    c.use_graphs     = h->use_graphs;
     if (h->spmv_kernel == 1)
       {
         c.rowblk   = h->d_rowblk.p;
@@ -944,7 +946,8 @@ extern "C"
     // bits 8..: chunk size of the atomics mode in units of 4096 cells (0 = default 32768)
     if ((use_multigrid >> 8) > 0)
       h->chunk_cells = (int64_t)(use_multigrid >> 8) * 4096;
-    h->spmv_kernel = (use_multigrid & 16) ? 0 : 1; // bit 4: fall back to the warp-per-row SpMV (A/B measurements)
+    h->spmv_kernel = (use_multigrid & 16) ? 0 : 1;
+    h->use_graphs  = (use_multigrid & 64) ? 0 : 1; // bit 6: no CUDA graphs (A/B measurements) // bit 4: fall back to the warp-per-row SpMV (A/B measurements)
     h->mg_theta = theta;
     h->mg_omega = omega;
     h->mg_nu    = nu;
@@ -1106,7 +1109,7 @@ extern "C"
     cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]);
     h->solve_ms    = ms;
     stats->seconds = ms * 1e-3;
-    h->launches += (int64_t)stats->iterations * 7 + stats->spmv_count + 8;
+    h->launches += 12; // setup / residual kernels outside the iteration
     if (solution)
       {
         PE_CUDA(cudaMemcpyAsync(solution, h->d_sol.p, sizeof(double) * (size_t)h->L, cudaMemcpyDeviceToHost, s));

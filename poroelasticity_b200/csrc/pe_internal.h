@@ -127,9 +127,9 @@ struct pe_handle
   // auxiliary-space multigrid preconditioner (pe_mg.cu); null = diagonal preconditioner only
   pe::MgHierarchy *mg = nullptr;
   pe::BlockPrecond *bp = nullptr;
-  int              use_mg = 1;
+  int              use_mg = 1, use_graphs = 1;
   double           mg_theta = 1.0, mg_omega = 0.6;
-  int              mg_nu = 1;
+  int              mg_nu = 2;
   double           precond_ms = 0.;
 
   // multi-GPU

@@ -21,7 +21,7 @@ namespace pe
     std::vector<MgLevel> lv;
     DevBuf<int32_t>      vdof, pint, hedge, vedge;
     double               omega = 0.6, theta = 1.0;
-    int                  nu    = 1;
+    int                  nu    = 2;
     ~MgHierarchy();
   };
   // 0 = built, 1 = no hierarchy for this mesh (fallback: diagonal preconditioner), -1 = CUDA error

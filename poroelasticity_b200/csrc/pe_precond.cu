@@ -67,6 +67,63 @@ namespace pe
         }
     }
 
+    // compact copy of the sub-block values, once per solve: val[k] = values[src[k]]
+    __global__ void
+    k_sub_gather_values(const int64_t n, const uint32_t *__restrict__ src, const double *__restrict__ values,
+                        double *__restrict__ val)
+    {
+      const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      if (k < n)
+        val[k] = __ldg(values + src[k]);
+    }
+    // streamed sub-block product (same scheme as k_spmv_stream): a CTA owns a run of sub-rows holding
+    // <= kSubNnz entries; coalesced value/column streaming with all loads batched, row sums from smem,
+    // epilogue  out[row] = a[row] + m[row] * (b[row] - sum)   (null a -> 0, null m -> 1, null b -> +sum)
+    constexpr int kSubNnz = 2048;
+    __global__ void __launch_bounds__(256)
+    k_sub_stream(const int32_t *__restrict__ rowblk, const int32_t *__restrict__ rows, const int32_t *__restrict__ rp,
+                 const int32_t *__restrict__ col, const double *__restrict__ val, const double *x, const double *a,
+                 const double *__restrict__ m, const double *b, double *out)
+    {
+      __shared__ double prod[kSubNnz];
+      const int r0 = rowblk[blockIdx.x], r1 = rowblk[blockIdx.x + 1];
+      const int k0 = rp[r0], n = rp[r1] - k0;
+      constexpr int PER = kSubNnz / 256;
+      int32_t       cc[PER];
+      double        vv[PER];
+#pragma unroll
+      for (int u = 0; u < PER; ++u)
+        {
+          const int i = threadIdx.x + u * 256;
+          cc[u]       = i < n ? __ldg(col + k0 + i) : -1;
+        }
+#pragma unroll
+      for (int u = 0; u < PER; ++u)
+        {
+          const int i = threadIdx.x + u * 256;
+          vv[u]       = i < n ? __ldcs(val + k0 + i) : 0.;
+        }
+#pragma unroll
+      for (int u = 0; u < PER; ++u)
+        if (cc[u] >= 0)
+          prod[threadIdx.x + u * 256] = vv[u] * x[cc[u]];
+      __syncthreads();
+      for (int r = r0 + threadIdx.x; r < r1; r += 256)
+        {
+          const int bb = rp[r] - k0, ee = rp[r + 1] - k0;
+          double    s  = 0.;
+          for (int k = bb; k < ee; ++k)
+            s += prod[k];
+          const int row = rows[r];
+          double    v   = b ? b[row] - s : s;
+          if (m)
+            v *= m[row];
+          if (a)
+            v += a[row];
+          out[row] = v;
+        }
+    }
+
     // t = [bubble: pinv r, other u: 0]; z = pinv r on Dirichlet-masked / all u dofs as default
     __global__ void
     k_pre_u(const int64_t n_u, const uint8_t *__restrict__ cls, const double *__restrict__ pinv,
@@ -283,7 +340,24 @@ namespace pe
         return cudaMemcpyAsync(dev.p, host.data(), host.size() * sizeof(host[0]), cudaMemcpyHostToDevice, s) ==
                cudaSuccess;
       };
-      const bool ok = up(out.rows, rows) && up(out.rp, rp) && up(out.col, col) && up(out.src, src);
+      // row runs for the streamed product
+      std::vector<int32_t> blk(1, 0);
+      {
+        int r = 0;
+        const int nr = (int)rows.size();
+        while (r < nr)
+          {
+            int e = r + 1;
+            while (e < nr && rp[e + 1] - rp[r] <= kSubNnz && e - r < 256)
+              ++e;
+            blk.push_back(e);
+            r = e;
+          }
+      }
+      out.n_blk = (int)blk.size() - 1;
+      out.nnz   = (int64_t)col.size();
+      const bool ok = up(out.rows, rows) && up(out.rp, rp) && up(out.col, col) && up(out.src, src) && up(out.rowblk, blk) &&
+                      out.val.alloc(col.size()) == cudaSuccess;
       cudaStreamSynchronize(s);
       return ok;
     };
@@ -320,6 +394,12 @@ namespace pe
                  int64_t *launches)
   {
     bp.values = values;
+    for (SubCsr *sc : {&bp.Abu, &bp.Avb, &bp.Sif, &bp.Sfi})
+      if (sc->nnz > 0)
+        {
+          k_sub_gather_values<<<gb(sc->nnz, 256), 256, 0, s>>>(sc->nnz, sc->src.p, values, sc->val.p);
+          ++*launches;
+        }
     k_pint_dinv<<<gb(bp.n_pint), 128, 0, s>>>(bp.n_pint, bp.pint_rows.p, diag, bp.pint_area.p, gamma, bp.dinv.p);
     if (bp.halo)
       bp.halo(bp.comm_ctx, bp.dinv.p); // D_i of the neighbours' interior pressures
@@ -347,14 +427,11 @@ namespace pe
       bp.halo(bp.comm_ctx, bp.t.p);
     if (bp.has_bubbles)
       {
-        k_sub_spmv<4><<<gb((int64_t)bp.Avb.n_rows * 4), 128, 0, s>>>(bp.Avb.n_rows, bp.Avb.rows.p, bp.Avb.rp.p, bp.Avb.col.p,
-                                                                      bp.Avb.src.p, bp.values, bp.t.p, nullptr, nullptr,
-                                                                      nullptr, bp.t2.p);
+        k_sub_stream<<<(unsigned)bp.Avb.n_blk, 256, 0, s>>>(bp.Avb.rowblk.p, bp.Avb.rows.p, bp.Avb.rp.p, bp.Avb.col.p, bp.Avb.val.p, bp.t.p, nullptr, nullptr, nullptr, bp.t2.p);
         ++*launches;
       }
     // rf' = r_f - S_fi t_i   -> t2 (face entries)
-    k_sub_spmv<1><<<gb(bp.Sfi.n_rows), 128, 0, s>>>(bp.Sfi.n_rows, bp.Sfi.rows.p, bp.Sfi.rp.p, bp.Sfi.col.p, bp.Sfi.src.p,
-                                                     bp.values, bp.t.p, nullptr, nullptr, r, bp.t2.p);
+    k_sub_stream<<<(unsigned)bp.Sfi.n_blk, 256, 0, s>>>(bp.Sfi.rowblk.p, bp.Sfi.rows.p, bp.Sfi.rp.p, bp.Sfi.col.p, bp.Sfi.val.p, bp.t.p, nullptr, nullptr, r, bp.t2.p);
     k_gather_u2<<<gb(nv), 128, 0, s>>>(nv, L, mg.vdof.p, L0.mask_u.p, r, bp.has_bubbles ? bp.t2.p : nullptr, L0.bu.p);
     k_gather_f<<<gb(nv), 128, 0, s>>>(N, L, mg.hedge.p, mg.vedge.p, L0.mask_p.p, bp.t2.p, L0.bp.p);
     *launches += 3;
@@ -371,15 +448,13 @@ namespace pe
     if (bp.has_bubbles)
       {
         // z_b = y1 + pinv_b (r_b - A_bb y1 - A_bv x_v),  t = (x_v, y1)
-        k_sub_spmv<8><<<gb((int64_t)bp.Abu.n_rows * 8), 128, 0, s>>>(bp.Abu.n_rows, bp.Abu.rows.p, bp.Abu.rp.p, bp.Abu.col.p,
-                                                                      bp.Abu.src.p, bp.values, bp.t.p, bp.t.p, pinv, r, z);
+        k_sub_stream<<<(unsigned)bp.Abu.n_blk, 256, 0, s>>>(bp.Abu.rowblk.p, bp.Abu.rows.p, bp.Abu.rp.p, bp.Abu.col.p, bp.Abu.val.p, bp.t.p, bp.t.p, pinv, r, z);
         ++*launches;
       }
     if (bp.halo)
       bp.halo(bp.comm_ctx, z); // face pressures of the neighbours
     // z_i = dinv_i (r_i - S_if z_f)
-    k_sub_spmv<4><<<gb((int64_t)bp.Sif.n_rows * 4), 128, 0, s>>>(bp.Sif.n_rows, bp.Sif.rows.p, bp.Sif.rp.p, bp.Sif.col.p,
-                                                                  bp.Sif.src.p, bp.values, z, nullptr, bp.dinv.p, r, z);
+    k_sub_stream<<<(unsigned)bp.Sif.n_blk, 256, 0, s>>>(bp.Sif.rowblk.p, bp.Sif.rows.p, bp.Sif.rp.p, bp.Sif.col.p, bp.Sif.val.p, z, nullptr, bp.dinv.p, r, z);
     ++*launches;
   }
 } // namespace pe

@@ -10,8 +10,10 @@ namespace pe
 {
   struct SubCsr
   {
-    int              n_rows = 0;
-    DevBuf<int32_t>  rows, rp, col;
+    int              n_rows = 0, n_blk = 0;
+    int64_t          nnz = 0;
+    DevBuf<int32_t>  rows, rp, col, rowblk;
+    DevBuf<double>   val; // compact copy of the block's values, refreshed once per solve
     DevBuf<uint32_t> src; // index into the assembled CSR values
   };
   struct BlockPrecond

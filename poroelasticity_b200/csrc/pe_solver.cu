@@ -566,36 +566,75 @@ namespace pe
     // scaled to ||b||: the exact-residual check below decides what is reported.
     const int check_every = 4;
     double    eta_target  = rel_tol * eta0;
+    // one MINRES iteration with the vector roles (v, v_old, z, z_new, w, w_old) as given
+    auto iteration = [&](double *v_, double *vo_, double *z_, double *zn_, double *w_, double *wo_) {
+      if (c.halo)
+        c.halo(c.halo_ctx, z_);
+      spmv_signed(c, z_, p, &st->d1);
+      if (c.allreduce)
+        c.allreduce(c.halo_ctx, &st->d1, 1);
+      k_minres_scalars_a<<<1, 1, 0, s>>>(st);
+      if (c.precond_apply)
+        {
+          k_minres_lanczos<<<g, 256, 0, s>>>(L, st, p, v_, vo_, nullptr, zn_, nullptr);
+          c.precond_apply(c.precond_ctx, vo_ /* = v_new */, zn_);
+          k_dot<<<g, 256, 0, s>>>(L, zn_, vo_, &st->d2);
+        }
+      else if (c.precond_add)
+        {
+          k_minres_lanczos<<<g, 256, 0, s>>>(L, st, p, v_, vo_, pinv, zn_, nullptr);
+          c.precond_add(c.precond_ctx, vo_ /* = v_new */, zn_);
+          k_dot<<<g, 256, 0, s>>>(L, zn_, vo_, &st->d2);
+        }
+      else
+        k_minres_lanczos<<<g, 256, 0, s>>>(L, st, p, v_, vo_, pinv, zn_, &st->d2);
+      if (c.allreduce)
+        c.allreduce(c.halo_ctx, &st->d2, 1);
+      k_minres_scalars_b<<<1, 1, 0, s>>>(st);
+      k_minres_update<<<g, 256, 0, s>>>(L, st, z_, w_, wo_, x);
+      k_minres_advance<<<1, 1, 0, s>>>(st);
+      if (c.launch_counter)
+        *c.launch_counter += 7; // SpMV, Lanczos, dot, update, three scalar kernels
+    };
+    // Single GPU: the iteration (~100 launches, most of them small multigrid kernels) is captured
+    // once per parity of the buffer rotation into a CUDA graph and replayed: launch-bound -> one
+    // graph launch per iteration.
+    cudaGraphExec_t gexec[2]    = {nullptr, nullptr};
+    int64_t         glaunches[2] = {0, 0};
+    const bool      use_graph   = c.use_graphs && !c.halo && !c.allreduce;
+    if (use_graph && !conv)
+      for (int par = 0; par < 2; ++par)
+        {
+          cudaGraph_t   graph = nullptr;
+          const int64_t l0    = c.launch_counter ? *c.launch_counter : 0;
+          if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+            break;
+          if (par == 0)
+            iteration(v, v_old, z, z_new, w, w_old);
+          else
+            iteration(v_old, v, z_new, z, w_old, w);
+          if (cudaStreamEndCapture(s, &graph) != cudaSuccess || graph == nullptr)
+            break;
+          glaunches[par] = c.launch_counter ? *c.launch_counter - l0 : 0;
+          if (c.launch_counter)
+            *c.launch_counter = l0; // nothing ran yet
+          if (cudaGraphInstantiate(&gexec[par], graph, 0) != cudaSuccess)
+            gexec[par] = nullptr;
+          cudaGraphDestroy(graph);
+        }
+    const bool graphs_ok = use_graph && gexec[0] && gexec[1];
     while (!conv && it < max_it)
       {
         for (int k = 0; k < check_every && it < max_it; ++k, ++it)
           {
-            if (c.halo)
-              c.halo(c.halo_ctx, z);
-            spmv_signed(c, z, p, &st->d1);
-            ++spmv;
-            if (c.allreduce)
-              c.allreduce(c.halo_ctx, &st->d1, 1);
-            k_minres_scalars_a<<<1, 1, 0, s>>>(st);
-            if (c.precond_apply)
+            if (graphs_ok)
               {
-                k_minres_lanczos<<<g, 256, 0, s>>>(L, st, p, v, v_old, nullptr, z_new, nullptr);
-                c.precond_apply(c.precond_ctx, v_old /* = v_new */, z_new);
-                k_dot<<<g, 256, 0, s>>>(L, z_new, v_old, &st->d2);
-              }
-            else if (c.precond_add)
-              {
-                k_minres_lanczos<<<g, 256, 0, s>>>(L, st, p, v, v_old, pinv, z_new, nullptr);
-                c.precond_add(c.precond_ctx, v_old /* = v_new */, z_new);
-                k_dot<<<g, 256, 0, s>>>(L, z_new, v_old, &st->d2);
+                cudaGraphLaunch(gexec[it & 1], s);
+                if (c.launch_counter)
+                  *c.launch_counter += glaunches[it & 1];
               }
             else
-              k_minres_lanczos<<<g, 256, 0, s>>>(L, st, p, v, v_old, pinv, z_new, &st->d2);
-            if (c.allreduce)
-              c.allreduce(c.halo_ctx, &st->d2, 1);
-            k_minres_scalars_b<<<1, 1, 0, s>>>(st);
-            k_minres_update<<<g, 256, 0, s>>>(L, st, z, w, w_old, x);
-            k_minres_advance<<<1, 1, 0, s>>>(st);
+              iteration(v, v_old, z, z_new, w, w_old);
             std::swap(v, v_old);
             std::swap(w, w_old);
             std::swap(z, z_new);
@@ -631,6 +670,9 @@ namespace pe
               }
           }
       }
+    for (int par = 0; par < 2; ++par)
+      if (gexec[par])
+        cudaGraphExecDestroy(gexec[par]);
     // final true residual
     if (c.halo)
       c.halo(c.halo_ctx, x);

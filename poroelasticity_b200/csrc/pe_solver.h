@@ -29,6 +29,8 @@ namespace pe
     // optional additive part of the preconditioner: z += M_aux^{-1} r  (multigrid, pe_mg.cu)
     void (*precond_add)(void *ctx, const double *r, double *z) = nullptr;
     void *precond_ctx                                          = nullptr;
+    int      use_graphs     = 1;       // capture the MINRES iteration into CUDA graphs (single GPU)
+    int64_t *launch_counter = nullptr; // kernels launched (graph replays counted node by node)
     // full replacement of the diagonal preconditioner: z = P^{-1} r  (pe_precond.cu)
     void (*precond_apply)(void *ctx, const double *r, double *z) = nullptr;
   };

@@ -177,7 +177,7 @@ class BiotSystem:
             self._ck(rc)
         return sol
 
-    def set_solver_options(self, use_multigrid=1, theta=1.0, omega=0.8, nu=2):
+    def set_solver_options(self, use_multigrid=1, theta=1.0, omega=0.6, nu=2):
         self._ck(self.L.pe_set_solver_options(self.h, use_multigrid, theta, omega, nu))
 
     def solution(self):

@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import poroelasticity_b200 as pb
 nrefs = [int(a) for a in sys.argv[1].split(",")] if len(sys.argv) > 1 else [6, 8, 10]
-opts = [(1, 1.0, 0.6, 1), (1, 1.0, 0.6, 2), (17, 1.0, 0.6, 1)]
+opts = [(1, 1.0, 0.6, 1), (1, 1.0, 0.6, 1), (1, 1.0, 0.6, 2), (65, 1.0, 0.6, 1)]
 for nref in nrefs:
     b = pb.PoroElasBR1WG()
     t0 = time.time(); s = b.make_grid_and_dofs(nref); ts = time.time() - t0
