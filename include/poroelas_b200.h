@@ -184,6 +184,8 @@ int pe_local_matrices_bench(pe_handle *h, double t, double time_step, int64_t ch
 /* postprocess_errors BR1new:1251-1349 / CGQ1:2229-2357: squared errors of the device solution at
  * time t: e[0] = ||p_int - p||^2, e[1] = ||u_h - u||^2, e[2] = |u_h - u|_H1^2  (QGauss(3)). */
 int pe_step_errors(pe_handle *h, double t, double e[3]);
+/* run() accumulates dt*e over the steps and prints the square roots: L2L2Error_intp, L2L2Error_u,
+ * L2h1semiError_u, L2h1Error_u = sqrt(sum dt (e[1]+e[2]))  (BR1new:2251-2266). */
 
 /* the solver's SpMV kernel alone, `repeats` back-to-back launches on the handle's stream timed with
  * CUDA events (roofline measurement; x = current solution vector): average ms per launch */

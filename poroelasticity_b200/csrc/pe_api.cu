@@ -163,6 +163,14 @@ namespace
           bnd.push_back((int32_t)a);
       }
     h->n_bnd = (int64_t)bnd.size();
+    h->d_is_ghost.release();
+    if (pt.world > 1)
+      {
+        std::vector<uint8_t> gh((size_t)n_asm);
+        for (int64_t a = 0; a < n_asm; ++a)
+          gh[a] = pt.asm_cells[a] < pt.cell_begin || pt.asm_cells[a] >= pt.cell_end;
+        PE_CUDA(upload(h->d_is_ghost, gh.data(), gh.size(), s));
+      }
     // boundary cells per colour (bnd is ascending in asm index, asm order is colour-major)
     h->bnd_color_begin.assign((size_t)pt.n_colors + 1, 0);
     for (int col = 0; col <= pt.n_colors; ++col)
@@ -1286,9 +1294,30 @@ extern "C"
   }
 
   int
-  pe_step_errors(pe_handle *h, double, double *)
+  pe_step_errors(pe_handle *h, double t, double *e)
   {
-    return fail(h, PE_ERR_ARG, "pe_step_errors: not implemented yet");
+    if (!h || !e)
+      return PE_ERR_ARG;
+    if (h->cfg.element != PE_BR1_WG && h->cfg.element != PE_CGQ1_WG)
+      return fail(h, PE_ERR_ARG, "pe_step_errors: element not implemented yet");
+    PE_TRY
+    const int rc = ensure_device(h);
+    if (rc != PE_OK)
+      return rc;
+    if (h->d_scal.n < 64)
+      PE_CUDA(h->d_scal.alloc(64));
+    if (h->part.world > 1)
+      comm_halo_exchange(h, h->d_sol.p);
+    const DevParams P = make_params(h, t, h->last_dt);
+    const AsmArgs   a = make_args(h, false);
+    PE_CUDA(launch_step_errors(h->cfg.element, a, P, h->d_is_ghost.p, h->d_scal.p + 32, h->stream));
+    ++h->launches;
+    if (h->part.world > 1)
+      comm_allreduce(h, h->d_scal.p + 32, 3);
+    PE_CUDA(cudaMemcpyAsync(e, h->d_scal.p + 32, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    PE_CUDA(cudaStreamSynchronize(h->stream));
+    return PE_OK;
+    PE_CATCH
   }
 
   int

@@ -372,6 +372,124 @@ namespace pe
     cell_kernel<EL, SW>(G, a.kcell ? a.kcell[c] : a.k_scalar, P, old, E);
   }
 
+  // ---------------------------------------------------------------------------------------------
+  // postprocess_errors (PoroElasBR1WG_new.cc:1251-1349, PoroElasCGQ1_WG.cc:2229-2357): per-step squared
+  // errors of the device solution against the manufactured solution, QGauss(3) on every owned cell:
+  //   e[0] = ||p_int - p||^2   e[1] = ||u_h - u||^2   e[2] = ||grad u_h - grad u||^2
+  // (integrate_difference + compute_global_error = sqrt of the sum over cells of the cell integrals)
+  // ---------------------------------------------------------------------------------------------
+  template <int EL>
+  __global__ void __launch_bounds__(128)
+  k_step_errors(const AsmArgs a, const DevParams P, const uint8_t *__restrict__ is_ghost, double *__restrict__ e)
+  {
+    constexpr int NL = Elem<EL>::NL, NS = Elem<EL>::NS;
+    const int64_t c  = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double        ep = 0., eu = 0., eg = 0.;
+    if (c < a.n_asm && !(is_ghost && is_ghost[c]))
+      {
+        double  vx[4], vy[4], sol[NL];
+        int32_t idx[NL];
+        load_cell<EL>(a, c, vx, vy, idx, sol);
+        Geom G;
+        G.set(vx, vy);
+        const double ph = sol[Elem<EL>::PINT];
+#pragma unroll 1
+        for (int qi = 0; qi < 9; ++qi)
+          {
+            QPoint<NS> q;
+            eval_qpoint<NS>(G, qi, q);
+            double s[NS];
+            shape_values<NS>(q.xi, q.eta, s);
+            const double idet = q.wh / q.jxw; // 1/det
+            double       ux = 0., uy = 0., gxx = 0., gxy = 0., gyx = 0., gyy = 0.;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              {
+                ux += sol[2 * k] * s[k];
+                uy += sol[2 * k + 1] * s[k];
+                gxx += sol[2 * k] * q.nx[k];
+                gxy += sol[2 * k] * q.ny[k];
+                gyx += sol[2 * k + 1] * q.nx[k];
+                gyy += sol[2 * k + 1] * q.ny[k];
+              }
+            if (EL == 0)
+              {
+#pragma unroll
+                for (int f = 0; f < 4; ++f)
+                  {
+                    const double cf = sol[(8 + 2 * f) % NL];
+                    if (f < 2)
+                      {
+                        ux += cf * s[(4 + f) % NS];
+                        gxx += cf * q.nx[(4 + f) % NS];
+                        gxy += cf * q.ny[(4 + f) % NS];
+                      }
+                    else
+                      {
+                        uy += cf * s[(4 + f) % NS];
+                        gyx += cf * q.nx[(4 + f) % NS];
+                        gyy += cf * q.ny[(4 + f) % NS];
+                      }
+                  }
+              }
+            gxx *= idet;
+            gxy *= idet;
+            gyx *= idet;
+            gyy *= idet;
+            double px, py, ex = 0., ey = 0., exx = 0., exy = 0., pe = 0.;
+            G.point(q.xi, q.eta, px, py);
+            if (P.case_id == 1)
+              {
+                double sx, cx, sy, cy;
+                sincospi(px, &sx, &cx);
+                sincospi(py, &sy, &cy);
+                ex  = P.u_coef * sx * cy;
+                ey  = P.u_coef * cx * sy;
+                exx = P.u_coef * M_PI * cx * cy;  // d u_x / dx = d u_y / dy   (BR1new:278-283)
+                exy = -P.u_coef * M_PI * sx * sy; // d u_x / dy = d u_y / dx
+                pe  = P.p_coef * cx * cy;
+              }
+            ep += (ph - pe) * (ph - pe) * q.jxw;
+            eu += ((ux - ex) * (ux - ex) + (uy - ey) * (uy - ey)) * q.jxw;
+            eg += ((gxx - exx) * (gxx - exx) + (gxy - exy) * (gxy - exy) + (gyx - exy) * (gyx - exy) +
+                   (gyy - exx) * (gyy - exx)) *
+                  q.jxw;
+          }
+      }
+    __shared__ double sh[3][4];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      {
+        ep += __shfl_xor_sync(0xffffffffu, ep, o);
+        eu += __shfl_xor_sync(0xffffffffu, eu, o);
+        eg += __shfl_xor_sync(0xffffffffu, eg, o);
+      }
+    if ((threadIdx.x & 31) == 0)
+      {
+        sh[0][threadIdx.x >> 5] = ep;
+        sh[1][threadIdx.x >> 5] = eu;
+        sh[2][threadIdx.x >> 5] = eg;
+      }
+    __syncthreads();
+    if (threadIdx.x < 3)
+      atomicAdd(e + threadIdx.x, sh[threadIdx.x][0] + sh[threadIdx.x][1] + sh[threadIdx.x][2] + sh[threadIdx.x][3]);
+  }
+
+  cudaError_t
+  launch_step_errors(const int element, const AsmArgs &a, const DevParams &P, const uint8_t *is_ghost, double *e,
+                     cudaStream_t s)
+  {
+    cudaMemsetAsync(e, 0, 3 * sizeof(double), s);
+    if (a.n_asm == 0)
+      return cudaSuccess;
+    const unsigned g = (unsigned)((a.n_asm + 127) / 128);
+    if (element == 0)
+      k_step_errors<0><<<g, 128, 0, s>>>(a, P, is_ghost, e);
+    else
+      k_step_errors<1><<<g, 128, 0, s>>>(a, P, is_ghost, e);
+    return cudaGetLastError();
+  }
+
   // K = exp(sigma Z), Z by Box-Muller from the counter generator keyed on (seed, global cell id)
   __device__ __forceinline__ uint64_t
   d_splitmix64(uint64_t z)

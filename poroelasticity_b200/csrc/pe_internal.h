@@ -116,7 +116,7 @@ struct pe_handle
   int64_t              n_rowblk = 0;
   int                  spmv_kernel = 1; // 1 = stream, 0 = warp per row
   pe::DevBuf<int64_t>  d_rowptr;
-  pe::DevBuf<uint8_t>  d_off;
+  pe::DevBuf<uint8_t>  d_off, d_is_ghost; // d_is_ghost: 1 for ghost cells (multi-GPU only, else unallocated)
   pe::DevBuf<int>      d_err;
   // solver work vectors (each L+H long so that any of them can be the SpMV input)
   pe::DevBuf<double> d_w[10];

@@ -35,6 +35,8 @@ namespace pe
                                       int *n_launches);
   cudaError_t launch_local_matrices(int element, const AsmArgs &a, const DevParams &P, int64_t first, int64_t n,
                                     double *out, double *rhs_out, cudaStream_t s);
+  cudaError_t launch_step_errors(int element, const AsmArgs &a, const DevParams &P, const uint8_t *is_ghost, double *e,
+                                 cudaStream_t s);
   cudaError_t launch_lognormal(int64_t n, const int64_t *cell_ids, int64_t first, double sigma, uint64_t seed,
                                double *k, cudaStream_t s);
   cudaError_t launch_sum(const double *x, size_t n, double *out, cudaStream_t s);

@@ -222,3 +222,31 @@ def test_cpp_host_driver_runs():
     assert out.returncode == 0, out.stdout + out.stderr
     assert "Number of degrees of freedom: 1922 (1122+256+544)" in out.stdout
     assert out.stdout.count("Time step") == 4
+
+
+@pytest.mark.parametrize("el", [BR1_WG, CGQ1_WG])
+def test_error_norms_three_significant_digits(el):
+    """run(): backward Euler to T = 1 with dt = 1/4 on a 16x16 mesh; the l2-in-time error norms the
+    reference prints (BR1new:2251-2266) from the CUDA path vs the oracle (LU solve + CPU norms) must
+    agree to 3 significant digits (north_star); the per-step squared norms are compared tighter."""
+    import scipy.sparse.linalg as spla
+    dt, nref = 0.25, 4
+    o, b = make_pair(el, nref, dt=dt)
+    b.rel_tol = 1e-12
+    old = np.zeros(o.n_dofs)
+    acc_ref, acc = np.zeros(3), np.zeros(3)
+    t = dt
+    while t <= 1.0:
+        v_ref, r_ref, _ = o.assemble(t, old)
+        old = spla.splu(o.csr(v_ref).tocsc()).solve(r_ref)
+        e_ref = o.step_errors(t, old)
+        b.assemble_system(t)
+        b.solve_time_step(want_solution=False)
+        e = b.step_errors(t)
+        assert np.allclose(e, e_ref, rtol=1e-6), (e, e_ref)
+        acc_ref += dt * e_ref
+        acc += dt * e
+        t += dt
+    norms = np.sqrt([acc[0], acc[1], acc[2], acc[1] + acc[2]])
+    norms_ref = np.sqrt([acc_ref[0], acc_ref[1], acc_ref[2], acc_ref[1] + acc_ref[2]])
+    assert np.all(np.abs(norms - norms_ref) <= 5e-4 * norms_ref), (norms, norms_ref)
