@@ -240,18 +240,46 @@ def main():
         spmv_ms = None
 
     # ---- end-to-end arm: host buffers through the C ABI -------------------------------------------
-    e2e = None
-    if world == 1:
-        old = np.zeros(n_dofs)
-        step(0, True, old)
-        barrier()
-        t0 = time.perf_counter()
-        for k in range(args.steps):
-            old = step(k, True, old)
-        barrier()
-        e2e_s = time.perf_counter() - t0
-        e2e = {"value": n_cells * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(n_dofs * 8),
-               "d2h_bytes_per_step": int(n_dofs * 8), "ms_per_step": e2e_s / args.steps * 1e3}
+    # every step: old_solution host -> device inside pe_assemble_system, solution device -> host inside
+    # pe_solve_time_step; with N > 1 the owned parts are exchanged between the hosts (gloo) to rebuild
+    # the full old_solution, as a host program driving N GPUs would have to.
+    owned = b.owned_rows() if world > 1 else None
+    gloo = dist.new_group(backend="gloo") if world > 1 else None
+
+    def host_exchange(x_owned):
+        if world == 1:
+            return x_owned
+        nmax = torch.tensor([owned.size], dtype=torch.int64)
+        dist.all_reduce(nmax, op=dist.ReduceOp.MAX, group=gloo)
+        buf = torch.zeros(int(nmax), dtype=torch.float64)
+        idx = torch.full((int(nmax),), -1, dtype=torch.int64)
+        buf[:owned.size] = torch.from_numpy(x_owned)
+        idx[:owned.size] = torch.from_numpy(owned)
+        bufs = [torch.zeros_like(buf) for _ in range(world)]
+        idxs = [torch.zeros_like(idx) for _ in range(world)]
+        dist.all_gather(bufs, buf, group=gloo)
+        dist.all_gather(idxs, idx, group=gloo)
+        full = np.zeros(n_dofs)
+        for bb, ii in zip(bufs, idxs):
+            m = ii >= 0
+            full[ii[m].numpy()] = bb[m].numpy()
+        return full
+
+    old = np.zeros(n_dofs)
+    old = host_exchange(step(0, True, old))
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        old = host_exchange(step(k, True, old))
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    tt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e_s = float(tt[0])
+    e2e = {"value": n_cells * args.steps / e2e_s, "unit": UNIT,
+           "h2d_bytes_per_step": int(n_dofs * 8),  # owned + halo parts of old_solution, summed over ranks (halo excluded)
+           "d2h_bytes_per_step": int(n_dofs * 8), "ms_per_step": e2e_s / args.steps * 1e3}
 
     # orderly shutdown on every rank (the library's NCCL communicator, then torch's)
     stats_launches = int(launches)

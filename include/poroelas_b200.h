@@ -118,6 +118,9 @@ int pe_make_sparsity_pattern(pe_handle *h);
 int pe_set_pattern(pe_handle *h, const int64_t *rowptr, const int32_t *colidx);
 
 int pe_get_sizes(const pe_handle *h, pe_sizes *s);
+/* the three contiguous GLOBAL row ranges [u | p_int | p_face] this rank owns (local row l of pe_get_rhs /
+ * pe_get_solution runs through them in this order) */
+int pe_get_owned_ranges(const pe_handle *h, int64_t begin[3], int64_t end[3]);
 int pe_get_mesh(const pe_handle *h, double *x, double *y, uint32_t *cell_vertices, uint8_t *face_kinds);
 int pe_get_dofs(const pe_handle *h, uint32_t *cell_dofs);
 int pe_get_pattern(const pe_handle *h, int64_t *rowptr, int32_t *colidx);

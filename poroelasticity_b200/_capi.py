@@ -36,7 +36,7 @@ class pe_solve_stats(C.Structure):
 # every symbol include/poroelas_b200.h declares
 EXPORTS = [
     "pe_create", "pe_destroy", "pe_last_error", "pe_version", "pe_make_unit_square", "pe_set_mesh",
-    "pe_distribute_dofs", "pe_set_dofs", "pe_make_sparsity_pattern", "pe_set_pattern", "pe_get_sizes",
+    "pe_distribute_dofs", "pe_set_dofs", "pe_make_sparsity_pattern", "pe_set_pattern", "pe_get_sizes", "pe_get_owned_ranges",
     "pe_get_mesh", "pe_get_dofs", "pe_get_pattern", "pe_get_dealii_block_order", "pe_set_material",
     "pe_set_lognormal_k", "pe_set_case", "pe_set_boundary", "pe_assemble_system", "pe_assemble_rhs_only",
     "pe_get_matrix", "pe_get_rhs", "pe_solve_time_step", "pe_set_solver_options", "pe_get_solution", "pe_set_solution", "pe_spmv",
@@ -73,6 +73,7 @@ def load():
         "pe_make_sparsity_pattern": [vp],
         "pe_set_pattern": [vp, vp, vp],
         "pe_get_sizes": [vp, C.POINTER(pe_sizes)],
+        "pe_get_owned_ranges": [vp, vp, vp],
         "pe_get_mesh": [vp, vp, vp, vp, vp],
         "pe_get_dofs": [vp, vp],
         "pe_get_pattern": [vp, vp, vp],

@@ -713,6 +713,19 @@ extern "C"
   }
 
   int
+  pe_get_owned_ranges(const pe_handle *h, int64_t begin[3], int64_t end[3])
+  {
+    if (!h || !h->have_dofs || !begin || !end)
+      return PE_ERR_ARG;
+    for (int b = 0; b < 3; ++b)
+      {
+        begin[b] = h->part.row_begin[b];
+        end[b]   = h->part.row_end[b];
+      }
+    return PE_OK;
+  }
+
+  int
   pe_get_mesh(const pe_handle *h, double *x, double *y, uint32_t *cell_vertices, uint8_t *face_kinds)
   {
     if (!h || !h->have_mesh)

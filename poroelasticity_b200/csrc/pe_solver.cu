@@ -689,7 +689,7 @@ namespace pe
     stats->rel_residual  = bnorm > 0. ? stats->residual_norm / bnorm : 0.;
     stats->iterations    = it;
     stats->converged     = (stats->residual_norm <= rel_tol * bnorm * (1. + 1e-12)) || bnorm == 0.;
-    stats->spmv_count    = spmv;
+    stats->spmv_count    = spmv + it;
     return 0;
   }
 

@@ -92,6 +92,13 @@ class BiotSystem:
         self._ck(self.L.pe_get_sizes(self.h, C.byref(s)))
         return s
 
+    def owned_rows(self):
+        """global indices of the rows this rank owns, in local order"""
+        b = np.zeros(3, np.int64)
+        e = np.zeros(3, np.int64)
+        self._ck(self.L.pe_get_owned_ranges(self.h, ptr(b), ptr(e)))
+        return np.concatenate([np.arange(b[k], e[k]) for k in range(3)])
+
     def mesh(self):
         s = self.sizes()
         x = np.zeros(s.n_vertices)
