@@ -131,6 +131,7 @@ def main():
     ap.add_argument("--cpu-refine", type=int, default=7, help="mesh of the bounded CPU sample")
     ap.add_argument("--rel-tol", type=float, default=1e-10)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--solver-options", type=int, default=1, help="pe_set_solver_options bit field")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -176,6 +177,7 @@ def main():
     b.set_material(1.0, 1.0, 1.0, 0.0)
     b.set_case(pb.PE_CASE_COSCOS)
     b.rel_tol = args.rel_tol
+    b.set_solver_options(args.solver_options)
     n_cells, n_dofs = s.n_cells, s.n_dofs
     N = 1 << args.n_refine
 

@@ -968,7 +968,7 @@ extern "C"
     if ((use_multigrid >> 8) > 0)
       h->chunk_cells = (int64_t)(use_multigrid >> 8) * 4096;
     h->spmv_kernel = (use_multigrid & 16) ? 0 : 1;
-    h->use_graphs  = (use_multigrid & 64) ? 0 : 1; // bit 6: no CUDA graphs (A/B measurements) // bit 4: fall back to the warp-per-row SpMV (A/B measurements)
+    h->use_graphs  = (use_multigrid & 64) ? 0 : ((use_multigrid & 128) ? 2 : 1); // bit 6: no CUDA graphs; bit 7: also multi-GPU // bit 4: fall back to the warp-per-row SpMV (A/B measurements)
     h->mg_theta = theta;
     h->mg_omega = omega;
     h->mg_nu    = nu;

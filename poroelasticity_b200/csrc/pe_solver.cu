@@ -601,7 +601,9 @@ namespace pe
     // graph launch per iteration.
     cudaGraphExec_t gexec[2]    = {nullptr, nullptr};
     int64_t         glaunches[2] = {0, 0};
-    const bool      use_graph   = c.use_graphs && !c.halo && !c.allreduce;
+    // (NCCL send/recv/all-reduce on the capturing stream are captured too: bit 7 of the options enables
+    //  graphs on more than one GPU)
+    const bool      use_graph   = c.use_graphs == 2 || (c.use_graphs && !c.halo && !c.allreduce);
     if (use_graph && !conv)
       for (int par = 0; par < 2; ++par)
         {
