@@ -76,7 +76,9 @@ typedef struct pe_sizes {
   int64_t cell_begin, cell_end;         /* owned cells (contiguous in deal.II active-cell order) */
   int64_t n_owned_rows, nnz_owned;      /* rows owned = dofs first touched by an owned cell */
   int64_t n_ghost_cells;                /* cells assembled redundantly for owned rows */
-  int64_t reserved[3];
+  /* the Krylov solver's own operator (three-field form, pruned CSR; 0 before the first solve) */
+  int64_t solver_rows, solver_nnz;
+  int64_t reserved[1];
 } pe_sizes;
 
 typedef struct pe_solve_stats {

@@ -24,7 +24,7 @@ class pe_config(C.Structure):
 class pe_sizes(C.Structure):
     _fields_ = [(k, C.c_int64) for k in
                 ("n_cells", "n_vertices", "n_loc", "n_u", "n_pint", "n_pface", "n_dofs", "nnz", "cell_begin",
-                 "cell_end", "n_owned_rows", "nnz_owned", "n_ghost_cells")] + [("reserved", C.c_int64 * 3)]
+                 "cell_end", "n_owned_rows", "nnz_owned", "n_ghost_cells", "solver_rows", "solver_nnz")] + [("reserved", C.c_int64 * 1)]
 
 
 class pe_solve_stats(C.Structure):

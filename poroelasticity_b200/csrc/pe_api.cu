@@ -2,6 +2,7 @@
 // device residency of the mesh / DoF / CSR arrays, kernel launches, timing.  No CPU compute path:
 // every entry point that produces numbers launches the CUDA kernels or fails.
 #include "pe_internal.h"
+#include "pe_k3.h"
 #include "pe_kernels.h"
 #include "pe_mg.h"
 #include "pe_precond.h"
@@ -23,6 +24,7 @@ namespace pe
   void comm_destroy(pe_handle *h);
   int  comm_setup_halo(pe_handle *h);
   void comm_halo_exchange(void *ctx, double *x);
+  void comm_halo_exchange3(void *ctx, double *x);
   void comm_allreduce(void *ctx, double *v, int n);
   int  comm_unique_id(uint8_t id[128]);
 } // namespace pe
@@ -109,6 +111,8 @@ namespace
     h->mg                  = nullptr;
     delete h->bp;
     h->bp                  = nullptr;
+    delete h->k3;
+    h->k3                  = nullptr;
     cudaStream_t     s     = h->stream;
     const int        n_loc = h->dofs.n_loc;
     const Partition &pt    = h->part;
@@ -399,8 +403,13 @@ namespace
     cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]);
     h->assemble_kernel_ms = ms;
     h->last_dt            = dt;
+    h->last_t             = t;
     if (do_matrix)
-      h->matrix_valid = true;
+      {
+        h->matrix_valid = true;
+        if (h->k3)
+          h->k3->values_valid = false;
+      }
     return PE_OK;
   }
 
@@ -431,6 +440,211 @@ namespace
         c.halo_ctx  = h;
       }
     return c;
+  }
+
+  // ---- three-field MINRES solve (pe_k3.h) ------------------------------------------------------------
+  void
+  hook_precond3(void *ctx, const double *r, double *z)
+  {
+    pe_handle *h = (pe_handle *)ctx;
+    precond_apply(*h->bp, *h->mg, h->d_pinv.p, r, z, h->stream, &h->launches);
+    k3_precond_xi(*h->k3, h->mu, r, z, h->stream);
+    ++h->launches;
+  }
+  void
+  hook_true_residual(void *ctx, const double *x3, double *nrm2_dev)
+  {
+    // || b - A (u, p) || with the reference's own matrix: the (u, p) part of x3 is a two-field vector
+    pe_handle *h = (pe_handle *)ctx;
+    SolverCtx  c = make_solver_ctx(h);
+    if (c.halo)
+      c.halo(c.halo_ctx, const_cast<double *>(x3));
+    residual_norm2(c, h->d_rhs.p, x3, h->d_w[9].p, nrm2_dev);
+    h->launches += 2;
+  }
+
+  // the solver operator: second assembly pass A0 = A(lambda0, alpha = 1) into k3.values0, K3 values,
+  // block preconditioner data.  Once per assembled matrix.
+  int
+  update_solver_operator(pe_handle *h)
+  {
+    K3System    &k = *h->k3;
+    cudaStream_t s = h->stream;
+    if (k.values0.n < (size_t)h->nnz)
+      if (k.values0.alloc((size_t)h->nnz) != cudaSuccess)
+        return 2;
+    // lambda = lambda0 + lambda_s with the xi block carrying lambda_s (>= a floor so that 1/lambda_s exists)
+    const double lambda_s = std::max(h->lambda, 1e-6 * h->mu);
+    const double lambda0  = h->lambda - lambda_s;
+    DevParams    P        = make_params(h, h->last_t, h->last_dt);
+    P.lambda              = lambda0;
+    P.alpha               = 1.;
+    AsmArgs a             = make_args(h, true);
+    a.values              = k.values0.p;
+    a.rhs                 = nullptr; // matrix only
+    a.sol                 = nullptr;
+    int nl                = 0;
+    cudaError_t e;
+    if (h->part.scatter_mode == 0)
+      e = launch_assemble_chunked(h->cfg.element, a, P, (int)h->chunk_cell_begin.size() - 1, h->chunk_cell_begin.data(),
+                                  h->chunk_zero.data(), s, &nl);
+    else
+      e = launch_assemble(h->cfg.element, a, P, h->part.n_colors, h->part.color_begin.data(), h->bnd_color_begin.data(), s,
+                          &nl);
+    h->launches += nl;
+    if (e != cudaSuccess)
+      return 1;
+    // diagonal of A0 (with the halo part), Jacobi inverse for the u block
+    SolverCtx c0 = make_solver_ctx(h);
+    c0.values    = k.values0.p;
+    if (build_preconditioner(c0, k.diag0.p, h->d_pinv.p) != 0)
+      return 1;
+    h->launches += 2;
+    if (k3_fill_values(k, lambda_s, h->alpha, s, &h->launches) != 0)
+      return 1;
+    if (h->use_mg && h->mg && h->mg->ready && h->bp && h->bp->ready)
+      {
+        h->mg->omega = h->mg_omega;
+        h->mg->nu    = h->mg_nu;
+        // pressure block of the preconditioner: C + alpha^2/lambda_s W_int (C already holds c0 M)
+        const double extra = h->alpha * h->alpha / lambda_s;
+        if (mg_assemble(*h->mg, h->d_k_morton.p, h->k_scalar, lambda0, h->mu, h->last_dt, h->c0 + extra, s, &h->launches) != 0)
+          return 1;
+        if (precond_update(*h->bp, k.values0.p, k.diag0.p, extra, s, &h->launches) != 0)
+          return 1;
+      }
+    return 0;
+  }
+
+  // once per mesh / pattern (not part of the timed solve): K3 structure, multigrid topology, sub-block lists
+  int
+  prepare_three_field(pe_handle *h)
+  {
+    cudaStream_t s        = h->stream;
+    auto         to_local = [h](uint32_t g) { return global_to_local(h, g); };
+    if (!h->k3)
+      {
+        h->k3        = new K3System;
+        const int rc = k3_build_structure(*h->k3, h->mesh, h->dofs, h->part, h->d_rowptr.p, h->d_colidx.p, s);
+        if (rc != 0)
+          {
+            delete h->k3;
+            h->k3 = nullptr;
+            return rc < 0 ? 1 : PE_ERR_PATTERN;
+          }
+      }
+    if (h->use_mg && !h->mg)
+      {
+        h->mg = new MgHierarchy;
+        if (mg_build_topology(*h->mg, h->mesh, h->dofs, to_local, s) < 0)
+          return 1;
+      }
+    if (h->use_mg && h->mg->ready && !h->bp)
+      {
+        h->bp = new BlockPrecond;
+        if (precond_build_structure(*h->bp, h->mesh, h->dofs, h->pat, h->part, to_local, s) < 0)
+          return 1;
+        if (h->part.world > 1)
+          {
+            h->bp->halo      = comm_halo_exchange;
+            h->bp->allreduce = comm_allreduce;
+            h->bp->comm_ctx  = h;
+          }
+      }
+    const size_t n3 = (size_t)h->k3->n_phys();
+    for (int i = 0; i < 10; ++i)
+      if (h->d_w[i].n < n3)
+        if (h->d_w[i].alloc(n3) != cudaSuccess)
+          return 2;
+    if (h->d_pinv.n < n3)
+      if (h->d_pinv.alloc(n3) != cudaSuccess)
+        return 2;
+    return 0;
+  }
+
+  SolverCtx
+  make_solver_ctx3(pe_handle *h)
+  {
+    const K3System &k = *h->k3;
+    SolverCtx c3      = make_solver_ctx(h);
+    c3.L              = k.n_rows();
+    c3.H              = k.H + k.Hx;
+    c3.n_pos          = k.n_rows(); // signs are part of K3
+    c3.rowptr         = k.rowptr.p;
+    c3.colidx         = k.colidx.p;
+    c3.values         = k.val.p;
+    c3.rowblk         = h->spmv_kernel == 1 ? k.rowblk.p : nullptr;
+    c3.n_rowblk       = h->spmv_kernel == 1 ? k.n_rowblk : 0;
+    c3.gap.at         = k.L;
+    c3.gap.len        = k.H;
+    c3.precond_ctx    = h;
+    if (h->part.world > 1)
+      c3.halo = comm_halo_exchange3;
+    return c3;
+  }
+
+  int
+  solve_three_field(pe_handle *h, const double rel_tol, const int max_iterations, pe_solve_stats *stats)
+  {
+    cudaStream_t s = h->stream;
+    {
+      const int rc = prepare_three_field(h);
+      if (rc != 0)
+        return rc;
+    }
+    K3System    &k  = *h->k3;
+    const size_t n3 = (size_t)k.n_phys();
+    if (cudaEventRecord(h->ev[3], s) != cudaSuccess)
+      return 1;
+    // ---- once per assembled matrix ----------------------------------------------------------------------
+    if (!k.values_valid)
+      {
+        const int rc = update_solver_operator(h);
+        if (rc != 0)
+          return rc;
+      }
+    const bool block_pc = h->use_mg && h->mg && h->mg->ready && h->bp && h->bp->ready;
+    // ---- this right-hand side ----------------------------------------------------------------------------
+    double *b3 = h->d_w[7].p, *x3 = h->d_w[8].p;
+    if (k3_make_rhs(k, h->d_rhs.p, h->d_rowptr.p, h->d_colidx.p, h->d_values.p, b3, s) != 0)
+      return 1;
+    // initial guess: the previous solution (old_solution) with its consistent xi
+    cudaMemsetAsync(x3, 0, sizeof(double) * n3, s);
+    cudaMemcpyAsync(x3, h->d_sol.p, sizeof(double) * (size_t)h->L, cudaMemcpyDeviceToDevice, s);
+    if (h->part.world > 1)
+      comm_halo_exchange(h, x3);
+    if (k3_init_xi(k, x3, s) != 0)
+      return 1;
+    h->launches += 4;
+    SolverCtx c      = make_solver_ctx(h);
+    SolverCtx c3     = make_solver_ctx3(h);
+    c3.true_residual = hook_true_residual;
+    const double *pinv3 = nullptr;
+    if (block_pc)
+      c3.precond_apply = hook_precond3;
+    else
+      {
+        // no refinement hierarchy: inverse block diagonal of K3
+        if (k3_make_pinv(k, h->mu, h->d_w[10].n >= n3 ? h->d_w[10].p : (h->d_w[10].alloc(n3), h->d_w[10].p), s) != 0)
+          return 1;
+        pinv3 = h->d_w[10].p;
+      }
+    // ||b|| of the reference system: what rel_tol refers to
+    {
+      double *d = h->d_scal.p + 40;
+      cudaMemsetAsync(d, 0, sizeof(double), s);
+      norm2(c, h->d_rhs.p, d);
+      if (c.allreduce)
+        c.allreduce(c.halo_ctx, d, 1);
+      cudaMemcpyAsync(h->h_scal + 8, d, sizeof(double), cudaMemcpyDeviceToHost, s);
+      if (cudaStreamSynchronize(s) != cudaSuccess)
+        return 1;
+      c3.bnorm2 = h->h_scal[8];
+    }
+    double *work[7] = {h->d_w[0].p, h->d_w[1].p, h->d_w[2].p, h->d_w[3].p, h->d_w[4].p, h->d_w[5].p, h->d_w[6].p};
+    const int rc    = minres_solve(c3, b3, x3, pinv3, work, (MinresState *)h->d_scal.p, h->h_scal, rel_tol, max_iterations, stats);
+    cudaMemcpyAsync(h->d_sol.p, x3, sizeof(double) * (size_t)h->L, cudaMemcpyDeviceToDevice, s);
+    return rc == 0 ? 0 : 1;
   }
 } // namespace
 
@@ -519,6 +733,8 @@ extern "C"
     h->mg = nullptr;
     delete h->bp;
     h->bp = nullptr;
+    delete h->k3;
+    h->k3 = nullptr;
     for (auto &ev : h->ev)
       if (ev)
         cudaEventDestroy(ev);
@@ -708,6 +924,11 @@ extern "C"
         s->nnz_owned     = (int64_t)h->pat.colidx.size();
         s->nnz           = s->nnz_owned; // global count only known on one GPU
         s->n_ghost_cells = h->part.n_ghost_cells;
+      }
+    if (h->k3 && h->k3->built)
+      {
+        s->solver_rows = h->k3->n_rows();
+        s->solver_nnz  = h->k3->nnz;
       }
     return PE_OK;
   }
@@ -981,11 +1202,22 @@ extern "C"
     if (!h || repeats <= 0 || !ms_per_launch || !h->device_ready || !h->matrix_valid)
       return fail(h, PE_ERR_ARG, "pe_bench_spmv: assemble first");
     PE_TRY
-    const size_t n = (size_t)(h->L + h->H);
+    size_t n = (size_t)(h->L + h->H);
     for (int k = 0; k < 2; ++k)
       if (h->d_w[k].n < n)
         PE_CUDA(h->d_w[k].alloc(n));
     SolverCtx c = make_solver_ctx(h);
+    if (h->cfg.element != PE_WG_Q2RT2)
+      {
+        // the solver's own operator: the pruned three-field matrix K3
+        int rc = prepare_three_field(h);
+        if (rc == 0 && !h->k3->values_valid)
+          rc = update_solver_operator(h);
+        if (rc != 0)
+          return fail(h, PE_ERR_CUDA, "pe_bench_spmv: solver operator setup failed");
+        c = make_solver_ctx3(h);
+        PE_CUDA(cudaMemsetAsync(h->d_w[0].p, 0, sizeof(double) * (size_t)h->k3->n_phys(), h->stream));
+      }
     PE_CUDA(cudaMemcpyAsync(h->d_w[0].p, h->d_rhs.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
     for (int k = 0; k < 3; ++k)
       spmv_signed(c, h->d_w[0].p, h->d_w[1].p, nullptr);
@@ -1014,113 +1246,29 @@ extern "C"
       stats = &local;
     std::memset(stats, 0, sizeof(*stats));
     const size_t n = (size_t)(h->L + h->H);
-    for (int k = 0; k < 9; ++k)
-      if (h->d_w[k].n < n)
-        PE_CUDA(h->d_w[k].alloc(n));
-    if (h->d_pinv.n < n)
-      PE_CUDA(h->d_pinv.alloc(n));
+    if (h->cfg.element == PE_WG_Q2RT2)
+      for (int k = 0; k < 3; ++k)
+        if (h->d_w[k].n < n)
+          PE_CUDA(h->d_w[k].alloc(n));
     if (h->d_scal.n < 64)
       PE_CUDA(h->d_scal.alloc(64));
     cudaStream_t s = h->stream;
     SolverCtx    c = make_solver_ctx(h);
-    // once per mesh (not timed as part of the solve): multigrid topology, sub-block index lists
-    if (h->cfg.element != PE_WG_Q2RT2 && h->use_mg)
-      {
-        if (!h->mg)
-          {
-            h->mg = new MgHierarchy;
-            const int mrc = mg_build_topology(*h->mg, h->mesh, h->dofs,
-                                              [h](uint32_t g) { return global_to_local(h, g); }, s);
-            if (mrc < 0)
-              return cuda_fail(h, cudaGetLastError(), "mg_build_topology");
-          }
-        if (h->mg->ready && !(h->use_mg == 2 && h->part.world == 1) && !h->bp)
-          {
-            h->bp = new BlockPrecond;
-            if (precond_build_structure(*h->bp, h->mesh, h->dofs, h->pat, h->part,
-                                        [h](uint32_t g) { return global_to_local(h, g); }, s) < 0)
-              return cuda_fail(h, cudaGetLastError(), "precond_build_structure");
-            if (h->part.world > 1)
-              {
-                h->bp->halo      = comm_halo_exchange;
-                h->bp->allreduce = comm_allreduce;
-                h->bp->comm_ctx  = h;
-              }
-          }
-      }
-    PE_CUDA(cudaEventRecord(h->ev[3], s));
-    int rc;
-    // initial guess: the previous solution (old_solution), already in d_sol
+    int          rc;
     if (h->cfg.element == PE_WG_Q2RT2)
       {
+        PE_CUDA(cudaEventRecord(h->ev[3], s));
         double *work[3] = {h->d_w[0].p, h->d_w[1].p, h->d_w[2].p};
         PE_CUDA(cudaMemsetAsync(h->d_sol.p, 0, sizeof(double) * n, s)); // deal.II: solution starts at 0
         rc = cg_solve(c, h->d_rhs.p, h->d_sol.p, work, h->d_scal.p, h->h_scal, rel_tol, max_iterations, stats);
       }
     else
       {
-        if (build_preconditioner(c, h->d_w[7].p, h->d_pinv.p) != 0)
-          return cuda_fail(h, cudaGetLastError(), "build_preconditioner");
-        // multigrid part: hierarchy topology once per mesh, operators re-discretised every solve
-        if (h->use_mg)
-          {
-            if (!h->mg)
-              {
-                h->mg = new MgHierarchy;
-                const int mrc = mg_build_topology(*h->mg, h->mesh, h->dofs,
-                                                  [h](uint32_t g) { return global_to_local(h, g); }, s);
-                if (mrc < 0)
-                  return cuda_fail(h, cudaGetLastError(), "mg_build_topology");
-              }
-            if (h->mg->ready)
-              {
-                h->mg->omega = h->mg_omega;
-                h->mg->nu    = h->mg_nu;
-                // reaction coefficient of the pressure auxiliary operator: c0 + alpha^2/(lambda+2mu)
-                const double gamma = h->c0 + h->alpha * h->alpha / (h->lambda + 2. * h->mu);
-                if (mg_assemble(*h->mg, h->d_k_morton.p, h->k_scalar, h->lambda, h->mu, h->last_dt, gamma, s, &h->launches) != 0)
-                  return cuda_fail(h, cudaGetLastError(), "mg_assemble");
-                if (h->use_mg == 2 && h->part.world == 1)
-                  {
-                    // additive variant: theta D^{-1} + Pi V Pi^T on both blocks
-                    if (h->mg_theta != 1.0)
-                      scale_vector(c, h->d_pinv.p, h->mg_theta);
-                    c.precond_add = [](void *ctx, const double *r, double *z) {
-                      pe_handle *hh = (pe_handle *)ctx;
-                      mg_apply_add(*hh->mg, r, z, hh->stream, &hh->launches);
-                    };
-                  }
-                else
-                  {
-                    if (!h->bp)
-                      {
-                        h->bp = new BlockPrecond;
-                        if (precond_build_structure(*h->bp, h->mesh, h->dofs, h->pat, h->part,
-                                                    [h](uint32_t g) { return global_to_local(h, g); }, s) < 0)
-                          return cuda_fail(h, cudaGetLastError(), "precond_build_structure");
-                        if (h->part.world > 1)
-                          {
-                            h->bp->halo      = comm_halo_exchange;
-                            h->bp->allreduce = comm_allreduce;
-                            h->bp->comm_ctx  = h;
-                          }
-                      }
-                    if (h->bp->ready)
-                      {
-                        if (precond_update(*h->bp, h->d_values.p, h->d_w[7].p, gamma, s, &h->launches) != 0)
-                          return cuda_fail(h, cudaGetLastError(), "precond_update");
-                        c.precond_apply = [](void *ctx, const double *r, double *z) {
-                          pe_handle *hh = (pe_handle *)ctx;
-                          precond_apply(*hh->bp, *hh->mg, hh->d_pinv.p, r, z, hh->stream, &hh->launches);
-                        };
-                      }
-                  }
-                c.precond_ctx = h;
-              }
-          }
-        double *work[7] = {h->d_w[0].p, h->d_w[1].p, h->d_w[2].p, h->d_w[3].p, h->d_w[4].p, h->d_w[5].p, h->d_w[6].p};
-        rc = minres_solve(c, h->d_rhs.p, h->d_sol.p, h->d_pinv.p, work, (MinresState *)h->d_scal.p, h->h_scal,
-                          rel_tol, max_iterations, stats);
+        rc = solve_three_field(h, rel_tol, max_iterations, stats);
+        if (rc > 0)
+          return rc == 1 ? cuda_fail(h, cudaGetLastError(), "three-field solver setup") : PE_ERR_ALLOC;
+        if (rc == PE_ERR_PATTERN)
+          return rc;
       }
     PE_CUDA(cudaEventRecord(h->ev[4], s));
     PE_CUDA(cudaEventSynchronize(h->ev[4]));

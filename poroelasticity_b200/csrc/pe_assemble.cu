@@ -116,7 +116,7 @@ namespace pe
     __device__ __forceinline__ void
     rhs(const int i, const double v)
     {
-      if (rs[i] < 0)
+      if (rs[i] < 0 || rhsp == nullptr) // rhsp == nullptr: matrix-only pass (solver operator A0)
         return;
       if (!ATOMIC && ((rhs_first >> i) & 1u))
         rhsp[row[i]] = v;
@@ -335,6 +335,8 @@ namespace pe
                   }
               }
           }
+        if (a.rhs == nullptr)
+          continue;
         if (!a.atomic_mode && ((rf >> i) & 1u))
           a.rhs[idx[i]] = val;
         else if (val != 0.)

@@ -5,6 +5,7 @@
 // and by owner rank inside each block, so every (peer, block) pair is ONE contiguous slice of the
 // halo part of a vector and is received in place.
 #include "pe_internal.h"
+#include "pe_k3.h"
 
 #include <nccl.h>
 
@@ -21,6 +22,16 @@ namespace pe
       const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
       if (i < n)
         buf[i] = x[rows[i]];
+    }
+
+    // buf[i] = x[rows[i] + shift]
+    __global__ void
+    k_gather_shift(const int64_t n, const int32_t *__restrict__ rows, const int64_t shift, const double *__restrict__ x,
+                   double *__restrict__ buf)
+    {
+      const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      if (i < n)
+        buf[i] = x[rows[i] + shift];
     }
 
     struct PeerPlan
@@ -193,7 +204,8 @@ namespace pe
                   }
                 hp.send_rows[k] = (int32_t)l;
               }
-            if (hp.d_send_rows.alloc(want.size()) != cudaSuccess || hp.d_send_buf.alloc(want.size()) != cudaSuccess)
+            if (hp.d_send_rows.alloc(want.size()) != cudaSuccess || hp.d_send_buf.alloc(want.size()) != cudaSuccess ||
+                hp.d_send_buf_xi.alloc((size_t)pl.send_cnt[1]) != cudaSuccess)
               return PE_ERR_ALLOC;
             cudaMemcpy(hp.d_send_rows.p, hp.send_rows.data(), sizeof(int32_t) * want.size(), cudaMemcpyHostToDevice);
           }
@@ -231,6 +243,58 @@ namespace pe
             if (pl.recv_cnt[b])
               ncclRecv(x + h->L + pl.recv_off[b], (size_t)pl.recv_cnt[b], ncclDouble, pl.rank, c->comm, s);
           }
+      }
+    ncclGroupEnd();
+  }
+
+  // three-field vectors (pe_k3.h): the (u, p) part as above plus the xi unknowns of the interior
+  // pressures in the halo, in ONE NCCL group
+  void
+  comm_halo_exchange3(void *ctx, double *x)
+  {
+    pe_handle *h = (pe_handle *)ctx;
+    CommState *c = cs(h);
+    if (!c || h->peers.empty() || !h->k3)
+      return;
+    const K3System &k = *h->k3;
+    cudaStream_t    s = h->stream;
+    for (size_t q = 0; q < h->peers.size(); ++q)
+      {
+        HaloPeer       &hp = h->peers[q];
+        const PeerPlan &pl = c->plan[q];
+        if (hp.send_rows.empty())
+          continue;
+        const int64_t n = (int64_t)hp.send_rows.size();
+        k_gather<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, hp.d_send_rows.p, x, hp.d_send_buf.p);
+        ++h->launches;
+        const int64_t nx = pl.send_cnt[1];
+        if (nx > 0)
+          {
+            // row r of the interior-pressure block -> xi at L + H + (r - pint_begin)
+            k_gather_shift<<<(unsigned)((nx + 255) / 256), 256, 0, s>>>(nx, hp.d_send_rows.p + pl.send_cnt[0],
+                                                                       k.L + k.H - k.pint_begin, x, hp.d_send_buf_xi.p);
+            ++h->launches;
+          }
+      }
+    ncclGroupStart();
+    for (size_t q = 0; q < h->peers.size(); ++q)
+      {
+        HaloPeer       &hp = h->peers[q];
+        const PeerPlan &pl = c->plan[q];
+        int64_t         so = 0;
+        for (int b = 0; b < 3; ++b)
+          {
+            if (pl.send_cnt[b])
+              ncclSend(hp.d_send_buf.p + so, (size_t)pl.send_cnt[b], ncclDouble, pl.rank, c->comm, s);
+            so += pl.send_cnt[b];
+            if (pl.recv_cnt[b])
+              ncclRecv(x + h->L + pl.recv_off[b], (size_t)pl.recv_cnt[b], ncclDouble, pl.rank, c->comm, s);
+          }
+        if (pl.send_cnt[1])
+          ncclSend(hp.d_send_buf_xi.p, (size_t)pl.send_cnt[1], ncclDouble, pl.rank, c->comm, s);
+        if (pl.recv_cnt[1])
+          ncclRecv(x + k.L + k.H + k.Lx + (h->L + pl.recv_off[1] - k.hu_end), (size_t)pl.recv_cnt[1], ncclDouble, pl.rank,
+                   c->comm, s);
       }
     ncclGroupEnd();
   }

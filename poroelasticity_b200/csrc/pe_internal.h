@@ -19,7 +19,7 @@
 #include <vector>
 
 struct ncclComm;
-namespace pe { struct MgHierarchy; struct BlockPrecond; }
+namespace pe { struct MgHierarchy; struct BlockPrecond; struct K3System; }
 
 namespace pe
 {
@@ -75,7 +75,7 @@ namespace pe
     std::vector<int32_t> send_rows; // local owned rows this peer needs from us
     int64_t              recv_off = 0, recv_cnt = 0; // slice of our halo [L + recv_off, ...)
     DevBuf<int32_t>      d_send_rows;
-    DevBuf<double>       d_send_buf;
+    DevBuf<double>       d_send_buf, d_send_buf_xi;
   };
 } // namespace pe
 
@@ -119,7 +119,7 @@ struct pe_handle
   pe::DevBuf<uint8_t>  d_off, d_is_ghost; // d_is_ghost: 1 for ghost cells (multi-GPU only, else unallocated)
   pe::DevBuf<int>      d_err;
   // solver work vectors (each L+H long so that any of them can be the SpMV input)
-  pe::DevBuf<double> d_w[10];
+  pe::DevBuf<double> d_w[12];
   pe::DevBuf<double> d_pinv;   // block-Jacobi preconditioner (inverse diagonal)
   pe::DevBuf<double> d_scal;   // small scalar scratch (dots)
   double            *h_scal = nullptr; // pinned
@@ -127,6 +127,9 @@ struct pe_handle
   // auxiliary-space multigrid preconditioner (pe_mg.cu); null = diagonal preconditioner only
   pe::MgHierarchy *mg = nullptr;
   pe::BlockPrecond *bp = nullptr;
+  // three-field solver matrix (pe_k3.h); rebuilt values after every matrix assembly
+  pe::K3System *k3 = nullptr;
+  double        last_t = 0.;
   int              use_mg = 1, use_graphs = 1;
   double           mg_theta = 1.0, mg_omega = 0.6;
   int              mg_nu = 2;

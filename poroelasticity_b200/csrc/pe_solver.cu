@@ -18,6 +18,14 @@
 
 namespace pe
 {
+  // logical row / vector index -> physical vector index (three-field vectors keep the halo of the
+  // (u, p) part between the owned (u, p) part and the owned xi part, pe_k3.h)
+  __device__ __forceinline__ int64_t
+  phys(const int64_t i, const Gap g)
+  {
+    return i + (i >= g.at ? g.len : 0);
+  }
+
   // ---------------------------------------------------------------------------------------------
   // CSR SpMV, one warp per row (BR1-WG rows hold 10..46 entries, 31.5 on average).
   // Algorithmic traffic 12 B per entry + 20 B per row.
@@ -28,7 +36,7 @@ namespace pe
   __global__ void __launch_bounds__(256)
   k_spmv(const int64_t n_rows, const int64_t n_pos, const int64_t *__restrict__ rowptr,
          const int32_t *__restrict__ colidx, const double *__restrict__ values, const double *__restrict__ x,
-         double *__restrict__ y, double *__restrict__ dot)
+         double *__restrict__ y, double *__restrict__ dot, const Gap gap)
   {
     const int     lane   = threadIdx.x & 31;
     const int64_t warp0  = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -47,9 +55,9 @@ namespace pe
           {
             if (r >= n_pos)
               s = -s;
-            y[r] = s;
+            y[phys(r, gap)] = s;
             if (DOT)
-              dacc += s * x[r];
+              dacc += s * x[phys(r, gap)];
           }
       }
     if (DOT)
@@ -80,7 +88,7 @@ namespace pe
   __global__ void __launch_bounds__(256)
   k_spmv_stream(const int64_t n_pos, const int32_t *__restrict__ rowblk, const int64_t *__restrict__ rowptr,
                 const int32_t *__restrict__ colidx, const double *__restrict__ values, const double *__restrict__ x,
-                double *__restrict__ y, double *__restrict__ dot)
+                double *__restrict__ y, double *__restrict__ dot, const Gap gap)
   {
     __shared__ double prod[kStreamNnz];
     const int     r0 = rowblk[blockIdx.x], r1 = rowblk[blockIdx.x + 1];
@@ -120,9 +128,9 @@ namespace pe
               s += prod[k];
             if (r >= n_pos)
               s = -s;
-            y[r] = s;
+            y[phys(r, gap)] = s;
             if (DOT)
-              dacc += s * x[r];
+              dacc += s * x[phys(r, gap)];
           }
       }
     else
@@ -145,9 +153,9 @@ namespace pe
               s += red[w];
             if (r0 >= n_pos)
               s = -s;
-            y[r0] = s;
+            y[phys(r0, gap)] = s;
             if (DOT)
-              dacc = s * x[r0];
+              dacc = s * x[phys(r0, gap)];
           }
       }
     if (DOT)
@@ -260,12 +268,13 @@ namespace pe
   // v = D(b - A x) is prepared by the caller; z = pinv .* v ; d2 += <z, v>
   __global__ void
   k_apply_precond_dot(const int64_t n, const double *__restrict__ pinv, const double *__restrict__ v,
-                      double *__restrict__ z, double *__restrict__ dot)
+                      double *__restrict__ z, double *__restrict__ dot, const Gap gap)
   {
     double s = 0.;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < n; l += (int64_t)gridDim.x * blockDim.x)
       {
-        const double zi = pinv[i] * v[i];
+        const int64_t i  = phys(l, gap);
+        const double  zi = pinv[i] * v[i];
         z[i]            = zi;
         s += zi * v[i];
       }
@@ -297,13 +306,14 @@ namespace pe
   __global__ void
   k_minres_lanczos(const int64_t n, const MinresState *__restrict__ st, const double *__restrict__ p,
                    const double *__restrict__ v, double *__restrict__ v_old, const double *__restrict__ pinv,
-                   double *__restrict__ z_new, double *__restrict__ dot)
+                   double *__restrict__ z_new, double *__restrict__ dot, const Gap gap)
   {
     const double ig = 1. / st->gamma, dg = st->delta / st->gamma, go = st->gamma / st->gamma_old;
     double       s  = 0.;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < n; l += (int64_t)gridDim.x * blockDim.x)
       {
-        const double vn = p[i] * ig - dg * v[i] - go * v_old[i];
+        const int64_t i  = phys(l, gap);
+        const double  vn = p[i] * ig - dg * v[i] - go * v_old[i];
         v_old[i]        = vn;
         if (pinv)
           {
@@ -320,11 +330,15 @@ namespace pe
       }
   }
   __global__ void
-  k_dot(const int64_t n, const double *__restrict__ a, const double *__restrict__ b, double *__restrict__ dot)
+  k_dot(const int64_t n, const double *__restrict__ a, const double *__restrict__ b, double *__restrict__ dot,
+        const Gap gap)
   {
     double s = 0.;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-      s += a[i] * b[i];
+    for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < n; l += (int64_t)gridDim.x * blockDim.x)
+      {
+        const int64_t i = phys(l, gap);
+        s += a[i] * b[i];
+      }
     s = block_sum(s);
     if (threadIdx.x == 0)
       atomicAdd(dot, s);
@@ -353,12 +367,13 @@ namespace pe
   // w_new = (z/gamma - a3 w_old - a2 w)/a1  (written over w_old);  x += cx w_new
   __global__ void
   k_minres_update(const int64_t n, const MinresState *__restrict__ st, const double *__restrict__ z,
-                  const double *__restrict__ w, double *__restrict__ w_old, double *__restrict__ x)
+                  const double *__restrict__ w, double *__restrict__ w_old, double *__restrict__ x, const Gap gap)
   {
     const double ig = 1. / st->gamma, a2 = st->a2, a3 = st->a3, ia1 = 1. / st->a1, cx = st->cx;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < n; l += (int64_t)gridDim.x * blockDim.x)
       {
-        const double wn = (z[i] * ig - a3 * w_old[i] - a2 * w[i]) * ia1;
+        const int64_t i  = phys(l, gap);
+        const double  wn = (z[i] * ig - a3 * w_old[i] - a2 * w[i]) * ia1;
         w_old[i]        = wn;
         x[i] += cx * wn;
       }
@@ -374,12 +389,13 @@ namespace pe
   // r = sign .* (b - y)   and   optional ||.||^2
   __global__ void
   k_residual(const int64_t n, const int64_t n_pos, const double *__restrict__ b, const double *__restrict__ y_signed,
-             double *__restrict__ r, double *__restrict__ nrm2)
+             double *__restrict__ r, double *__restrict__ nrm2, const Gap gap)
   {
     double s = 0.;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < n; l += (int64_t)gridDim.x * blockDim.x)
       {
-        const double bi = i >= n_pos ? -b[i] : b[i];
+        const int64_t i  = phys(l, gap);
+        const double  bi = l >= n_pos ? -b[i] : b[i];
         const double ri = bi - y_signed[i];
         if (r)
           r[i] = ri;
@@ -390,11 +406,14 @@ namespace pe
       atomicAdd(nrm2, s);
   }
   __global__ void
-  k_norm2(const int64_t n, const double *__restrict__ x, double *__restrict__ nrm2)
+  k_norm2(const int64_t n, const double *__restrict__ x, double *__restrict__ nrm2, const Gap gap)
   {
     double s = 0.;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-      s += x[i] * x[i];
+    for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < n; l += (int64_t)gridDim.x * blockDim.x)
+      {
+        const int64_t i = phys(l, gap);
+        s += x[i] * x[i];
+      }
     s = block_sum(s);
     if (threadIdx.x == 0)
       atomicAdd(nrm2, s);
@@ -453,7 +472,7 @@ namespace pe
       return cudaSuccess;
     const int64_t want = (n_rows * 32 + 255) / 256;
     const unsigned g   = (unsigned)std::min<int64_t>(want, 148 * 64);
-    k_spmv<false><<<g, 256, 0, s>>>(n_rows, n_rows, rowptr, colidx, values, x, y, nullptr);
+    k_spmv<false><<<g, 256, 0, s>>>(n_rows, n_rows, rowptr, colidx, values, x, y, nullptr, Gap{});
     return cudaGetLastError();
   }
 
@@ -469,17 +488,17 @@ namespace pe
     if (c.rowblk && c.n_rowblk > 0)
       {
         if (dot)
-          k_spmv_stream<true><<<(unsigned)c.n_rowblk, 256, 0, c.stream>>>(c.n_pos, c.rowblk, c.rowptr, c.colidx, c.values, x, y, dot);
+          k_spmv_stream<true><<<(unsigned)c.n_rowblk, 256, 0, c.stream>>>(c.n_pos, c.rowblk, c.rowptr, c.colidx, c.values, x, y, dot, c.gap);
         else
-          k_spmv_stream<false><<<(unsigned)c.n_rowblk, 256, 0, c.stream>>>(c.n_pos, c.rowblk, c.rowptr, c.colidx, c.values, x, y, nullptr);
+          k_spmv_stream<false><<<(unsigned)c.n_rowblk, 256, 0, c.stream>>>(c.n_pos, c.rowblk, c.rowptr, c.colidx, c.values, x, y, nullptr, c.gap);
         return;
       }
     const int64_t want = (c.L * 32 + 255) / 256;
     const unsigned g   = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, 148 * 64));
     if (dot)
-      k_spmv<true><<<g, 256, 0, c.stream>>>(c.L, c.n_pos, c.rowptr, c.colidx, c.values, x, y, dot);
+      k_spmv<true><<<g, 256, 0, c.stream>>>(c.L, c.n_pos, c.rowptr, c.colidx, c.values, x, y, dot, c.gap);
     else
-      k_spmv<false><<<g, 256, 0, c.stream>>>(c.L, c.n_pos, c.rowptr, c.colidx, c.values, x, y, nullptr);
+      k_spmv<false><<<g, 256, 0, c.stream>>>(c.L, c.n_pos, c.rowptr, c.colidx, c.values, x, y, nullptr, c.gap);
   }
 
   __global__ void
@@ -494,6 +513,26 @@ namespace pe
   {
     if (c.L > 0)
       k_scale<<<(unsigned)((c.L + 255) / 256), 256, 0, c.stream>>>(c.L, x, a);
+  }
+
+  void
+  residual_norm2(const SolverCtx &c, const double *b, const double *x, double *y, double *nrm2_dev)
+  {
+    SolverCtx cc = c;
+    cc.n_pos     = c.L;
+    spmv_signed(cc, x, y, nullptr);
+    k_residual<<<vec_grid(c.L), 256, 0, c.stream>>>(c.L, c.L, b, y, nullptr, nrm2_dev, c.gap);
+  }
+  void
+  norm2(const SolverCtx &c, const double *x, double *nrm2_dev)
+  {
+    k_norm2<<<vec_grid(c.L), 256, 0, c.stream>>>(c.L, x, nrm2_dev, c.gap);
+  }
+  void
+  extract_diagonal(const SolverCtx &c, double *diag)
+  {
+    if (c.L > 0)
+      k_diag<<<(unsigned)((c.L + 255) / 256), 256, 0, c.stream>>>(c.L, c.rowptr, c.colidx, c.values, diag);
   }
 
   int
@@ -527,7 +566,7 @@ namespace pe
     cudaMemsetAsync(w_old, 0, sizeof(double) * (size_t)(L + c.H), s);
     cudaMemsetAsync(w, 0, sizeof(double) * (size_t)(L + c.H), s);
     // ||b||
-    k_norm2<<<g, 256, 0, s>>>(L, b, &st->d1);
+    k_norm2<<<g, 256, 0, s>>>(L, b, &st->d1, c.gap);
     if (c.allreduce)
       c.allreduce(c.halo_ctx, &st->d1, 1);
     cudaMemcpyAsync(h_pinned, &st->d1, sizeof(double), cudaMemcpyDeviceToHost, s);
@@ -537,30 +576,48 @@ namespace pe
       c.halo(c.halo_ctx, x);
     spmv_signed(c, x, p, nullptr);
     ++spmv;
-    k_residual<<<g, 256, 0, s>>>(L, c.n_pos, b, p, v, nullptr);
+    k_residual<<<g, 256, 0, s>>>(L, c.n_pos, b, p, v, nullptr, c.gap);
     if (c.precond_apply)
       {
         c.precond_apply(c.precond_ctx, v, z);
-        k_dot<<<g, 256, 0, s>>>(L, z, v, &st->d2);
+        k_dot<<<g, 256, 0, s>>>(L, z, v, &st->d2, c.gap);
       }
     else if (c.precond_add)
       {
-        k_apply_precond_dot<<<g, 256, 0, s>>>(L, pinv, v, z, &st->d1); // d1 is scratch here
+        k_apply_precond_dot<<<g, 256, 0, s>>>(L, pinv, v, z, &st->d1, c.gap); // d1 is scratch here
         cudaMemsetAsync(&st->d1, 0, sizeof(double), s);
         c.precond_add(c.precond_ctx, v, z);
-        k_dot<<<g, 256, 0, s>>>(L, z, v, &st->d2);
+        k_dot<<<g, 256, 0, s>>>(L, z, v, &st->d2, c.gap);
       }
     else
-      k_apply_precond_dot<<<g, 256, 0, s>>>(L, pinv, v, z, &st->d2);
+      k_apply_precond_dot<<<g, 256, 0, s>>>(L, pinv, v, z, &st->d2, c.gap);
     if (c.allreduce)
       c.allreduce(c.halo_ctx, &st->d2, 1);
     k_minres_init<<<1, 1, 0, s>>>(st);
     cudaMemcpyAsync(h_pinned + 1, &st->eta0, sizeof(double), cudaMemcpyDeviceToHost, s);
     cudaStreamSynchronize(s);
-    const double bnorm = std::sqrt(h_pinned[0]);
+    const double bnorm = c.bnorm2 >= 0. ? std::sqrt(c.bnorm2) : std::sqrt(h_pinned[0]);
     const double eta0  = h_pinned[1];
     stats->rhs_norm    = bnorm;
     int  it            = 0;
+    // squared norm of the true residual of the current iterate into st->d1 (summed over the ranks)
+    auto true_residual = [&]() {
+      cudaMemsetAsync(&st->d1, 0, sizeof(double), s);
+      if (c.true_residual)
+        c.true_residual(c.precond_ctx, x, &st->d1);
+      else
+        {
+          if (c.halo)
+            c.halo(c.halo_ctx, x);
+          spmv_signed(c, x, p, nullptr);
+          k_residual<<<g, 256, 0, s>>>(L, c.n_pos, b, p, nullptr, &st->d1, c.gap);
+        }
+      ++spmv;
+      if (c.allreduce)
+        c.allreduce(c.halo_ctx, &st->d1, 1);
+      cudaMemcpyAsync(h_pinned + 3, &st->d1, sizeof(double), cudaMemcpyDeviceToHost, s);
+      cudaMemsetAsync(&st->d1, 0, sizeof(double), s);
+    };
     bool conv          = (eta0 == 0.);
     // stopping test on the preconditioned residual estimate |eta| relative to its initial value
     // scaled to ||b||: the exact-residual check below decides what is reported.
@@ -576,22 +633,22 @@ namespace pe
       k_minres_scalars_a<<<1, 1, 0, s>>>(st);
       if (c.precond_apply)
         {
-          k_minres_lanczos<<<g, 256, 0, s>>>(L, st, p, v_, vo_, nullptr, zn_, nullptr);
+          k_minres_lanczos<<<g, 256, 0, s>>>(L, st, p, v_, vo_, nullptr, zn_, nullptr, c.gap);
           c.precond_apply(c.precond_ctx, vo_ /* = v_new */, zn_);
-          k_dot<<<g, 256, 0, s>>>(L, zn_, vo_, &st->d2);
+          k_dot<<<g, 256, 0, s>>>(L, zn_, vo_, &st->d2, c.gap);
         }
       else if (c.precond_add)
         {
-          k_minres_lanczos<<<g, 256, 0, s>>>(L, st, p, v_, vo_, pinv, zn_, nullptr);
+          k_minres_lanczos<<<g, 256, 0, s>>>(L, st, p, v_, vo_, pinv, zn_, nullptr, c.gap);
           c.precond_add(c.precond_ctx, vo_ /* = v_new */, zn_);
-          k_dot<<<g, 256, 0, s>>>(L, zn_, vo_, &st->d2);
+          k_dot<<<g, 256, 0, s>>>(L, zn_, vo_, &st->d2, c.gap);
         }
       else
-        k_minres_lanczos<<<g, 256, 0, s>>>(L, st, p, v_, vo_, pinv, zn_, &st->d2);
+        k_minres_lanczos<<<g, 256, 0, s>>>(L, st, p, v_, vo_, pinv, zn_, &st->d2, c.gap);
       if (c.allreduce)
         c.allreduce(c.halo_ctx, &st->d2, 1);
       k_minres_scalars_b<<<1, 1, 0, s>>>(st);
-      k_minres_update<<<g, 256, 0, s>>>(L, st, z_, w_, wo_, x);
+      k_minres_update<<<g, 256, 0, s>>>(L, st, z_, w_, wo_, x, c.gap);
       k_minres_advance<<<1, 1, 0, s>>>(st);
       if (c.launch_counter)
         *c.launch_counter += 7; // SpMV, Lanczos, dot, update, three scalar kernels
@@ -650,16 +707,7 @@ namespace pe
         if (eta <= eta_target)
           {
             // the preconditioned norm is only an estimate: confirm with the true residual
-            if (c.halo)
-              c.halo(c.halo_ctx, x);
-            spmv_signed(c, x, p, nullptr);
-            ++spmv;
-            cudaMemsetAsync(&st->d1, 0, sizeof(double), s);
-            k_residual<<<g, 256, 0, s>>>(L, c.n_pos, b, p, nullptr, &st->d1);
-            if (c.allreduce)
-              c.allreduce(c.halo_ctx, &st->d1, 1);
-            cudaMemcpyAsync(h_pinned + 3, &st->d1, sizeof(double), cudaMemcpyDeviceToHost, s);
-            cudaMemsetAsync(&st->d1, 0, sizeof(double), s);
+            true_residual();
             cudaStreamSynchronize(s);
             const double rn = std::sqrt(h_pinned[3]);
             if (rn <= rel_tol * bnorm || bnorm == 0.)
@@ -676,15 +724,7 @@ namespace pe
       if (gexec[par])
         cudaGraphExecDestroy(gexec[par]);
     // final true residual
-    if (c.halo)
-      c.halo(c.halo_ctx, x);
-    spmv_signed(c, x, p, nullptr);
-    ++spmv;
-    cudaMemsetAsync(&st->d1, 0, sizeof(double), s);
-    k_residual<<<g, 256, 0, s>>>(L, c.n_pos, b, p, nullptr, &st->d1);
-    if (c.allreduce)
-      c.allreduce(c.halo_ctx, &st->d1, 1);
-    cudaMemcpyAsync(h_pinned + 3, &st->d1, sizeof(double), cudaMemcpyDeviceToHost, s);
+    true_residual();
     if (cudaStreamSynchronize(s) != cudaSuccess)
       return -1;
     stats->residual_norm = std::sqrt(h_pinned[3]);
@@ -709,7 +749,7 @@ namespace pe
     SolverCtx cc = c;
     cc.n_pos     = L; // no sign flip: SPD system
     cudaMemsetAsync(st, 0, sizeof(CgState), s);
-    k_norm2<<<g, 256, 0, s>>>(L, b, &st->pAp);
+    k_norm2<<<g, 256, 0, s>>>(L, b, &st->pAp, Gap{});
     if (c.allreduce)
       c.allreduce(c.halo_ctx, &st->pAp, 1);
     cudaMemcpyAsync(h_pinned, &st->pAp, sizeof(double), cudaMemcpyDeviceToHost, s);
@@ -718,7 +758,7 @@ namespace pe
       c.halo(c.halo_ctx, x);
     spmv_signed(cc, x, Ap, nullptr);
     ++spmv;
-    k_residual<<<g, 256, 0, s>>>(L, L, b, Ap, r, &st->rr);
+    k_residual<<<g, 256, 0, s>>>(L, L, b, Ap, r, &st->rr, Gap{});
     if (c.allreduce)
       c.allreduce(c.halo_ctx, &st->rr, 1);
     cudaMemcpyAsync(p, r, sizeof(double) * (size_t)L, cudaMemcpyDeviceToDevice, s);

@@ -10,6 +10,11 @@
 namespace pe
 {
   struct MinresState;
+  // logical index i of an owned unknown -> physical vector index i + (i >= at ? len : 0)   (pe_k3.h)
+  struct Gap
+  {
+    int64_t at = INT64_MAX, len = 0;
+  };
   struct SolverCtx
   {
     int64_t        L = 0, H = 0;    // owned rows, halo columns
@@ -33,11 +38,20 @@ namespace pe
     int64_t *launch_counter = nullptr; // kernels launched (graph replays counted node by node)
     // full replacement of the diagonal preconditioner: z = P^{-1} r  (pe_precond.cu)
     void (*precond_apply)(void *ctx, const double *r, double *z) = nullptr;
+    Gap    gap;                 // vector layout of the owned unknowns (three-field system)
+    double bnorm2 = -1.;        // >= 0: ||b||^2 the stopping test is relative to (else computed from b)
+    // optional: *nrm2_dev += ||true residual(x)||^2 of this rank (else b - A x with the ctx matrix)
+    void (*true_residual)(void *ctx, const double *x, double *nrm2_dev) = nullptr;
   };
 
   void   build_row_blocks(int64_t n_rows, const int64_t *rowptr, std::vector<int32_t> &blk);
   void   spmv_signed(const SolverCtx &c, const double *x, double *y, double *dot);
   void   scale_vector(const SolverCtx &c, double *x, double a);
+  // *nrm2_dev += || b - A x ||^2 over the owned rows (plain A: no sign flip); y = A x is scratch (L long)
+  void   residual_norm2(const SolverCtx &c, const double *b, const double *x, double *y, double *nrm2_dev);
+  void   norm2(const SolverCtx &c, const double *x, double *nrm2_dev);
+  // diag[r] = A(r, r) for the ctx matrix (owned rows)
+  void   extract_diagonal(const SolverCtx &c, double *diag);
   int    build_preconditioner(const SolverCtx &c, double *diag_full, double *pinv);
   int    minres_solve(const SolverCtx &c, const double *b, double *x, const double *pinv, double *work[7],
                       MinresState *st, double *h_pinned, double rel_tol, int max_it, pe_solve_stats *stats);
