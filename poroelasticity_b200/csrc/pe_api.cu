@@ -2,6 +2,7 @@
 // device residency of the mesh / DoF / CSR arrays, kernel launches, timing.  No CPU compute path:
 // every entry point that produces numbers launches the CUDA kernels or fails.
 #include "pe_internal.h"
+#include "pe_cmg.h"
 #include "pe_k3.h"
 #include "pe_kernels.h"
 #include "pe_mg.h"
@@ -113,6 +114,8 @@ namespace
     h->bp                  = nullptr;
     delete h->k3;
     h->k3                  = nullptr;
+    delete h->cmg;
+    h->cmg                 = nullptr;
     cudaStream_t     s     = h->stream;
     const int        n_loc = h->dofs.n_loc;
     const Partition &pt    = h->part;
@@ -447,7 +450,7 @@ namespace
   hook_precond3(void *ctx, const double *r, double *z)
   {
     pe_handle *h = (pe_handle *)ctx;
-    precond_apply(*h->bp, *h->mg, h->d_pinv.p, r, z, h->stream, &h->launches);
+    precond_apply(*h->bp, *h->mg, *h->cmg, h->d_pinv.p, r, z, h->stream, &h->launches);
     k3_precond_xi(*h->k3, h->mu, r, z, h->stream);
     ++h->launches;
   }
@@ -502,13 +505,18 @@ namespace
     h->launches += 2;
     if (k3_fill_values(k, lambda_s, h->alpha, s, &h->launches) != 0)
       return 1;
-    if (h->use_mg && h->mg && h->mg->ready && h->bp && h->bp->ready)
+    if (h->use_mg && h->mg && h->mg->ready && h->bp && h->bp->ready && h->cmg && h->cmg->ready)
       {
         h->mg->omega = h->mg_omega;
         h->mg->nu    = h->mg_nu;
+        h->cmg->nu   = h->mg_nu;
         // pressure block of the preconditioner: C + alpha^2/lambda_s W_int (C already holds c0 M)
         const double extra = h->alpha * h->alpha / lambda_s;
-        if (mg_assemble(*h->mg, h->d_k_morton.p, h->k_scalar, lambda0, h->mu, h->last_dt, h->c0 + extra, s, &h->launches) != 0)
+        if (mg_assemble(*h->mg, h->d_k_morton.p, h->k_scalar, lambda0, h->mu, h->last_dt, h->c0 + extra, s, &h->launches,
+                        false) != 0)
+          return 1;
+        if (cmg_assemble(*h->cmg, h->d_vx.p, h->d_vy.p, h->d_k_morton.p, h->k_scalar, h->last_dt, h->c0 + extra, s,
+                         &h->launches) != 0)
           return 1;
         if (precond_update(*h->bp, k.values0.p, k.diag0.p, extra, s, &h->launches) != 0)
           return 1;
@@ -537,6 +545,12 @@ namespace
       {
         h->mg = new MgHierarchy;
         if (mg_build_topology(*h->mg, h->mesh, h->dofs, to_local, s) < 0)
+          return 1;
+      }
+    if (h->use_mg && h->mg->ready && !h->cmg)
+      {
+        h->cmg = new CellMg;
+        if (cmg_build_topology(*h->cmg, h->mesh, s) < 0)
           return 1;
       }
     if (h->use_mg && h->mg->ready && !h->bp)
@@ -603,7 +617,7 @@ namespace
         if (rc != 0)
           return rc;
       }
-    const bool block_pc = h->use_mg && h->mg && h->mg->ready && h->bp && h->bp->ready;
+    const bool block_pc = h->use_mg && h->mg && h->mg->ready && h->bp && h->bp->ready && h->cmg && h->cmg->ready;
     // ---- this right-hand side ----------------------------------------------------------------------------
     double *b3 = h->d_w[7].p, *x3 = h->d_w[8].p;
     if (k3_make_rhs(k, h->d_rhs.p, h->d_rowptr.p, h->d_colidx.p, h->d_values.p, b3, s) != 0)
@@ -735,6 +749,8 @@ extern "C"
     h->bp = nullptr;
     delete h->k3;
     h->k3 = nullptr;
+    delete h->cmg;
+    h->cmg = nullptr;
     for (auto &ev : h->ev)
       if (ev)
         cudaEventDestroy(ev);

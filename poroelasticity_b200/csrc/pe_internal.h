@@ -19,7 +19,7 @@
 #include <vector>
 
 struct ncclComm;
-namespace pe { struct MgHierarchy; struct BlockPrecond; struct K3System; }
+namespace pe { struct MgHierarchy; struct BlockPrecond; struct K3System; struct CellMg; }
 
 namespace pe
 {
@@ -127,6 +127,7 @@ struct pe_handle
   // auxiliary-space multigrid preconditioner (pe_mg.cu); null = diagonal preconditioner only
   pe::MgHierarchy *mg = nullptr;
   pe::BlockPrecond *bp = nullptr;
+  pe::CellMg       *cmg = nullptr; // cell-centred multigrid of the pressure block (pe_cmg.h)
   // three-field solver matrix (pe_k3.h); rebuilt values after every matrix assembly
   pe::K3System *k3 = nullptr;
   double        last_t = 0.;

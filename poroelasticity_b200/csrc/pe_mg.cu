@@ -548,14 +548,15 @@ namespace pe
   // refactorises every step; the "cached" mode of SURVEY 8(f).1 would skip this)
   int
   mg_assemble(MgHierarchy &mg, const double *kcell_fine /* Morton, may be null */, const double k_scalar,
-              const double lambda, const double mu, const double dt, const double gamma, cudaStream_t s, int64_t *launches)
+              const double lambda, const double mu, const double dt, const double gamma, cudaStream_t s, int64_t *launches,
+              const bool with_p)
   {
     for (size_t l = 0; l < mg.lv.size(); ++l)
       {
         MgLevel  &L  = mg.lv[l];
         const int nv = (L.N + 1) * (L.N + 1);
         const double *kc = nullptr;
-        if (kcell_fine)
+        if (kcell_fine && with_p)
           {
             if (l == 0)
               kc = kcell_fine;
@@ -568,8 +569,9 @@ namespace pe
               }
           }
         k_mg_assemble<2><<<g1(nv), 128, 0, s>>>(L.N, L.x.p, L.y.p, nullptr, 1., L.mask_u.p, mu, lambda, L.st_u.p, L.dinv_u.p);
-        k_mg_assemble<1><<<g1(nv), 128, 0, s>>>(L.N, L.x.p, L.y.p, kc, k_scalar, L.mask_p.p, dt, gamma, L.st_p.p, L.dinv_p.p);
-        *launches += 2;
+        if (with_p)
+          k_mg_assemble<1><<<g1(nv), 128, 0, s>>>(L.N, L.x.p, L.y.p, kc, k_scalar, L.mask_p.p, dt, gamma, L.st_p.p, L.dinv_p.p);
+        *launches += with_p ? 2 : 1;
       }
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
   }

@@ -28,8 +28,9 @@ namespace pe
   // to_local: global dof id -> local id on this rank (owned < L <= halo) or -1 if not visible
   int  mg_build_topology(MgHierarchy &mg, const HostMesh &mesh, const HostDofs &dofs,
                          const std::function<int32_t(uint32_t)> &to_local, cudaStream_t s);
+  // with_p = false: only the displacement operators (the pressure block uses pe_cmg.h)
   int  mg_assemble(MgHierarchy &mg, const double *kcell_fine, double k_scalar, double lambda, double mu, double dt,
-                   double gamma, cudaStream_t s, int64_t *launches);
+                   double gamma, cudaStream_t s, int64_t *launches, bool with_p = true);
   // V-cycle on level-0 right-hand side lv[0].bu (nc = 2) / lv[0].bp (nc = 1); result in lv[0].wu[2] / wp[2]
   void mg_vcycle(MgHierarchy &mg, int nc, cudaStream_t s, int64_t *launches);
   void mg_apply_add(MgHierarchy &mg, const double *r, double *z, cudaStream_t s, int64_t *launches);

@@ -69,12 +69,35 @@ namespace pe
 
     // compact copy of the sub-block values, once per solve: val[k] = values[src[k]]
     __global__ void
-    k_sub_gather_values(const int64_t n, const uint32_t *__restrict__ src, const double *__restrict__ values,
-                        double *__restrict__ val)
+    k_sub_gather_values(const int64_t n, const uint32_t *__restrict__ src, const uint8_t *__restrict__ neg,
+                        const double *__restrict__ values, double *__restrict__ val)
     {
       const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
       if (k < n)
-        val[k] = __ldg(values + src[k]);
+        {
+          const double v = __ldg(values + src[k]);
+          val[k]         = (neg && neg[k]) ? -v : v;
+        }
+    }
+    // on the owned face rows: y1 = omega_F dinvF g  (first Jacobi sweep on F from zero)
+    __global__ void
+    k_face_scale(const int n, const int32_t *__restrict__ rows, const double *__restrict__ wdinv,
+                 const double *__restrict__ g, double *__restrict__ y)
+    {
+      const int r = blockIdx.x * blockDim.x + threadIdx.x;
+      if (r >= n)
+        return;
+      const int row = rows[r];
+      y[row]        = wdinv[row] * g[row];
+    }
+    __global__ void
+    k_face_wdinv(const int n, const int32_t *__restrict__ rows, const double *__restrict__ dinv, const double omega,
+                 double *__restrict__ wdinv)
+    {
+      const int r = blockIdx.x * blockDim.x + threadIdx.x;
+      if (r >= n)
+        return;
+      wdinv[rows[r]] = omega * dinv[rows[r]];
     }
     // streamed sub-block product (same scheme as k_spmv_stream): a CTA owns a run of sub-rows holding
     // <= kSubNnz entries; coalesced value/column streaming with all loads batched, row sums from smem,
@@ -312,9 +335,10 @@ namespace pe
         pint_rows.push_back(to_local(d.cell_dofs[(size_t)c * n_loc + n_loc - 1]));
         area_of_pint.push_back(0.5 * ((x3 - x0) * (y2 - y1) - (x2 - x1) * (y3 - y0)));
       }
-    auto build = [&](const int row_cls, const int col_mask, SubCsr &out) -> bool {
+    auto build = [&](const int row_cls, const int col_mask, SubCsr &out, const int neg_mask = 0) -> bool {
       std::vector<int32_t>  rows, rp(1, 0), col;
       std::vector<uint32_t> src;
+      std::vector<uint8_t>  neg;
       for (int64_t r = 0; r < L; ++r)
         {
           if (cls[r] != row_cls)
@@ -327,6 +351,8 @@ namespace pe
                 {
                   col.push_back(cc);
                   src.push_back((uint32_t)k);
+                  if (neg_mask)
+                    neg.push_back((uint8_t)((neg_mask >> cls[cc]) & 1));
                 }
             }
           rp.push_back((int32_t)col.size());
@@ -357,7 +383,7 @@ namespace pe
       out.n_blk = (int)blk.size() - 1;
       out.nnz   = (int64_t)col.size();
       const bool ok = up(out.rows, rows) && up(out.rp, rp) && up(out.col, col) && up(out.src, src) && up(out.rowblk, blk) &&
-                      out.val.alloc(col.size()) == cudaSuccess;
+                      (neg.empty() || up(out.neg, neg)) && out.val.alloc(col.size()) == cudaSuccess;
       cudaStreamSynchronize(s);
       return ok;
     };
@@ -366,7 +392,8 @@ namespace pe
       if (!build(CLS_BUBBLE, (1 << CLS_VERTEX) | (1 << CLS_BUBBLE), bp.Abu) ||
           !build(CLS_VERTEX, 1 << CLS_BUBBLE, bp.Avb))
         return -1;
-    if (!build(CLS_PINT, 1 << CLS_PFACE, bp.Sif) || !build(CLS_PFACE, 1 << CLS_PINT, bp.Sfi))
+    if (!build(CLS_PINT, 1 << CLS_PFACE, bp.Sif) || !build(CLS_PFACE, 1 << CLS_PINT, bp.Sfi) ||
+        !build(CLS_PFACE, (1 << CLS_PINT) | (1 << CLS_PFACE), bp.Spf, 1 << CLS_PINT))
       return -1;
     if (bp.cls.alloc(cls.size()) != cudaSuccess || bp.pint_rows.alloc(pint_rows.size()) != cudaSuccess ||
         bp.pint_area.alloc(area_of_pint.size()) != cudaSuccess)
@@ -374,8 +401,11 @@ namespace pe
     cudaMemcpyAsync(bp.cls.p, cls.data(), cls.size(), cudaMemcpyHostToDevice, s);
     cudaMemcpyAsync(bp.pint_rows.p, pint_rows.data(), pint_rows.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s);
     cudaMemcpyAsync(bp.pint_area.p, area_of_pint.data(), area_of_pint.size() * sizeof(double), cudaMemcpyHostToDevice, s);
-    if (bp.t.alloc((size_t)LH) != cudaSuccess || bp.t2.alloc((size_t)LH) != cudaSuccess || bp.dinv.alloc((size_t)LH) != cudaSuccess)
+    if (bp.t.alloc((size_t)LH) != cudaSuccess || bp.t2.alloc((size_t)LH) != cudaSuccess || bp.dinv.alloc((size_t)LH) != cudaSuccess ||
+        bp.t3.alloc((size_t)LH) != cudaSuccess || bp.wdinv.alloc((size_t)LH) != cudaSuccess)
       return -1;
+    cudaMemsetAsync(bp.t3.p, 0, sizeof(double) * (size_t)LH, s);
+    cudaMemsetAsync(bp.wdinv.p, 0, sizeof(double) * (size_t)LH, s);
     cudaMemsetAsync(bp.t.p, 0, sizeof(double) * (size_t)LH, s);
     cudaMemsetAsync(bp.t2.p, 0, sizeof(double) * (size_t)LH, s);
     cudaMemsetAsync(bp.dinv.p, 0, sizeof(double) * (size_t)LH, s);
@@ -394,10 +424,10 @@ namespace pe
                  int64_t *launches)
   {
     bp.values = values;
-    for (SubCsr *sc : {&bp.Abu, &bp.Avb, &bp.Sif, &bp.Sfi})
+    for (SubCsr *sc : {&bp.Abu, &bp.Avb, &bp.Sif, &bp.Sfi, &bp.Spf})
       if (sc->nnz > 0)
         {
-          k_sub_gather_values<<<gb(sc->nnz, 256), 256, 0, s>>>(sc->nnz, sc->src.p, values, sc->val.p);
+          k_sub_gather_values<<<gb(sc->nnz, 256), 256, 0, s>>>(sc->nnz, sc->src.p, sc->neg.p, values, sc->val.p);
           ++*launches;
         }
     k_pint_dinv<<<gb(bp.n_pint), 128, 0, s>>>(bp.n_pint, bp.pint_rows.p, diag, bp.pint_area.p, gamma, bp.dinv.p);
@@ -405,20 +435,26 @@ namespace pe
       bp.halo(bp.comm_ctx, bp.dinv.p); // D_i of the neighbours' interior pressures
     k_face_dinv<<<gb(bp.Sfi.n_rows), 128, 0, s>>>(bp.Sfi.n_rows, bp.Sfi.rows.p, bp.Sfi.rp.p, bp.Sfi.col.p, bp.Sfi.src.p,
                                                    values, diag, bp.dinv.p);
-    *launches += 2;
+    k_face_wdinv<<<gb(bp.Sfi.n_rows), 128, 0, s>>>(bp.Sfi.n_rows, bp.Sfi.rows.p, bp.dinv.p, bp.omega_f, bp.wdinv.p);
+    *launches += 3;
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
   }
 
   // ---- z = P^{-1} r ---------------------------------------------------------------------------------
   // Multi-GPU: sub-block products need the neighbours' entries (halo exchange of t and z); the two
-  // V-cycles run replicated on every rank on the all-reduced vertex-grid right-hand sides.
+  // V-cycles run replicated on every rank on the all-reduced grid right-hand sides.
   void
-  precond_apply(BlockPrecond &bp, MgHierarchy &mg, const double *pinv, const double *r, double *z, cudaStream_t s,
-                int64_t *launches)
+  precond_apply(BlockPrecond &bp, MgHierarchy &mg, CellMg &cm, const double *pinv, const double *r, double *z,
+                cudaStream_t s, int64_t *launches)
   {
     MgLevel      &L0 = mg.lv[0];
     const int     N  = L0.N, nv = (N + 1) * (N + 1);
     const int64_t L  = bp.n;
+    auto sub = [&](const SubCsr &S, const double *x, const double *a, const double *m, const double *b, double *out) {
+      if (S.n_blk > 0)
+        k_sub_stream<<<(unsigned)S.n_blk, 256, 0, s>>>(S.rowblk.p, S.rows.p, S.rp.p, S.col.p, S.val.p, x, a, m, b, out);
+      ++*launches;
+    };
     // local Jacobi parts:  u: z = pinv r, t = y1 on bubbles;  p_int: t_i = dinv_i r_i
     k_pre_u<<<gb(bp.n_u, 256), 256, 0, s>>>(bp.n_u, bp.cls.p, pinv, r, bp.t.p, z);
     k_pre_p<<<gb(bp.n_pint), 128, 0, s>>>(bp.n_pint, bp.pint_rows.p, bp.dinv.p, r, bp.t.p);
@@ -426,35 +462,52 @@ namespace pe
     if (bp.halo)
       bp.halo(bp.comm_ctx, bp.t.p);
     if (bp.has_bubbles)
-      {
-        k_sub_stream<<<(unsigned)bp.Avb.n_blk, 256, 0, s>>>(bp.Avb.rowblk.p, bp.Avb.rows.p, bp.Avb.rp.p, bp.Avb.col.p, bp.Avb.val.p, bp.t.p, nullptr, nullptr, nullptr, bp.t2.p);
-        ++*launches;
-      }
-    // rf' = r_f - S_fi t_i   -> t2 (face entries)
-    k_sub_stream<<<(unsigned)bp.Sfi.n_blk, 256, 0, s>>>(bp.Sfi.rowblk.p, bp.Sfi.rows.p, bp.Sfi.rp.p, bp.Sfi.col.p, bp.Sfi.val.p, bp.t.p, nullptr, nullptr, r, bp.t2.p);
+      sub(bp.Avb, bp.t.p, nullptr, nullptr, nullptr, bp.t2.p);
+    // ---- displacement block: vertex V-cycle on the residual after the bubble sweep
     k_gather_u2<<<gb(nv), 128, 0, s>>>(nv, L, mg.vdof.p, L0.mask_u.p, r, bp.has_bubbles ? bp.t2.p : nullptr, L0.bu.p);
-    k_gather_f<<<gb(nv), 128, 0, s>>>(N, L, mg.hedge.p, mg.vedge.p, L0.mask_p.p, bp.t2.p, L0.bp.p);
-    *launches += 3;
+    ++*launches;
     if (bp.allreduce)
-      {
-        bp.allreduce(bp.comm_ctx, L0.bu.p, 2 * nv);
-        bp.allreduce(bp.comm_ctx, L0.bp.p, nv);
-      }
+      bp.allreduce(bp.comm_ctx, L0.bu.p, 2 * nv);
     mg_vcycle(mg, 2, s, launches);
-    mg_vcycle(mg, 1, s, launches);
     k_scatter_u2<<<gb(nv), 128, 0, s>>>(nv, mg.vdof.p, L0.mask_u.p, L0.wu[2].p, z, bp.t.p);
-    k_scatter_f<<<gb(2 * (int64_t)N * (N + 1)), 128, 0, s>>>(N, L, mg.hedge.p, mg.vedge.p, L0.wp[2].p, bp.dinv.p, bp.t2.p, z);
-    *launches += 2;
+    ++*launches;
+    // ---- pressure block: interior pressures eliminated exactly; on the face Schur complement
+    //      F = S_ff - S_fi D_i^{-1} S_if:  Jacobi, cell-space correction (pe_cmg.h), Jacobi
+    // g = r_f - S_fi D_i^{-1} r_i   -> t2 (face entries)
+    sub(bp.Sfi, bp.t.p, nullptr, nullptr, r, bp.t2.p);
+    // y1 = omega dinvF g            -> t (face entries)
+    k_face_scale<<<gb(bp.Sfi.n_rows), 128, 0, s>>>(bp.Sfi.n_rows, bp.Sfi.rows.p, bp.wdinv.p, bp.t2.p, bp.t.p);
+    ++*launches;
+    // F y = S_ff y - S_fi q,  q = D_i^{-1} S_if y  (q on the p_int entries of t, y on its face entries)
+    auto apply_q = [&]() {
+      if (bp.halo)
+        bp.halo(bp.comm_ctx, bp.t.p);
+      sub(bp.Sif, bp.t.p, nullptr, bp.dinv.p, nullptr, bp.t.p);
+      if (bp.halo)
+        bp.halo(bp.comm_ctx, bp.t.p);
+    };
+    apply_q();
+    // res = g - F y1                -> t3 (face entries)
+    sub(bp.Spf, bp.t.p, nullptr, nullptr, bp.t2.p, bp.t3.p);
+    cmg_gather(cm, L, mg.hedge.p, mg.vedge.p, bp.t3.p, s);
+    ++*launches;
+    if (bp.allreduce)
+      bp.allreduce(bp.comm_ctx, cm.lv[0].b.p, N * N);
+    const double *e = cmg_vcycle(cm, s, launches);
+    // y2 = y1 + Pi_c e              -> t (face entries)
+    cmg_scatter(cm, L, mg.hedge.p, mg.vedge.p, e, bp.t.p, bp.t.p, s);
+    ++*launches;
+    apply_q();
+    // z_f = y2 + omega dinvF (g - F y2)
+    sub(bp.Spf, bp.t.p, bp.t.p, bp.wdinv.p, bp.t2.p, z);
     if (bp.has_bubbles)
       {
         // z_b = y1 + pinv_b (r_b - A_bb y1 - A_bv x_v),  t = (x_v, y1)
-        k_sub_stream<<<(unsigned)bp.Abu.n_blk, 256, 0, s>>>(bp.Abu.rowblk.p, bp.Abu.rows.p, bp.Abu.rp.p, bp.Abu.col.p, bp.Abu.val.p, bp.t.p, bp.t.p, pinv, r, z);
-        ++*launches;
+        sub(bp.Abu, bp.t.p, bp.t.p, pinv, r, z);
       }
     if (bp.halo)
       bp.halo(bp.comm_ctx, z); // face pressures of the neighbours
     // z_i = dinv_i (r_i - S_if z_f)
-    k_sub_stream<<<(unsigned)bp.Sif.n_blk, 256, 0, s>>>(bp.Sif.rowblk.p, bp.Sif.rows.p, bp.Sif.rp.p, bp.Sif.col.p, bp.Sif.val.p, z, nullptr, bp.dinv.p, r, z);
-    ++*launches;
+    sub(bp.Sif, z, nullptr, bp.dinv.p, r, z);
   }
 } // namespace pe

@@ -2,6 +2,7 @@
 #pragma once
 #include "pe_host.h"
 #include "pe_internal.h"
+#include "pe_cmg.h"
 #include "pe_mg.h"
 
 #include <functional>
@@ -15,6 +16,7 @@ namespace pe
     DevBuf<int32_t>  rows, rp, col, rowblk;
     DevBuf<double>   val; // compact copy of the block's values, refreshed once per solve
     DevBuf<uint32_t> src; // index into the assembled CSR values
+    DevBuf<uint8_t>  neg; // optional: 1 = the entry enters the compact copy with flipped sign
   };
   struct BlockPrecond
   {
@@ -25,10 +27,11 @@ namespace pe
     void (*halo)(void *ctx, double *x)             = nullptr;
     void (*allreduce)(void *ctx, double *v, int n) = nullptr;
     void *comm_ctx                                 = nullptr;
-    SubCsr          Abu, Avb, Sif, Sfi;
+    SubCsr          Abu, Avb, Sif, Sfi, Spf; // Spf: p_face rows x [-S_fi | S_ff]
     DevBuf<uint8_t> cls;
     DevBuf<int32_t> pint_rows;
-    DevBuf<double>  pint_area, t, t2, dinv;
+    DevBuf<double>  pint_area, t, t2, t3, dinv, wdinv; // wdinv = omega_F / diag(F) on the face rows
+    double          omega_f = 0.7;
     const double   *values = nullptr;
     ~BlockPrecond();
   };
@@ -36,6 +39,6 @@ namespace pe
                                const Partition &part, const std::function<int32_t(uint32_t)> &to_local, cudaStream_t s);
   int  precond_update(BlockPrecond &bp, const double *values, const double *diag, double gamma, cudaStream_t s,
                       int64_t *launches);
-  void precond_apply(BlockPrecond &bp, MgHierarchy &mg, const double *pinv, const double *r, double *z, cudaStream_t s,
-                     int64_t *launches);
+  void precond_apply(BlockPrecond &bp, MgHierarchy &mg, CellMg &cm, const double *pinv, const double *r, double *z,
+                     cudaStream_t s, int64_t *launches);
 } // namespace pe
