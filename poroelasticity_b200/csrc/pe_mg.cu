@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <functional>
 
 namespace pe
@@ -266,6 +267,163 @@ namespace pe
         }
       for (int v = threadIdx.x; v < NC * nv; v += blockDim.x)
         xo[v] = x0[v];
+    }
+
+    // ---- all levels with N <= kFusedN in ONE single-CTA launch: vectors in shared memory, stencils from L2 --------
+    // (every small level costs ~7 launches of 3-9 us each in the graph; fused: one ~50 us kernel)
+    constexpr int kFusedN   = 32;
+    constexpr int kFusedLev = 6;
+    struct FusedArgs
+    {
+      int            nlev;
+      int            N[kFusedLev];
+      const double  *st[kFusedLev], *dinv[kFusedLev];
+      const uint8_t *mask[kFusedLev];
+      const double  *b0;
+      double        *out;
+    };
+    template <int NC>
+    __device__ __forceinline__ void
+    jacobi_point(const int N, const int v, const double *__restrict__ st, const double *__restrict__ dinv, const double *b,
+                 const double *xi, double *xo, const double omega)
+    {
+      const int nv = (N + 1) * (N + 1);
+      double    r[NC];
+      if (xi)
+        {
+          stencil_row<NC>(N, v, st, xi, r);
+#pragma unroll
+          for (int c = 0; c < NC; ++c)
+            r[c] = b[c * nv + v] - r[c];
+        }
+      else
+        {
+#pragma unroll
+          for (int c = 0; c < NC; ++c)
+            r[c] = b[c * nv + v];
+        }
+      if (NC == 1)
+        xo[v] = (xi ? xi[v] : 0.) + omega * dinv[v] * r[0];
+      else
+        {
+          const double d00 = dinv[v], d01 = dinv[(size_t)nv + v], d10 = dinv[(size_t)2 * nv + v], d11 = dinv[(size_t)3 * nv + v];
+          xo[v]      = (xi ? xi[v] : 0.) + omega * (d00 * r[0] + d01 * r[NC - 1]);
+          xo[nv + v] = (xi ? xi[nv + v] : 0.) + omega * (d10 * r[0] + d11 * r[NC - 1]);
+        }
+    }
+    template <int NC>
+    __global__ void __launch_bounds__(1024)
+    k_mg_fused(const FusedArgs a, const double omega, const int nu, const int coarse_sweeps)
+    {
+      extern __shared__ double sm[]; // per level: b, x0, x1 (NC * nv each)
+      double *B[kFusedLev], *X[kFusedLev], *Y[kFusedLev];
+      {
+        double *p = sm;
+        for (int m = 0; m < a.nlev; ++m)
+          {
+            const int n = NC * (a.N[m] + 1) * (a.N[m] + 1);
+            B[m] = p;
+            X[m] = p + n;
+            Y[m] = p + 2 * n;
+            p += 3 * n;
+          }
+      }
+      const int t = threadIdx.x, nt = blockDim.x;
+      {
+        const int n = NC * (a.N[0] + 1) * (a.N[0] + 1);
+        for (int i = t; i < n; i += nt)
+          B[0][i] = a.b0[i];
+      }
+      __syncthreads();
+      // ---- down
+      for (int m = 0; m < a.nlev; ++m)
+        {
+          const int  N = a.N[m], nv = (N + 1) * (N + 1);
+          const bool last = m + 1 == a.nlev;
+          const int  sweeps = last ? coarse_sweeps : nu;
+          for (int v = t; v < nv; v += nt)
+            jacobi_point<NC>(N, v, a.st[m], a.dinv[m], B[m], nullptr, X[m], omega);
+          __syncthreads();
+          for (int k = 1; k < sweeps; ++k)
+            {
+              for (int v = t; v < nv; v += nt)
+                jacobi_point<NC>(N, v, a.st[m], a.dinv[m], B[m], X[m], Y[m], omega);
+              __syncthreads();
+              double *q = X[m];
+              X[m]      = Y[m];
+              Y[m]      = q;
+            }
+          if (last)
+            break;
+          // residual -> Y[m]; full-weighting restriction -> B[m+1]
+          for (int v = t; v < nv; v += nt)
+            {
+              double ax[NC];
+              stencil_row<NC>(N, v, a.st[m], X[m], ax);
+#pragma unroll
+              for (int c = 0; c < NC; ++c)
+                Y[m][c * nv + v] = B[m][c * nv + v] - ax[c];
+            }
+          __syncthreads();
+          const int Nc = N / 2, Vc = Nc + 1, nvc = Vc * Vc, Vf = N + 1;
+          for (int vc = t; vc < nvc; vc += nt)
+            {
+              const int I = vc % Vc, J = vc / Vc;
+              double    sres[NC];
+#pragma unroll
+              for (int c = 0; c < NC; ++c)
+                sres[c] = 0.;
+              if (!(a.mask[m + 1] && a.mask[m + 1][vc]))
+                for (int dj = -1; dj <= 1; ++dj)
+                  for (int di = -1; di <= 1; ++di)
+                    {
+                      const int fi = 2 * I + di, fj = 2 * J + dj;
+                      if (fi < 0 || fj < 0 || fi > N || fj > N)
+                        continue;
+                      const double w = (di == 0 ? 1. : .5) * (dj == 0 ? 1. : .5);
+#pragma unroll
+                      for (int c = 0; c < NC; ++c)
+                        sres[c] += w * Y[m][c * nv + fj * Vf + fi];
+                    }
+#pragma unroll
+              for (int c = 0; c < NC; ++c)
+                B[m + 1][c * nvc + vc] = sres[c];
+            }
+          __syncthreads();
+        }
+      // ---- up
+      for (int m = a.nlev - 2; m >= 0; --m)
+        {
+          const int N = a.N[m], Vf = N + 1, nv = Vf * Vf, Nc = N / 2, Vc = Nc + 1, nvc = Vc * Vc;
+          for (int v = t; v < nv; v += nt)
+            {
+              if (a.mask[m] && a.mask[m][v])
+                continue;
+              const int i = v % Vf, j = v / Vf;
+              const int I0 = i >> 1, J0 = j >> 1, I1 = (i + 1) >> 1, J1 = (j + 1) >> 1;
+#pragma unroll
+              for (int c = 0; c < NC; ++c)
+                {
+                  const double *q = X[m + 1] + c * nvc;
+                  X[m][c * nv + v] += 0.25 * (q[J0 * Vc + I0] + q[J0 * Vc + I1] + q[J1 * Vc + I0] + q[J1 * Vc + I1]);
+                }
+            }
+          __syncthreads();
+          for (int k = 0; k < nu; ++k)
+            {
+              for (int v = t; v < nv; v += nt)
+                jacobi_point<NC>(N, v, a.st[m], a.dinv[m], B[m], X[m], Y[m], omega);
+              __syncthreads();
+              double *q = X[m];
+              X[m]      = Y[m];
+              Y[m]      = q;
+            }
+        }
+      {
+        const int n = NC * (a.N[0] + 1) * (a.N[0] + 1);
+        for (int i = t; i < n; i += nt)
+          a.out[i] = X[0][i];
+      }
     }
 
     // r = b - A x
@@ -588,6 +746,38 @@ namespace pe
     double       *x0   = NC == 2 ? L.wu[0].p : L.wp[0].p;
     double       *x1   = NC == 2 ? L.wu[1].p : L.wp[1].p;
     const bool    last = l + 1 == mg.lv.size();
+    static const int fused_n = [] {
+      const char *e = getenv("PE_MG_FUSED_N"); // tuning hook: largest level handled by the single-CTA kernel
+      return e ? std::min(kFusedN, atoi(e)) : kFusedN;
+    }();
+    if (L.N <= fused_n && !last)
+      {
+        FusedArgs a{};
+        a.nlev = 0;
+        for (size_t q = l; q < mg.lv.size() && a.nlev < kFusedLev; ++q)
+          {
+            MgLevel &Q     = mg.lv[q];
+            a.N[a.nlev]    = Q.N;
+            a.st[a.nlev]   = NC == 2 ? Q.st_u.p : Q.st_p.p;
+            a.dinv[a.nlev] = NC == 2 ? Q.dinv_u.p : Q.dinv_p.p;
+            a.mask[a.nlev] = NC == 2 ? Q.mask_u.p : Q.mask_p.p;
+            ++a.nlev;
+          }
+        a.b0  = b;
+        a.out = NC == 2 ? L.wu[2].p : L.wp[2].p;
+        size_t smem = 0;
+        for (int m = 0; m < a.nlev; ++m)
+          smem += sizeof(double) * 3 * NC * (size_t)(a.N[m] + 1) * (a.N[m] + 1);
+        static bool attr_set[3] = {false, false, false};
+        if (!attr_set[NC])
+          {
+            cudaFuncSetAttribute(k_mg_fused<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+            attr_set[NC] = true;
+          }
+        k_mg_fused<NC><<<1, 1024, smem, s>>>(a, omega, nu, 24);
+        ++*launches;
+        return;
+      }
     if (last)
       {
         // coarse solve: 24 Jacobi sweeps in one launch, result straight into w[2]

@@ -298,7 +298,15 @@ namespace pe
     }
   } // namespace
 
-  BlockPrecond::~BlockPrecond() = default;
+  BlockPrecond::~BlockPrecond()
+  {
+    if (ev_fork)
+      cudaEventDestroy(ev_fork);
+    if (ev_join)
+      cudaEventDestroy(ev_join);
+    if (s2)
+      cudaStreamDestroy(s2);
+  }
 
   // ---- once per mesh: dof classes and the sub-block index lists ------------------------------------
   // Local numbering: owned rows [0, L), halo columns [L, L+H).  pat holds the owned rows with GLOBAL
@@ -411,6 +419,12 @@ namespace pe
     cudaMemsetAsync(bp.dinv.p, 0, sizeof(double) * (size_t)LH, s);
     if (cudaStreamSynchronize(s) != cudaSuccess)
       return -1;
+    if (part.world == 1 && !bp.s2)
+      {
+        cudaStreamCreateWithFlags(&bp.s2, cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&bp.ev_fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&bp.ev_join, cudaEventDisableTiming);
+      }
     bp.n_u     = part.local_off[1]; // owned displacement rows come first
     bp.n       = L;
     bp.n_pint  = (int)pint_rows.size();
@@ -450,9 +464,10 @@ namespace pe
     MgLevel      &L0 = mg.lv[0];
     const int     N  = L0.N, nv = (N + 1) * (N + 1);
     const int64_t L  = bp.n;
-    auto sub = [&](const SubCsr &S, const double *x, const double *a, const double *m, const double *b, double *out) {
+    auto sub = [&](cudaStream_t st, const SubCsr &S, const double *x, const double *a, const double *m, const double *b,
+                   double *out) {
       if (S.n_blk > 0)
-        k_sub_stream<<<(unsigned)S.n_blk, 256, 0, s>>>(S.rowblk.p, S.rows.p, S.rp.p, S.col.p, S.val.p, x, a, m, b, out);
+        k_sub_stream<<<(unsigned)S.n_blk, 256, 0, st>>>(S.rowblk.p, S.rows.p, S.rp.p, S.col.p, S.val.p, x, a, m, b, out);
       ++*launches;
     };
     // local Jacobi parts:  u: z = pinv r, t = y1 on bubbles;  p_int: t_i = dinv_i r_i
@@ -461,9 +476,18 @@ namespace pe
     *launches += 2;
     if (bp.halo)
       bp.halo(bp.comm_ctx, bp.t.p);
+    // The displacement and the pressure part touch disjoint entries of t, t2, z: on one GPU the pressure
+    // pipeline is forked onto a second stream (inside the captured CUDA graph: a parallel branch).
+    const bool   fork = bp.s2 != nullptr && !bp.halo;
+    cudaStream_t sp   = fork ? bp.s2 : s;
+    if (fork)
+      {
+        cudaEventRecord(bp.ev_fork, s);
+        cudaStreamWaitEvent(sp, bp.ev_fork, 0);
+      }
+    // ---- displacement block: bubble sweep, vertex V-cycle on the updated residual, bubble sweep
     if (bp.has_bubbles)
-      sub(bp.Avb, bp.t.p, nullptr, nullptr, nullptr, bp.t2.p);
-    // ---- displacement block: vertex V-cycle on the residual after the bubble sweep
+      sub(s, bp.Avb, bp.t.p, nullptr, nullptr, nullptr, bp.t2.p);
     k_gather_u2<<<gb(nv), 128, 0, s>>>(nv, L, mg.vdof.p, L0.mask_u.p, r, bp.has_bubbles ? bp.t2.p : nullptr, L0.bu.p);
     ++*launches;
     if (bp.allreduce)
@@ -471,43 +495,47 @@ namespace pe
     mg_vcycle(mg, 2, s, launches);
     k_scatter_u2<<<gb(nv), 128, 0, s>>>(nv, mg.vdof.p, L0.mask_u.p, L0.wu[2].p, z, bp.t.p);
     ++*launches;
+    if (bp.has_bubbles && fork)
+      sub(s, bp.Abu, bp.t.p, bp.t.p, pinv, r, z); // z_b = y1 + pinv_b (r_b - A_bb y1 - A_bv x_v),  t = (x_v, y1)
     // ---- pressure block: interior pressures eliminated exactly; on the face Schur complement
     //      F = S_ff - S_fi D_i^{-1} S_if:  Jacobi, cell-space correction (pe_cmg.h), Jacobi
     // g = r_f - S_fi D_i^{-1} r_i   -> t2 (face entries)
-    sub(bp.Sfi, bp.t.p, nullptr, nullptr, r, bp.t2.p);
+    sub(sp, bp.Sfi, bp.t.p, nullptr, nullptr, r, bp.t2.p);
     // y1 = omega dinvF g            -> t (face entries)
-    k_face_scale<<<gb(bp.Sfi.n_rows), 128, 0, s>>>(bp.Sfi.n_rows, bp.Sfi.rows.p, bp.wdinv.p, bp.t2.p, bp.t.p);
+    k_face_scale<<<gb(bp.Sfi.n_rows), 128, 0, sp>>>(bp.Sfi.n_rows, bp.Sfi.rows.p, bp.wdinv.p, bp.t2.p, bp.t.p);
     ++*launches;
     // F y = S_ff y - S_fi q,  q = D_i^{-1} S_if y  (q on the p_int entries of t, y on its face entries)
     auto apply_q = [&]() {
       if (bp.halo)
         bp.halo(bp.comm_ctx, bp.t.p);
-      sub(bp.Sif, bp.t.p, nullptr, bp.dinv.p, nullptr, bp.t.p);
+      sub(sp, bp.Sif, bp.t.p, nullptr, bp.dinv.p, nullptr, bp.t.p);
       if (bp.halo)
         bp.halo(bp.comm_ctx, bp.t.p);
     };
     apply_q();
     // res = g - F y1                -> t3 (face entries)
-    sub(bp.Spf, bp.t.p, nullptr, nullptr, bp.t2.p, bp.t3.p);
-    cmg_gather(cm, L, mg.hedge.p, mg.vedge.p, bp.t3.p, s);
+    sub(sp, bp.Spf, bp.t.p, nullptr, nullptr, bp.t2.p, bp.t3.p);
+    cmg_gather(cm, L, mg.hedge.p, mg.vedge.p, bp.t3.p, sp);
     ++*launches;
     if (bp.allreduce)
       bp.allreduce(bp.comm_ctx, cm.lv[0].b.p, N * N);
-    const double *e = cmg_vcycle(cm, s, launches);
+    const double *e = cmg_vcycle(cm, sp, launches);
     // y2 = y1 + Pi_c e              -> t (face entries)
-    cmg_scatter(cm, L, mg.hedge.p, mg.vedge.p, e, bp.t.p, bp.t.p, s);
+    cmg_scatter(cm, L, mg.hedge.p, mg.vedge.p, e, bp.t.p, bp.t.p, sp);
     ++*launches;
     apply_q();
     // z_f = y2 + omega dinvF (g - F y2)
-    sub(bp.Spf, bp.t.p, bp.t.p, bp.wdinv.p, bp.t2.p, z);
-    if (bp.has_bubbles)
-      {
-        // z_b = y1 + pinv_b (r_b - A_bb y1 - A_bv x_v),  t = (x_v, y1)
-        sub(bp.Abu, bp.t.p, bp.t.p, pinv, r, z);
-      }
+    sub(sp, bp.Spf, bp.t.p, bp.t.p, bp.wdinv.p, bp.t2.p, z);
+    if (bp.has_bubbles && !fork)
+      sub(s, bp.Abu, bp.t.p, bp.t.p, pinv, r, z);
     if (bp.halo)
       bp.halo(bp.comm_ctx, z); // face pressures of the neighbours
     // z_i = dinv_i (r_i - S_if z_f)
-    sub(bp.Sif, z, nullptr, bp.dinv.p, r, z);
+    sub(sp, bp.Sif, z, nullptr, bp.dinv.p, r, z);
+    if (fork)
+      {
+        cudaEventRecord(bp.ev_join, sp);
+        cudaStreamWaitEvent(s, bp.ev_join, 0);
+      }
   }
 } // namespace pe

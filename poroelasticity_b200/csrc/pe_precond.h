@@ -33,6 +33,9 @@ namespace pe
     DevBuf<double>  pint_area, t, t2, t3, dinv, wdinv; // wdinv = omega_F / diag(F) on the face rows
     double          omega_f = 0.7;
     const double   *values = nullptr;
+    // single GPU: the pressure pipeline runs on a forked stream beside the displacement V-cycle
+    cudaStream_t    s2 = nullptr;
+    cudaEvent_t     ev_fork = nullptr, ev_join = nullptr;
     ~BlockPrecond();
   };
   int  precond_build_structure(BlockPrecond &bp, const HostMesh &mesh, const HostDofs &d, const HostPattern &pat,
