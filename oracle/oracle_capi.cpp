@@ -1,5 +1,6 @@
 // TEST INFRASTRUCTURE ONLY -- C entry points onto the oracle for ctypes (tests/, smoke(), bench.py
 // cpu_baseline / --impl reference).  Never linked into or loaded by poroelasticity_b200.
+#include "esm_oracle.hpp"
 #include "poro_oracle.hpp"
 
 #include <chrono>
@@ -214,5 +215,85 @@ extern "C"
   orc_u01(std::uint64_t seed, std::uint64_t id, std::uint64_t k)
   {
     return u01(seed, id, k);
+  }
+
+  // ---- EltStiffMat.cc (WGDarcyEquation<2>, WG(Q2,Q2;RT[2])) -------------------------------------------
+  void *
+  orc_esm_create(int n_refine, double distort, std::uint64_t seed)
+  {
+    return new esm::Problem(esm::make_problem(n_refine, distort, seed));
+  }
+  void
+  orc_esm_destroy(void *h)
+  {
+    delete (esm::Problem *)h;
+  }
+  // sizes: [n_cells, n_vertices, n_loc, n_dofs, nnz]
+  void
+  orc_esm_sizes(void *h, std::int64_t *s)
+  {
+    esm::Problem *P = (esm::Problem *)h;
+    s[0]            = P->mesh.n_cells();
+    s[1]            = (std::int64_t)P->mesh.vx.size();
+    s[2]            = esm::kNLoc;
+    s[3]            = P->n_dofs;
+    s[4]            = (std::int64_t)P->pattern.colidx.size();
+  }
+  void
+  orc_esm_get_mesh(void *h, double *vx, double *vy, std::uint32_t *cell_vertices)
+  {
+    esm::Problem *P = (esm::Problem *)h;
+    std::copy(P->mesh.vx.begin(), P->mesh.vx.end(), vx);
+    std::copy(P->mesh.vy.begin(), P->mesh.vy.end(), vy);
+    std::copy(P->mesh.cell_vertices.begin(), P->mesh.cell_vertices.end(), cell_vertices);
+  }
+  void
+  orc_esm_get_dofs(void *h, std::uint32_t *cell_dofs)
+  {
+    esm::Problem *P = (esm::Problem *)h;
+    std::copy(P->cell_dofs.begin(), P->cell_dofs.end(), cell_dofs);
+  }
+  void
+  orc_esm_get_pattern(void *h, std::int64_t *rowptr, std::int32_t *colidx)
+  {
+    esm::Problem *P = (esm::Problem *)h;
+    std::copy(P->pattern.rowptr.begin(), P->pattern.rowptr.end(), rowptr);
+    std::copy(P->pattern.colidx.begin(), P->pattern.colidx.end(), colidx);
+  }
+  void
+  orc_esm_set_kcell(void *h, const double *k)
+  {
+    esm::Problem *P = (esm::Problem *)h;
+    std::copy(k, k + P->mesh.n_cells(), P->kcell.begin());
+  }
+  // local matrices / right-hand sides of cells [first, first+n); returns seconds
+  double
+  orc_esm_local_matrices(void *h, int first, int n, double *A, double *b)
+  {
+    esm::Problem       *P  = (esm::Problem *)h;
+    const auto          t0 = std::chrono::steady_clock::now();
+    std::vector<double> Al, bl;
+    for (int c = 0; c < n; ++c)
+      {
+        esm::assemble_cell(*P, first + c, Al, bl);
+        if (A)
+          std::copy(Al.begin(), Al.end(), A + (size_t)c * esm::kNLoc * esm::kNLoc);
+        if (b)
+          std::copy(bl.begin(), bl.end(), b + (size_t)c * esm::kNLoc);
+      }
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
+  // assemble_system: CSR values, rhs, solution (boundary values set); returns seconds
+  double
+  orc_esm_assemble(void *h, double *values, double *rhs, double *solution, int with_boundary_values)
+  {
+    esm::Problem       *P  = (esm::Problem *)h;
+    const auto          t0 = std::chrono::steady_clock::now();
+    std::vector<double> v, r, s;
+    esm::assemble(*P, v, r, s, with_boundary_values != 0);
+    std::copy(v.begin(), v.end(), values);
+    std::copy(r.begin(), r.end(), rhs);
+    std::copy(s.begin(), s.end(), solution);
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   }
 }

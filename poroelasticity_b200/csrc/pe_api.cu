@@ -312,6 +312,36 @@ namespace
         if (rc != PE_OK)
           return rc;
       }
+    if (h->dofs.element == PE_WG_Q2RT2)
+      {
+        // interpolate_boundary_values(dof_handler, 0, BoundaryValues, boundary_values, face_pressure_mask), ESM:565-571:
+        // the three FE_FaceQ(2) dofs of every pressure-Dirichlet face, support points t = 0, 1/2, 1 along the line
+        h->esm_bdofs.clear();
+        h->esm_bx.clear();
+        h->esm_by.clear();
+        std::vector<uint8_t> isb((size_t)(h->L + h->H), 0);
+        for (int64_t c = 0; c < h->mesh.n_cells; ++c)
+          for (int f = 0; f < 4; ++f)
+            if (h->mesh.face_kinds[4 * c + f] & PE_FACE_DIR_P)
+              {
+                const uint32_t v0 = h->mesh.cell_vertices[4 * c + kFaceVertex[f][0]],
+                               v1 = h->mesh.cell_vertices[4 * c + kFaceVertex[f][1]];
+                for (int k = 0; k < 3; ++k)
+                  {
+                    const int32_t l = to_local(h->dofs.cell_dofs[(size_t)c * n_loc + 3 * f + k]);
+                    if (l < 0 || l >= h->L || isb[l])
+                      continue;
+                    isb[l] = 1;
+                    h->esm_bdofs.push_back(l);
+                    h->esm_bx.push_back(h->mesh.x[v0] + .5 * k * (h->mesh.x[v1] - h->mesh.x[v0]));
+                    h->esm_by.push_back(h->mesh.y[v0] + .5 * k * (h->mesh.y[v1] - h->mesh.y[v0]));
+                  }
+              }
+        PE_CUDA(upload(h->d_esm_bdofs, h->esm_bdofs.data(), h->esm_bdofs.size(), s));
+        PE_CUDA(upload(h->d_esm_isbnd, isb.data(), isb.size(), s));
+        PE_CUDA(h->d_esm_bvals.alloc(h->esm_bdofs.size()));
+        PE_CUDA(cudaStreamSynchronize(s));
+      }
     h->device_ready = true;
     h->matrix_valid = false;
     return PE_OK;
@@ -366,8 +396,6 @@ namespace
   int
   assemble_impl(pe_handle *h, const double t, const double dt, const double *old_solution, const bool do_matrix)
   {
-    if (h->cfg.element != PE_BR1_WG && h->cfg.element != PE_CGQ1_WG)
-      return fail(h, PE_ERR_ARG, "assemble_system: element not implemented yet");
     int rc = ensure_device(h);
     if (rc != PE_OK)
       return rc;
@@ -375,6 +403,38 @@ namespace
       return fail(h, PE_ERR_ARG, "pe_assemble_rhs_only needs a previous pe_assemble_system");
     cudaStream_t s = h->stream;
     PE_CUDA(cudaEventRecord(h->ev[0], s));
+    if (h->cfg.element == PE_WG_Q2RT2)
+      {
+        // WGDarcyEquation::assemble_system, ESM:333-578 (stationary: t, dt and old_solution are not used)
+        if (h->part.world != 1)
+          return fail(h, PE_ERR_ARG, "WG_Q2RT2: one GPU only");
+        PE_CUDA(cudaMemsetAsync(h->d_values.p, 0, sizeof(double) * (size_t)h->nnz, s));
+        PE_CUDA(cudaMemsetAsync(h->d_rhs.p, 0, sizeof(double) * (size_t)(h->L + h->H), s));
+        PE_CUDA(cudaMemsetAsync(h->d_sol.p, 0, sizeof(double) * (size_t)(h->L + h->H), s)); // solution.reinit, ESM:303
+        const AsmArgs a = make_args(h, true);
+        PE_CUDA(cudaEventRecord(h->ev[1], s));
+        int nl = 0;
+        PE_CUDA(launch_esm_assemble(a, h->case_id, s, &nl));
+        // BoundaryValues::value at the support points (ESM:147), then apply_boundary_values (ESM:572-575)
+        std::vector<double> bv(h->esm_bdofs.size(), 0.);
+        if (h->case_id == PE_CASE_DARCY_COSCOS)
+          for (size_t k = 0; k < bv.size(); ++k)
+            bv[k] = std::cos(M_PI * h->esm_bx[k]) * std::cos(M_PI * h->esm_by[k]);
+        if (!bv.empty())
+          PE_CUDA(cudaMemcpyAsync(h->d_esm_bvals.p, bv.data(), sizeof(double) * bv.size(), cudaMemcpyHostToDevice, s));
+        PE_CUDA(launch_esm_boundary_values((int)bv.size(), h->d_esm_bdofs.p, h->d_esm_bvals.p, h->d_esm_isbnd.p,
+                                           h->d_rowptr.p, h->d_colidx.p, h->d_values.p, h->d_rhs.p, h->d_sol.p, s));
+        h->launches += nl + 2;
+        PE_CUDA(cudaEventRecord(h->ev[2], s));
+        PE_CUDA(cudaEventSynchronize(h->ev[2]));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev[0], h->ev[2]);
+        h->assemble_ms = ms;
+        cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]);
+        h->assemble_kernel_ms = ms;
+        h->matrix_valid       = true;
+        return PE_OK;
+      }
     if (old_solution)
       {
         rc = upload_global_vector(h, old_solution, h->d_sol.p);
@@ -1275,7 +1335,7 @@ extern "C"
       {
         PE_CUDA(cudaEventRecord(h->ev[3], s));
         double *work[3] = {h->d_w[0].p, h->d_w[1].p, h->d_w[2].p};
-        PE_CUDA(cudaMemsetAsync(h->d_sol.p, 0, sizeof(double) * n, s)); // deal.II: solution starts at 0
+        // initial guess = `solution` as left by apply_boundary_values (boundary values set, zero elsewhere)
         rc = cg_solve(c, h->d_rhs.p, h->d_sol.p, work, h->d_scal.p, h->h_scal, rel_tol, max_iterations, stats);
       }
     else
@@ -1312,8 +1372,6 @@ extern "C"
   {
     if (!h || !h->have_mesh || !out || n <= 0 || first_cell < 0 || first_cell + n > h->mesh.n_cells)
       return fail(h, PE_ERR_ARG, "pe_local_matrices: bad argument");
-    if (h->cfg.element != PE_BR1_WG && h->cfg.element != PE_CGQ1_WG)
-      return fail(h, PE_ERR_ARG, "pe_local_matrices: element not implemented yet");
     if (h->part.world != 1)
       return fail(h, PE_ERR_ARG, "pe_local_matrices: one GPU only");
     if (h->device < 0)
@@ -1367,6 +1425,17 @@ extern "C"
     PE_CUDA(o.alloc(nn * (size_t)n));
     if (rhs_out)
       PE_CUDA(ro.alloc((size_t)n_loc * n));
+    if (h->cfg.element == PE_WG_Q2RT2)
+      {
+        // the warp-per-cell kernel writes out[n][21][21] / rhs_out[n][21] directly
+        PE_CUDA(launch_esm_local_matrices(a, h->case_id, 0, n, o.p, rhs_out ? ro.p : nullptr, s));
+        ++h->launches;
+        PE_CUDA(cudaMemcpyAsync(out, o.p, sizeof(double) * nn * (size_t)n, cudaMemcpyDeviceToHost, s));
+        if (rhs_out)
+          PE_CUDA(cudaMemcpyAsync(rhs_out, ro.p, sizeof(double) * (size_t)n_loc * n, cudaMemcpyDeviceToHost, s));
+        PE_CUDA(cudaStreamSynchronize(s));
+        return PE_OK;
+      }
     const DevParams P = make_params(h, t, time_step);
     PE_CUDA(launch_local_matrices(h->cfg.element, a, P, 0, n, o.p, rhs_out ? ro.p : nullptr, s));
     ++h->launches;
@@ -1395,8 +1464,6 @@ extern "C"
   {
     if (!h || !h->have_mesh || chunk_cells <= 0 || repeats <= 0)
       return fail(h, PE_ERR_ARG, "pe_local_matrices_bench: bad argument");
-    if (h->cfg.element != PE_BR1_WG && h->cfg.element != PE_CGQ1_WG)
-      return fail(h, PE_ERR_ARG, "pe_local_matrices_bench: element not implemented yet");
     if (h->device < 0)
       return fail(h, PE_ERR_NO_DEVICE, "no hot path without a GPU");
     PE_TRY
@@ -1444,7 +1511,10 @@ extern "C"
         for (int64_t first = 0; first < nc; first += chunk_cells)
           {
             const int64_t n = std::min(chunk_cells, nc - first);
-            PE_CUDA(launch_local_matrices(h->cfg.element, a, P, first, n, o.p, nullptr, s));
+            if (h->cfg.element == PE_WG_Q2RT2)
+              PE_CUDA(launch_esm_local_matrices(a, h->case_id, first, n, o.p, nullptr, s));
+            else
+              PE_CUDA(launch_local_matrices(h->cfg.element, a, P, first, n, o.p, nullptr, s));
             ++h->launches;
             if (rep == 0)
               {

@@ -559,10 +559,10 @@ namespace pe
     const int64_t n = n_asm * n_loc;
     if (n == 0)
       return cudaSuccess;
-    uint16_t slot_h[17 * 17];
+    uint16_t slot_h[21 * 21];
     for (int i = 0; i < n_loc; ++i)
       for (int j = 0; j < n_loc; ++j)
-        slot_h[i * n_loc + j] = (uint16_t)(n_loc == 17 ? SlotMap<0>::slot(i, j) : SlotMap<1>::slot(i, j));
+        slot_h[i * n_loc + j] = (uint16_t)(n_loc == 17 ? SlotMap<0>::slot(i, j) : (n_loc == 13 ? SlotMap<1>::slot(i, j) : i * n_loc + j));
     uint16_t *slot_d = nullptr;
     cudaError_t     e      = cudaMalloc((void **)&slot_d, sizeof(uint16_t) * n_loc * n_loc);
     if (e != cudaSuccess)
@@ -580,7 +580,7 @@ namespace pe
   int
   scatter_table_words(const int n_loc)
   {
-    return n_loc == 17 ? SlotMap<0>::word_begin(3) : SlotMap<1>::word_begin(3);
+    return n_loc == 17 ? SlotMap<0>::word_begin(3) : (n_loc == 13 ? SlotMap<1>::word_begin(3) : (n_loc * n_loc + 3) / 4);
   }
 
   template <int EL>

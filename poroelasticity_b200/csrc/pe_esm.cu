@@ -1,0 +1,409 @@
+// WG(Q2,Q2;RT[2]) Darcy element of EltStiffMat.cc (WGDarcyEquation<2>): cell kernel, scatter, boundary
+// values.  Replaces EltStiffMat.cc:397-576 (RT Gram matrix + gauss_jordan 413-429, F 437-477, C = F M^-1
+// 478, the q,i,j,k,l loop 483-502, rhs 505-513, distribute_local_to_global 551-552,
+// interpolate_boundary_values + apply_boundary_values 565-576).
+//
+// Lean form.  With the contravariant Piola map w = J w^/det J both parts of the weak-gradient right-hand
+// side are independent of the cell geometry:  int phi div w = int^ phi^ div^ w^  and  int_f phi w.n =
+// int_f^ phi^ w^.n^, so F (21 x 24) is ONE constant matrix for every quadrilateral.  For K = k I the
+// K-weighted Gram matrix is k M, hence  A = k F M^-1 F^T = k Y^T Y  with  L L^T = M (Cholesky), L Y = F^T.
+// The RT[2] space is spanned by shifted Legendre products (the local matrix depends on the space only,
+// not on its basis; on a parallelogram M is block diagonal and close to diagonal).
+// One warp builds one cell: M and Y live in shared memory (9 KB per warp); ~45 kflop per cell, the only
+// compute-bound kernel of the path (AI ~ 42 flop/B against the 3.6 KB written per cell).
+#include "pe_internal.h"
+#include "pe_kernels.h"
+
+#include <cmath>
+#include <vector>
+
+namespace pe
+{
+  namespace
+  {
+    constexpr int kRt = 24, kLoc = 21, kQ = 16;
+
+    struct EsmTables
+    {
+      double F[kLoc * kRt];   // weak-gradient right-hand side, constant
+      double px[kQ * 12];     // x-carriers P_a(xi) P_b(eta), a = k % 4, b = k / 4, at the 16 Gauss points
+      double py[kQ * 12];     // y-carriers, a = k % 3, b = k / 3
+      double pv[kQ * 9];      // FE_DGQ(2) values (Lagrange at 0, 1/2, 1; x fastest)
+      double qx[kQ], qy[kQ], qw[kQ];
+    };
+    __constant__ EsmTables cT;
+
+    void
+    gauss4(double x[4], double w[4])
+    {
+      // QGauss<1>(4) on [0,1]
+      const double a = std::sqrt(3. / 7. - 2. / 7. * std::sqrt(6. / 5.)), b = std::sqrt(3. / 7. + 2. / 7. * std::sqrt(6. / 5.));
+      const double wa = (18. + std::sqrt(30.)) / 36., wb = (18. - std::sqrt(30.)) / 36.;
+      x[0] = .5 - .5 * b;
+      x[1] = .5 - .5 * a;
+      x[2] = .5 + .5 * a;
+      x[3] = .5 + .5 * b;
+      w[0] = w[3] = .5 * wb;
+      w[1] = w[2] = .5 * wa;
+    }
+    void
+    legendre01(const double x, double P[4], double dP[4])
+    {
+      const double s = 2. * x - 1.;
+      P[0]  = 1.;
+      P[1]  = s;
+      P[2]  = .5 * (3. * s * s - 1.);
+      P[3]  = .5 * (5. * s * s * s - 3. * s);
+      dP[0] = 0.;
+      dP[1] = 2.;
+      dP[2] = 6. * s;
+      dP[3] = 15. * s * s - 3.;
+    }
+    void
+    lagrange3(const double x, double L[3])
+    {
+      L[0] = 2. * (x - .5) * (x - 1.);
+      L[1] = -4. * x * (x - 1.);
+      L[2] = 2. * x * (x - .5);
+    }
+    // reference RT[2] basis: k < 12: (P_a P_b, 0), a = k%4, b = k/4;  k >= 12: (0, P_a P_b), a = (k-12)%3, b = (k-12)/3
+    void
+    rt2_ref(const double xi, const double eta, double w[kRt][2], double dv[kRt])
+    {
+      double Px[4], dPx[4], Py[4], dPy[4];
+      legendre01(xi, Px, dPx);
+      legendre01(eta, Py, dPy);
+      for (int k = 0; k < 12; ++k)
+        {
+          w[k][0] = Px[k % 4] * Py[k / 4];
+          w[k][1] = 0.;
+          dv[k]   = dPx[k % 4] * Py[k / 4];
+          w[12 + k][0] = 0.;
+          w[12 + k][1] = Px[k % 3] * Py[k / 3];
+          dv[12 + k]   = Px[k % 3] * dPy[k / 3];
+        }
+    }
+    bool tables_ready = false;
+    cudaError_t
+    upload_tables()
+    {
+      if (tables_ready)
+        return cudaSuccess;
+      static EsmTables T;
+      double           gx[4], gw[4];
+      gauss4(gx, gw);
+      for (int i = 0; i < kLoc * kRt; ++i)
+        T.F[i] = 0.;
+      for (int qj = 0; qj < 4; ++qj)
+        for (int qi = 0; qi < 4; ++qi)
+          {
+            const int    q  = qj * 4 + qi;
+            const double xi = gx[qi], eta = gx[qj], wq = gw[qi] * gw[qj];
+            T.qx[q] = xi;
+            T.qy[q] = eta;
+            T.qw[q] = wq;
+            double w[kRt][2], dv[kRt], Lx[3], Ly[3];
+            rt2_ref(xi, eta, w, dv);
+            lagrange3(xi, Lx);
+            lagrange3(eta, Ly);
+            for (int k = 0; k < 12; ++k)
+              {
+                T.px[q * 12 + k] = w[k][0];
+                T.py[q * 12 + k] = w[12 + k][1];
+              }
+            for (int j = 0; j < 3; ++j)
+              for (int i = 0; i < 3; ++i)
+                {
+                  T.pv[q * 9 + 3 * j + i] = Lx[i] * Ly[j];
+                  // interior part of F: - int phi_i div w_k                          ESM:437-452
+                  for (int k = 0; k < kRt; ++k)
+                    T.F[(12 + 3 * j + i) * kRt + k] -= Lx[i] * Ly[j] * dv[k] * wq;
+                }
+          }
+      // face part of F: + int_f phi_i (w_k . n)                                       ESM:454-476
+      for (int f = 0; f < 4; ++f)
+        for (int q = 0; q < 4; ++q)
+          {
+            const double t = gx[q], xi = f == 0 ? 0. : (f == 1 ? 1. : t), eta = f == 2 ? 0. : (f == 3 ? 1. : t);
+            const double nx = f == 0 ? -1. : (f == 1 ? 1. : 0.), ny = f == 2 ? -1. : (f == 3 ? 1. : 0.);
+            double       w[kRt][2], dv[kRt], L[3];
+            rt2_ref(xi, eta, w, dv);
+            lagrange3(t, L);
+            for (int i = 0; i < 3; ++i)
+              for (int k = 0; k < kRt; ++k)
+                T.F[(3 * f + i) * kRt + k] += L[i] * (w[k][0] * nx + w[k][1] * ny) * gw[q];
+          }
+      const cudaError_t e = cudaMemcpyToSymbol(cT, &T, sizeof(T));
+      tables_ready        = e == cudaSuccess;
+      return e;
+    }
+
+    constexpr int kWarps = 4;
+    constexpr int kMld   = 25; // leading dimension of M in shared memory (bank-conflict padding)
+
+    struct EsmArgs
+    {
+      int64_t         n_asm, first, n;
+      const double   *vx, *vy, *kcell;
+      double          k_scalar;
+      const uint32_t *cv;
+      const int32_t  *cdofs;
+      const int64_t  *rowptr;
+      const uint8_t  *off;
+      double         *values, *rhs; // assembly mode
+      double         *out, *rhs_out; // dense mode: out[n][21][21], rhs_out[n][21]
+      int             case_id;
+    };
+
+    template <bool DENSE>
+    __global__ void __launch_bounds__(kWarps * 32)
+    k_esm_cell(const EsmArgs a)
+    {
+      __shared__ double sM[kWarps][kRt * kMld];
+      __shared__ double sY[kWarps][kRt * kLoc];
+      __shared__ double  sG[kWarps][kQ * 4]; // per Gauss point: g00, g01, g11 (J^T J w / det)
+      __shared__ int64_t sRow[kWarps][kLoc]; // CSR row starts of the 21 local dofs
+      const int     warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+      const int64_t t    = (int64_t)blockIdx.x * kWarps + warp;
+      if (t >= a.n)
+        return;
+      const int64_t c = a.first + t;
+      double       *M = sM[warp], *Y = sY[warp], *G = sG[warp];
+      // ---- geometry at the Gauss points (lanes 0..15)
+      double vx[4], vy[4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+        {
+          const uint32_t vi = a.cv[(size_t)v * a.n_asm + c];
+          vx[v]             = __ldg(a.vx + vi);
+          vy[v]             = __ldg(a.vy + vi);
+        }
+      Geom geo;
+      geo.set(vx, vy);
+      double fq = 0.; // f(x_q) JxW_q of this lane's Gauss point
+      if (lane < kQ)
+        {
+          double j00, j01, j10, j11;
+          geo.jac(cT.qx[lane], cT.qy[lane], j00, j01, j10, j11);
+          const double det = j00 * j11 - j01 * j10, r = cT.qw[lane] / det;
+          G[lane * 4 + 0]  = r * (j00 * j00 + j10 * j10);
+          G[lane * 4 + 1]  = r * (j00 * j01 + j10 * j11);
+          G[lane * 4 + 2]  = r * (j01 * j01 + j11 * j11);
+          if (a.case_id == PE_CASE_DARCY_COSCOS)
+            {
+              double px, py;
+              geo.point(cT.qx[lane], cT.qy[lane], px, py);
+              fq = 2. * M_PI * M_PI * cospi(px) * cospi(py) * det * cT.qw[lane]; // RightHandSide, ESM:167
+            }
+        }
+      __syncwarp();
+      // ---- Gram matrix of the Piola-mapped basis:  M_ij = sum_q (J w^_i).(J w^_j) w_q / det       ESM:413-426
+      for (int e = lane; e < kRt * kRt; e += 32)
+        {
+          const int i = e / kRt, j = e % kRt;
+          double    s = 0.;
+          if (i < 12 && j < 12)
+            {
+#pragma unroll 4
+              for (int q = 0; q < kQ; ++q)
+                s += G[q * 4 + 0] * cT.px[q * 12 + i] * cT.px[q * 12 + j];
+            }
+          else if (i >= 12 && j >= 12)
+            {
+#pragma unroll 4
+              for (int q = 0; q < kQ; ++q)
+                s += G[q * 4 + 2] * cT.py[q * 12 + i - 12] * cT.py[q * 12 + j - 12];
+            }
+          else
+            {
+              const int ix = i < 12 ? i : j, iy = (i < 12 ? j : i) - 12;
+#pragma unroll 4
+              for (int q = 0; q < kQ; ++q)
+                s += G[q * 4 + 1] * cT.px[q * 12 + ix] * cT.py[q * 12 + iy];
+            }
+          M[i * kMld + j] = s;
+        }
+      // Y = F^T (24 x 21)
+      for (int e = lane; e < kRt * kLoc; e += 32)
+        Y[e] = cT.F[(e % kLoc) * kRt + e / kLoc];
+      __syncwarp();
+      // ---- Cholesky M = L L^T (lower triangle of M, in place); replaces gauss_jordan, ESM:429
+      for (int k = 0; k < kRt; ++k)
+        {
+          const double dkk = sqrt(M[k * kMld + k]);
+          __syncwarp();
+          if (lane == k)
+            M[k * kMld + k] = dkk;
+          if (lane > k && lane < kRt)
+            M[lane * kMld + k] /= dkk;
+          __syncwarp();
+          if (lane > k && lane < kRt)
+            {
+              const double lik = M[lane * kMld + k];
+              for (int j = k + 1; j <= lane; ++j)
+                M[lane * kMld + j] -= lik * M[j * kMld + k];
+            }
+          __syncwarp();
+        }
+      // ---- L Y = F^T: lane = column of Y (one local dof), forward substitution
+      if (lane < kLoc)
+        for (int r = 0; r < kRt; ++r)
+          {
+            double s = Y[r * kLoc + lane];
+            for (int q = 0; q < r; ++q)
+              s -= M[r * kMld + q] * Y[q * kLoc + lane];
+            Y[r * kLoc + lane] = s / M[r * kMld + r];
+          }
+      __syncwarp();
+      // ---- A = k Y^T Y  (C M_K C^T of ESM:478-502) and the right-hand side (ESM:505-513)
+      const double kperm = a.kcell ? a.kcell[c] : a.k_scalar;
+      double       bi    = 0.; // lanes 0..8: b of interior dof `lane`
+      for (int q = 0; q < kQ; ++q)
+        {
+          const double f = __shfl_sync(0xffffffffu, fq, q);
+          if (lane < 9)
+            bi += f * cT.pv[q * 9 + lane];
+        }
+      if (!DENSE && lane < kLoc)
+        sRow[warp][lane] = a.rowptr[a.cdofs[(size_t)lane * a.n_asm + c]];
+      __syncwarp();
+      for (int e = lane; e < kLoc * kLoc; e += 32)
+        {
+          const int i = e / kLoc, j = e % kLoc;
+          double    s = 0.;
+#pragma unroll 8
+          for (int r = 0; r < kRt; ++r)
+            s += Y[r * kLoc + i] * Y[r * kLoc + j];
+          s *= kperm;
+          if (DENSE)
+            a.out[(size_t)t * kLoc * kLoc + e] = s;
+          else
+            {
+              const uint32_t o = a.off[((size_t)(e >> 2) * a.n_asm + c) * 4 + (e & 3)];
+              atomicAdd(a.values + sRow[warp][i] + (o & 127u), s);
+            }
+        }
+      const double bsh = __shfl_sync(0xffffffffu, bi, lane >= 12 ? lane - 12 : 0);
+      if (DENSE)
+        {
+          if (a.rhs_out && lane < kLoc)
+            a.rhs_out[(size_t)t * kLoc + lane] = lane >= 12 ? bsh : 0.;
+        }
+      else if (lane < 9)
+        {
+          const int32_t r2 = a.cdofs[(size_t)(12 + lane) * a.n_asm + c];
+          if (bi != 0.)
+            atomicAdd(a.rhs + r2, bi);
+        }
+    }
+
+    // ---- MatrixTools::apply_boundary_values (ESM:572-575), two passes ------------------------------------
+    // pass 1: eliminate the column of every boundary dof d:  rhs_r -= a_rd g_d (free rows r), a_rd = 0
+    __global__ void
+    k_esm_bv_columns(const int n, const int32_t *__restrict__ dofs, const double *__restrict__ vals,
+                     const uint8_t *__restrict__ is_bnd, const int64_t *__restrict__ rowptr,
+                     const int32_t *__restrict__ colidx, double *__restrict__ values, double *__restrict__ rhs)
+    {
+      const int t = blockIdx.x * blockDim.x + threadIdx.x;
+      if (t >= n)
+        return;
+      const int32_t d = dofs[t];
+      const double  g = vals[t];
+      for (int64_t k = rowptr[d]; k < rowptr[d + 1]; ++k)
+        {
+          const int32_t r = colidx[k]; // symmetric pattern: the rows that couple to d
+          if (r == d)
+            continue;
+          for (int64_t k2 = rowptr[r]; k2 < rowptr[r + 1]; ++k2)
+            if (colidx[k2] == d)
+              {
+                const double v = values[k2];
+                if (!is_bnd[r] && v != 0. && g != 0.)
+                  atomicAdd(rhs + r, -v * g);
+                values[k2] = 0.;
+                break;
+              }
+        }
+    }
+    // pass 2: the rows of the boundary dofs: zero except the diagonal, rhs = diag g, solution = g
+    __global__ void
+    k_esm_bv_rows(const int n, const int32_t *__restrict__ dofs, const double *__restrict__ vals,
+                  const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx, double *__restrict__ values,
+                  double *__restrict__ rhs, double *__restrict__ sol)
+    {
+      const int t = blockIdx.x * blockDim.x + threadIdx.x;
+      if (t >= n)
+        return;
+      const int32_t d    = dofs[t];
+      double        diag = 0.;
+      for (int64_t k = rowptr[d]; k < rowptr[d + 1]; ++k)
+        if (colidx[k] == d)
+          diag = values[k];
+        else
+          values[k] = 0.;
+      rhs[d] = diag * vals[t];
+      sol[d] = vals[t];
+    }
+  } // namespace
+
+  cudaError_t
+  launch_esm_assemble(const AsmArgs &a, const int case_id, cudaStream_t s, int *n_launches)
+  {
+    cudaError_t e = upload_tables();
+    if (e != cudaSuccess || a.n_asm == 0)
+      return e;
+    EsmArgs x{};
+    x.n_asm    = a.n_asm;
+    x.first    = 0;
+    x.n        = a.n_asm;
+    x.vx       = a.vx;
+    x.vy       = a.vy;
+    x.kcell    = a.kcell;
+    x.k_scalar = a.k_scalar;
+    x.cv       = a.cv;
+    x.cdofs    = a.cdofs;
+    x.rowptr   = a.rowptr;
+    x.off      = a.off;
+    x.values   = a.values;
+    x.rhs      = a.rhs;
+    x.case_id  = case_id;
+    k_esm_cell<false><<<(unsigned)((x.n + kWarps - 1) / kWarps), kWarps * 32, 0, s>>>(x);
+    ++*n_launches;
+    return cudaGetLastError();
+  }
+
+  cudaError_t
+  launch_esm_local_matrices(const AsmArgs &a, const int case_id, const int64_t first, const int64_t n, double *out,
+                            double *rhs_out, cudaStream_t s)
+  {
+    cudaError_t e = upload_tables();
+    if (e != cudaSuccess || n == 0)
+      return e;
+    EsmArgs x{};
+    x.n_asm    = a.n_asm;
+    x.first    = first;
+    x.n        = n;
+    x.vx       = a.vx;
+    x.vy       = a.vy;
+    x.kcell    = a.kcell;
+    x.k_scalar = a.k_scalar;
+    x.cv       = a.cv;
+    x.out      = out;
+    x.rhs_out  = rhs_out;
+    x.case_id  = case_id;
+    k_esm_cell<true><<<(unsigned)((n + kWarps - 1) / kWarps), kWarps * 32, 0, s>>>(x);
+    return cudaGetLastError();
+  }
+
+  cudaError_t
+  launch_esm_boundary_values(const int n, const int32_t *dofs, const double *vals, const uint8_t *is_bnd,
+                             const int64_t *rowptr, const int32_t *colidx, double *values, double *rhs, double *sol,
+                             cudaStream_t s)
+  {
+    if (n == 0)
+      return cudaSuccess;
+    k_esm_bv_columns<<<(n + 127) / 128, 128, 0, s>>>(n, dofs, vals, is_bnd, rowptr, colidx, values, rhs);
+    k_esm_bv_rows<<<(n + 127) / 128, 128, 0, s>>>(n, dofs, vals, rowptr, colidx, values, rhs, sol);
+    return cudaGetLastError();
+  }
+} // namespace pe

@@ -155,12 +155,15 @@ namespace pe
   void
   distribute_dofs(const HostMesh &m, const int element, HostDofs &d, Partition &part)
   {
-    if (element != 0 && element != 1)
+    if (element < 0 || element > 2)
       throw std::invalid_argument("distribute_dofs: element not supported");
     const int n_loc = element_n_loc(element);
     d.element       = element;
     d.n_loc         = n_loc;
-    const int      dpl   = (element == 0) ? 2 : 1; // dofs per line: (bubble, p_face) or (p_face)
+    // dofs per line: (bubble, p_face) | (p_face) | three FE_FaceQ(2) dofs.  WG_Q2RT2 (EltStiffMat.cc:297-298)
+    // has no vertex dofs, nine FE_DGQ(2) dofs per quad and is NOT renumbered: all its dofs are kept in
+    // block 0 so that the stable block sort below is the identity.
+    const int      dpl   = (element == 0) ? 2 : (element == 1 ? 1 : 3);
     const int64_t  nc    = m.n_cells;
     const uint32_t inval = 0xffffffffu;
 
@@ -168,7 +171,7 @@ namespace pe
     std::vector<uint32_t> vdof((size_t)m.n_vertices, inval);
     EdgeTable             edges(m.n_vertices);
     std::vector<uint8_t>  block_of;
-    block_of.reserve((size_t)m.n_vertices * 2 + (size_t)nc * (2 * dpl + 1) + 16);
+    block_of.reserve((size_t)m.n_vertices * 2 + (size_t)nc * (2 * dpl + 9) + 16);
     d.cell_dofs.resize((size_t)nc * n_loc);
     // first-pass counter at the partition boundaries (cells nc*r/world)
     std::vector<int64_t> fp_at((size_t)part.world + 1, 0);
@@ -180,7 +183,7 @@ namespace pe
           fp_at[nb++] = next;
         const uint32_t *cv = &m.cell_vertices[4 * (size_t)c];
         uint32_t       *cd = &d.cell_dofs[(size_t)c * n_loc];
-        for (int v = 0; v < 4; ++v)
+        for (int v = 0; v < 4 && element != 2; ++v)
           {
             uint32_t &vd = vdof[cv[v]];
             if (vd == inval)
@@ -201,20 +204,40 @@ namespace pe
               {
                 e = next;
                 next += dpl;
-                if (element == 0)
-                  block_of.push_back(0); // bubble: FE_BernardiRaugel is non-primitive -> component 0
-                block_of.push_back(2);   // FE_FaceQ(0)
+                if (element == 2)
+                  for (int k = 0; k < 3; ++k)
+                    block_of.push_back(0);
+                else
+                  {
+                    if (element == 0)
+                      block_of.push_back(0); // bubble: FE_BernardiRaugel is non-primitive -> component 0
+                    block_of.push_back(2);   // FE_FaceQ(0)
+                  }
               }
             if (element == 0)
               {
                 cd[8 + 2 * f]     = e;
                 cd[8 + 2 * f + 1] = e + 1;
               }
-            else
+            else if (element == 1)
               cd[8 + f] = e;
+            else
+              for (int k = 0; k < 3; ++k)
+                cd[3 * f + k] = e + k;
           }
-        cd[n_loc - 1] = next++;
-        block_of.push_back(1); // FE_DGQ(0)
+        if (element == 2)
+          {
+            for (int k = 0; k < 9; ++k)
+              {
+                cd[12 + k] = next++;
+                block_of.push_back(0);
+              }
+          }
+        else
+          {
+            cd[n_loc - 1] = next++;
+            block_of.push_back(1); // FE_DGQ(0)
+          }
       }
     while (nb <= part.world)
       fp_at[nb++] = next;

@@ -136,6 +136,13 @@ struct pe_handle
   int              mg_nu = 2;
   double           precond_ms = 0.;
 
+  // WG_Q2RT2 (EltStiffMat.cc): boundary dofs of interpolate_boundary_values (ESM:565-571), physical support points
+  std::vector<int32_t> esm_bdofs;
+  std::vector<double>  esm_bx, esm_by;
+  pe::DevBuf<int32_t>  d_esm_bdofs;
+  pe::DevBuf<double>   d_esm_bvals;
+  pe::DevBuf<uint8_t>  d_esm_isbnd;
+
   // multi-GPU
   ncclComm                 *comm = nullptr;
   std::vector<pe::HaloPeer> peers;

@@ -41,6 +41,14 @@ namespace pe
                                double *k, cudaStream_t s);
   cudaError_t launch_sum(const double *x, size_t n, double *out, cudaStream_t s);
 
+  // ---- WG(Q2,Q2;RT[2]) element of EltStiffMat.cc (pe_esm.cu)
+  cudaError_t launch_esm_assemble(const AsmArgs &a, int case_id, cudaStream_t s, int *n_launches);
+  cudaError_t launch_esm_local_matrices(const AsmArgs &a, int case_id, int64_t first, int64_t n, double *out, double *rhs_out,
+                                        cudaStream_t s);
+  cudaError_t launch_esm_boundary_values(int n, const int32_t *dofs, const double *vals, const uint8_t *is_bnd,
+                                         const int64_t *rowptr, const int32_t *colidx, double *values, double *rhs,
+                                         double *sol, cudaStream_t s);
+
   // ---- solver kernels (pe_solver.cu)
   cudaError_t launch_spmv(int64_t n_rows, const int64_t *rowptr, const int32_t *colidx, const double *values,
                           const double *x, double *y, cudaStream_t s);

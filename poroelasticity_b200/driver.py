@@ -12,7 +12,7 @@ import math
 import numpy as np
 
 from . import _capi as capi
-from ._capi import (PE_BR1_WG, PE_CGQ1_WG, PE_WG_Q2RT2, PE_CASE_ZERO, PE_CASE_COSCOS, PE_FACE_DIR_U,
+from ._capi import (PE_BR1_WG, PE_CGQ1_WG, PE_WG_Q2RT2, PE_CASE_ZERO, PE_CASE_COSCOS, PE_CASE_DARCY_COSCOS, PE_FACE_DIR_U,
                     PE_FACE_DIR_P, PE_FACE_NEU_U, PoroElasError, pe_config, pe_sizes, pe_solve_stats, ptr)
 
 
@@ -276,3 +276,35 @@ class PoroElas_CGQ1_WG(BiotSystem):
     def __init__(self, **kw):
         super().__init__(**kw)
         self.time_step = 1.0 / 1024  # CGQ1:825
+
+
+class WGDarcyEquation(BiotSystem):
+    """WGDarcyEquation<2> of EltStiffMat.cc: WG(Q2,Q2;RT[2]) Darcy problem, stationary.
+    make_grid (ESM:242-289), setup_system (294-326), assemble_system (333-578), solve (583-590), run (985-996)."""
+    element = PE_WG_Q2RT2
+
+    def __init__(self, **kw):
+        super().__init__(**kw)
+        self.rel_tol, self.max_iterations = 1e-8, 1000  # SolverControl(1000, 1e-8 * ||rhs||), ESM:585
+
+    def make_grid(self, n_refine=1, distort=0.0, seed=12345):
+        # hyper_cube(0,1) + refine_global(1); every boundary face carries the pressure Dirichlet value
+        self._ck(self.L.pe_make_unit_square(self.h, n_refine, distort, seed, PE_FACE_DIR_P))
+
+    def setup_system(self):
+        self._ck(self.L.pe_distribute_dofs(self.h))
+        self._ck(self.L.pe_make_sparsity_pattern(self.h))
+        return self.sizes()
+
+    def assemble_system(self, t=0.0, old_solution=None, time_step=1.0):
+        self._ck(self.L.pe_assemble_system(self.h, 0.0, 1.0, None))
+
+    def solve(self, want_solution=True, check=True):
+        return self.solve_time_step(want_solution=want_solution, check=check)
+
+    def run(self, n_refine=1):
+        self.make_grid(n_refine)
+        self.setup_system()
+        self.set_case(PE_CASE_DARCY_COSCOS)
+        self.assemble_system()
+        return self.solve()

@@ -145,3 +145,71 @@ class Oracle:
         import scipy.sparse as sp
         rp, ci = self.pattern()
         return sp.csr_matrix((values, ci, rp), shape=(self.n_dofs, self.n_dofs))
+
+
+class EsmOracle:
+    """EltStiffMat.cc (WGDarcyEquation<2>) on the unit square: oracle/esm_oracle.hpp."""
+
+    def __init__(self, n_refine, distort=0.0, seed=12345):
+        self.L = lib()
+        L = self.L
+        L.orc_esm_create.restype = C.c_void_p
+        L.orc_esm_create.argtypes = [C.c_int, C.c_double, C.c_uint64]
+        L.orc_esm_destroy.argtypes = [C.c_void_p]
+        L.orc_esm_sizes.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_esm_get_mesh.argtypes = [C.c_void_p] * 4
+        L.orc_esm_get_dofs.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_esm_get_pattern.argtypes = [C.c_void_p] * 3
+        L.orc_esm_set_kcell.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_esm_local_matrices.restype = C.c_double
+        L.orc_esm_local_matrices.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_esm_assemble.restype = C.c_double
+        L.orc_esm_assemble.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        self.h = L.orc_esm_create(n_refine, distort, seed)
+        s = np.zeros(5, np.int64)
+        L.orc_esm_sizes(self.h, _p(s))
+        self.n_cells, self.n_vertices, self.n_loc, self.n_dofs, self.nnz = [int(x) for x in s]
+
+    def __del__(self):
+        try:
+            self.L.orc_esm_destroy(self.h)
+        except Exception:
+            pass
+
+    def mesh(self):
+        vx, vy = np.zeros(self.n_vertices), np.zeros(self.n_vertices)
+        cv = np.zeros((self.n_cells, 4), np.uint32)
+        self.L.orc_esm_get_mesh(self.h, _p(vx), _p(vy), _p(cv))
+        return vx, vy, cv
+
+    def cell_dofs(self):
+        cd = np.zeros((self.n_cells, self.n_loc), np.uint32)
+        self.L.orc_esm_get_dofs(self.h, _p(cd))
+        return cd
+
+    def pattern(self):
+        rp = np.zeros(self.n_dofs + 1, np.int64)
+        ci = np.zeros(self.nnz, np.int32)
+        self.L.orc_esm_get_pattern(self.h, _p(rp), _p(ci))
+        return rp, ci
+
+    def set_kcell(self, k):
+        k = np.ascontiguousarray(k, np.float64)
+        assert k.size == self.n_cells
+        self.L.orc_esm_set_kcell(self.h, _p(k))
+
+    def local_matrices(self, first, n):
+        A = np.zeros((n, self.n_loc, self.n_loc))
+        b = np.zeros((n, self.n_loc))
+        sec = self.L.orc_esm_local_matrices(self.h, first, n, _p(A), _p(b))
+        return A, b, sec
+
+    def assemble(self, with_boundary_values=True):
+        v, r, s = np.zeros(self.nnz), np.zeros(self.n_dofs), np.zeros(self.n_dofs)
+        sec = self.L.orc_esm_assemble(self.h, _p(v), _p(r), _p(s), 1 if with_boundary_values else 0)
+        return v, r, s, sec
+
+    def csr(self, values):
+        import scipy.sparse as sp
+        rp, ci = self.pattern()
+        return sp.csr_matrix((values, ci, rp), shape=(self.n_dofs, self.n_dofs))
