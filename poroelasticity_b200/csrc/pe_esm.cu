@@ -163,6 +163,16 @@ namespace pe
       __shared__ double sY[kWarps][kRt * kLoc];
       __shared__ double  sG[kWarps][kQ * 4]; // per Gauss point: g00, g01, g11 (J^T J w / det)
       __shared__ int64_t sRow[kWarps][kLoc]; // CSR row starts of the 21 local dofs
+      // reference tables: constant memory serialises lane-dependent addresses, shared memory does not
+      __shared__ double sPx[kQ * 12], sPy[kQ * 12], sFt[kRt * kLoc];
+      for (int e = threadIdx.x; e < kQ * 12; e += blockDim.x)
+        {
+          sPx[e] = cT.px[e];
+          sPy[e] = cT.py[e];
+        }
+      for (int e = threadIdx.x; e < kRt * kLoc; e += blockDim.x)
+        sFt[e] = cT.F[(e % kLoc) * kRt + e / kLoc]; // F^T (24 x 21)
+      __syncthreads();
       const int     warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
       const int64_t t    = (int64_t)blockIdx.x * kWarps + warp;
       if (t >= a.n)
@@ -206,26 +216,26 @@ namespace pe
             {
 #pragma unroll 4
               for (int q = 0; q < kQ; ++q)
-                s += G[q * 4 + 0] * cT.px[q * 12 + i] * cT.px[q * 12 + j];
+                s += G[q * 4 + 0] * sPx[q * 12 + i] * sPx[q * 12 + j];
             }
           else if (i >= 12 && j >= 12)
             {
 #pragma unroll 4
               for (int q = 0; q < kQ; ++q)
-                s += G[q * 4 + 2] * cT.py[q * 12 + i - 12] * cT.py[q * 12 + j - 12];
+                s += G[q * 4 + 2] * sPy[q * 12 + i - 12] * sPy[q * 12 + j - 12];
             }
           else
             {
               const int ix = i < 12 ? i : j, iy = (i < 12 ? j : i) - 12;
 #pragma unroll 4
               for (int q = 0; q < kQ; ++q)
-                s += G[q * 4 + 1] * cT.px[q * 12 + ix] * cT.py[q * 12 + iy];
+                s += G[q * 4 + 1] * sPx[q * 12 + ix] * sPy[q * 12 + iy];
             }
           M[i * kMld + j] = s;
         }
       // Y = F^T (24 x 21)
       for (int e = lane; e < kRt * kLoc; e += 32)
-        Y[e] = cT.F[(e % kLoc) * kRt + e / kLoc];
+        Y[e] = sFt[e];
       __syncwarp();
       // ---- Cholesky M = L L^T (lower triangle of M, in place); replaces gauss_jordan, ESM:429
       for (int k = 0; k < kRt; ++k)
