@@ -26,6 +26,12 @@ namespace pe
 {
   namespace
   {
+    // Stencil coefficients are STORED in single precision and used in double-precision arithmetic: the
+    // V-cycle is a preconditioner (any fixed symmetric positive definite operator serves MINRES), its
+    // smoothers are bound by the HBM traffic of the coefficients (ncu: 6.0 TB/s), and rounding the
+    // entries of a symmetric matrix keeps it symmetric.  288 -> 144 bytes per vertex and sweep.
+    using stencil_t = MgLevel::stencil_t;
+
     __device__ __forceinline__ uint32_t
     part1by1(uint32_t x)
     {
@@ -50,7 +56,7 @@ namespace pe
     __global__ void
     k_mg_assemble(const int N, const double *__restrict__ vx, const double *__restrict__ vy,
                   const double *__restrict__ kc, const double k_scalar, const uint8_t *__restrict__ mask,
-                  const double c_a /* mu | dt */, const double c_b /* lambda | gamma */, double *__restrict__ st,
+                  const double c_a /* mu | dt */, const double c_b /* lambda | gamma */, stencil_t *__restrict__ st,
                   double *__restrict__ dinv)
     {
       const int V = N + 1, nv = V * V;
@@ -148,12 +154,14 @@ namespace pe
       for (int k = 0; k < 9; ++k)
 #pragma unroll
         for (int e = 0; e < NC * NC; ++e)
-          st[(size_t)(k * NC * NC + e) * nv + v] = acc[k][e];
+          st[(size_t)(k * NC * NC + e) * nv + v] = (stencil_t)acc[k][e];
       if (NC == 1)
-        dinv[v] = acc[4][0] != 0. ? 1. / acc[4][0] : 0.;
+        dinv[v] = acc[4][0] != 0. ? 1. / (double)(stencil_t)acc[4][0] : 0.;
       else
         {
-          const double a00 = acc[4][0], a01 = acc[4][1 % (NC * NC)], a10 = acc[4][2 % (NC * NC)], a11 = acc[4][3 % (NC * NC)];
+          // the diagonal block as it is stored (rounded), so that the smoother inverts the stored operator
+          const double a00 = (stencil_t)acc[4][0], a01 = (stencil_t)acc[4][1 % (NC * NC)], a10 = (stencil_t)acc[4][2 % (NC * NC)],
+                       a11 = (stencil_t)acc[4][3 % (NC * NC)];
           const double d   = a00 * a11 - a01 * a10;
           const double id  = d != 0. ? 1. / d : 0.;
           dinv[v]                  = a11 * id;
@@ -166,7 +174,7 @@ namespace pe
     // (A x)[v] for the 9-point block stencil; x is [NC][nv]
     template <int NC>
     __device__ __forceinline__ void
-    stencil_row(const int N, const int v, const double *__restrict__ st, const double *__restrict__ x, double out[NC])
+    stencil_row(const int N, const int v, const stencil_t *__restrict__ st, const double *__restrict__ x, double out[NC])
     {
       const int V = N + 1, nv = V * V;
       const int i = v % V, j = v / V;
@@ -190,14 +198,14 @@ namespace pe
             for (int c = 0; c < NC; ++c)
 #pragma unroll
               for (int d = 0; d < NC; ++d)
-                out[c] += st[(size_t)(k * NC * NC + c * NC + d) * nv + v] * xv[d];
+                out[c] += (double)st[(size_t)(k * NC * NC + c * NC + d) * nv + v] * xv[d];
           }
     }
 
     // xo = xi + omega Dinv (b - A xi)     (xi == nullptr: xo = omega Dinv b)
     template <int NC>
     __global__ void
-    k_mg_jacobi(const int N, const double *__restrict__ st, const double *__restrict__ dinv,
+    k_mg_jacobi(const int N, const stencil_t *__restrict__ st, const double *__restrict__ dinv,
                 const double *__restrict__ b, const double *__restrict__ xi, double *__restrict__ xo, const double omega)
     {
       const int nv = (N + 1) * (N + 1);
@@ -232,7 +240,7 @@ namespace pe
     // (ping-pong in shared memory); replaces 24 tiny launches per V-cycle.
     template <int NC>
     __global__ void __launch_bounds__(1024)
-    k_mg_coarse(const int N, const double *__restrict__ st, const double *__restrict__ dinv,
+    k_mg_coarse(const int N, const stencil_t *__restrict__ st, const double *__restrict__ dinv,
                 const double *__restrict__ b, double *__restrict__ xo, const double omega, const int sweeps)
     {
       extern __shared__ double sm[]; // 2 * NC * nv
@@ -277,14 +285,15 @@ namespace pe
     {
       int            nlev;
       int            N[kFusedLev];
-      const double  *st[kFusedLev], *dinv[kFusedLev];
+      const stencil_t *st[kFusedLev];
+      const double    *dinv[kFusedLev];
       const uint8_t *mask[kFusedLev];
       const double  *b0;
       double        *out;
     };
     template <int NC>
     __device__ __forceinline__ void
-    jacobi_point(const int N, const int v, const double *__restrict__ st, const double *__restrict__ dinv, const double *b,
+    jacobi_point(const int N, const int v, const stencil_t *__restrict__ st, const double *__restrict__ dinv, const double *b,
                  const double *xi, double *xo, const double omega)
     {
       const int nv = (N + 1) * (N + 1);
@@ -429,7 +438,7 @@ namespace pe
     // r = b - A x
     template <int NC>
     __global__ void
-    k_mg_residual(const int N, const double *__restrict__ st, const double *__restrict__ b,
+    k_mg_residual(const int N, const stencil_t *__restrict__ st, const double *__restrict__ b,
                   const double *__restrict__ x, double *__restrict__ r)
     {
       const int nv = (N + 1) * (N + 1);
@@ -740,7 +749,7 @@ namespace pe
   {
     MgLevel      &L    = mg.lv[l];
     const int     nv   = (L.N + 1) * (L.N + 1);
-    const double *st   = NC == 2 ? L.st_u.p : L.st_p.p;
+    const stencil_t *st = NC == 2 ? L.st_u.p : L.st_p.p;
     const double *dinv = NC == 2 ? L.dinv_u.p : L.dinv_p.p;
     double       *b    = NC == 2 ? L.bu.p : L.bp.p;
     double       *x0   = NC == 2 ? L.wu[0].p : L.wp[0].p;

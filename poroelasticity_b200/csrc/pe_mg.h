@@ -11,7 +11,9 @@ namespace pe
   struct MgLevel
   {
     int             N = 0; // cells per side on this level
-    DevBuf<double>  x, y, kc, st_u, st_p, dinv_u, dinv_p, wu[3], wp[3], bu, bp;
+    using stencil_t = float; // storage type of the 9-point block stencils (arithmetic stays FP64, pe_mg.cu)
+    DevBuf<stencil_t> st_u, st_p;
+    DevBuf<double>    x, y, kc, dinv_u, dinv_p, wu[3], wp[3], bu, bp;
     DevBuf<uint8_t> mask_u, mask_p;
   };
   struct MgHierarchy

@@ -70,13 +70,13 @@ namespace pe
     // compact copy of the sub-block values, once per solve: val[k] = values[src[k]]
     __global__ void
     k_sub_gather_values(const int64_t n, const uint32_t *__restrict__ src, const uint8_t *__restrict__ neg,
-                        const double *__restrict__ values, double *__restrict__ val)
+                        const double *__restrict__ values, SubCsr::value_t *__restrict__ val)
     {
       const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
       if (k < n)
         {
           const double v = __ldg(values + src[k]);
-          val[k]         = (neg && neg[k]) ? -v : v;
+          val[k]         = (SubCsr::value_t)((neg && neg[k]) ? -v : v);
         }
     }
     // on the owned face rows: y1 = omega_F dinvF g  (first Jacobi sweep on F from zero)
@@ -105,7 +105,7 @@ namespace pe
     constexpr int kSubNnz = 2048;
     __global__ void __launch_bounds__(256)
     k_sub_stream(const int32_t *__restrict__ rowblk, const int32_t *__restrict__ rows, const int32_t *__restrict__ rp,
-                 const int32_t *__restrict__ col, const double *__restrict__ val, const double *x, const double *a,
+                 const int32_t *__restrict__ col, const SubCsr::value_t *__restrict__ val, const double *x, const double *a,
                  const double *__restrict__ m, const double *b, double *out)
     {
       __shared__ double prod[kSubNnz];
@@ -124,7 +124,7 @@ namespace pe
       for (int u = 0; u < PER; ++u)
         {
           const int i = threadIdx.x + u * 256;
-          vv[u]       = i < n ? __ldcs(val + k0 + i) : 0.;
+          vv[u]       = i < n ? (double)__ldcs(val + k0 + i) : 0.;
         }
 #pragma unroll
       for (int u = 0; u < PER; ++u)
