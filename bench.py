@@ -298,8 +298,12 @@ def main():
     roof = None
     if spmv_ms:
         ach = spmv_bytes / (spmv_ms * 1e-3) / 1e9
+        # DRAM bytes of one launch from the ncu --set full capture of this kernel on this workload
+        # (profiles/r01g_ncu_full_summary.md: 2.082 GB read + 65.4 MB written); other workloads: not captured
+        traffic = 2.147e9 if (world == 1 and args.n_refine == 10) else None
         roof = {"bound": "hbm", "kernel": "k_spmv_stream (three-field solver matrix, %d rows, %d entries)" % (rows_owned, nnz_owned), "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                "traffic": None, "bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_ms, "peak_source": peak_src}
+                "traffic": traffic, "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01g_ncu_full_summary.md",
+                "bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_ms, "peak_source": peak_src}
     line = {"metric": METRIC, "value": n_cells * args.steps / dev_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
