@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <climits>
 #include <exception>
@@ -26,7 +27,10 @@ namespace pe
   int  comm_setup_halo(pe_handle *h);
   void comm_halo_exchange(void *ctx, double *x);
   void comm_halo_exchange3(void *ctx, double *x);
+  void comm_exchange_rows(void *ctx, double *p, int64_t row_len, int n_comp, int64_t comp_stride, int64_t a, int64_t b);
+  void comm_allgather_rows(void *ctx, double *p, int64_t row_len, int n_comp, int64_t comp_stride, const int64_t *bounds);
   void comm_allreduce(void *ctx, double *v, int n);
+  void comm_allreduce2(void *ctx, const double *in, double *out, int n);
   int  comm_unique_id(uint8_t id[128]);
 } // namespace pe
 
@@ -612,6 +616,20 @@ namespace
         h->cmg = new CellMg;
         if (cmg_build_topology(*h->cmg, h->mesh, s) < 0)
           return 1;
+        // multi-GPU: the fine grid levels are distributed in row slabs (PE_MG_REPLICATED=1: every rank runs the
+        // complete V-cycles, the first multi-GPU version, kept for A/B measurements)
+        if (h->part.world > 1 && !getenv("PE_MG_REPLICATED"))
+          {
+            GridComm gc;
+            gc.rank           = h->part.rank;
+            gc.world          = h->part.world;
+            gc.ctx            = h;
+            gc.exchange_rows  = comm_exchange_rows;
+            gc.allgather_rows = comm_allgather_rows;
+            mg_set_comm(*h->mg, gc);
+            if (h->cmg->ready)
+              cmg_set_comm(*h->cmg, gc);
+          }
       }
     if (h->use_mg && h->mg->ready && !h->bp)
       {
@@ -620,8 +638,9 @@ namespace
           return 1;
         if (h->part.world > 1)
           {
-            h->bp->halo      = comm_halo_exchange;
-            h->bp->allreduce = comm_allreduce;
+            h->bp->halo       = comm_halo_exchange;
+            h->bp->allreduce  = comm_allreduce;
+            h->bp->allreduce2 = comm_allreduce2;
             h->bp->comm_ctx  = h;
           }
       }

@@ -202,10 +202,11 @@ namespace pe
     __global__ void
     k_cmg_jacobi(const int N, const double *__restrict__ tE, const double *__restrict__ tN,
                  const double *__restrict__ sig, const double *__restrict__ b, const double *__restrict__ xi,
-                 const double *__restrict__ xc, const double over, double *__restrict__ xo, const double omega)
+                 const double *__restrict__ xc, const double over, double *__restrict__ xo, const double omega,
+                 const int c_begin, const int c_end)
     {
-      const int t = blockIdx.x * blockDim.x + threadIdx.x;
-      if (t >= N * N)
+      const int t = c_begin + blockIdx.x * blockDim.x + threadIdx.x;
+      if (t >= c_end)
         return;
       const int i = t % N, j = t / N;
       double    diag, ax, xs;
@@ -230,11 +231,11 @@ namespace pe
     __global__ void
     k_cmg_restrict(const int Nf, const double *__restrict__ tE, const double *__restrict__ tN,
                    const double *__restrict__ sig, const double *__restrict__ b, const double *__restrict__ x,
-                   double *__restrict__ bc)
+                   double *__restrict__ bc, const int c_begin, const int c_end)
     {
       const int Nc = Nf >> 1;
-      const int t  = blockIdx.x * blockDim.x + threadIdx.x;
-      if (t >= Nc * Nc)
+      const int t  = c_begin + blockIdx.x * blockDim.x + threadIdx.x;
+      if (t >= c_end)
         return;
       const int I = t % Nc, J = t / Nc;
       double    s = 0.;
@@ -363,38 +364,40 @@ namespace pe
       return (d >= 0 && d < L) ? x[d] : 0.;
     }
     __global__ void
-    k_cmg_gather(const int N, const int64_t L, const int32_t *__restrict__ hedge, const int32_t *__restrict__ vedge,
-                 const double *__restrict__ wv_lo, const double *__restrict__ wv_hi, const double *__restrict__ wh_lo,
-                 const double *__restrict__ wh_hi, const double *__restrict__ res, double *__restrict__ rc)
+    k_cmg_gather(const int N, const CellBox bx, const int64_t L, const int32_t *__restrict__ hedge,
+                 const int32_t *__restrict__ vedge, const double *__restrict__ wv_lo, const double *__restrict__ wv_hi,
+                 const double *__restrict__ wh_lo, const double *__restrict__ wh_hi, const double *__restrict__ res,
+                 double *__restrict__ rc)
     {
-      const int t = blockIdx.x * blockDim.x + threadIdx.x;
-      if (t >= N * N)
+      const int bw = bx.i1 - bx.i0, q = blockIdx.x * blockDim.x + threadIdx.x;
+      if (q >= bw * (bx.j1 - bx.j0))
         return;
-      const int i = t % N, j = t / N, V = N + 1;
+      const int i = bx.i0 + q % bw, j = bx.j0 + q / bw, V = N + 1, t = j * N + i;
       const int ew = j * V + i, ee = ew + 1, es = j * N + i, en = es + N;
       rc[t] = wv_hi[ew] * owned_val(res, vedge[ew], L) + wv_lo[ee] * owned_val(res, vedge[ee], L) +
               wh_hi[es] * owned_val(res, hedge[es], L) + wh_lo[en] * owned_val(res, hedge[en], L);
     }
     __global__ void
-    k_cmg_scatter(const int N, const int64_t L, const int32_t *__restrict__ hedge, const int32_t *__restrict__ vedge,
-                  const double *__restrict__ wv_lo, const double *__restrict__ wv_hi, const double *__restrict__ wh_lo,
-                  const double *__restrict__ wh_hi, const double *__restrict__ e, const double *__restrict__ y1,
-                  double *__restrict__ y)
+    k_cmg_scatter(const int N, const CellBox bx, const int64_t L, const int32_t *__restrict__ hedge,
+                  const int32_t *__restrict__ vedge, const double *__restrict__ wv_lo, const double *__restrict__ wv_hi,
+                  const double *__restrict__ wh_lo, const double *__restrict__ wh_hi, const double *__restrict__ e,
+                  const double *__restrict__ y1, double *__restrict__ y)
     {
       const int V = N + 1;
       const int t = blockIdx.x * blockDim.x + threadIdx.x;
-      const int n_v = V * N, n_h = N * V;
+      const int bw = bx.i1 - bx.i0, bh = bx.j1 - bx.j0;
+      const int n_v = (bw + 1) * bh, n_h = bw * (bh + 1); // vertical / horizontal edges of the box
       int       d;
       double    c;
       if (t < n_v)
         {
-          const int i = t % V, j = t / V;
-          d           = vedge[t];
-          c           = (i > 0 ? wv_lo[t] * e[j * N + i - 1] : 0.) + (i < N ? wv_hi[t] * e[j * N + i] : 0.);
+          const int i = bx.i0 + t % (bw + 1), j = bx.j0 + t / (bw + 1), q = j * V + i;
+          d           = vedge[q];
+          c           = (i > 0 ? wv_lo[q] * e[j * N + i - 1] : 0.) + (i < N ? wv_hi[q] * e[j * N + i] : 0.);
         }
       else if (t < n_v + n_h)
         {
-          const int q = t - n_v, i = q % N, j = q / N;
+          const int u = t - n_v, i = bx.i0 + u % bw, j = bx.j0 + u / bw, q = j * N + i;
           d           = hedge[q];
           c           = (j > 0 ? wh_lo[q] * e[(j - 1) * N + i] : 0.) + (j < N ? wh_hi[q] * e[j * N + i] : 0.);
         }
@@ -521,20 +524,43 @@ namespace pe
   }
 
   void
-  cmg_gather(CellMg &cm, const int64_t L, const int32_t *hedge, const int32_t *vedge, const double *res, cudaStream_t s)
+  cmg_gather(CellMg &cm, const int64_t L, const int32_t *hedge, const int32_t *vedge, const double *res, const CellBox &box,
+             double *out, cudaStream_t s)
   {
-    const int N = cm.N0;
-    k_cmg_gather<<<g1(N * N), 128, 0, s>>>(N, L, hedge, vedge, cm.wv_lo.p, cm.wv_hi.p, cm.wh_lo.p, cm.wh_hi.p, res,
-                                           cm.lv[0].b.p);
+    const int N = cm.N0, n = (box.i1 - box.i0) * (box.j1 - box.j0);
+    if (n > 0)
+      k_cmg_gather<<<g1(n), 128, 0, s>>>(N, box, L, hedge, vedge, cm.wv_lo.p, cm.wv_hi.p, cm.wh_lo.p, cm.wh_hi.p, res, out);
   }
 
   void
   cmg_scatter(CellMg &cm, const int64_t L, const int32_t *hedge, const int32_t *vedge, const double *e, const double *y1,
-              double *y, cudaStream_t s)
+              double *y, const CellBox &box, cudaStream_t s)
   {
-    const int N = cm.N0;
-    k_cmg_scatter<<<g1(2 * N * (N + 1)), 128, 0, s>>>(N, L, hedge, vedge, cm.wv_lo.p, cm.wv_hi.p, cm.wh_lo.p, cm.wh_hi.p, e,
-                                                      y1, y);
+    const int N = cm.N0, bw = box.i1 - box.i0, bh = box.j1 - box.j0, n = (bw + 1) * bh + bw * (bh + 1);
+    if (n > 0)
+      k_cmg_scatter<<<g1(n), 128, 0, s>>>(N, box, L, hedge, vedge, cm.wv_lo.p, cm.wv_hi.p, cm.wh_lo.p, cm.wh_hi.p, e, y1, y);
+  }
+
+  void
+  cmg_set_comm(CellMg &cm, const GridComm &gc)
+  {
+    cm.gc     = gc;
+    cm.n_dist = 0;
+    cm.bounds.clear();
+    if (gc.world <= 1 || !gc.exchange_rows || !gc.allgather_rows)
+      return;
+    const int W = gc.world;
+    for (int l = 0; l < cm.n_fine; ++l)
+      {
+        const int N = cm.lv[(size_t)l].N;
+        if (N % (2 * W) != 0 || N / W < 8 || N <= 64)
+          break;
+        std::vector<int64_t> bd((size_t)W + 1);
+        for (int r = 0; r <= W; ++r)
+          bd[(size_t)r] = (int64_t)N * r / W;
+        cm.bounds.push_back(bd);
+        ++cm.n_dist;
+      }
   }
 
   const double *
@@ -544,22 +570,47 @@ namespace pe
     const double  om = cm.omega, ov = cm.over;
     const int     nu = std::max(1, cm.nu);
     std::vector<double *> cur((size_t)nf + 1, nullptr);
+    // slab of this rank on level l (all rows on replicated levels)
+    auto slab = [&](const int l, int64_t &ra, int64_t &rb) {
+      const bool dist = l < cm.n_dist;
+      ra              = dist ? cm.bounds[(size_t)l][(size_t)cm.gc.rank] : 0;
+      rb              = dist ? cm.bounds[(size_t)l][(size_t)cm.gc.rank + 1] : cm.lv[(size_t)l].N;
+      return dist;
+    };
     // ---- down
     for (int l = 0; l < nf; ++l)
       {
         CmgLevel &L = cm.lv[(size_t)l];
-        const int n = L.N * L.N;
-        double   *x0 = L.x0.p, *x1 = L.x1.p;
-        k_cmg_jacobi<<<g1(n), 128, 0, s>>>(L.N, L.tE.p, L.tN.p, L.sig.p, L.b.p, nullptr, nullptr, 0., x0, om);
+        int64_t   ra, rb;
+        const bool dist = slab(l, ra, rb);
+        const int  c0 = (int)(ra * L.N), c1 = (int)(rb * L.N), n = c1 - c0;
+        auto exchange = [&](double *p) {
+          if (dist)
+            cm.gc.exchange_rows(cm.gc.ctx, p, L.N, 1, 0, ra, rb);
+        };
+        double *x0 = L.x0.p, *x1 = L.x1.p;
+        k_cmg_jacobi<<<g1(n), 128, 0, s>>>(L.N, L.tE.p, L.tN.p, L.sig.p, L.b.p, nullptr, nullptr, 0., x0, om, c0, c1);
         for (int k = 1; k < nu; ++k)
           {
-            k_cmg_jacobi<<<g1(n), 128, 0, s>>>(L.N, L.tE.p, L.tN.p, L.sig.p, L.b.p, x0, nullptr, 0., x1, om);
+            exchange(x0);
+            k_cmg_jacobi<<<g1(n), 128, 0, s>>>(L.N, L.tE.p, L.tN.p, L.sig.p, L.b.p, x0, nullptr, 0., x1, om, c0, c1);
             std::swap(x0, x1);
           }
+        exchange(x0);
         cur[(size_t)l] = x0;
         CmgLevel &C    = cm.lv[(size_t)l + 1];
-        k_cmg_restrict<<<g1(C.N * C.N), 128, 0, s>>>(L.N, L.tE.p, L.tN.p, L.sig.p, L.b.p, x0, C.b.p);
+        const int64_t ca = ra / 2, cb = rb / 2; // slab bounds are even
+        k_cmg_restrict<<<g1((int)((cb - ca) * C.N)), 128, 0, s>>>(L.N, L.tE.p, L.tN.p, L.sig.p, L.b.p, x0, C.b.p,
+                                                                  (int)(ca * C.N), (int)(cb * C.N));
         *launches += nu + 1;
+        if (dist && l + 1 >= cm.n_dist)
+          {
+            // first replicated level: complete right-hand side on every rank
+            std::vector<int64_t> cbnd((size_t)cm.gc.world + 1);
+            for (int r = 0; r <= cm.gc.world; ++r)
+              cbnd[(size_t)r] = cm.bounds[(size_t)l][(size_t)r] / 2;
+            cm.gc.allgather_rows(cm.gc.ctx, C.b.p, C.N, 1, 0, cbnd.data());
+          }
       }
     // ---- coarse levels: one launch
     {
@@ -572,17 +623,32 @@ namespace pe
     for (int l = nf - 1; l >= 0; --l)
       {
         CmgLevel &L = cm.lv[(size_t)l];
-        const int n = L.N * L.N;
-        double   *x0 = cur[(size_t)l], *x1 = x0 == L.x0.p ? L.x1.p : L.x0.p;
-        k_cmg_jacobi<<<g1(n), 128, 0, s>>>(L.N, L.tE.p, L.tN.p, L.sig.p, L.b.p, x0, cur[(size_t)l + 1], ov, x1, om);
+        int64_t   ra, rb;
+        const bool dist = slab(l, ra, rb);
+        const int  c0 = (int)(ra * L.N), c1 = (int)(rb * L.N), n = c1 - c0;
+        auto exchange = [&](double *p) {
+          if (dist)
+            cm.gc.exchange_rows(cm.gc.ctx, p, L.N, 1, 0, ra, rb);
+        };
+        double *x0 = cur[(size_t)l], *x1 = x0 == L.x0.p ? L.x1.p : L.x0.p;
+        // x0 still carries its halo rows from the way down; the coarse result carries its own (below)
+        k_cmg_jacobi<<<g1(n), 128, 0, s>>>(L.N, L.tE.p, L.tN.p, L.sig.p, L.b.p, x0, cur[(size_t)l + 1], ov, x1, om, c0, c1);
         std::swap(x0, x1);
         for (int k = 1; k < nu; ++k)
           {
-            k_cmg_jacobi<<<g1(n), 128, 0, s>>>(L.N, L.tE.p, L.tN.p, L.sig.p, L.b.p, x0, nullptr, 0., x1, om);
+            exchange(x0);
+            k_cmg_jacobi<<<g1(n), 128, 0, s>>>(L.N, L.tE.p, L.tN.p, L.sig.p, L.b.p, x0, nullptr, 0., x1, om, c0, c1);
             std::swap(x0, x1);
           }
         cur[(size_t)l] = x0;
         *launches += nu;
+        if (dist)
+          {
+            if (l == 0)
+              cm.gc.allgather_rows(cm.gc.ctx, x0, L.N, 1, 0, cm.bounds[0].data());
+            else
+              exchange(x0); // the finer level corrects from my rows and one halo row on each side
+          }
       }
     return cur[0];
   }

@@ -44,7 +44,12 @@ namespace pe
     DevBuf<uint8_t> dir_v, dir_h; // 1: the face carries a pressure Dirichlet value
     double          omega = 0.7, over = 2.0;
     int             nu    = 2;
+    // multi-GPU: the first n_dist levels are distributed in row slabs of cells, bounds[l][r] = first cell row of rank r
+    GridComm                          gc;
+    int                               n_dist = 0;
+    std::vector<std::vector<int64_t>> bounds;
   };
+  void cmg_set_comm(CellMg &cm, const GridComm &gc);
 
   // 0 = built, 1 = mesh has no refine_global hierarchy, -1 = CUDA error
   int  cmg_build_topology(CellMg &cm, const HostMesh &mesh, cudaStream_t s);
@@ -52,10 +57,12 @@ namespace pe
   int  cmg_assemble(CellMg &cm, const double *vx, const double *vy, const double *kcell_morton, double k_scalar, double dt,
                     double gamma, cudaStream_t s, int64_t *launches);
   // rc = Pi_c^T res (owned faces only: d in [0, L)), res indexed through the edge -> dof maps
-  void cmg_gather(CellMg &cm, int64_t L, const int32_t *hedge, const int32_t *vedge, const double *res, cudaStream_t s);
+  // (only the cells / edges of `box` are visited; out = the level-0 right-hand side or a zero-padded local copy)
+  void cmg_gather(CellMg &cm, int64_t L, const int32_t *hedge, const int32_t *vedge, const double *res, const CellBox &box,
+                  double *out, cudaStream_t s);
   // lv[0].b -> approximate T^{-1} b in lv[0].x0 (result pointer returned)
   const double *cmg_vcycle(CellMg &cm, cudaStream_t s, int64_t *launches);
   // y[d] = y1[d] + (Pi_c e)[d] on owned faces
   void cmg_scatter(CellMg &cm, int64_t L, const int32_t *hedge, const int32_t *vedge, const double *e, const double *y1,
-                   double *y, cudaStream_t s);
+                   double *y, const CellBox &box, cudaStream_t s);
 } // namespace pe

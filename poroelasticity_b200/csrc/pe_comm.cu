@@ -299,6 +299,64 @@ namespace pe
     ncclGroupEnd();
   }
 
+  // ---- row slabs of the multigrid grids (GridComm hooks) ------------------------------------------------
+  void
+  comm_exchange_rows(void *ctx, double *p, int64_t row_len, int n_comp, int64_t comp_stride, int64_t a, int64_t b)
+  {
+    pe_handle *h = (pe_handle *)ctx;
+    CommState *c = cs(h);
+    if (!c)
+      return;
+    const int    me = h->part.rank, W = h->part.world;
+    cudaStream_t s  = h->stream;
+    ncclGroupStart();
+    for (int k = 0; k < n_comp; ++k)
+      {
+        double *q = p + (size_t)k * comp_stride;
+        if (me > 0)
+          {
+            ncclSend(q + a * row_len, (size_t)row_len, ncclDouble, me - 1, c->comm, s);
+            ncclRecv(q + (a - 1) * row_len, (size_t)row_len, ncclDouble, me - 1, c->comm, s);
+          }
+        if (me < W - 1)
+          {
+            ncclSend(q + (b - 1) * row_len, (size_t)row_len, ncclDouble, me + 1, c->comm, s);
+            ncclRecv(q + b * row_len, (size_t)row_len, ncclDouble, me + 1, c->comm, s);
+          }
+      }
+    ncclGroupEnd();
+  }
+  void
+  comm_allgather_rows(void *ctx, double *p, int64_t row_len, int n_comp, int64_t comp_stride, const int64_t *bounds)
+  {
+    pe_handle *h = (pe_handle *)ctx;
+    CommState *c = cs(h);
+    if (!c)
+      return;
+    const int    W = h->part.world;
+    cudaStream_t s = h->stream;
+    ncclGroupStart();
+    for (int q = 0; q < W; ++q)
+      for (int k = 0; k < n_comp; ++k)
+        {
+          double      *x = p + (size_t)k * comp_stride + bounds[q] * row_len;
+          const size_t n = (size_t)((bounds[q + 1] - bounds[q]) * row_len);
+          if (n)
+            ncclBroadcast(x, x, n, ncclDouble, q, c->comm, s);
+        }
+    ncclGroupEnd();
+  }
+
+  void
+  comm_allreduce2(void *ctx, const double *in, double *out, int n)
+  {
+    pe_handle *h = (pe_handle *)ctx;
+    CommState *c = cs(h);
+    if (!c)
+      return;
+    ncclAllReduce(in, out, (size_t)n, ncclDouble, ncclSum, c->comm, h->stream);
+  }
+
   void
   comm_allreduce(void *ctx, double *v, int n)
   {

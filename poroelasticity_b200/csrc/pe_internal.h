@@ -69,6 +69,26 @@ namespace pe
     }
   };
 
+  // Row-slab distribution of the multigrid grids (lexicographic, rows contiguous): rank r owns rows
+  // [bounds[r], bounds[r+1]) of every distributed level and keeps one halo row on each side, exchanged in
+  // place with the two neighbouring ranks.  Hooks are filled by pe_comm.cu (NCCL); world == 1: unused.
+  struct GridComm
+  {
+    int   rank = 0, world = 1;
+    void *ctx  = nullptr;
+    // send my first / last owned row (a, b-1) down / up, receive rows a-1 and b; n_comp arrays comp_stride apart
+    void (*exchange_rows)(void *ctx, double *p, int64_t row_len, int n_comp, int64_t comp_stride, int64_t a, int64_t b) = nullptr;
+    // every rank receives the slabs [bounds[q], bounds[q+1]) of all ranks q (in place)
+    void (*allgather_rows)(void *ctx, double *p, int64_t row_len, int n_comp, int64_t comp_stride, const int64_t *bounds) = nullptr;
+  };
+
+  // bounding box (cell indices, half open) of the cells a rank assembles on a structured mesh: the grid <-> Biot
+  // vector transfer kernels of the preconditioner only visit this part of the grids
+  struct CellBox
+  {
+    int i0 = 0, i1 = 0, j0 = 0, j1 = 0;
+  };
+
   struct HaloPeer
   {
     int                  rank = -1;

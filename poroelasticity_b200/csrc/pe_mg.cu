@@ -206,11 +206,12 @@ namespace pe
     template <int NC>
     __global__ void
     k_mg_jacobi(const int N, const stencil_t *__restrict__ st, const double *__restrict__ dinv,
-                const double *__restrict__ b, const double *__restrict__ xi, double *__restrict__ xo, const double omega)
+                const double *__restrict__ b, const double *__restrict__ xi, double *__restrict__ xo, const double omega,
+                const int v_begin, const int v_end)
     {
       const int nv = (N + 1) * (N + 1);
-      const int v  = blockIdx.x * blockDim.x + threadIdx.x;
-      if (v >= nv)
+      const int v  = v_begin + blockIdx.x * blockDim.x + threadIdx.x;
+      if (v >= v_end)
         return;
       double r[NC];
       if (xi)
@@ -439,11 +440,11 @@ namespace pe
     template <int NC>
     __global__ void
     k_mg_residual(const int N, const stencil_t *__restrict__ st, const double *__restrict__ b,
-                  const double *__restrict__ x, double *__restrict__ r)
+                  const double *__restrict__ x, double *__restrict__ r, const int v_begin, const int v_end)
     {
       const int nv = (N + 1) * (N + 1);
-      const int v  = blockIdx.x * blockDim.x + threadIdx.x;
-      if (v >= nv)
+      const int v  = v_begin + blockIdx.x * blockDim.x + threadIdx.x;
+      if (v >= v_end)
         return;
       double ax[NC];
       stencil_row<NC>(N, v, st, x, ax);
@@ -456,11 +457,11 @@ namespace pe
     template <int NC>
     __global__ void
     k_mg_restrict(const int Nf, const double *__restrict__ r, double *__restrict__ bc,
-                  const uint8_t *__restrict__ mask_c)
+                  const uint8_t *__restrict__ mask_c, const int v_begin, const int v_end)
     {
       const int Nc = Nf / 2, Vc = Nc + 1, nvc = Vc * Vc, Vf = Nf + 1, nvf = Vf * Vf;
-      const int vc = blockIdx.x * blockDim.x + threadIdx.x;
-      if (vc >= nvc)
+      const int vc = v_begin + blockIdx.x * blockDim.x + threadIdx.x;
+      if (vc >= v_end)
         return;
       const int I = vc % Vc, J = vc / Vc;
       double    s[NC];
@@ -489,11 +490,11 @@ namespace pe
     template <int NC>
     __global__ void
     k_mg_prolong_add(const int Nf, const double *__restrict__ xc, double *__restrict__ xf,
-                     const uint8_t *__restrict__ mask_f)
+                     const uint8_t *__restrict__ mask_f, const int v_begin, const int v_end)
     {
       const int Nc = Nf / 2, Vc = Nc + 1, nvc = Vc * Vc, Vf = Nf + 1, nvf = Vf * Vf;
-      const int vf = blockIdx.x * blockDim.x + threadIdx.x;
-      if (vf >= nvf)
+      const int vf = v_begin + blockIdx.x * blockDim.x + threadIdx.x;
+      if (vf >= v_end)
         return;
       if (mask_f && mask_f[vf])
         return;
@@ -796,37 +797,95 @@ namespace pe
         ++*launches;
         return;
       }
-    const int     pre  = nu;
+    // ---- this level: distributed in row slabs (multi-GPU, fine levels) or complete
+    const int     V    = L.N + 1;
+    const bool    dist = (int)l < mg.n_dist;
+    const int64_t ra = dist ? mg.bounds[l][(size_t)mg.gc.rank] : 0, rb = dist ? mg.bounds[l][(size_t)mg.gc.rank + 1] : V;
+    const int     v0 = (int)(ra * V), v1 = (int)(rb * V), nloc = v1 - v0;
+    auto exchange = [&](double *p) {
+      if (dist)
+        mg.gc.exchange_rows(mg.gc.ctx, p, V, NC, nv, ra, rb);
+    };
+    const int pre = nu;
     // pre-smoothing from x = 0
-    k_mg_jacobi<NC><<<g1(nv), 128, 0, s>>>(L.N, st, dinv, b, nullptr, x0, omega);
+    k_mg_jacobi<NC><<<g1(nloc), 128, 0, s>>>(L.N, st, dinv, b, nullptr, x0, omega, v0, v1);
     ++*launches;
     for (int k = 1; k < pre; ++k)
       {
-        k_mg_jacobi<NC><<<g1(nv), 128, 0, s>>>(L.N, st, dinv, b, x0, x1, omega);
+        exchange(x0);
+        k_mg_jacobi<NC><<<g1(nloc), 128, 0, s>>>(L.N, st, dinv, b, x0, x1, omega, v0, v1);
         ++*launches;
         std::swap(x0, x1);
       }
-    if (!last)
-      {
-        MgLevel  &C   = mg.lv[l + 1];
-        const int nvc = (C.N + 1) * (C.N + 1);
-        k_mg_residual<NC><<<g1(nv), 128, 0, s>>>(L.N, st, b, x0, x1);
-        k_mg_restrict<NC><<<g1(nvc), 128, 0, s>>>(L.N, x1, NC == 2 ? C.bu.p : C.bp.p, NC == 2 ? C.mask_u.p : C.mask_p.p);
-        *launches += 2;
-        vcycle<NC>(mg, l + 1, omega, nu, s, launches);
-        k_mg_prolong_add<NC><<<g1(nv), 128, 0, s>>>(L.N, NC == 2 ? C.wu[2].p : C.wp[2].p, x0,
-                                                     NC == 2 ? L.mask_u.p : L.mask_p.p);
-        ++*launches;
-        for (int k = 0; k < nu; ++k)
-          {
-            k_mg_jacobi<NC><<<g1(nv), 128, 0, s>>>(L.N, st, dinv, b, x0, x1, omega);
-            ++*launches;
-            std::swap(x0, x1);
-          }
-      }
+    {
+      MgLevel      &C      = mg.lv[l + 1];
+      const int     Vc     = C.N + 1, nvc = Vc * Vc;
+      const bool    dist_c = (int)l + 1 < mg.n_dist;
+      // coarse rows whose centre row 2J lies in my slab
+      const int64_t ca = dist ? (ra + 1) / 2 : 0, cb = dist ? (rb + 1) / 2 : Vc;
+      double       *bc = NC == 2 ? C.bu.p : C.bp.p;
+      exchange(x0);
+      k_mg_residual<NC><<<g1(nloc), 128, 0, s>>>(L.N, st, b, x0, x1, v0, v1);
+      exchange(x1);
+      k_mg_restrict<NC><<<g1((int)((cb - ca) * Vc)), 128, 0, s>>>(L.N, x1, bc, NC == 2 ? C.mask_u.p : C.mask_p.p,
+                                                                  (int)(ca * Vc), (int)(cb * Vc));
+      *launches += 2;
+      if (dist && !dist_c)
+        {
+          // first replicated level: every rank needs the complete right-hand side
+          std::vector<int64_t> cbnd((size_t)mg.gc.world + 1);
+          for (int r = 0; r <= mg.gc.world; ++r)
+            cbnd[(size_t)r] = (mg.bounds[l][(size_t)r] + 1) / 2;
+          mg.gc.allgather_rows(mg.gc.ctx, bc, Vc, NC, nvc, cbnd.data());
+        }
+      vcycle<NC>(mg, l + 1, omega, nu, s, launches);
+      k_mg_prolong_add<NC><<<g1(nloc), 128, 0, s>>>(L.N, NC == 2 ? C.wu[2].p : C.wp[2].p, x0,
+                                                    NC == 2 ? L.mask_u.p : L.mask_p.p, v0, v1);
+      ++*launches;
+      for (int k = 0; k < nu; ++k)
+        {
+          exchange(x0);
+          k_mg_jacobi<NC><<<g1(nloc), 128, 0, s>>>(L.N, st, dinv, b, x0, x1, omega, v0, v1);
+          ++*launches;
+          std::swap(x0, x1);
+        }
+    }
     // result of this level -> w[2]
     double *out = NC == 2 ? L.wu[2].p : L.wp[2].p;
-    cudaMemcpyAsync(out, x0, sizeof(double) * (size_t)NC * nv, cudaMemcpyDeviceToDevice, s);
+    for (int c = 0; c < NC; ++c)
+      cudaMemcpyAsync(out + (size_t)c * nv + v0, x0 + (size_t)c * nv + v0, sizeof(double) * (size_t)nloc,
+                      cudaMemcpyDeviceToDevice, s);
+    if (dist)
+      {
+        if (l == 0)
+          mg.gc.allgather_rows(mg.gc.ctx, out, V, NC, nv, mg.bounds[0].data()); // every rank scatters its own vertices
+        else
+          exchange(out); // the finer level prolongates from my rows and one halo row on each side
+      }
+  }
+
+  void
+  mg_set_comm(MgHierarchy &mg, const GridComm &gc)
+  {
+    mg.gc     = gc;
+    mg.n_dist = 0;
+    mg.bounds.clear();
+    if (gc.world <= 1 || !gc.exchange_rows || !gc.allgather_rows)
+      return;
+    const int W = gc.world;
+    for (size_t l = 0; l + 1 < mg.lv.size(); ++l)
+      {
+        const int N = mg.lv[l].N;
+        // distributed while every rank keeps >= 8 cell rows and the level is above the fused single-CTA levels
+        if (N % (2 * W) != 0 || N / W < 8 || N <= 64)
+          break;
+        std::vector<int64_t> bd((size_t)W + 1);
+        for (int r = 0; r < W; ++r)
+          bd[(size_t)r] = (int64_t)N * r / W;
+        bd[(size_t)W] = N + 1;
+        mg.bounds.push_back(bd);
+        ++mg.n_dist;
+      }
   }
 
   void

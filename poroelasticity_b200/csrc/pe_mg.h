@@ -24,6 +24,11 @@ namespace pe
     DevBuf<int32_t>      vdof, pint, hedge, vedge;
     double               omega = 0.6, theta = 1.0;
     int                  nu    = 2;
+    // multi-GPU: the first n_dist levels are distributed in row slabs (bounds[l][r] = first vertex row of
+    // rank r on level l), the coarser ones run replicated on every rank
+    GridComm                          gc;
+    int                               n_dist = 0;
+    std::vector<std::vector<int64_t>> bounds;
     ~MgHierarchy();
   };
   // 0 = built, 1 = no hierarchy for this mesh (fallback: diagonal preconditioner), -1 = CUDA error
@@ -35,5 +40,7 @@ namespace pe
                    double gamma, cudaStream_t s, int64_t *launches, bool with_p = true);
   // V-cycle on level-0 right-hand side lv[0].bu (nc = 2) / lv[0].bp (nc = 1); result in lv[0].wu[2] / wp[2]
   void mg_vcycle(MgHierarchy &mg, int nc, cudaStream_t s, int64_t *launches);
+  // choose the distributed levels for gc.world ranks (call after mg_build_topology)
+  void mg_set_comm(MgHierarchy &mg, const GridComm &gc);
   void mg_apply_add(MgHierarchy &mg, const double *r, double *z, cudaStream_t s, int64_t *launches);
 } // namespace pe

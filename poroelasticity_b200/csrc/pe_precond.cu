@@ -19,8 +19,10 @@
 #include "pe_internal.h"
 #include "pe_mg.h"
 #include "pe_precond.h"
+#include "pe_timer.h"
 
 #include <algorithm>
+#include <climits>
 #include <functional>
 
 namespace pe
@@ -161,12 +163,14 @@ namespace pe
     }
     // b_u[v] = r[d] - t2[d]
     __global__ void
-    k_gather_u2(const int nv, const int64_t L, const int32_t *__restrict__ vdof, const uint8_t *__restrict__ mask,
-                const double *__restrict__ r, const double *__restrict__ t2, double *__restrict__ bu)
+    k_gather_u2(const int nv, const int V, const CellBox bx, const int64_t L, const int32_t *__restrict__ vdof,
+                const uint8_t *__restrict__ mask, const double *__restrict__ r, const double *__restrict__ t2,
+                double *__restrict__ bu)
     {
-      const int v = blockIdx.x * blockDim.x + threadIdx.x;
-      if (v >= nv)
+      const int bw = bx.i1 - bx.i0 + 1, t = blockIdx.x * blockDim.x + threadIdx.x;
+      if (t >= bw * (bx.j1 - bx.j0 + 1))
         return;
+      const int v = (bx.j0 + t / bw) * V + bx.i0 + t % bw;
       const int  d       = vdof[v];
       const bool m       = (mask && mask[v]) || d < 0 || d >= L; // only the owner contributes (all-reduced)
       bu[v]              = m ? 0. : r[d] - (t2 ? t2[d] : 0.);
@@ -174,11 +178,15 @@ namespace pe
     }
     // z[d] = t[d] = x_v on free vertex dofs
     __global__ void
-    k_scatter_u2(const int nv, const int32_t *__restrict__ vdof, const uint8_t *__restrict__ mask,
-                 const double *__restrict__ xu, double *__restrict__ z, double *__restrict__ t)
+    k_scatter_u2(const int nv, const int V, const CellBox bx, const int32_t *__restrict__ vdof,
+                 const uint8_t *__restrict__ mask, const double *__restrict__ xu, double *__restrict__ z,
+                 double *__restrict__ t)
     {
-      const int v = blockIdx.x * blockDim.x + threadIdx.x;
-      if (v >= nv || (mask && mask[v]))
+      const int bw = bx.i1 - bx.i0 + 1, q = blockIdx.x * blockDim.x + threadIdx.x;
+      if (q >= bw * (bx.j1 - bx.j0 + 1))
+        return;
+      const int v = (bx.j0 + q / bw) * V + bx.i0 + q % bw;
+      if (mask && mask[v])
         return;
       const int d = vdof[v];
       if (d < 0)
@@ -419,6 +427,32 @@ namespace pe
     cudaMemsetAsync(bp.dinv.p, 0, sizeof(double) * (size_t)LH, s);
     if (cudaStreamSynchronize(s) != cudaSuccess)
       return -1;
+    {
+      // bounding box of the assembled cells (lexicographic vertex ids: cell (ci, cj) has vertex 0 = cj * V + ci)
+      const int V = (1 << mesh.n_refine) + 1;
+      CellBox   bx{INT32_MAX, 0, INT32_MAX, 0};
+      for (const int64_t c : part.asm_cells)
+        {
+          const uint32_t v0 = mesh.cell_vertices[4 * (size_t)c];
+          const int      ci = (int)(v0 % V), cj = (int)(v0 / V);
+          bx.i0 = std::min(bx.i0, ci);
+          bx.i1 = std::max(bx.i1, ci + 1);
+          bx.j0 = std::min(bx.j0, cj);
+          bx.j1 = std::max(bx.j1, cj + 1);
+        }
+      if (part.asm_cells.empty())
+        bx = CellBox{0, 0, 0, 0};
+      bp.box = bx;
+      if (part.world > 1)
+        {
+          const size_t nvv = (size_t)V * V, ncc = (size_t)(V - 1) * (V - 1);
+          if (bp.bu_local.alloc(2 * nvv) != cudaSuccess || bp.rc_local.alloc(ncc) != cudaSuccess)
+            return -1;
+          cudaMemsetAsync(bp.bu_local.p, 0, sizeof(double) * 2 * nvv, s);
+          cudaMemsetAsync(bp.rc_local.p, 0, sizeof(double) * ncc, s);
+          cudaStreamSynchronize(s);
+        }
+    }
     if (part.world == 1 && !bp.s2)
       {
         cudaStreamCreateWithFlags(&bp.s2, cudaStreamNonBlocking);
@@ -476,6 +510,7 @@ namespace pe
     *launches += 2;
     if (bp.halo)
       bp.halo(bp.comm_ctx, bp.t.p);
+    PE_MARK(s, "precond: local Jacobi + halo");
     // The displacement and the pressure part touch disjoint entries of t, t2, z: on one GPU the pressure
     // pipeline is forked onto a second stream (inside the captured CUDA graph: a parallel branch).
     const bool   fork = bp.s2 != nullptr && !bp.halo;
@@ -488,12 +523,17 @@ namespace pe
     // ---- displacement block: bubble sweep, vertex V-cycle on the updated residual, bubble sweep
     if (bp.has_bubbles)
       sub(s, bp.Avb, bp.t.p, nullptr, nullptr, nullptr, bp.t2.p);
-    k_gather_u2<<<gb(nv), 128, 0, s>>>(nv, L, mg.vdof.p, L0.mask_u.p, r, bp.has_bubbles ? bp.t2.p : nullptr, L0.bu.p);
+    const int nbox_v = (bp.box.i1 - bp.box.i0 + 1) * (bp.box.j1 - bp.box.j0 + 1);
+    k_gather_u2<<<gb(nbox_v), 128, 0, s>>>(nv, N + 1, bp.box, L, mg.vdof.p, L0.mask_u.p, r, bp.has_bubbles ? bp.t2.p : nullptr,
+                                           bp.allreduce2 ? bp.bu_local.p : L0.bu.p);
     ++*launches;
-    if (bp.allreduce)
-      bp.allreduce(bp.comm_ctx, L0.bu.p, 2 * nv);
+    PE_MARK(s, "precond: A_vb + vertex gather");
+    if (bp.allreduce2)
+      bp.allreduce2(bp.comm_ctx, bp.bu_local.p, L0.bu.p, 2 * nv);
+    PE_MARK(s, "precond: all-reduce vertex rhs");
     mg_vcycle(mg, 2, s, launches);
-    k_scatter_u2<<<gb(nv), 128, 0, s>>>(nv, mg.vdof.p, L0.mask_u.p, L0.wu[2].p, z, bp.t.p);
+    PE_MARK(s, "precond: vertex V-cycle");
+    k_scatter_u2<<<gb(nbox_v), 128, 0, s>>>(nv, N + 1, bp.box, mg.vdof.p, L0.mask_u.p, L0.wu[2].p, z, bp.t.p);
     ++*launches;
     if (bp.has_bubbles && fork)
       sub(s, bp.Abu, bp.t.p, bp.t.p, pinv, r, z); // z_b = y1 + pinv_b (r_b - A_bb y1 - A_bv x_v),  t = (x_v, y1)
@@ -515,13 +555,16 @@ namespace pe
     apply_q();
     // res = g - F y1                -> t3 (face entries)
     sub(sp, bp.Spf, bp.t.p, nullptr, nullptr, bp.t2.p, bp.t3.p);
-    cmg_gather(cm, L, mg.hedge.p, mg.vedge.p, bp.t3.p, sp);
+    cmg_gather(cm, L, mg.hedge.p, mg.vedge.p, bp.t3.p, bp.box, bp.allreduce2 ? bp.rc_local.p : cm.lv[0].b.p, sp);
     ++*launches;
-    if (bp.allreduce)
-      bp.allreduce(bp.comm_ctx, cm.lv[0].b.p, N * N);
+    PE_MARK(sp, "precond: face Schur products");
+    if (bp.allreduce2)
+      bp.allreduce2(bp.comm_ctx, bp.rc_local.p, cm.lv[0].b.p, N * N);
+    PE_MARK(sp, "precond: all-reduce cell rhs");
     const double *e = cmg_vcycle(cm, sp, launches);
+    PE_MARK(sp, "precond: cell V-cycle");
     // y2 = y1 + Pi_c e              -> t (face entries)
-    cmg_scatter(cm, L, mg.hedge.p, mg.vedge.p, e, bp.t.p, bp.t.p, sp);
+    cmg_scatter(cm, L, mg.hedge.p, mg.vedge.p, e, bp.t.p, bp.t.p, bp.box, sp);
     ++*launches;
     apply_q();
     // z_f = y2 + omega dinvF (g - F y2)
@@ -532,6 +575,7 @@ namespace pe
       bp.halo(bp.comm_ctx, z); // face pressures of the neighbours
     // z_i = dinv_i (r_i - S_if z_f)
     sub(sp, bp.Sif, z, nullptr, bp.dinv.p, r, z);
+    PE_MARK(sp, "precond: face Schur products");
     if (fork)
       {
         cudaEventRecord(bp.ev_join, sp);

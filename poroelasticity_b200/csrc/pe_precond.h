@@ -30,7 +30,10 @@ namespace pe
     // multi-GPU hooks (null on one GPU)
     void (*halo)(void *ctx, double *x)             = nullptr;
     void (*allreduce)(void *ctx, double *v, int n) = nullptr;
+    void (*allreduce2)(void *ctx, const double *in, double *out, int n) = nullptr; // out of place
     void *comm_ctx                                 = nullptr;
+    CellBox         box;                 // cells this rank assembles (all cells on one GPU)
+    DevBuf<double>  bu_local, rc_local;  // multi-GPU: this rank's contribution to the grid right-hand sides (zero outside box)
     SubCsr          Abu, Avb, Sif, Sfi, Spf; // Spf: p_face rows x [-S_fi | S_ff]
     DevBuf<uint8_t> cls;
     DevBuf<int32_t> pint_rows;

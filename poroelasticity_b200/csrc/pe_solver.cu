@@ -11,6 +11,7 @@
 #include "pe_internal.h"
 #include "pe_kernels.h"
 #include "pe_solver.h"
+#include "pe_timer.h"
 
 #include <cmath>
 #include <cstdio>
@@ -625,15 +626,19 @@ namespace pe
     double    eta_target  = rel_tol * eta0;
     // one MINRES iteration with the vector roles (v, v_old, z, z_new, w, w_old) as given
     auto iteration = [&](double *v_, double *vo_, double *z_, double *zn_, double *w_, double *wo_) {
+      PE_MARK(s, "minres: vector updates");
       if (c.halo)
         c.halo(c.halo_ctx, z_);
+      PE_MARK(s, "minres: halo exchange (K3)");
       spmv_signed(c, z_, p, &st->d1);
+      PE_MARK(s, "minres: SpMV K3");
       if (c.allreduce)
         c.allreduce(c.halo_ctx, &st->d1, 1);
       k_minres_scalars_a<<<1, 1, 0, s>>>(st);
       if (c.precond_apply)
         {
           k_minres_lanczos<<<g, 256, 0, s>>>(L, st, p, v_, vo_, nullptr, zn_, nullptr, c.gap);
+          PE_MARK(s, "minres: vector updates");
           c.precond_apply(c.precond_ctx, vo_ /* = v_new */, zn_);
           k_dot<<<g, 256, 0, s>>>(L, zn_, vo_, &st->d2, c.gap);
         }
@@ -732,6 +737,7 @@ namespace pe
     stats->iterations    = it;
     stats->converged     = (stats->residual_norm <= rel_tol * bnorm * (1. + 1e-12)) || bnorm == 0.;
     stats->spmv_count    = spmv + it;
+    PhaseTimer::get().flush(0, it);
     return 0;
   }
 

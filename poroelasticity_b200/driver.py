@@ -176,9 +176,10 @@ class BiotSystem:
         self._ck(self.L.pe_get_rhs(self.h, ptr(r)))
         return r
 
-    def solve_time_step(self, want_solution=True, check=True):
+    def solve_time_step(self, want_solution=True, check=True, out=None):
+        """out: optional caller-owned buffer for the solution (e.g. pinned host memory)"""
         n = self.sizes().n_owned_rows
-        sol = np.zeros(n) if want_solution else None
+        sol = (out if out is not None else np.zeros(n)) if want_solution else None
         rc = self.L.pe_solve_time_step(self.h, self.rel_tol, self.max_iterations, ptr(sol), C.byref(self.stats))
         if rc != 0 and (check or rc != capi.PE_ERR_NOT_CONVERGED):
             self._ck(rc)

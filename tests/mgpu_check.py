@@ -69,6 +69,36 @@ def main():
             old = x_ref
             t += dt
         b.close()
+    # ---- distributed grid levels (row slabs) against the replicated V-cycles: the two are the same operator, so
+    # MINRES must take the same number of iterations and return the same solution (N = 256: two distributed levels)
+    nref2 = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+    sols, its = [], []
+    for replicated in (True, False):
+        if replicated:
+            os.environ["PE_MG_REPLICATED"] = "1"
+        else:
+            os.environ.pop("PE_MG_REPLICATED", None)
+        b = pb.BiotSystem(element=BR1_WG, device=local, rank=rank, world_size=world)
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.frombuffer(bytearray(pb.comm_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(idt, 0)
+        b.comm_init(idt.cpu().numpy().tobytes())
+        b.make_grid_and_dofs(nref2, distort=0.1)
+        b.time_step = 0.1
+        b.set_material(100.0, 1.0, 1.0, 0.01)
+        b.set_lognormal_k(1.0, 7)
+        b.set_case(pb.PE_CASE_COSCOS)
+        b.assemble_system(0.1)
+        b.rel_tol = 1e-10
+        sols.append(b.solve_time_step())
+        its.append((b.stats.iterations, bool(b.stats.converged), b.stats.rel_residual))
+        b.close()
+    ed = np.linalg.norm(sols[0] - sols[1]) / np.linalg.norm(sols[0])
+    good = its[0][1] and its[1][1] and abs(its[0][0] - its[1][0]) <= 4 and ed < 1e-8
+    ok &= bool(good)
+    print("rank %d distributed vs replicated V-cycles (N=%d): iterations %d / %d, solution difference %.1e %s"
+          % (rank, 1 << nref2, its[0][0], its[1][0], ed, "OK" if good else "FAIL"), flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
