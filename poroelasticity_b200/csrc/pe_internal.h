@@ -15,6 +15,7 @@
 
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -88,6 +89,14 @@ namespace pe
   {
     int i0 = 0, i1 = 0, j0 = 0, j1 = 0;
   };
+
+  // smallest grid level (cells per side) that is distributed over the ranks; PE_MG_DIST_MIN_N overrides (tuning / tests)
+  inline int
+  dist_min_n()
+  {
+    const char *e = getenv("PE_MG_DIST_MIN_N");
+    return e ? atoi(e) : 1024;
+  }
 
   struct HaloPeer
   {

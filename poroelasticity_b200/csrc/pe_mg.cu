@@ -877,7 +877,9 @@ namespace pe
       {
         const int N = mg.lv[l].N;
         // distributed while every rank keeps >= 8 cell rows and the level is above the fused single-CTA levels
-        if (N % (2 * W) != 0 || N / W < 8 || N <= 64)
+        // a distributed level pays ~6 NCCL row exchanges (~45 us each, measured on 8 GPUs); below ~1024^2 the
+        // replicated sweep is cheaper than that latency
+        if (N % (2 * W) != 0 || N / W < 8 || N < dist_min_n())
           break;
         std::vector<int64_t> bd((size_t)W + 1);
         for (int r = 0; r < W; ++r)

@@ -72,6 +72,7 @@ def main():
     # ---- distributed grid levels (row slabs) against the replicated V-cycles: the two are the same operator, so
     # MINRES must take the same number of iterations and return the same solution (N = 256: two distributed levels)
     nref2 = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+    os.environ["PE_MG_DIST_MIN_N"] = "128"   # distribute the 256^2 and 128^2 levels of this small mesh
     sols, its = [], []
     for replicated in (True, False):
         if replicated:
