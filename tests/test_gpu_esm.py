@@ -95,3 +95,18 @@ def test_cfg5_secondary_checksum():
     one = b.local_matrices(0, 1)[0]
     assert abs(cs) <= 1e-9 * np.abs(one).sum() * o.n_cells
     assert sec > 0.0
+
+
+def test_cpp_host_driver_runs():
+    """host/eltstiffmat: the C++ twin of EltStiffMat.cc's main() on top of the C ABI, shipped refinement."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "host", "eltstiffmat")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(root, "host")])
+    out = subprocess.run([exe, "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "Number of active cells: 4" in out.stdout
+    assert "Number of rt degrees of freedom: 84" in out.stdout
+    assert "Number of dof: 72" in out.stdout
