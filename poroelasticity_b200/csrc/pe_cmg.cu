@@ -256,7 +256,7 @@ namespace pe
     __global__ void __launch_bounds__(1024)
     k_cmg_coarse(const int N0, const double *__restrict__ tE, const double *__restrict__ tN,
                  const double *__restrict__ sig, const double *__restrict__ b_in, double *__restrict__ x_out,
-                 const double omega, const double over, const int nu)
+                 const double omega, const double omega2, const double over, const int nu)
     {
       __shared__ double sb[kCoarseCells], sx[2][kCoarseCells];
       int               cur[6]; // which of sx[0], sx[1] holds the iterate of level m
@@ -293,7 +293,7 @@ namespace pe
                 {
                   double dg, ax;
                   stencil(n, i, j, te, tn, sg, sx[w] + off, dg, ax);
-                  sx[w ^ 1][off + t] = dg > 0. ? sx[w][off + t] + omega * (sb[off + t] - ax) / dg : 0.;
+                  sx[w ^ 1][off + t] = dg > 0. ? sx[w][off + t] + ((k & 1) ? omega2 : omega) * (sb[off + t] - ax) / dg : 0.;
                 }
               w ^= 1;
               __syncthreads();
@@ -340,7 +340,7 @@ namespace pe
                       stencil(n, i, j, te, tn, sg, sx[w] + off, dg, ax);
                       xs = sx[w][off + t];
                     }
-                  sx[w ^ 1][off + t] = dg > 0. ? xs + omega * (sb[off + t] - ax) / dg : 0.;
+                  sx[w ^ 1][off + t] = dg > 0. ? xs + (((nu - 1 - k) & 1) ? omega2 : omega) * (sb[off + t] - ax) / dg : 0.;
                 }
               w ^= 1;
               __syncthreads();
@@ -569,7 +569,7 @@ namespace pe
   cmg_vcycle(CellMg &cm, cudaStream_t s, int64_t *launches)
   {
     const int     nf = cm.n_fine;
-    const double  om = cm.omega, ov = cm.over;
+    const double  om = cm.omega, om2 = cm.omega2, ov = cm.over;
     const int     nu = std::max(1, cm.nu);
     std::vector<double *> cur((size_t)nf + 1, nullptr);
     // slab of this rank on level l (all rows on replicated levels)
@@ -595,7 +595,7 @@ namespace pe
         for (int k = 1; k < nu; ++k)
           {
             exchange(x0);
-            k_cmg_jacobi<<<g1(n), 128, 0, s>>>(L.N, L.tE.p, L.tN.p, L.sig.p, L.b.p, x0, nullptr, 0., x1, om, c0, c1);
+            k_cmg_jacobi<<<g1(n), 128, 0, s>>>(L.N, L.tE.p, L.tN.p, L.sig.p, L.b.p, x0, nullptr, 0., x1, (k & 1) ? om2 : om, c0, c1);
             std::swap(x0, x1);
           }
         exchange(x0);
@@ -617,7 +617,7 @@ namespace pe
     // ---- coarse levels: one launch
     {
       CmgLevel &C = cm.lv[(size_t)nf];
-      k_cmg_coarse<<<1, 1024, 0, s>>>(C.N, cm.c_tE.p, cm.c_tN.p, cm.c_sig.p, C.b.p, C.x0.p, om, ov, nu);
+      k_cmg_coarse<<<1, 1024, 0, s>>>(C.N, cm.c_tE.p, cm.c_tN.p, cm.c_sig.p, C.b.p, C.x0.p, om, om2, ov, nu);
       ++*launches;
       cur[(size_t)nf] = C.x0.p;
     }
@@ -634,12 +634,14 @@ namespace pe
         };
         double *x0 = cur[(size_t)l], *x1 = x0 == L.x0.p ? L.x1.p : L.x0.p;
         // x0 still carries its halo rows from the way down; the coarse result carries its own (below)
-        k_cmg_jacobi<<<g1(n), 128, 0, s>>>(L.N, L.tE.p, L.tN.p, L.sig.p, L.b.p, x0, cur[(size_t)l + 1], ov, x1, om, c0, c1);
+        k_cmg_jacobi<<<g1(n), 128, 0, s>>>(L.N, L.tE.p, L.tN.p, L.sig.p, L.b.p, x0, cur[(size_t)l + 1], ov, x1,
+                                           ((nu - 1) & 1) ? om2 : om, c0, c1);
         std::swap(x0, x1);
         for (int k = 1; k < nu; ++k)
           {
             exchange(x0);
-            k_cmg_jacobi<<<g1(n), 128, 0, s>>>(L.N, L.tE.p, L.tN.p, L.sig.p, L.b.p, x0, nullptr, 0., x1, om, c0, c1);
+            k_cmg_jacobi<<<g1(n), 128, 0, s>>>(L.N, L.tE.p, L.tN.p, L.sig.p, L.b.p, x0, nullptr, 0., x1,
+                                               ((nu - 1 - k) & 1) ? om2 : om, c0, c1);
             std::swap(x0, x1);
           }
         cur[(size_t)l] = x0;

@@ -42,7 +42,7 @@ namespace pe
     // vertical edge [j*(N+1)+i] and horizontal edge [j*N+i]; 0 for pressure-Dirichlet faces
     DevBuf<double>  wv_lo, wv_hi, wh_lo, wh_hi;
     DevBuf<uint8_t> dir_v, dir_h; // 1: the face carries a pressure Dirichlet value
-    double          omega = 0.7, over = 2.0;
+    double          omega = 0.6, omega2 = 1.2, over = 2.0; // smoothing sweeps alternate between omega and omega2
     int             nu    = 2;
     // multi-GPU: the first n_dist levels are distributed in row slabs of cells, bounds[l][r] = first cell row of rank r
     GridComm                          gc;

@@ -291,6 +291,7 @@ namespace pe
       const uint8_t *mask[kFusedLev];
       const double  *b0;
       double        *out;
+      const double  *coarse_inv; // dense inverse of the last level (n*n + flag), or null
     };
     template <int NC>
     __device__ __forceinline__ void
@@ -323,7 +324,7 @@ namespace pe
     }
     template <int NC>
     __global__ void __launch_bounds__(1024)
-    k_mg_fused(const FusedArgs a, const double omega, const int nu, const int coarse_sweeps)
+    k_mg_fused(const FusedArgs a, const double omega, const double omega2, const int nu, const int coarse_sweeps)
     {
       extern __shared__ double sm[]; // per level: b, x0, x1 (NC * nv each)
       double *B[kFusedLev], *X[kFusedLev], *Y[kFusedLev];
@@ -351,13 +352,28 @@ namespace pe
           const int  N = a.N[m], nv = (N + 1) * (N + 1);
           const bool last = m + 1 == a.nlev;
           const int  sweeps = last ? coarse_sweeps : nu;
+          if (last && a.coarse_inv && a.coarse_inv[NC * nv * NC * nv] == 1.)
+            {
+              // exact coarse solve: x = A^{-1} b with the precomputed dense inverse
+              const int n = NC * nv;
+              for (int r = t; r < n; r += nt)
+                {
+                  double sum = 0.;
+                  for (int c = 0; c < n; ++c)
+                    sum += a.coarse_inv[r * n + c] * B[m][c];
+                  X[m][r] = sum;
+                }
+              __syncthreads();
+              break;
+            }
           for (int v = t; v < nv; v += nt)
             jacobi_point<NC>(N, v, a.st[m], a.dinv[m], B[m], nullptr, X[m], omega);
           __syncthreads();
           for (int k = 1; k < sweeps; ++k)
             {
+              const double om = (k & 1) ? omega2 : omega; // alternating (Chebyshev-like) weights
               for (int v = t; v < nv; v += nt)
-                jacobi_point<NC>(N, v, a.st[m], a.dinv[m], B[m], X[m], Y[m], omega);
+                jacobi_point<NC>(N, v, a.st[m], a.dinv[m], B[m], X[m], Y[m], om);
               __syncthreads();
               double *q = X[m];
               X[m]      = Y[m];
@@ -421,8 +437,9 @@ namespace pe
           __syncthreads();
           for (int k = 0; k < nu; ++k)
             {
+              const double om = ((nu - 1 - k) & 1) ? omega2 : omega;
               for (int v = t; v < nv; v += nt)
-                jacobi_point<NC>(N, v, a.st[m], a.dinv[m], B[m], X[m], Y[m], omega);
+                jacobi_point<NC>(N, v, a.st[m], a.dinv[m], B[m], X[m], Y[m], om);
               __syncthreads();
               double *q = X[m];
               X[m]      = Y[m];
@@ -434,6 +451,93 @@ namespace pe
         for (int i = t; i < n; i += nt)
           a.out[i] = X[0][i];
       }
+    }
+
+    // dense inverse of the coarsest-level operator (N = 2: 9 vertices, NC * 9 unknowns), one thread, once per
+    // assembled matrix.  inv[n*n] row-major, inv[n*n] = 1 if the factorisation succeeded (0: singular, e.g. pure
+    // traction problems -> the fused kernel falls back to Jacobi sweeps).
+    template <int NC>
+    __global__ void
+    k_mg_coarse_inverse(const int N, const stencil_t *__restrict__ st, double *__restrict__ inv)
+    {
+      constexpr int MAXN = NC * 25;
+      const int     V = N + 1, nv = V * V, n = NC * nv;
+      if (threadIdx.x != 0 || blockIdx.x != 0 || n > MAXN)
+        return;
+      __shared__ double A[MAXN * MAXN], B[MAXN * MAXN];
+      for (int e = 0; e < n * n; ++e)
+        {
+          A[e] = 0.;
+          B[e] = 0.;
+        }
+      for (int v = 0; v < nv; ++v)
+        {
+          const int i = v % V, j = v / V;
+          for (int dj = -1; dj <= 1; ++dj)
+            for (int di = -1; di <= 1; ++di)
+              {
+                const int wi = i + di, wj = j + dj;
+                if (wi < 0 || wj < 0 || wi > N || wj > N)
+                  continue;
+                const int w = wj * V + wi, k = (dj + 1) * 3 + (di + 1);
+                for (int c = 0; c < NC; ++c)
+                  for (int d = 0; d < NC; ++d)
+                    A[(c * nv + v) * n + d * nv + w] = (double)st[(size_t)(k * NC * NC + c * NC + d) * nv + v];
+              }
+        }
+      for (int r = 0; r < n; ++r)
+        B[r * n + r] = 1.;
+      double amax = 0.;
+      for (int e = 0; e < n * n; ++e)
+        amax = fmax(amax, fabs(A[e]));
+      bool ok = amax > 0.;
+      for (int k = 0; k < n && ok; ++k)
+        {
+          int    p  = k;
+          double pm = fabs(A[k * n + k]);
+          for (int r = k + 1; r < n; ++r)
+            if (fabs(A[r * n + k]) > pm)
+              {
+                pm = fabs(A[r * n + k]);
+                p  = r;
+              }
+          if (pm < 1e-12 * amax)
+            {
+              ok = false;
+              break;
+            }
+          if (p != k)
+            for (int c = 0; c < n; ++c)
+              {
+                const double ta = A[k * n + c], tb = B[k * n + c];
+                A[k * n + c]    = A[p * n + c];
+                B[k * n + c]    = B[p * n + c];
+                A[p * n + c]    = ta;
+                B[p * n + c]    = tb;
+              }
+          const double ip = 1. / A[k * n + k];
+          for (int c = 0; c < n; ++c)
+            {
+              A[k * n + c] *= ip;
+              B[k * n + c] *= ip;
+            }
+          for (int r = 0; r < n; ++r)
+            if (r != k)
+              {
+                const double f = A[r * n + k];
+                if (f != 0.)
+                  for (int c = 0; c < n; ++c)
+                    {
+                      A[r * n + c] -= f * A[k * n + c];
+                      B[r * n + c] -= f * B[k * n + c];
+                    }
+              }
+        }
+      // symmetrise (the operator is symmetric; rounding of the elimination is not)
+      for (int r = 0; r < n; ++r)
+        for (int c = 0; c < n; ++c)
+          inv[r * n + c] = ok ? .5 * (B[r * n + c] + B[c * n + r]) : 0.;
+      inv[n * n] = ok ? 1. : 0.;
     }
 
     // r = b - A x
@@ -741,6 +845,19 @@ namespace pe
           k_mg_assemble<1><<<g1(nv), 128, 0, s>>>(L.N, L.x.p, L.y.p, kc, k_scalar, L.mask_p.p, dt, gamma, L.st_p.p, L.dinv_p.p);
         *launches += with_p ? 2 : 1;
       }
+    {
+      // exact coarse solve of the displacement hierarchy (replaces 24 Jacobi sweeps = 24 latency-bound phases of
+      // the single-CTA kernel)
+      MgLevel  &C = mg.lv.back();
+      const int n = 2 * (C.N + 1) * (C.N + 1);
+      if (C.N == 2)
+        {
+          if (mg.coarse_inv_u.n < (size_t)n * n + 1 && mg.coarse_inv_u.alloc((size_t)n * n + 1) != cudaSuccess)
+            return -1;
+          k_mg_coarse_inverse<2><<<1, 32, 0, s>>>(C.N, C.st_u.p, mg.coarse_inv_u.p);
+          ++*launches;
+        }
+    }
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
   }
 
@@ -775,6 +892,7 @@ namespace pe
           }
         a.b0  = b;
         a.out = NC == 2 ? L.wu[2].p : L.wp[2].p;
+        a.coarse_inv = (NC == 2 && l + (size_t)a.nlev == mg.lv.size() && mg.coarse_inv_u.n > 0) ? mg.coarse_inv_u.p : nullptr;
         size_t smem = 0;
         for (int m = 0; m < a.nlev; ++m)
           smem += sizeof(double) * 3 * NC * (size_t)(a.N[m] + 1) * (a.N[m] + 1);
@@ -784,7 +902,7 @@ namespace pe
             cudaFuncSetAttribute(k_mg_fused<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
             attr_set[NC] = true;
           }
-        k_mg_fused<NC><<<1, 1024, smem, s>>>(a, omega, nu, 24);
+        k_mg_fused<NC><<<1, 1024, smem, s>>>(a, omega, mg.omega2 > 0. ? mg.omega2 : omega, nu, 24);
         ++*launches;
         return;
       }
@@ -810,10 +928,11 @@ namespace pe
     // pre-smoothing from x = 0
     k_mg_jacobi<NC><<<g1(nloc), 128, 0, s>>>(L.N, st, dinv, b, nullptr, x0, omega, v0, v1);
     ++*launches;
+    const double omega2 = mg.omega2 > 0. ? mg.omega2 : omega; // sweeps alternate between the two weights
     for (int k = 1; k < pre; ++k)
       {
         exchange(x0);
-        k_mg_jacobi<NC><<<g1(nloc), 128, 0, s>>>(L.N, st, dinv, b, x0, x1, omega, v0, v1);
+        k_mg_jacobi<NC><<<g1(nloc), 128, 0, s>>>(L.N, st, dinv, b, x0, x1, (k & 1) ? omega2 : omega, v0, v1);
         ++*launches;
         std::swap(x0, x1);
       }
@@ -845,7 +964,7 @@ namespace pe
       for (int k = 0; k < nu; ++k)
         {
           exchange(x0);
-          k_mg_jacobi<NC><<<g1(nloc), 128, 0, s>>>(L.N, st, dinv, b, x0, x1, omega, v0, v1);
+          k_mg_jacobi<NC><<<g1(nloc), 128, 0, s>>>(L.N, st, dinv, b, x0, x1, ((nu - 1 - k) & 1) ? omega2 : omega, v0, v1);
           ++*launches;
           std::swap(x0, x1);
         }

@@ -22,7 +22,9 @@ namespace pe
     int                  N0    = 0;
     std::vector<MgLevel> lv;
     DevBuf<int32_t>      vdof, pint, hedge, vedge;
+    DevBuf<double>       coarse_inv_u; // dense inverse of the coarsest displacement operator (+ validity flag)
     double               omega = 0.6, theta = 1.0;
+    double               omega2 = 0.; // weight of every second smoothing sweep (<= 0: same as omega)
     int                  nu    = 2;
     // multi-GPU: the first n_dist levels are distributed in row slabs (bounds[l][r] = first vertex row of
     // rank r on level l), the coarser ones run replicated on every rank

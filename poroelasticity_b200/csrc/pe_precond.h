@@ -38,7 +38,7 @@ namespace pe
     DevBuf<uint8_t> cls;
     DevBuf<int32_t> pint_rows;
     DevBuf<double>  pint_area, t, t2, t3, dinv, wdinv; // wdinv = omega_F / diag(F) on the face rows
-    double          omega_f = 0.7;
+    double          omega_f = 0.65;
     const double   *values = nullptr;
     // single GPU: the pressure pipeline runs on a forked stream beside the displacement V-cycle
     cudaStream_t    s2 = nullptr;
