@@ -251,34 +251,37 @@ def main():
 
     # ---- end-to-end arm: host buffers through the C ABI -------------------------------------------
     # every step: old_solution host -> device inside pe_assemble_system, solution device -> host inside
-    # pe_solve_time_step; with N > 1 the owned parts are exchanged between the hosts (gloo) to rebuild
-    # the full old_solution, as a host program driving N GPUs would have to.
-    owned = b.owned_rows() if world > 1 else None
-    gloo = dist.new_group(backend="gloo") if world > 1 else None
-
-    def host_exchange(x_owned):
-        if world == 1:
-            return x_owned
-        nmax = torch.tensor([owned.size], dtype=torch.int64)
-        dist.all_reduce(nmax, op=dist.ReduceOp.MAX, group=gloo)
-        buf = torch.zeros(int(nmax), dtype=torch.float64)
-        idx = torch.full((int(nmax),), -1, dtype=torch.int64)
-        buf[:owned.size] = torch.from_numpy(x_owned)
-        idx[:owned.size] = torch.from_numpy(owned)
-        bufs = [torch.zeros_like(buf) for _ in range(world)]
-        idxs = [torch.zeros_like(idx) for _ in range(world)]
-        dist.all_gather(bufs, buf, group=gloo)
-        dist.all_gather(idxs, idx, group=gloo)
-        full = np.zeros(n_dofs)
-        for bb, ii in zip(bufs, idxs):
-            m = ii >= 0
-            full[ii[m].numpy()] = bb[m].numpy()
-        return full
-
-    # two pinned host buffers: old_solution (n_dofs, global order) and the owned part of the new solution
-    old = torch.zeros(n_dofs, dtype=torch.float64).pin_memory().numpy()
+    # pe_solve_time_step.
+    # Host side of the N-GPU program: one process per GPU on ONE node, so old_solution (n_dofs doubles, global
+    # order) lives in a POSIX shared-memory segment that every rank maps and registers as pinned memory.  Per
+    # step every rank copies its owned part D2H into its pinned buffer, writes it into its three contiguous
+    # global ranges of the shared vector, and after a barrier reads its owned + halo entries from it (H2D inside
+    # pe_assemble_system).  No rank can leave the solve (NCCL collectives) before all ranks have finished reading.
+    shm = None
     if world == 1:
+        old = torch.zeros(n_dofs, dtype=torch.float64).pin_memory().numpy()
         pinned_sol = torch.zeros(n_dofs, dtype=torch.float64).pin_memory().numpy()
+    else:
+        from multiprocessing import shared_memory
+        names = [None]
+        if rank == 0:
+            shm = shared_memory.SharedMemory(create=True, size=n_dofs * 8)
+            names[0] = shm.name
+        dist.broadcast_object_list(names, src=0)
+        if rank != 0:
+            shm = shared_memory.SharedMemory(name=names[0])
+            try:  # Python < 3.13 also registers ATTACHED segments with the resource tracker: rank 0 owns the unlink
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(shm._name, "shared_memory")
+            except Exception:
+                pass
+        old = np.ndarray((n_dofs,), dtype=np.float64, buffer=shm.buf)
+        if rank == 0:
+            old[:] = 0.0
+        rc = torch.cuda.cudart().cudaHostRegister(old.ctypes.data, n_dofs * 8, 0)
+        say("cudaHostRegister of the shared old_solution: %s" % (rc,))
+        rb, re_ = b.owned_ranges()
+        dist.barrier()
 
     def e2e_step(k):
         nonlocal old, pinned_sol
@@ -286,7 +289,12 @@ def main():
         if world == 1:
             old, pinned_sol = pinned_sol, old      # old_solution = solution (BR1new:2241): swap the host buffers
         else:
-            old[:] = host_exchange(x)
+            o = 0
+            for q in range(3):
+                n = int(re_[q] - rb[q])
+                old[int(rb[q]):int(re_[q])] = x[o:o + n]
+                o += n
+            dist.barrier()
 
     e2e_step(0)
     barrier()
@@ -300,7 +308,7 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     e2e_s = float(tt[0])
     e2e = {"value": n_cells * args.steps / e2e_s, "unit": UNIT,
-           "h2d_bytes_per_step": int(n_dofs * 8),  # owned + halo parts of old_solution, summed over ranks (halo excluded)
+           "h2d_bytes_per_step": int(n_dofs * 8),  # owned parts of old_solution summed over the ranks (halo entries not counted)
            "d2h_bytes_per_step": int(n_dofs * 8), "ms_per_step": e2e_s / args.steps * 1e3}
 
     # orderly shutdown on every rank (the library's NCCL communicator, then torch's)
@@ -308,6 +316,11 @@ def main():
     b.close()
     if world > 1:
         dist.barrier()
+        torch.cuda.cudart().cudaHostUnregister(old.ctypes.data)
+        del old
+        shm.close()
+        if rank == 0:
+            shm.unlink()
         dist.destroy_process_group()
     if rank != 0:
         return

@@ -152,6 +152,8 @@ struct pe_handle
   pe::DevBuf<double> d_pinv;   // block-Jacobi preconditioner (inverse diagonal)
   pe::DevBuf<double> d_scal;   // small scalar scratch (dots)
   double            *h_scal = nullptr; // pinned
+  double            *h_stage = nullptr; // pinned staging buffer for the halo part of a host vector (multi-GPU)
+  size_t             h_stage_n = 0;
 
   // auxiliary-space multigrid preconditioner (pe_mg.cu); null = diagonal preconditioner only
   pe::MgHierarchy *mg = nullptr;

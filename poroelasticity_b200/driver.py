@@ -92,6 +92,13 @@ class BiotSystem:
         self._ck(self.L.pe_get_sizes(self.h, C.byref(s)))
         return s
 
+    def owned_ranges(self):
+        """the three contiguous global row ranges [begin, end) this rank owns (u | p_int | p_face)"""
+        b = np.zeros(3, np.int64)
+        e = np.zeros(3, np.int64)
+        self._ck(self.L.pe_get_owned_ranges(self.h, ptr(b), ptr(e)))
+        return b, e
+
     def owned_rows(self):
         """global indices of the rows this rank owns, in local order"""
         b = np.zeros(3, np.int64)
