@@ -342,7 +342,9 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "PoroElasBR1WG 2D unit square %dx%d quads, coscos, dt=0.1, backward Euler" % (N, N),
                        "n_dofs": n_dofs, "nnz": s.nnz if world == 1 else None, "rel_tol": args.rel_tol,
-                       "l2": "inputs (GB-sized CSR arrays) exceed L2; no flush needed", "setup_s": t_setup},
+                       "l2": "inputs (GB-sized CSR arrays) exceed L2; no flush needed", "setup_s": t_setup,
+                       "scaling_note": "BASELINE.json configs: [1] 1024^2 on 1 B200, [2] 4096^2 partitioned across 2/4/8 B200; "
+                                       "strong scaling holds among N = 2, 4, 8 (same mesh)"},
             "s_per_time_step": dev_s / args.steps, "assemble_ms": sum(asm_ms) / len(asm_ms),
             "assembly_cells_per_s": n_cells / asm_kernel_s, "solve_ms": sum(sol_ms) / len(sol_ms),
             "solver": {"method": "MINRES on the three-field (u, total pressure, p) form + block preconditioner (bubble Jacobi x Q1 V-cycle; cell mass; p_int elimination + face V-cycle)", "iterations": iters, "spmv": spmvs,
