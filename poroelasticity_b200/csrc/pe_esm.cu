@@ -9,8 +9,8 @@
 // K-weighted Gram matrix is k M, hence  A = k F M^-1 F^T = k Y^T Y  with  L L^T = M (Cholesky), L Y = F^T.
 // The RT[2] space is spanned by shifted Legendre products (the local matrix depends on the space only,
 // not on its basis; on a parallelogram M is block diagonal and close to diagonal).
-// One warp builds one cell: M and Y live in shared memory (9 KB per warp); ~45 kflop per cell, the only
-// compute-bound kernel of the path (AI ~ 42 flop/B against the 3.6 KB written per cell).
+// One warp builds one cell with M, L and Y in registers (rows / columns exchanged by warp shuffles); ~45 kflop
+// per cell, the only compute-bound kernel of the path (AI ~ 42 flop/B against 3.6 KB written).
 #include "pe_internal.h"
 #include "pe_kernels.h"
 
@@ -139,7 +139,6 @@ namespace pe
     }
 
     constexpr int kWarps = 4;
-    constexpr int kMld   = 25; // leading dimension of M in shared memory (bank-conflict padding)
 
     struct EsmArgs
     {
@@ -155,16 +154,22 @@ namespace pe
       int             case_id;
     };
 
+    // One warp per cell, everything but the final 21 x 21 block in REGISTERS: lane i holds row i of the Gram
+    // matrix M (later of its Cholesky factor L), lane c holds column c of Y = L^{-1} F^T, lane i accumulates row
+    // i of A = k Y^T Y; rows / columns travel between lanes by warp shuffles with compile-time register
+    // indices (all loops over matrix indices are fully unrolled).  The first version kept M and Y in shared
+    // memory and was bound by the latency of ~3 dependent shared-memory round trips per update (ncu: FP64 pipe
+    // 19 %, 3.98e7 cells/s).
     template <bool DENSE>
     __global__ void __launch_bounds__(kWarps * 32)
     k_esm_cell(const EsmArgs a)
     {
-      __shared__ double sM[kWarps][kRt * kMld];
-      __shared__ double sY[kWarps][kRt * kLoc];
-      __shared__ double  sG[kWarps][kQ * 4]; // per Gauss point: g00, g01, g11 (J^T J w / det)
-      __shared__ int64_t sRow[kWarps][kLoc]; // CSR row starts of the 21 local dofs
+      __shared__ double  sG[kWarps][kQ * 4];       // per Gauss point: g00, g01, g11 (J^T J w / det)
+      __shared__ double  sA[kWarps][kLoc * kLoc];  // the finished local matrix, for coalesced output
+      __shared__ int64_t sRow[kWarps][kLoc];       // CSR row starts of the 21 local dofs
       // reference tables: constant memory serialises lane-dependent addresses, shared memory does not
-      __shared__ double sPx[kQ * 12], sPy[kQ * 12], sFt[kRt * kLoc];
+      __shared__ __align__(16) double sPx[kQ * 12], sPy[kQ * 12];
+      __shared__ double               sFt[kRt * kLoc];
       for (int e = threadIdx.x; e < kQ * 12; e += blockDim.x)
         {
           sPx[e] = cT.px[e];
@@ -173,12 +178,13 @@ namespace pe
       for (int e = threadIdx.x; e < kRt * kLoc; e += blockDim.x)
         sFt[e] = cT.F[(e % kLoc) * kRt + e / kLoc]; // F^T (24 x 21)
       __syncthreads();
-      const int     warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-      const int64_t t    = (int64_t)blockIdx.x * kWarps + warp;
+      const int      warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+      const int64_t  t    = (int64_t)blockIdx.x * kWarps + warp;
       if (t >= a.n)
         return;
-      const int64_t c = a.first + t;
-      double       *M = sM[warp], *Y = sY[warp], *G = sG[warp];
+      constexpr unsigned FULL = 0xffffffffu;
+      const int64_t      c    = a.first + t;
+      double            *G    = sG[warp];
       // ---- geometry at the Gauss points (lanes 0..15)
       double vx[4], vy[4];
 #pragma unroll
@@ -206,94 +212,94 @@ namespace pe
               fq = 2. * M_PI * M_PI * cospi(px) * cospi(py) * det * cT.qw[lane]; // RightHandSide, ESM:167
             }
         }
-      __syncwarp();
-      // ---- Gram matrix of the Piola-mapped basis:  M_ij = sum_q (J w^_i).(J w^_j) w_q / det       ESM:413-426
-      for (int e = lane; e < kRt * kRt; e += 32)
-        {
-          const int i = e / kRt, j = e % kRt;
-          double    s = 0.;
-          if (i < 12 && j < 12)
-            {
-#pragma unroll 4
-              for (int q = 0; q < kQ; ++q)
-                s += G[q * 4 + 0] * sPx[q * 12 + i] * sPx[q * 12 + j];
-            }
-          else if (i >= 12 && j >= 12)
-            {
-#pragma unroll 4
-              for (int q = 0; q < kQ; ++q)
-                s += G[q * 4 + 2] * sPy[q * 12 + i - 12] * sPy[q * 12 + j - 12];
-            }
-          else
-            {
-              const int ix = i < 12 ? i : j, iy = (i < 12 ? j : i) - 12;
-#pragma unroll 4
-              for (int q = 0; q < kQ; ++q)
-                s += G[q * 4 + 1] * sPx[q * 12 + ix] * sPy[q * 12 + iy];
-            }
-          M[i * kMld + j] = s;
-        }
-      // Y = F^T (24 x 21)
-      for (int e = lane; e < kRt * kLoc; e += 32)
-        Y[e] = sFt[e];
-      __syncwarp();
-      // ---- Cholesky M = L L^T (lower triangle of M, in place); replaces gauss_jordan, ESM:429
-      for (int k = 0; k < kRt; ++k)
-        {
-          const double dkk = sqrt(M[k * kMld + k]);
-          __syncwarp();
-          if (lane == k)
-            M[k * kMld + k] = dkk;
-          if (lane > k && lane < kRt)
-            M[lane * kMld + k] /= dkk;
-          __syncwarp();
-          if (lane > k && lane < kRt)
-            {
-              const double lik = M[lane * kMld + k];
-              for (int j = k + 1; j <= lane; ++j)
-                M[lane * kMld + j] -= lik * M[j * kMld + k];
-            }
-          __syncwarp();
-        }
-      // ---- L Y = F^T: lane = column of Y (one local dof), forward substitution
-      if (lane < kLoc)
-        for (int r = 0; r < kRt; ++r)
-          {
-            double s = Y[r * kLoc + lane];
-            for (int q = 0; q < r; ++q)
-              s -= M[r * kMld + q] * Y[q * kLoc + lane];
-            Y[r * kLoc + lane] = s / M[r * kMld + r];
-          }
-      __syncwarp();
-      // ---- A = k Y^T Y  (C M_K C^T of ESM:478-502) and the right-hand side (ESM:505-513)
-      const double kperm = a.kcell ? a.kcell[c] : a.k_scalar;
-      double       bi    = 0.; // lanes 0..8: b of interior dof `lane`
-      for (int q = 0; q < kQ; ++q)
-        {
-          const double f = __shfl_sync(0xffffffffu, fq, q);
-          if (lane < 9)
-            bi += f * cT.pv[q * 9 + lane];
-        }
       if (!DENSE && lane < kLoc)
         sRow[warp][lane] = a.rowptr[a.cdofs[(size_t)lane * a.n_asm + c]];
       __syncwarp();
+      // ---- row `lane` of the Gram matrix of the Piola-mapped basis                              ESM:413-426
+      //      M_ij = sum_q (J w^_i).(J w^_j) w_q / det ; lanes >= 24 carry a harmless copy of row 23
+      const int  li   = lane < kRt ? lane : kRt - 1;
+      const bool is_x = li < 12;
+      double     M[kRt];
+#pragma unroll
+      for (int j = 0; j < kRt; ++j)
+        M[j] = 0.;
+#pragma unroll 2
+      for (int q = 0; q < kQ; ++q)
+        {
+          const double mine = is_x ? sPx[q * 12 + li] : sPy[q * 12 + li - 12];
+          const double wx = mine * (is_x ? G[q * 4 + 0] : G[q * 4 + 1]), wy = mine * (is_x ? G[q * 4 + 1] : G[q * 4 + 2]);
+#pragma unroll
+          for (int j = 0; j < 12; j += 2)
+            {
+              const double2 ox = *reinterpret_cast<const double2 *>(&sPx[q * 12 + j]);
+              const double2 oy = *reinterpret_cast<const double2 *>(&sPy[q * 12 + j]);
+              M[j] += wx * ox.x;
+              M[j + 1] += wx * ox.y;
+              M[12 + j] += wy * oy.x;
+              M[12 + j + 1] += wy * oy.y;
+            }
+        }
+      // ---- Cholesky M = L L^T, right-looking; replaces gauss_jordan (ESM:429).  After step k: M[k] = L_ik
+      double invd[kRt];
+#pragma unroll
+      for (int k = 0; k < kRt; ++k)
+        {
+          const double dkk = __shfl_sync(FULL, M[k], k);
+          invd[k]          = rsqrt(dkk);
+          const double lik = M[k] * invd[k]; // L_ik for lanes i > k, L_kk = sqrt(M_kk) on lane k
+          M[k]             = lik;
+#pragma unroll
+          for (int j = k + 1; j < kRt; ++j)
+            {
+              const double ljk = __shfl_sync(FULL, lik, j);
+              M[j] -= lik * ljk; // meaningful for i >= j; the upper triangle is never read
+            }
+        }
+      // ---- L Y = F^T: lane = column of Y (one local dof), forward substitution with L rows from their lanes
+      const int lc = lane < kLoc ? lane : kLoc - 1;
+      double    Y[kRt];
+#pragma unroll
+      for (int r = 0; r < kRt; ++r)
+        {
+          double sacc = sFt[r * kLoc + lc];
+#pragma unroll
+          for (int q = 0; q < r; ++q)
+            sacc -= __shfl_sync(FULL, M[q], r) * Y[q];
+          Y[r] = sacc * invd[r];
+        }
+      // ---- A = k Y^T Y  (C M_K C^T of ESM:478-502): lane i builds row i
+      const double kperm = a.kcell ? a.kcell[c] : a.k_scalar;
+      double      *A     = sA[warp];
+#pragma unroll
+      for (int j = 0; j < kLoc; ++j)
+        {
+          double sacc = 0.;
+#pragma unroll
+          for (int r = 0; r < kRt; ++r)
+            sacc += Y[r] * __shfl_sync(FULL, Y[r], j);
+          if (lane < kLoc)
+            A[lane * kLoc + j] = kperm * sacc;
+        }
+      // ---- right-hand side (ESM:505-513)
+      double bi = 0.; // lanes 0..8: b of interior dof `lane`
+      for (int q = 0; q < kQ; ++q)
+        {
+          const double f = __shfl_sync(FULL, fq, q);
+          if (lane < 9)
+            bi += f * cT.pv[q * 9 + lane];
+        }
+      __syncwarp();
       for (int e = lane; e < kLoc * kLoc; e += 32)
         {
-          const int i = e / kLoc, j = e % kLoc;
-          double    s = 0.;
-#pragma unroll 8
-          for (int r = 0; r < kRt; ++r)
-            s += Y[r * kLoc + i] * Y[r * kLoc + j];
-          s *= kperm;
           if (DENSE)
-            a.out[(size_t)t * kLoc * kLoc + e] = s;
+            a.out[(size_t)t * kLoc * kLoc + e] = A[e];
           else
             {
               const uint32_t o = a.off[((size_t)(e >> 2) * a.n_asm + c) * 4 + (e & 3)];
-              atomicAdd(a.values + sRow[warp][i] + (o & 127u), s);
+              atomicAdd(a.values + sRow[warp][e / kLoc] + (o & 127u), A[e]);
             }
         }
-      const double bsh = __shfl_sync(0xffffffffu, bi, lane >= 12 ? lane - 12 : 0);
+      const double bsh = __shfl_sync(FULL, bi, lane >= 12 ? lane - 12 : 0);
       if (DENSE)
         {
           if (a.rhs_out && lane < kLoc)
