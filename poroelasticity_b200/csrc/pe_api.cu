@@ -604,8 +604,7 @@ namespace
           h->bp->omega_f = atof(e);
         // pressure block of the preconditioner: C + alpha^2/lambda_s W_int (C already holds c0 M)
         const double extra = h->alpha * h->alpha / lambda_s;
-        if (mg_assemble(*h->mg, h->d_k_morton.p, h->k_scalar, lambda0, h->mu, h->last_dt, h->c0 + extra, s, &h->launches,
-                        false) != 0)
+        if (mg_assemble(*h->mg, h->d_k_morton.p, h->k_scalar, lambda0, h->mu, h->last_dt, h->c0 + extra, s, &h->launches) != 0)
           return 1;
         if (cmg_assemble(*h->cmg, h->d_vx.p, h->d_vy.p, h->d_k_morton.p, h->k_scalar, h->last_dt, h->c0 + extra, s,
                          &h->launches) != 0)

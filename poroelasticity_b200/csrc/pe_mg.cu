@@ -613,88 +613,6 @@ namespace pe
         }
     }
 
-    // ---- maps between the Biot vector and the vertex grids ------------------------------------------
-    // b_u[v] = r[vdof[v] + c]   (Pi_u^T: Q1 is the vertex-dof subspace); masked vertices get 0
-    __global__ void
-    k_mg_gather_u(const int nv, const int32_t *__restrict__ vdof, const uint8_t *__restrict__ mask,
-                  const double *__restrict__ r, double *__restrict__ bu)
-    {
-      const int v = blockIdx.x * blockDim.x + threadIdx.x;
-      if (v >= nv)
-        return;
-      const bool m       = mask && mask[v];
-      const int  d       = vdof[v];
-      bu[v]              = m ? 0. : r[d];
-      bu[(size_t)nv + v] = m ? 0. : r[d + 1];
-    }
-    __global__ void
-    k_mg_scatter_u(const int nv, const int32_t *__restrict__ vdof, const uint8_t *__restrict__ mask,
-                   const double *__restrict__ xu, double *__restrict__ z)
-    {
-      const int v = blockIdx.x * blockDim.x + threadIdx.x;
-      if (v >= nv || (mask && mask[v]))
-        return;
-      const int d = vdof[v];
-      z[d] += xu[v];
-      z[d + 1] += xu[(size_t)nv + v];
-    }
-    // Pi_p^T r: b_p[v] = 1/4 sum_{cells at v} r_int + 1/2 sum_{edges at v} r_face
-    __global__ void
-    k_mg_gather_p(const int N, const int32_t *__restrict__ pint_dof /* [N*N] by (cj*N+ci) */,
-                  const int32_t *__restrict__ hedge /* [(N+1)*N]: edge (i,j)-(i+1,j) at j*N+i */,
-                  const int32_t *__restrict__ vedge /* [N*(N+1)]: edge (i,j)-(i,j+1) at j*(N+1)+i */,
-                  const uint8_t *__restrict__ mask, const double *__restrict__ r, double *__restrict__ bp)
-    {
-      const int V = N + 1, nv = V * V;
-      const int v = blockIdx.x * blockDim.x + threadIdx.x;
-      if (v >= nv)
-        return;
-      if (mask && mask[v])
-        {
-          bp[v] = 0.;
-          return;
-        }
-      const int i = v % V, j = v / V;
-      double    s = 0.;
-      for (int cj = j - 1; cj <= j; ++cj)
-        for (int ci = i - 1; ci <= i; ++ci)
-          if (ci >= 0 && cj >= 0 && ci < N && cj < N)
-            s += 0.25 * r[pint_dof[cj * N + ci]];
-      if (i > 0)
-        s += 0.5 * r[hedge[j * N + i - 1]];
-      if (i < N)
-        s += 0.5 * r[hedge[j * N + i]];
-      if (j > 0)
-        s += 0.5 * r[vedge[(j - 1) * V + i]];
-      if (j < N)
-        s += 0.5 * r[vedge[j * V + i]];
-      bp[v] = s;
-    }
-    // z += Pi_p x_p : cells, horizontal edges, vertical edges in one launch
-    __global__ void
-    k_mg_scatter_p(const int N, const int32_t *__restrict__ pint_dof, const int32_t *__restrict__ hedge,
-                   const int32_t *__restrict__ vedge, const double *__restrict__ xp, double *__restrict__ z)
-    {
-      const int V = N + 1;
-      const int t = blockIdx.x * blockDim.x + threadIdx.x;
-      const int n_c = N * N, n_h = V * N, n_v = N * V;
-      if (t < n_c)
-        {
-          const int ci = t % N, cj = t / N;
-          const int v0 = cj * V + ci;
-          z[pint_dof[t]] += 0.25 * (xp[v0] + xp[v0 + 1] + xp[v0 + V] + xp[v0 + V + 1]);
-        }
-      else if (t < n_c + n_h)
-        {
-          const int e = t - n_c, i = e % N, j = e / N;
-          z[hedge[e]] += 0.5 * (xp[j * V + i] + xp[j * V + i + 1]);
-        }
-      else if (t < n_c + n_h + n_v)
-        {
-          const int e = t - n_c - n_h, i = e % V, j = e / V;
-          z[vedge[e]] += 0.5 * (xp[j * V + i] + xp[(j + 1) * V + i]);
-        }
-    }
     // coarse arrays by injection / averaging
     __global__ void
     k_mg_coarsen_geometry(const int Nc, const double *__restrict__ xf, const double *__restrict__ yf,
@@ -711,17 +629,6 @@ namespace pe
       mu_c[v] = mu_f[f];
       mp_c[v] = mp_f[f];
     }
-    __global__ void
-    k_mg_coarsen_k(const int n_coarse_cells, const double *__restrict__ kf, double *__restrict__ kcoarse)
-    {
-      const int c = blockIdx.x * blockDim.x + threadIdx.x;
-      if (c >= n_coarse_cells)
-        return;
-      // children of Morton cell c are 4c..4c+3; harmonic-arithmetic compromise: geometric mean
-      const double a = kf[4 * c], b = kf[4 * c + 1], d = kf[4 * c + 2], e = kf[4 * c + 3];
-      kcoarse[c]     = exp(0.25 * (log(a) + log(b) + log(d) + log(e)));
-    }
-
     inline unsigned
     g1(const int n)
     {
@@ -801,13 +708,12 @@ namespace pe
             k_mg_coarsen_geometry<<<g1((int)nv), 128, 0, s>>>(L.N, F.x.p, F.y.p, F.mask_u.p, F.mask_p.p, L.x.p, L.y.p,
                                                                L.mask_u.p, L.mask_p.p);
           }
-        if (L.kc.alloc((size_t)L.N * L.N) || L.st_u.alloc(36 * nv) || L.st_p.alloc(9 * nv) || L.dinv_u.alloc(4 * nv) ||
-            L.dinv_p.alloc(nv))
+        if (L.st_u.alloc(36 * nv) || L.dinv_u.alloc(4 * nv))
           return -1;
         for (int k = 0; k < 3; ++k)
-          if (L.wu[k].alloc(2 * nv) || L.wp[k].alloc(nv))
+          if (L.wu[k].alloc(2 * nv))
             return -1;
-        if (L.bu.alloc(2 * nv) || L.bp.alloc(nv))
+        if (L.bu.alloc(2 * nv))
           return -1;
       }
     if (cudaStreamSynchronize(s) != cudaSuccess)
@@ -820,30 +726,18 @@ namespace pe
   // refactorises every step; the "cached" mode of SURVEY 8(f).1 would skip this)
   int
   mg_assemble(MgHierarchy &mg, const double *kcell_fine /* Morton, may be null */, const double k_scalar,
-              const double lambda, const double mu, const double dt, const double gamma, cudaStream_t s, int64_t *launches,
-              const bool with_p)
+              const double lambda, const double mu, const double dt, const double gamma, cudaStream_t s, int64_t *launches)
   {
+    (void)kcell_fine; // the pressure block has its own cell-centred hierarchy (pe_cmg.cu)
+    (void)k_scalar;
+    (void)dt;
+    (void)gamma;
     for (size_t l = 0; l < mg.lv.size(); ++l)
       {
         MgLevel  &L  = mg.lv[l];
         const int nv = (L.N + 1) * (L.N + 1);
-        const double *kc = nullptr;
-        if (kcell_fine && with_p)
-          {
-            if (l == 0)
-              kc = kcell_fine;
-            else
-              {
-                const double *kf = l == 1 ? kcell_fine : mg.lv[l - 1].kc.p;
-                k_mg_coarsen_k<<<g1(L.N * L.N), 128, 0, s>>>(L.N * L.N, kf, L.kc.p);
-                ++*launches;
-                kc = L.kc.p;
-              }
-          }
         k_mg_assemble<2><<<g1(nv), 128, 0, s>>>(L.N, L.x.p, L.y.p, nullptr, 1., L.mask_u.p, mu, lambda, L.st_u.p, L.dinv_u.p);
-        if (with_p)
-          k_mg_assemble<1><<<g1(nv), 128, 0, s>>>(L.N, L.x.p, L.y.p, kc, k_scalar, L.mask_p.p, dt, gamma, L.st_p.p, L.dinv_p.p);
-        *launches += with_p ? 2 : 1;
+        ++*launches;
       }
     {
       // exact coarse solve of the displacement hierarchy (replaces 24 Jacobi sweeps = 24 latency-bound phases of
@@ -867,11 +761,11 @@ namespace pe
   {
     MgLevel      &L    = mg.lv[l];
     const int     nv   = (L.N + 1) * (L.N + 1);
-    const stencil_t *st = NC == 2 ? L.st_u.p : L.st_p.p;
-    const double *dinv = NC == 2 ? L.dinv_u.p : L.dinv_p.p;
-    double       *b    = NC == 2 ? L.bu.p : L.bp.p;
-    double       *x0   = NC == 2 ? L.wu[0].p : L.wp[0].p;
-    double       *x1   = NC == 2 ? L.wu[1].p : L.wp[1].p;
+    const stencil_t *st = L.st_u.p;
+    const double *dinv = L.dinv_u.p;
+    double       *b    = L.bu.p;
+    double       *x0   = L.wu[0].p;
+    double       *x1   = L.wu[1].p;
     const bool    last = l + 1 == mg.lv.size();
     static const int fused_n = [] {
       const char *e = getenv("PE_MG_FUSED_N"); // tuning hook: largest level handled by the single-CTA kernel
@@ -885,13 +779,13 @@ namespace pe
           {
             MgLevel &Q     = mg.lv[q];
             a.N[a.nlev]    = Q.N;
-            a.st[a.nlev]   = NC == 2 ? Q.st_u.p : Q.st_p.p;
-            a.dinv[a.nlev] = NC == 2 ? Q.dinv_u.p : Q.dinv_p.p;
-            a.mask[a.nlev] = NC == 2 ? Q.mask_u.p : Q.mask_p.p;
+            a.st[a.nlev]   = Q.st_u.p;
+            a.dinv[a.nlev] = Q.dinv_u.p;
+            a.mask[a.nlev] = Q.mask_u.p;
             ++a.nlev;
           }
         a.b0  = b;
-        a.out = NC == 2 ? L.wu[2].p : L.wp[2].p;
+        a.out = L.wu[2].p;
         a.coarse_inv = (NC == 2 && l + (size_t)a.nlev == mg.lv.size() && mg.coarse_inv_u.n > 0) ? mg.coarse_inv_u.p : nullptr;
         size_t smem = 0;
         for (int m = 0; m < a.nlev; ++m)
@@ -910,7 +804,7 @@ namespace pe
       {
         // coarse solve: 24 Jacobi sweeps in one launch, result straight into w[2]
         const int threads = std::min(1024, ((nv + 31) / 32) * 32);
-        k_mg_coarse<NC><<<1, threads, sizeof(double) * 2 * NC * nv, s>>>(L.N, st, dinv, b, NC == 2 ? L.wu[2].p : L.wp[2].p,
+        k_mg_coarse<NC><<<1, threads, sizeof(double) * 2 * NC * nv, s>>>(L.N, st, dinv, b, L.wu[2].p,
                                                                          omega, 24);
         ++*launches;
         return;
@@ -942,11 +836,11 @@ namespace pe
       const bool    dist_c = (int)l + 1 < mg.n_dist;
       // coarse rows whose centre row 2J lies in my slab
       const int64_t ca = dist ? (ra + 1) / 2 : 0, cb = dist ? (rb + 1) / 2 : Vc;
-      double       *bc = NC == 2 ? C.bu.p : C.bp.p;
+      double       *bc = C.bu.p;
       exchange(x0);
       k_mg_residual<NC><<<g1(nloc), 128, 0, s>>>(L.N, st, b, x0, x1, v0, v1);
       exchange(x1);
-      k_mg_restrict<NC><<<g1((int)((cb - ca) * Vc)), 128, 0, s>>>(L.N, x1, bc, NC == 2 ? C.mask_u.p : C.mask_p.p,
+      k_mg_restrict<NC><<<g1((int)((cb - ca) * Vc)), 128, 0, s>>>(L.N, x1, bc, C.mask_u.p,
                                                                   (int)(ca * Vc), (int)(cb * Vc));
       *launches += 2;
       if (dist && !dist_c)
@@ -958,8 +852,8 @@ namespace pe
           mg.gc.allgather_rows(mg.gc.ctx, bc, Vc, NC, nvc, cbnd.data());
         }
       vcycle<NC>(mg, l + 1, omega, nu, s, launches);
-      k_mg_prolong_add<NC><<<g1(nloc), 128, 0, s>>>(L.N, NC == 2 ? C.wu[2].p : C.wp[2].p, x0,
-                                                    NC == 2 ? L.mask_u.p : L.mask_p.p, v0, v1);
+      k_mg_prolong_add<NC><<<g1(nloc), 128, 0, s>>>(L.N, C.wu[2].p, x0,
+                                                    L.mask_u.p, v0, v1);
       ++*launches;
       for (int k = 0; k < nu; ++k)
         {
@@ -970,7 +864,7 @@ namespace pe
         }
     }
     // result of this level -> w[2]
-    double *out = NC == 2 ? L.wu[2].p : L.wp[2].p;
+    double *out = L.wu[2].p;
     for (int c = 0; c < NC; ++c)
       cudaMemcpyAsync(out + (size_t)c * nv + v0, x0 + (size_t)c * nv + v0, sizeof(double) * (size_t)nloc,
                       cudaMemcpyDeviceToDevice, s);
@@ -1012,26 +906,8 @@ namespace pe
   void
   mg_vcycle(MgHierarchy &mg, const int nc, cudaStream_t s, int64_t *launches)
   {
-    if (nc == 2)
-      vcycle<2>(mg, 0, mg.omega, mg.nu, s, launches);
-    else
-      vcycle<1>(mg, 0, mg.omega, mg.nu, s, launches);
+    (void)nc; // only the vector (displacement) hierarchy lives here
+    vcycle<2>(mg, 0, mg.omega, mg.nu, s, launches);
   }
 
-  // z += Pi_u V_u Pi_u^T r + Pi_p V_p Pi_p^T r
-  void
-  mg_apply_add(MgHierarchy &mg, const double *r, double *z, cudaStream_t s, int64_t *launches)
-  {
-    MgLevel  &L  = mg.lv[0];
-    const int N  = L.N, nv = (N + 1) * (N + 1);
-    k_mg_gather_u<<<g1(nv), 128, 0, s>>>(nv, mg.vdof.p, L.mask_u.p, r, L.bu.p);
-    k_mg_gather_p<<<g1(nv), 128, 0, s>>>(N, mg.pint.p, mg.hedge.p, mg.vedge.p, L.mask_p.p, r, L.bp.p);
-    *launches += 2;
-    vcycle<2>(mg, 0, mg.omega, mg.nu, s, launches);
-    vcycle<1>(mg, 0, mg.omega, mg.nu, s, launches);
-    k_mg_scatter_u<<<g1(nv), 128, 0, s>>>(nv, mg.vdof.p, L.mask_u.p, L.wu[2].p, z);
-    const int np = N * N + 2 * N * (N + 1);
-    k_mg_scatter_p<<<g1(np), 128, 0, s>>>(N, mg.pint.p, mg.hedge.p, mg.vedge.p, L.wp[2].p, z);
-    *launches += 2;
-  }
 } // namespace pe

@@ -12,8 +12,8 @@ namespace pe
   {
     int             N = 0; // cells per side on this level
     using stencil_t = float; // storage type of the 9-point block stencils (arithmetic stays FP64, pe_mg.cu)
-    DevBuf<stencil_t> st_u, st_p;
-    DevBuf<double>    x, y, kc, dinv_u, dinv_p, wu[3], wp[3], bu, bp;
+    DevBuf<stencil_t> st_u;
+    DevBuf<double>    x, y, dinv_u, wu[3], bu;
     DevBuf<uint8_t> mask_u, mask_p;
   };
   struct MgHierarchy
@@ -37,12 +37,11 @@ namespace pe
   // to_local: global dof id -> local id on this rank (owned < L <= halo) or -1 if not visible
   int  mg_build_topology(MgHierarchy &mg, const HostMesh &mesh, const HostDofs &dofs,
                          const std::function<int32_t(uint32_t)> &to_local, cudaStream_t s);
-  // with_p = false: only the displacement operators (the pressure block uses pe_cmg.h)
+  // displacement operators only (the pressure block has its own cell-centred hierarchy, pe_cmg.h)
   int  mg_assemble(MgHierarchy &mg, const double *kcell_fine, double k_scalar, double lambda, double mu, double dt,
-                   double gamma, cudaStream_t s, int64_t *launches, bool with_p = true);
+                   double gamma, cudaStream_t s, int64_t *launches);
   // V-cycle on level-0 right-hand side lv[0].bu (nc = 2) / lv[0].bp (nc = 1); result in lv[0].wu[2] / wp[2]
   void mg_vcycle(MgHierarchy &mg, int nc, cudaStream_t s, int64_t *launches);
   // choose the distributed levels for gc.world ranks (call after mg_build_topology)
   void mg_set_comm(MgHierarchy &mg, const GridComm &gc);
-  void mg_apply_add(MgHierarchy &mg, const double *r, double *z, cudaStream_t s, int64_t *launches);
 } // namespace pe

@@ -37,38 +37,6 @@ namespace pe
       CLS_PFACE  = 3
     };
 
-    // out[row] = a[row] + m[row] * (b[row] - sum_k values[src[k]] x[col[k]])   (null a -> 0, null m -> 1,
-    // null b -> 0 and the sign of the sum flips to +)
-    template <int TPR>
-    __global__ void
-    k_sub_spmv(const int n_rows, const int32_t *__restrict__ rows, const int32_t *__restrict__ rp,
-               const int32_t *__restrict__ col, const uint32_t *__restrict__ src, const double *__restrict__ values,
-               const double *x, const double *a, const double *__restrict__ m, const double *b, double *out)
-    {
-      const int t   = blockIdx.x * blockDim.x + threadIdx.x;
-      const int r   = t / TPR, sub = t % TPR;
-      double    s   = 0.;
-      int       row = 0;
-      if (r < n_rows)
-        {
-          row = rows[r];
-          for (int k = rp[r] + sub; k < rp[r + 1]; k += TPR)
-            s += values[src[k]] * x[col[k]];
-        }
-#pragma unroll
-      for (int o = TPR / 2; o > 0; o >>= 1)
-        s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (r < n_rows && sub == 0)
-        {
-          double v = b ? b[row] - s : s;
-          if (m)
-            v *= m[row];
-          if (a)
-            v += a[row];
-          out[row] = v;
-        }
-    }
-
     // compact copy of the sub-block values, once per solve: val[k] = values[src[k]]
     __global__ void
     k_sub_gather_values(const int64_t n, const uint32_t *__restrict__ src, const uint8_t *__restrict__ neg,
@@ -238,67 +206,6 @@ namespace pe
       const int row = rows[k];
       t[row]        = dinv[row] * r[row];
     }
-    // b_p[v] = 1/2 sum_{edges at v} rf[edge]
-    __device__ __forceinline__ double
-    owned_val(const double *__restrict__ x, const int d, const int64_t L)
-    {
-      return (d >= 0 && d < L) ? x[d] : 0.;
-    }
-    __global__ void
-    k_gather_f(const int N, const int64_t L, const int32_t *__restrict__ hedge, const int32_t *__restrict__ vedge,
-               const uint8_t *__restrict__ mask, const double *__restrict__ rf, double *__restrict__ bp)
-    {
-      const int V = N + 1, nv = V * V;
-      const int v = blockIdx.x * blockDim.x + threadIdx.x;
-      if (v >= nv)
-        return;
-      if (mask && mask[v])
-        {
-          bp[v] = 0.;
-          return;
-        }
-      const int i = v % V, j = v / V;
-      double    s = 0.;
-      if (i > 0)
-        s += owned_val(rf, hedge[j * N + i - 1], L);
-      if (i < N)
-        s += owned_val(rf, hedge[j * N + i], L);
-      if (j > 0)
-        s += owned_val(rf, vedge[(j - 1) * V + i], L);
-      if (j < N)
-        s += owned_val(rf, vedge[j * V + i], L);
-      bp[v] = 0.5 * s;
-    }
-    // z_f = dinvF rf + 1/2 (x_a + x_b)
-    __global__ void
-    k_scatter_f(const int N, const int64_t L, const int32_t *__restrict__ hedge, const int32_t *__restrict__ vedge,
-                const double *__restrict__ xp, const double *__restrict__ dinv, const double *__restrict__ rf,
-                double *__restrict__ z)
-    {
-      const int V = N + 1;
-      const int t = blockIdx.x * blockDim.x + threadIdx.x;
-      const int n_h = V * N, n_v = N * V;
-      int       d;
-      double    c;
-      if (t < n_h)
-        {
-          const int i = t % N, j = t / N;
-          d           = hedge[t];
-          c           = 0.5 * (xp[j * V + i] + xp[j * V + i + 1]);
-        }
-      else if (t < n_h + n_v)
-        {
-          const int e = t - n_h, i = e % V, j = e / V;
-          d           = vedge[e];
-          c           = 0.5 * (xp[j * V + i] + xp[(j + 1) * V + i]);
-        }
-      else
-        return;
-      if (d < 0 || d >= L)
-        return; // owned faces only; halo faces arrive by halo exchange
-      z[d] = dinv[d] * rf[d] + c;
-    }
-
     inline unsigned
     gb(const int64_t n, const int b = 128)
     {

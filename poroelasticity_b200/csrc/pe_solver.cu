@@ -583,13 +583,6 @@ namespace pe
         c.precond_apply(c.precond_ctx, v, z);
         k_dot<<<g, 256, 0, s>>>(L, z, v, &st->d2, c.gap);
       }
-    else if (c.precond_add)
-      {
-        k_apply_precond_dot<<<g, 256, 0, s>>>(L, pinv, v, z, &st->d1, c.gap); // d1 is scratch here
-        cudaMemsetAsync(&st->d1, 0, sizeof(double), s);
-        c.precond_add(c.precond_ctx, v, z);
-        k_dot<<<g, 256, 0, s>>>(L, z, v, &st->d2, c.gap);
-      }
     else
       k_apply_precond_dot<<<g, 256, 0, s>>>(L, pinv, v, z, &st->d2, c.gap);
     if (c.allreduce)
@@ -640,12 +633,6 @@ namespace pe
           k_minres_lanczos<<<g, 256, 0, s>>>(L, st, p, v_, vo_, nullptr, zn_, nullptr, c.gap);
           PE_MARK(s, "minres: vector updates");
           c.precond_apply(c.precond_ctx, vo_ /* = v_new */, zn_);
-          k_dot<<<g, 256, 0, s>>>(L, zn_, vo_, &st->d2, c.gap);
-        }
-      else if (c.precond_add)
-        {
-          k_minres_lanczos<<<g, 256, 0, s>>>(L, st, p, v_, vo_, pinv, zn_, nullptr, c.gap);
-          c.precond_add(c.precond_ctx, vo_ /* = v_new */, zn_);
           k_dot<<<g, 256, 0, s>>>(L, zn_, vo_, &st->d2, c.gap);
         }
       else

@@ -31,8 +31,6 @@ namespace pe
     void (*halo)(void *ctx, double *x)               = nullptr;
     void (*allreduce)(void *ctx, double *v, int n)   = nullptr;
     void *halo_ctx                                   = nullptr;
-    // optional additive part of the preconditioner: z += M_aux^{-1} r  (multigrid, pe_mg.cu)
-    void (*precond_add)(void *ctx, const double *r, double *z) = nullptr;
     void *precond_ctx                                          = nullptr;
     int      use_graphs     = 1;       // capture the MINRES iteration into CUDA graphs (single GPU)
     int64_t *launch_counter = nullptr; // kernels launched (graph replays counted node by node)
