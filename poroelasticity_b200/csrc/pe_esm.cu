@@ -165,7 +165,10 @@ namespace pe
     k_esm_cell(const EsmArgs a)
     {
       __shared__ double  sG[kWarps][kQ * 4];       // per Gauss point: g00, g01, g11 (J^T J w / det)
-      __shared__ double  sA[kWarps][kLoc * kLoc];  // the finished local matrix, for coalesced output
+      // per warp: the Cholesky factor L (24 x 24, later overwritten by the finished 21 x 21 block) and Y (24 x 21);
+      // rows of L / columns of Y are read back as BROADCASTS (one address per warp), two doubles per LDS.128
+      __shared__ __align__(16) double sL[kWarps][kRt * kRt];
+      __shared__ __align__(16) double sYs[kWarps][kRt * (kLoc + 1)];
       __shared__ int64_t sRow[kWarps][kLoc];       // CSR row starts of the 21 local dofs
       // reference tables: constant memory serialises lane-dependent addresses, shared memory does not
       __shared__ __align__(16) double sPx[kQ * 12], sPy[kQ * 12];
@@ -255,7 +258,16 @@ namespace pe
               M[j] -= lik * ljk; // meaningful for i >= j; the upper triangle is never read
             }
         }
-      // ---- L Y = F^T: lane = column of Y (one local dof), forward substitution with L rows from their lanes
+      // ---- L Y = F^T: lane = column of Y (one local dof); the rows of L come back from shared memory as
+      //      broadcasts (the shuffle version of this loop and of Y^T Y cost ~1,600 of the 2,200 SHFL per cell)
+      double *Ls = sL[warp], *Ys = sYs[warp];
+      if (lane < kRt)
+        {
+#pragma unroll
+          for (int q = 0; q < kRt; ++q)
+            Ls[lane * kRt + q] = M[q];
+        }
+      __syncwarp();
       const int lc = lane < kLoc ? lane : kLoc - 1;
       double    Y[kRt];
 #pragma unroll
@@ -263,22 +275,44 @@ namespace pe
         {
           double sacc = sFt[r * kLoc + lc];
 #pragma unroll
-          for (int q = 0; q < r; ++q)
-            sacc -= __shfl_sync(FULL, M[q], r) * Y[q];
+          for (int q = 0; q + 1 < r; q += 2)
+            {
+              const double2 l2 = *reinterpret_cast<const double2 *>(&Ls[r * kRt + q]);
+              sacc -= l2.x * Y[q] + l2.y * Y[q + 1];
+            }
+          if (r & 1)
+            sacc -= Ls[r * kRt + r - 1] * Y[r - 1];
           Y[r] = sacc * invd[r];
+          if (lane < kLoc)
+            Ys[r * (kLoc + 1) + lane] = Y[r];
         }
-      // ---- A = k Y^T Y  (C M_K C^T of ESM:478-502): lane i builds row i
+      __syncwarp();
+      // ---- A = k Y^T Y  (C M_K C^T of ESM:478-502): lane i builds row i, columns of Y broadcast from shared memory
       const double kperm = a.kcell ? a.kcell[c] : a.k_scalar;
-      double      *A     = sA[warp];
+      double       Arow[kLoc];
 #pragma unroll
       for (int j = 0; j < kLoc; ++j)
-        {
-          double sacc = 0.;
+        Arow[j] = 0.;
 #pragma unroll
-          for (int r = 0; r < kRt; ++r)
-            sacc += Y[r] * __shfl_sync(FULL, Y[r], j);
-          if (lane < kLoc)
-            A[lane * kLoc + j] = kperm * sacc;
+      for (int r = 0; r < kRt; ++r)
+        {
+          const double yr = Y[r];
+#pragma unroll
+          for (int j = 0; j + 1 < kLoc; j += 2)
+            {
+              const double2 y2 = *reinterpret_cast<const double2 *>(&Ys[r * (kLoc + 1) + j]);
+              Arow[j] += yr * y2.x;
+              Arow[j + 1] += yr * y2.y;
+            }
+          Arow[kLoc - 1] += yr * Ys[r * (kLoc + 1) + kLoc - 1];
+        }
+      __syncwarp();
+      double *A = Ls; // L is dead: reuse its storage for the finished block (coalesced output below)
+      if (lane < kLoc)
+        {
+#pragma unroll
+          for (int j = 0; j < kLoc; ++j)
+            A[lane * kLoc + j] = kperm * Arow[j];
         }
       // ---- right-hand side (ESM:505-513)
       double bi = 0.; // lanes 0..8: b of interior dof `lane`
