@@ -29,6 +29,8 @@ namespace pe
   void comm_halo_exchange3(void *ctx, double *x);
   void comm_exchange_rows(void *ctx, double *p, int64_t row_len, int n_comp, int64_t comp_stride, int64_t a, int64_t b);
   void comm_allgather_rows(void *ctx, double *p, int64_t row_len, int n_comp, int64_t comp_stride, const int64_t *bounds);
+  void comm_reduce_rows(void *ctx, const double *in, double *out, int64_t row_len, int n_comp, int64_t comp_stride,
+                        const int64_t *bounds);
   void comm_allreduce(void *ctx, double *v, int n);
   void comm_allreduce2(void *ctx, const double *in, double *out, int n);
   int  comm_unique_id(uint8_t id[128]);
@@ -653,6 +655,7 @@ namespace
             gc.ctx            = h;
             gc.exchange_rows  = comm_exchange_rows;
             gc.allgather_rows = comm_allgather_rows;
+            gc.reduce_rows    = comm_reduce_rows;
             mg_set_comm(*h->mg, gc);
             if (h->cmg->ready)
               cmg_set_comm(*h->cmg, gc);

@@ -348,6 +348,28 @@ namespace pe
   }
 
   void
+  comm_reduce_rows(void *ctx, const double *in, double *out, int64_t row_len, int n_comp, int64_t comp_stride,
+                   const int64_t *bounds)
+  {
+    pe_handle *h = (pe_handle *)ctx;
+    CommState *c = cs(h);
+    if (!c)
+      return;
+    const int    W = h->part.world;
+    cudaStream_t s = h->stream;
+    ncclGroupStart();
+    for (int q = 0; q < W; ++q)
+      for (int k = 0; k < n_comp; ++k)
+        {
+          const size_t off = (size_t)k * comp_stride + bounds[q] * row_len;
+          const size_t n   = (size_t)((bounds[q + 1] - bounds[q]) * row_len);
+          if (n)
+            ncclReduce(in + off, out + off, n, ncclDouble, ncclSum, q, c->comm, s);
+        }
+    ncclGroupEnd();
+  }
+
+  void
   comm_allreduce2(void *ctx, const double *in, double *out, int n)
   {
     pe_handle *h = (pe_handle *)ctx;

@@ -81,6 +81,10 @@ namespace pe
     void (*exchange_rows)(void *ctx, double *p, int64_t row_len, int n_comp, int64_t comp_stride, int64_t a, int64_t b) = nullptr;
     // every rank receives the slabs [bounds[q], bounds[q+1]) of all ranks q (in place)
     void (*allgather_rows)(void *ctx, double *p, int64_t row_len, int n_comp, int64_t comp_stride, const int64_t *bounds) = nullptr;
+    // out[slab of rank q] = sum over the ranks of in[slab of rank q], delivered to rank q only (half the traffic of
+    // an all-reduce: a distributed level only needs its own rows of the right-hand side)
+    void (*reduce_rows)(void *ctx, const double *in, double *out, int64_t row_len, int n_comp, int64_t comp_stride,
+                        const int64_t *bounds) = nullptr;
   };
 
   // bounding box (cell indices, half open) of the cells a rank assembles on a structured mesh: the grid <-> Biot

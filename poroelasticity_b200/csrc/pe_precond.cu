@@ -436,7 +436,13 @@ namespace pe
     ++*launches;
     PE_MARK(s, "precond: A_vb + vertex gather");
     if (bp.allreduce2)
-      bp.allreduce2(bp.comm_ctx, bp.bu_local.p, L0.bu.p, 2 * nv);
+      {
+        // a distributed finest level only needs its own rows: reduce to the slab owners (half the traffic)
+        if (mg.n_dist > 0 && mg.gc.reduce_rows)
+          mg.gc.reduce_rows(mg.gc.ctx, bp.bu_local.p, L0.bu.p, N + 1, 2, nv, mg.bounds[0].data());
+        else
+          bp.allreduce2(bp.comm_ctx, bp.bu_local.p, L0.bu.p, 2 * nv);
+      }
     PE_MARK(s, "precond: all-reduce vertex rhs");
     mg_vcycle(mg, 2, s, launches);
     PE_MARK(s, "precond: vertex V-cycle");
@@ -466,7 +472,12 @@ namespace pe
     ++*launches;
     PE_MARK(sp, "precond: face Schur products");
     if (bp.allreduce2)
-      bp.allreduce2(bp.comm_ctx, bp.rc_local.p, cm.lv[0].b.p, N * N);
+      {
+        if (cm.n_dist > 0 && cm.gc.reduce_rows)
+          cm.gc.reduce_rows(cm.gc.ctx, bp.rc_local.p, cm.lv[0].b.p, N, 1, 0, cm.bounds[0].data());
+        else
+          bp.allreduce2(bp.comm_ctx, bp.rc_local.p, cm.lv[0].b.p, N * N);
+      }
     PE_MARK(sp, "precond: all-reduce cell rhs");
     const double *e = cmg_vcycle(cm, sp, launches);
     PE_MARK(sp, "precond: cell V-cycle");
