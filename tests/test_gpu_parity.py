@@ -328,3 +328,59 @@ def test_user_mesh_without_hierarchy_solves_with_large_lambda():
     x = b.solve_time_step()
     x_ref = spla.splu(o.csr(v_ref).tocsc()).solve(r_ref)
     assert np.linalg.norm(x - x_ref) <= 1e-7 * np.linalg.norm(x_ref)
+
+
+def test_shipped_cantilever_configuration():
+    """PoroElasBR1WG_new.cc as shipped (BR1new:163,551-558,981-983): cantilever bracket, K = 1e-7 I,
+    lambda = 1e6/7, mu = 1e6/28, alpha = 0.93, c0 = 0, dt = 0.01, zero body force / source, u = 0 on x = 0,
+    traction (0,-1) on y = 1, no pressure Dirichlet data.  Two backward-Euler steps against sparse LU."""
+    import scipy.sparse.linalg as spla
+    lam, mu, alpha, c0, dt, kperm = 1e6 / 7, 1e6 / 28, 0.93, 0.0, 0.01, 1e-7
+    nref = 4
+    o = Oracle(BR1_WG, nref, bc_mode=1)
+    o.set_material(lam, mu, alpha, c0, dt)
+    o.set_case(CASE_ZERO)
+    o.set_kcell(np.full(o.n_cells, kperm))
+    b = pb.BiotSystem(element=BR1_WG)
+    b.make_grid_and_dofs(nref)
+    b.set_face_kinds(o.mesh()[3], traction=(0.0, -1.0))
+    b.time_step = dt
+    b.set_material(lam, mu, alpha, c0, kperm)
+    b.set_case(pb.PE_CASE_ZERO)
+    b.rel_tol, b.max_iterations = 1e-11, 4000
+    old = np.zeros(o.n_dofs)
+    for step in range(2):
+        t = dt * (step + 1)
+        v_ref, r_ref, _ = o.assemble(t, old)
+        x_ref = spla.splu(o.csr(v_ref).tocsc()).solve(r_ref)
+        b.assemble_system(t)
+        assert rel(b.system_matrix(), v_ref) < TOL_MAT
+        assert rel(b.system_rhs(), r_ref) < TOL_MAT
+        x = b.solve_time_step(check=False)
+        assert b.stats.converged, (b.stats.iterations, b.stats.rel_residual)
+        nu = o.n_u
+        assert np.linalg.norm(x[:nu] - x_ref[:nu]) <= TOL_SOL * np.linalg.norm(x_ref[:nu])
+        assert np.linalg.norm(x[nu:] - x_ref[nu:]) <= 1e-6 * np.linalg.norm(x_ref[nu:])
+        old = x_ref
+
+
+def test_rhs_only_mode_reuses_matrix_and_solver_operator():
+    """SURVEY 8(f).1 'cached' mode: pe_assemble_rhs_only keeps the matrix (it is time independent, BR1new:687
+    rebuilds it anyway) and with it the solver's three-field operator; the right-hand side and the solution are
+    those of a full assemble_system."""
+    o, b = make_pair(BR1_WG, 4, lam=10.0, c0=0.02)
+    b.rel_tol = 1e-12
+    b.assemble_system(0.1)
+    v1 = b.system_matrix()
+    x1 = b.solve_time_step()
+    b.assemble_rhs_only(0.2)
+    r_cached = b.system_rhs()
+    assert np.array_equal(b.system_matrix(), v1)
+    x_cached = b.solve_time_step()
+    b2 = make_pair(BR1_WG, 4, lam=10.0, c0=0.02)[1]
+    b2.rel_tol = 1e-12
+    b2.set_solution(x1)
+    b2.assemble_system(0.2)
+    assert rel(r_cached, b2.system_rhs()) < 1e-13
+    x_full = b2.solve_time_step()
+    assert np.linalg.norm(x_cached - x_full) <= 1e-9 * np.linalg.norm(x_full)
