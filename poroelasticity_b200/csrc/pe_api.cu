@@ -267,9 +267,53 @@ namespace
       DevBuf<int32_t> d_rci;
       PE_CUDA(upload(d_rcp, pt.adj_ptr.data(), pt.adj_ptr.size(), s));
       PE_CUDA(upload(d_rci, rc.data(), rc.size(), s));
+      // gather assembly tables (Biot elements, atomics mode): slot bytes per CSR entry + adjacent cells per row
+      h->gather_ok = false;
+      h->d_gsrc.release();
+      h->d_rowadj.release();
+      DevBuf<int> d_bad;
+      // measured slower than the RED scatter (4.15 ms against 2.23 ms at N = 1024: both move 193 M eight-byte
+      // contributions through L2 one 32-byte sector at a time), kept as an opt-in alternative: PE_ASM_GATHER=1
+      const bool  want_gather = pt.scatter_mode == 0 && h->dofs.element != PE_WG_Q2RT2 && getenv("PE_ASM_GATHER");
+      if (want_gather)
+        {
+          bool ok = true;
+          std::vector<int32_t> ra((size_t)4 * h->L, -1);
+          for (int64_t l = 0; l < h->L && ok; ++l)
+            {
+              const int64_t n = pt.adj_ptr[l + 1] - pt.adj_ptr[l];
+              if (n > 4)
+                ok = false;
+              for (int64_t k = 0; k < n && ok; ++k)
+                ra[(size_t)4 * l + k] = rc[pt.adj_ptr[l] + k];
+            }
+          if (ok && h->d_gsrc.alloc((size_t)4 * h->nnz) == cudaSuccess && d_bad.alloc(1) == cudaSuccess &&
+              upload(h->d_rowadj, ra.data(), ra.size(), s) == cudaSuccess)
+            {
+              PE_CUDA(cudaMemsetAsync(h->d_gsrc.p, 0xFF, (size_t)4 * h->nnz, s));
+              PE_CUDA(cudaMemsetAsync(d_bad.p, 0, sizeof(int), s));
+              h->gather_ok = true;
+            }
+          else
+            {
+              cudaGetLastError();
+              h->d_gsrc.release();
+            }
+        }
       PE_CUDA(launch_scatter_offsets(n_loc, n_asm, h->L, h->d_cdofs.p, h->d_rowptr.p, h->d_colidx.p, d_rcp.p, d_rci.p,
-                                     h->d_off.p, h->d_rhs_first.p, h->d_err.p, s));
+                                     h->d_off.p, h->d_rhs_first.p, h->d_err.p, h->gather_ok ? h->d_gsrc.p : nullptr, d_bad.p, s));
       PE_CUDA(cudaStreamSynchronize(s));
+      if (h->gather_ok)
+        {
+          int bad = 0;
+          PE_CUDA(cudaMemcpy(&bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost));
+          if (bad)
+            {
+              h->gather_ok = false;
+              h->d_gsrc.release();
+              h->d_rowadj.release();
+            }
+        }
     }
     ++h->launches;
     int err = 0;
@@ -282,6 +326,7 @@ namespace
     // chunks for the atomics mode: rows first touched by asm cells [c0, c1) are contiguous per block
     h->chunk_cell_begin.clear();
     h->chunk_zero.clear();
+    h->chunk_rows.clear();
     if (pt.scatter_mode == 0)
       {
         std::vector<int32_t> pos((size_t)h->mesh.n_cells, -1);
@@ -308,6 +353,8 @@ namespace
                 const int64_t rb = std::lower_bound(bb, be, (int32_t)c1) - owner.begin();
                 h->chunk_zero.push_back(h->pat.rowptr[ra]);
                 h->chunk_zero.push_back(h->pat.rowptr[rb]);
+                h->chunk_rows.push_back(ra);
+                h->chunk_rows.push_back(rb);
               }
           }
         h->chunk_cell_begin.push_back(n_asm);
@@ -377,6 +424,26 @@ namespace
     a.do_matrix = do_matrix ? 1 : 0;
     a.atomic_mode = h->part.scatter_mode == 0 ? 1 : 0;
     return a;
+  }
+
+  // matrix (+ rhs) assembly of all cells into a.values / a.rhs in the mode chosen at setup
+  cudaError_t
+  run_assembly(pe_handle *h, const AsmArgs &a, const DevParams &P, int *nl)
+  {
+    cudaStream_t s = h->stream;
+    if (h->part.scatter_mode != 0)
+      return launch_assemble(h->cfg.element, a, P, h->part.n_colors, h->part.color_begin.data(), h->bnd_color_begin.data(), s, nl);
+    const int n_chunks = (int)h->chunk_cell_begin.size() - 1;
+    if (h->gather_ok)
+      {
+        const int    nz = h->cfg.element == PE_BR1_WG ? NzCount<0>::value : NzCount<1>::value;
+        const size_t nT = (size_t)nz * h->chunk_cells;
+        if (h->d_T.n < nT && h->d_T.alloc(nT) != cudaSuccess)
+          return cudaErrorMemoryAllocation;
+        return launch_assemble_gather(h->cfg.element, a, P, n_chunks, h->chunk_cell_begin.data(), h->chunk_rows.data(),
+                                      h->d_T.p, h->chunk_cells, h->d_gsrc.p, h->d_rowadj.p, s, nl);
+      }
+    return launch_assemble_chunked(h->cfg.element, a, P, n_chunks, h->chunk_cell_begin.data(), h->chunk_zero.data(), s, nl);
   }
 
   // host vector in global block order -> device vector in local numbering (owned + halo)
@@ -473,8 +540,7 @@ namespace
     PE_CUDA(cudaEventRecord(h->ev[1], s));
     int nl = 0;
     if (h->part.scatter_mode == 0 && do_matrix)
-      PE_CUDA(launch_assemble_chunked(h->cfg.element, a, P, (int)h->chunk_cell_begin.size() - 1,
-                                      h->chunk_cell_begin.data(), h->chunk_zero.data(), s, &nl));
+      PE_CUDA(run_assembly(h, a, P, &nl));
     else
       PE_CUDA(launch_assemble(h->cfg.element, a, P, h->part.n_colors, h->part.color_begin.data(),
                               h->bnd_color_begin.data(), s, &nl));
@@ -569,12 +635,7 @@ namespace
     a.sol                 = nullptr;
     int nl                = 0;
     cudaError_t e;
-    if (h->part.scatter_mode == 0)
-      e = launch_assemble_chunked(h->cfg.element, a, P, (int)h->chunk_cell_begin.size() - 1, h->chunk_cell_begin.data(),
-                                  h->chunk_zero.data(), s, &nl);
-    else
-      e = launch_assemble(h->cfg.element, a, P, h->part.n_colors, h->part.color_begin.data(), h->bnd_color_begin.data(), s,
-                          &nl);
+    e = run_assembly(h, a, P, &nl);
     h->launches += nl;
     if (e != cudaSuccess)
       return 1;

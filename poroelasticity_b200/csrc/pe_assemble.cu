@@ -23,7 +23,9 @@ namespace pe
                     const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
                     const int64_t *__restrict__ rc_ptr, const int32_t *__restrict__ rc_idx,
                     const uint16_t *__restrict__ slot /* [n_loc*n_loc] */, uint8_t *__restrict__ off /* [4*words][n_asm] */,
-                    uint32_t *__restrict__ rhs_first, int *__restrict__ err)
+                    uint32_t *__restrict__ rhs_first, int *__restrict__ err,
+                    const uint8_t *__restrict__ nzs /* [n_loc*n_loc] non-zero slot or 255 */,
+                    uint8_t *__restrict__ gsrc /* [nnz][4] or null */, int *__restrict__ gather_bad)
   {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_asm * n_loc)
@@ -82,6 +84,18 @@ namespace pe
           }
         const int sl = slot[i * n_loc + j];
         off[((size_t)(sl >> 2) * n_asm + c) * 4 + (sl & 3)] = (uint8_t)((lo - b) | (first == c ? 128 : 0));
+        // gather table: CSR entry (r, col) receives non-zero slot nzs(i,j) of the s-th cell adjacent to row r
+        if (gsrc)
+          {
+            int sidx = -1;
+            for (int64_t k = cb; k < ce; ++k)
+              if (rc_idx[k] == c)
+                sidx = (int)(k - cb);
+            if (ce - cb > 4 || sidx < 0)
+              atomicExch(gather_bad, 1); // a row with more than four adjacent cells: no gather assembly
+            else if (nzs[i * n_loc + j] != 255)
+              gsrc[(size_t)lo * 4 + sidx] = nzs[i * n_loc + j];
+          }
       }
   }
 
@@ -250,6 +264,158 @@ namespace pe
       {
         const int64_t k = i < n0 ? b0 + i : (i < n0 + n1 ? b1 + (i - n0) : b2 + (i - n0 - n1));
         v[k]            = 0.;
+      }
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // Gather assembly (opt-in alternative, PE_ASM_GATHER=1, meshes whose rows touch <= 4 cells): no atomics on the
+  // bulk of the entries.  MEASURED SLOWER than the RED scatter on B200 (N = 1024: 4.15 ms against 2.23 ms): the
+  // staged contributions are written coalesced but read back one 32-byte sector per 8-byte entry, i.e. the same
+  // 193 M L2 transactions as the REDs plus the staging traffic.
+  //   phase A  per chunk of Morton-consecutive cells: the cell kernels stage every structurally non-zero local
+  //            entry at T[nz][cell in chunk] with plain coalesced stores (the same access pattern as the dense
+  //            local-matrix kernel, 61 % of the HBM roof).  Rows first touched by an EARLIER chunk (2 % of the
+  //            cells of a 32 Ki chunk sit on its low boundary) are updated with RED as before.
+  //   phase B  one warp per row first touched by the chunk: lane e sums, for CSR entry e of the row, the staged
+  //            contributions of the <= 4 adjacent cells of the chunk (one table word per entry: four slot bytes)
+  //            and stores the value -- which also replaces the memset of the matrix.  Cells of LATER chunks add
+  //            their share with RED when their chunk runs (stream order), boundary cells at the very end.
+  // ---------------------------------------------------------------------------------------------
+  struct GatherArgs
+  {
+    double        *T;        // [NZ][chunk_stride]
+    int64_t        chunk_stride;
+    int64_t        row_begin[3], row_end[3]; // local rows first touched by this chunk, per block (u | p_int | p_face)
+    const uint8_t *gsrc;     // [nnz][4]
+    const int32_t *rowadj;   // [L][4] asm indices of the cells adjacent to a row, -1 padded
+  };
+
+  template <int EL, int NL>
+  struct TileEmit
+  {
+    double        *T, *values, *rhsp;
+    const uint8_t *off;
+    int64_t        n_asm, c;
+    uint32_t       own; // bit i: local dof i is a row first touched by this chunk
+    int64_t        rs[NL];
+    int32_t        row[NL];
+    __device__ __forceinline__ void
+    rhs(const int i, const double v)
+    {
+      if (rs[i] < 0 || rhsp == nullptr)
+        return;
+      if (v != 0.)
+        atomicAdd(rhsp + row[i], v);
+    }
+  };
+  // T is indexed [nz * stride + cell]; T points at this cell's column
+  template <int EL, int NL>
+  struct TileEmitS : TileEmit<EL, NL>
+  {
+    int64_t stride;
+    __device__ __forceinline__ void
+    mat(const int i, const int j, const double v)
+    {
+      const int nz = nzslot<EL>(i, j);
+      if (nz < 0 || this->rs[i] < 0)
+        return;
+      if ((this->own >> i) & 1u)
+        this->T[(size_t)nz * stride] = v;
+      else if (v != 0.)
+        {
+          const int      sl = SlotMap<EL>::slot(i, j);
+          const uint32_t o  = this->off[((size_t)(sl >> 2) * this->n_asm + this->c) * 4 + (sl & 3)];
+          atomicAdd(this->values + this->rs[i] + (o & 127u), v);
+        }
+    }
+  };
+
+  template <int EL, int SW>
+  __device__ __forceinline__ void
+  assemble_gather_body(const AsmArgs &a, const DevParams &P, const GatherArgs &g)
+  {
+    constexpr int NL = Elem<EL>::NL;
+    const int64_t t  = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t c  = a.a_begin + t;
+    if (c >= a.a_end)
+      return;
+    double *Tc = g.T + t;
+    if (a.flags[c] != 0u)
+      {
+        // boundary cells are assembled by k_assemble_boundary at the end: their staged contribution is zero
+        if (SW == 1)
+          for (int z = 0; z < NzCount<EL>::value; ++z)
+            Tc[(size_t)z * g.chunk_stride] = 0.;
+        return;
+      }
+    double  vx[4], vy[4], old[NL];
+    int32_t idx[NL];
+    load_cell<EL>(a, c, vx, vy, idx, old);
+    Geom G;
+    G.set(vx, vy);
+    TileEmitS<EL, NL> E;
+    E.T      = Tc;
+    E.stride = g.chunk_stride;
+    E.values = a.values;
+    E.rhsp   = a.rhs;
+    E.off    = a.off;
+    E.n_asm  = a.n_asm;
+    E.c      = c;
+    E.own    = 0u;
+#pragma unroll
+    for (int i = 0; i < NL; ++i)
+      {
+        E.row[i] = idx[i];
+        E.rs[i]  = idx[i] < a.L ? __ldg(a.rowptr + idx[i]) : -1;
+        const int blk = SlotMap<EL>::kind(i) <= 1 ? 0 : (SlotMap<EL>::kind(i) == 3 ? 1 : 2);
+        if (idx[i] >= g.row_begin[blk] && idx[i] < g.row_end[blk])
+          E.own |= 1u << i;
+      }
+    cell_kernel<EL, SW>(G, a.kcell ? a.kcell[c] : a.k_scalar, P, old, E);
+  }
+  template <int EL>
+  __global__ void __launch_bounds__(128)
+  k_assemble_gatherA(const AsmArgs a, const DevParams P, const GatherArgs g)
+  {
+    if (blockIdx.y == 0)
+      assemble_gather_body<EL, 1>(a, P, g);
+    else if (blockIdx.y == 1)
+      assemble_gather_body<EL, 2>(a, P, g);
+    else
+      assemble_gather_body<EL, 4>(a, P, g);
+  }
+  // phase B: warp per row
+  __global__ void __launch_bounds__(256)
+  k_assemble_gatherB(const AsmArgs a, const GatherArgs g)
+  {
+    const int64_t w    = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int     lane = threadIdx.x & 31;
+    const int64_t n0 = g.row_end[0] - g.row_begin[0], n1 = g.row_end[1] - g.row_begin[1], n2 = g.row_end[2] - g.row_begin[2];
+    if (w >= n0 + n1 + n2)
+      return;
+    const int64_t r = w < n0 ? g.row_begin[0] + w : (w < n0 + n1 ? g.row_begin[1] + (w - n0) : g.row_begin[2] + (w - n0 - n1));
+    // cells of this chunk adjacent to the row (column index inside T), -1: none / a later chunk
+    int64_t cell[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      {
+        const int32_t ac = __ldg(g.rowadj + 4 * r + q);
+        cell[q]          = (ac >= a.a_begin && ac < a.a_end) ? ac - a.a_begin : -1;
+      }
+    const int64_t b = __ldg(a.rowptr + r), e = __ldg(a.rowptr + r + 1);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(g.gsrc);
+    for (int64_t k = b + lane; k < e; k += 32)
+      {
+        const uint32_t wq = __ldg(src + k);
+        double         v  = 0.;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          {
+            const uint32_t nz = (wq >> (8 * q)) & 255u;
+            if (nz != 255u && cell[q] >= 0)
+              v += g.T[(size_t)nz * g.chunk_stride + cell[q]];
+          }
+        a.values[k] = v;
       }
   }
 
@@ -554,7 +720,7 @@ namespace pe
   cudaError_t
   launch_scatter_offsets(const int n_loc, const int64_t n_asm, const int64_t L, const int32_t *cdofs,
                          const int64_t *rowptr, const int32_t *colidx, const int64_t *rc_ptr, const int32_t *rc_idx,
-                         uint8_t *off, uint32_t *rhs_first, int *err, cudaStream_t s)
+                         uint8_t *off, uint32_t *rhs_first, int *err, uint8_t *gsrc, int *gather_bad, cudaStream_t s)
   {
     const int64_t n = n_asm * n_loc;
     if (n == 0)
@@ -563,17 +729,31 @@ namespace pe
     for (int i = 0; i < n_loc; ++i)
       for (int j = 0; j < n_loc; ++j)
         slot_h[i * n_loc + j] = (uint16_t)(n_loc == 17 ? SlotMap<0>::slot(i, j) : (n_loc == 13 ? SlotMap<1>::slot(i, j) : i * n_loc + j));
+    uint8_t nz_h[21 * 21];
+    for (int i = 0; i < n_loc; ++i)
+      for (int j = 0; j < n_loc; ++j)
+        {
+          const int z         = n_loc == 17 ? nzslot<0>(i, j) : (n_loc == 13 ? nzslot<1>(i, j) : -1);
+          nz_h[i * n_loc + j] = z < 0 ? 255 : (uint8_t)z;
+        }
     uint16_t *slot_d = nullptr;
+    uint8_t  *nz_d   = nullptr;
     cudaError_t     e      = cudaMalloc((void **)&slot_d, sizeof(uint16_t) * n_loc * n_loc);
     if (e != cudaSuccess)
       return e;
+    e = cudaMalloc((void **)&nz_d, n_loc * n_loc);
+    if (e != cudaSuccess)
+      return e;
     cudaMemcpyAsync(slot_d, slot_h, sizeof(uint16_t) * n_loc * n_loc, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(nz_d, nz_h, n_loc * n_loc, cudaMemcpyHostToDevice, s);
     cudaMemsetAsync(rhs_first, 0, sizeof(uint32_t) * (size_t)n_asm, s);
     k_scatter_offsets<<<grid_for(n, 256), 256, 0, s>>>(n_loc, n_asm, L, cdofs, rowptr, colidx, rc_ptr, rc_idx, slot_d, off,
-                                                        rhs_first, err);
+                                                        rhs_first, err, nz_d, (n_loc == 17 || n_loc == 13) ? gsrc : nullptr,
+                                                        gather_bad);
     e = cudaGetLastError();
     cudaStreamSynchronize(s);
     cudaFree(slot_d);
+    cudaFree(nz_d);
     return e;
   }
 
@@ -659,6 +839,61 @@ namespace pe
     AsmArgs a   = a0;
     a.bnd_begin = 0;
     a.bnd_end   = a0.n_bnd;
+    if (a.n_bnd > 0)
+      {
+        if (element == 0)
+          k_assemble_boundary<0><<<grid_for(a.n_bnd, 64), 64, 0, s>>>(a, P);
+        else
+          k_assemble_boundary<1><<<grid_for(a.n_bnd, 64), 64, 0, s>>>(a, P);
+        ++*n_launches;
+      }
+    return cudaGetLastError();
+  }
+
+  cudaError_t
+  launch_assemble_gather(const int element, const AsmArgs &a0, const DevParams &P, const int n_chunks,
+                         const int64_t *chunk_cell_begin, const int64_t *chunk_rows /* [n_chunks][6] */, double *T,
+                         const int64_t chunk_stride, const uint8_t *gsrc, const int32_t *rowadj, cudaStream_t s,
+                         int *n_launches)
+  {
+    for (int ch = 0; ch < n_chunks; ++ch)
+      {
+        AsmArgs a = a0;
+        a.a_begin = chunk_cell_begin[ch];
+        a.a_end   = chunk_cell_begin[ch + 1];
+        GatherArgs g;
+        g.T            = T;
+        g.chunk_stride = chunk_stride;
+        g.gsrc         = gsrc;
+        g.rowadj       = rowadj;
+        int64_t n_rows = 0;
+        for (int b = 0; b < 3; ++b)
+          {
+            g.row_begin[b] = chunk_rows[6 * ch + 2 * b];
+            g.row_end[b]   = chunk_rows[6 * ch + 2 * b + 1];
+            n_rows += g.row_end[b] - g.row_begin[b];
+          }
+        const int64_t n = a.a_end - a.a_begin;
+        if (n > 0)
+          {
+            const dim3 grid(grid_for(n, 128), 3);
+            if (element == 0)
+              k_assemble_gatherA<0><<<grid, 128, 0, s>>>(a, P, g);
+            else
+              k_assemble_gatherA<1><<<grid, 128, 0, s>>>(a, P, g);
+            ++*n_launches;
+          }
+        if (n_rows > 0)
+          {
+            k_assemble_gatherB<<<grid_for(n_rows * 32, 256), 256, 0, s>>>(a, g);
+            ++*n_launches;
+          }
+      }
+    // boundary cells last (their rows hold the interior contributions by now)
+    AsmArgs a   = a0;
+    a.bnd_begin = 0;
+    a.bnd_end   = a0.n_bnd;
+    a.atomic_mode = 1;
     if (a.n_bnd > 0)
       {
         if (element == 0)

@@ -131,6 +131,43 @@ namespace pe
     }
   };
 
+  // ---------------------------------------------------------------------------------------------
+  // Numbering of the STRUCTURALLY NON-ZERO entries of the local matrix (the u <-> p_face block is zero,
+  // SURVEY 8(a) row A5): row-major over (i, j), zeros skipped.  193 (BR1) / 105 (CGQ1) entries: one byte.
+  // Used by the gather assembly (pe_assemble.cu): entry nz of cell c is staged at T[nz][c].
+  // Closed-form arithmetic so that it folds to a constant for compile-time (i, j).  -1 = structural zero.
+  // ---------------------------------------------------------------------------------------------
+  template <int EL>
+  __host__ __device__ constexpr int
+  nzslot(const int i, const int j)
+  {
+    using SM     = SlotMap<EL>;
+    const int ki = SM::kind(i), kj = SM::kind(j); // 0,1: displacement, 2: p_face, 3: p_int
+    if ((ki <= 1 && kj == 2) || (ki == 2 && kj <= 1))
+      return -1;
+    constexpr int NU = Elem<EL>::NU, USZ = NU + 1, PSZ = 5; // non-zeros in a u row / a p_face row
+    // first slot of row i
+    int base = 0;
+    if (EL == 0)
+      base = i < 8 ? USZ * i : (i == 16 ? 8 * USZ + 4 * (USZ + PSZ) : 8 * USZ + ((i - 8) / 2) * (USZ + PSZ) + (((i - 8) & 1) ? USZ : 0));
+    else
+      base = i < 8 ? USZ * i : (i == 12 ? 8 * USZ + 4 * PSZ : 8 * USZ + (i - 8) * PSZ);
+    // rank of column j among the non-zeros of the row
+    int rank = 0;
+    if (ki <= 1)
+      rank = kj == 3 ? NU : SM::ui(j);
+    else if (ki == 2)
+      rank = kj == 3 ? 4 : SM::p5(j) - 1;
+    else
+      rank = j;
+    return base + rank;
+  }
+  template <int EL>
+  struct NzCount
+  {
+    static constexpr int value = EL == 0 ? 193 : 105;
+  };
+
   struct Geom
   {
     double x0, y0;                     // vertex 0

@@ -143,7 +143,13 @@ struct pe_handle
   pe::DevBuf<double>   d_k_morton; // per-cell K in cell (Morton) order for the multigrid levels
   std::vector<int64_t> bnd_color_begin;
   // atomics mode: chunks of asm cells and the value ranges (3 per chunk) zeroed before each chunk
-  std::vector<int64_t> chunk_cell_begin, chunk_zero;
+  std::vector<int64_t> chunk_cell_begin, chunk_zero, chunk_rows;
+  // gather assembly (pe_assemble.cu): four slot bytes per CSR entry, the <= 4 cells adjacent to every owned row,
+  // the staging buffer T[NZ][chunk_cells]; opt-in (PE_ASM_GATHER=1), measured slower than the default RED scatter
+  bool                 gather_ok = false;
+  pe::DevBuf<uint8_t>  d_gsrc;
+  pe::DevBuf<int32_t>  d_rowadj;
+  pe::DevBuf<double>   d_T;
   int64_t              chunk_cells = 32768;
   pe::DevBuf<int32_t>  d_cdofs, d_colidx, d_bnd_list, d_rowblk;
   int64_t              n_rowblk = 0;

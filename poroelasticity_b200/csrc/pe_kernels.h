@@ -26,13 +26,19 @@ namespace pe
 
   cudaError_t launch_scatter_offsets(int n_loc, int64_t n_asm, int64_t L, const int32_t *cdofs,
                                      const int64_t *rowptr, const int32_t *colidx, const int64_t *rc_ptr,
-                                     const int32_t *rc_idx, uint8_t *off, uint32_t *rhs_first, int *err, cudaStream_t s);
+                                     const int32_t *rc_idx, uint8_t *off, uint32_t *rhs_first, int *err, uint8_t *gsrc,
+                                     int *gather_bad, cudaStream_t s);
   int         scatter_table_words(int n_loc); // 32-bit words per cell of the scatter-offset table
   cudaError_t launch_assemble(int element, const AsmArgs &a, const DevParams &P, int n_colors, const int64_t *color_begin,
                               const int64_t *bnd_color_begin, cudaStream_t s, int *n_launches);
   cudaError_t launch_assemble_chunked(int element, const AsmArgs &a, const DevParams &P, int n_chunks,
                                       const int64_t *chunk_cell_begin, const int64_t *chunk_zero, cudaStream_t s,
                                       int *n_launches);
+  // gather assembly (pe_assemble.cu): staged local entries + one warp per row, atomics only across chunk boundaries
+  cudaError_t launch_assemble_gather(int element, const AsmArgs &a, const DevParams &P, int n_chunks,
+                                     const int64_t *chunk_cell_begin, const int64_t *chunk_rows, double *T,
+                                     int64_t chunk_stride, const uint8_t *gsrc, const int32_t *rowadj, cudaStream_t s,
+                                     int *n_launches);
   cudaError_t launch_local_matrices(int element, const AsmArgs &a, const DevParams &P, int64_t first, int64_t n,
                                     double *out, double *rhs_out, cudaStream_t s);
   cudaError_t launch_step_errors(int element, const AsmArgs &a, const DevParams &P, const uint8_t *is_ghost, double *e,

@@ -384,3 +384,21 @@ def test_rhs_only_mode_reuses_matrix_and_solver_operator():
     assert rel(r_cached, b2.system_rhs()) < 1e-13
     x_full = b2.solve_time_step()
     assert np.linalg.norm(x_cached - x_full) <= 1e-9 * np.linalg.norm(x_full)
+
+
+@pytest.mark.parametrize("el", [BR1_WG, CGQ1_WG])
+def test_gather_assembly_alternative_matches(el, monkeypatch):
+    """PE_ASM_GATHER=1: staged local entries + one warp per row instead of RED scatter (measured slower, kept as
+    an alternative like the colour-ordered mode): same matrix and right-hand side."""
+    import scipy.sparse.linalg as spla
+    o, b0 = make_pair(el, 5, distort=0.1, lam=2.0, c0=0.01)
+    v_ref, r_ref, _ = o.assemble(0.3)
+    monkeypatch.setenv("PE_ASM_GATHER", "1")
+    b = make_pair(el, 5, distort=0.1, lam=2.0, c0=0.01)[1]
+    b.assemble_system(0.3)
+    assert rel(b.system_matrix(), v_ref) < TOL_MAT
+    assert rel(b.system_rhs(), r_ref) < TOL_MAT
+    b.rel_tol = 1e-12
+    x = b.solve_time_step()
+    x_ref = spla.splu(o.csr(v_ref).tocsc()).solve(r_ref)
+    assert np.linalg.norm(x - x_ref) <= TOL_SOL * np.linalg.norm(x_ref)
