@@ -1198,6 +1198,7 @@ extern "C"
     h->c0          = c0;
     h->k_scalar    = k_scalar;
     h->k_lognormal = false;
+    h->matrix_valid = false; // the assembled matrix (and the solver operator built from it) belongs to the old data
     if (k_cell)
       {
         if (!h->have_mesh)
