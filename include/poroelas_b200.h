@@ -195,6 +195,9 @@ int pe_step_errors(pe_handle *h, double t, double e[3]);
 /* the solver's SpMV kernel alone, `repeats` back-to-back launches on the handle's stream timed with
  * CUDA events (roofline measurement; x = current solution vector): average ms per launch */
 int pe_bench_spmv(pe_handle *h, int repeats, double *ms_per_launch);
+/* FP64 roofline denominator: a dependent-chain-free DFMA loop on every SM of the handle's device, timed with CUDA
+ * events (the driver's MEASURED_PEAKS.json holds no FP64 figure): achieved TFLOP/s */
+int pe_bench_fp64(pe_handle *h, double *tflops);
 
 /* ---- multi-GPU (one process per GPU) --------------------------------------------------------- */
 /* 128-byte NCCL unique id made on rank 0 and broadcast by the host program (torch.distributed,

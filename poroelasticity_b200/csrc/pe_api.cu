@@ -1386,6 +1386,22 @@ extern "C"
   }
 
   int
+  pe_bench_fp64(pe_handle *h, double *tflops)
+  {
+    if (!h || !tflops || h->device < 0)
+      return fail(h, PE_ERR_ARG, "pe_bench_fp64: bad argument");
+    PE_TRY
+    if (h->d_scal.n < 64)
+      PE_CUDA(h->d_scal.alloc(64));
+    double sec = 0., flop = 0.;
+    PE_CUDA(launch_fp64_peak(h->d_scal.p + 48, h->ev[5], h->ev[6], h->stream, &sec, &flop));
+    *tflops = flop / sec * 1e-12;
+    ++h->launches;
+    return PE_OK;
+    PE_CATCH
+  }
+
+  int
   pe_bench_spmv(pe_handle *h, int repeats, double *ms_per_launch)
   {
     if (!h || repeats <= 0 || !ms_per_launch || !h->device_ready || !h->matrix_valid)

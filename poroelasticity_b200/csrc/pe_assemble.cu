@@ -7,6 +7,7 @@
 #include "pe_kernels.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace pe
 {
@@ -253,6 +254,16 @@ namespace pe
       assemble_interior_body<EL, 2, true, true>(a, P);
     else
       assemble_interior_body<EL, 4, true, true>(a, P);
+  }
+  // the X and Q sweeps alone (163 / 186 registers: three CTAs per SM instead of the two the Y sweep's 252 allow)
+  template <int EL>
+  __global__ void __launch_bounds__(128, 3)
+  k_assemble_interior_xq(const AsmArgs a, const DevParams P)
+  {
+    if (blockIdx.y == 0)
+      assemble_interior_body<EL, 1, true, true>(a, P);
+    else
+      assemble_interior_body<EL, 2, true, true>(a, P);
   }
   // zero up to three ranges of the CSR values (the rows first touched by a chunk of cells)
   __global__ void
@@ -825,7 +836,23 @@ namespace pe
             ++*n_launches;
           }
         const int64_t n = a.a_end - a.a_begin;
-        if (n > 0)
+        static const bool split = getenv("PE_ASM_SPLIT") != nullptr; // A/B hook: Y sweep in its own launch
+        if (n > 0 && split)
+          {
+            const dim3 g2(grid_for(n, 128), 2);
+            if (element == 0)
+              {
+                k_assemble_interior_xq<0><<<g2, 128, 0, s>>>(a, P);
+                k_assemble_interior<0, 4, true, true><<<grid_for(n, 128), 128, 0, s>>>(a, P);
+              }
+            else
+              {
+                k_assemble_interior_xq<1><<<g2, 128, 0, s>>>(a, P);
+                k_assemble_interior<1, 4, true, true><<<grid_for(n, 128), 128, 0, s>>>(a, P);
+              }
+            *n_launches += 2;
+          }
+        else if (n > 0)
           {
             const dim3 g(grid_for(n, 128), 3);
             if (element == 0)
@@ -954,6 +981,45 @@ namespace pe
     if (n == 0)
       return cudaSuccess;
     k_lognormal<<<grid_for(n, 256), 256, 0, s>>>(n, cell_ids, first, sigma, seed, k);
+    return cudaGetLastError();
+  }
+
+  // FP64 roofline denominator: 16 independent FMA chains per thread, no memory traffic
+  __global__ void __launch_bounds__(256)
+  k_fp64_peak(const int iters, const double a, const double b, double *__restrict__ sink)
+  {
+    double x[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      x[k] = (double)(threadIdx.x + k) * 1e-3;
+    for (int it = 0; it < iters; ++it)
+      {
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+          x[k] = fma(x[k], a, b);
+      }
+    double s = 0.;
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      s += x[k];
+    if (s == 12345.678) // never true: keeps the chains alive
+      sink[0] = s;
+  }
+  cudaError_t
+  launch_fp64_peak(double *sink, cudaEvent_t e0, cudaEvent_t e1, cudaStream_t s, double *seconds, double *flop)
+  {
+    const int    iters = 1 << 14, grid = 148 * 16, block = 256;
+    k_fp64_peak<<<grid, block, 0, s>>>(256, 0.999999, 1e-7, sink); // warm-up
+    cudaEventRecord(e0, s);
+    k_fp64_peak<<<grid, block, 0, s>>>(iters, 0.999999, 1e-7, sink);
+    cudaEventRecord(e1, s);
+    cudaError_t e = cudaEventSynchronize(e1);
+    if (e != cudaSuccess)
+      return e;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *seconds = ms * 1e-3;
+    *flop    = 2. * 16. * (double)iters * (double)grid * (double)block;
     return cudaGetLastError();
   }
 

@@ -46,6 +46,8 @@ namespace pe
   cudaError_t launch_lognormal(int64_t n, const int64_t *cell_ids, int64_t first, double sigma, uint64_t seed,
                                double *k, cudaStream_t s);
   cudaError_t launch_sum(const double *x, size_t n, double *out, cudaStream_t s);
+  // DFMA peak of the device (16 independent chains per thread, all SMs): seconds and flop of the timed launch
+  cudaError_t launch_fp64_peak(double *sink, cudaEvent_t e0, cudaEvent_t e1, cudaStream_t s, double *seconds, double *flop);
 
   // ---- WG(Q2,Q2;RT[2]) element of EltStiffMat.cc (pe_esm.cu)
   cudaError_t launch_esm_assemble(const AsmArgs &a, int case_id, cudaStream_t s, int *n_launches);

@@ -215,6 +215,12 @@ class BiotSystem:
         self._ck(self.L.pe_bench_spmv(self.h, repeats, C.byref(ms)))
         return ms.value
 
+    def bench_fp64(self):
+        """measured DFMA throughput of the device in TFLOP/s (FP64 roofline denominator)"""
+        t = C.c_double()
+        self._ck(self.L.pe_bench_fp64(self.h, C.byref(t)))
+        return t.value
+
     def local_matrices(self, first, n, t=0.0, old_solution=None, time_step=None, want_rhs=False):
         dt = self.time_step if time_step is None else time_step
         nl = self.sizes().n_loc

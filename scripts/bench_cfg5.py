@@ -14,5 +14,8 @@ cs, sec = b.local_matrices_bench(chunk, repeats=3, t=0.1)
 n = 1 << (2 * nref)
 nl = {0: 17, 1: 13, 2: 21}[el]
 bytes_per_cell = 64 + 8 + 8 * nl * nl
-print(json.dumps({"cfg": 5, "element": el, "cells": n, "distort": distort, "chunk_cells": chunk, "seconds": sec, "cells_per_s": n / sec,
+fp64 = b.bench_fp64()
+flop_per_cell = {0: 9.0e3, 1: 5.0e3, 2: 45.0e3}[el]   # lean FP64 work per cell
+print(json.dumps({"fp64_peak_measured_tflops": fp64, "tflops": n * flop_per_cell / sec * 1e-12,
+                  "frac_of_fp64_peak": n * flop_per_cell / sec * 1e-12 / fp64, "cfg": 5, "element": el, "cells": n, "distort": distort, "chunk_cells": chunk, "seconds": sec, "cells_per_s": n / sec,
                   "GBps_algorithmic": n * bytes_per_cell / sec / 1e9, "frac_of_6547": n * bytes_per_cell / sec / 1e9 / 6547.2, "checksum": cs, "mesh_s": ts}))
