@@ -255,16 +255,6 @@ namespace pe
     else
       assemble_interior_body<EL, 4, true, true>(a, P);
   }
-  // the X and Q sweeps alone (163 / 186 registers: three CTAs per SM instead of the two the Y sweep's 252 allow)
-  template <int EL>
-  __global__ void __launch_bounds__(128, 3)
-  k_assemble_interior_xq(const AsmArgs a, const DevParams P)
-  {
-    if (blockIdx.y == 0)
-      assemble_interior_body<EL, 1, true, true>(a, P);
-    else
-      assemble_interior_body<EL, 2, true, true>(a, P);
-  }
   // zero up to three ranges of the CSR values (the rows first touched by a chunk of cells)
   __global__ void
   k_zero_ranges(double *__restrict__ v, const int64_t b0, const int64_t e0, const int64_t b1, const int64_t e1,
@@ -836,23 +826,9 @@ namespace pe
             ++*n_launches;
           }
         const int64_t n = a.a_end - a.a_begin;
-        static const bool split = getenv("PE_ASM_SPLIT") != nullptr; // A/B hook: Y sweep in its own launch
-        if (n > 0 && split)
-          {
-            const dim3 g2(grid_for(n, 128), 2);
-            if (element == 0)
-              {
-                k_assemble_interior_xq<0><<<g2, 128, 0, s>>>(a, P);
-                k_assemble_interior<0, 4, true, true><<<grid_for(n, 128), 128, 0, s>>>(a, P);
-              }
-            else
-              {
-                k_assemble_interior_xq<1><<<g2, 128, 0, s>>>(a, P);
-                k_assemble_interior<1, 4, true, true><<<grid_for(n, 128), 128, 0, s>>>(a, P);
-              }
-            *n_launches += 2;
-          }
-        else if (n > 0)
+        // (the Y sweep in a launch of its own, so that X and Q run at 3 CTAs per SM, measured slower: 2.41 ms
+        //  against 2.23 ms at N = 1024)
+        if (n > 0)
           {
             const dim3 g(grid_for(n, 128), 3);
             if (element == 0)
