@@ -88,3 +88,14 @@ def test_host_numbering_and_pattern_bit_exact(nref):
     rp, ci = b.pattern()
     rp2, ci2 = o.pattern()
     assert np.array_equal(rp, rp2) and np.array_equal(ci, ci2)
+
+
+def test_local_matrix_equals_exact_rational_derivation():
+    """tests/golden/esm_exact_unit_square.npy: the 21 x 21 matrix derived with exact rational arithmetic on a
+    monomial RT[2] basis (scripts/derive_esm_kat.py) -- independent of the oracle's basis, quadrature and inverse."""
+    import os
+    A = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "esm_exact_unit_square.npy"))
+    assert abs(np.trace(A) - 496.0 / 5.0) < 1e-12 and abs(A[0, 0] - 32.0 / 15.0) < 1e-14 and abs(A[12, 12] - 148.0 / 45.0) < 1e-14
+    o = EsmOracle(0)  # one cell: the unit square
+    Ao = o.local_matrices(0, 1)[0][0]
+    assert np.abs(Ao - A).max() < 1e-12 * np.abs(A).max()

@@ -110,3 +110,16 @@ def test_cpp_host_driver_runs():
     assert "Number of active cells: 4" in out.stdout
     assert "Number of rt degrees of freedom: 84" in out.stdout
     assert "Number of dof: 72" in out.stdout
+
+
+def test_local_matrix_equals_exact_rational_derivation():
+    """The CUDA kernel against the exact (sympy) unit-square matrix of scripts/derive_esm_kat.py."""
+    import os
+    A = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "esm_exact_unit_square.npy"))
+    b = pb.WGDarcyEquation()
+    b.make_grid(0)
+    assert rel(b.local_matrices(0, 1)[0], A) < 1e-12
+    # the local matrix is invariant under uniform refinement (2-D Darcy) -- any cell of a finer Cartesian mesh
+    b2 = pb.WGDarcyEquation()
+    b2.make_grid(5)
+    assert rel(b2.local_matrices(777, 1)[0], A) < 1e-12
