@@ -80,6 +80,14 @@ extern "C"
     Problem *P = (Problem *)h;
     std::copy(k, k + P->mesh.n_cells(), P->kcell.begin());
   }
+  // overwrite the vertex coordinates (same topology): rectangles and other affine / bilinear images of the mesh
+  void
+  orc_set_vertices(void *h, const double *vx, const double *vy)
+  {
+    Problem *P = (Problem *)h;
+    std::copy(vx, vx + P->mesh.vx.size(), P->mesh.vx.begin());
+    std::copy(vy, vy + P->mesh.vy.size(), P->mesh.vy.begin());
+  }
   void
   orc_set_traction(void *h, double tx, double ty)
   {

@@ -34,6 +34,7 @@ def lib():
         _lib.orc_set_case.argtypes = [C.c_void_p, C.c_int] + [C.c_double] * 5
         _lib.orc_set_kcell.argtypes = [C.c_void_p, C.c_void_p]
         _lib.orc_set_traction.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        _lib.orc_set_vertices.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.orc_set_face_kind.argtypes = [C.c_void_p, C.c_void_p]
         _lib.orc_sizes.argtypes = [C.c_void_p, C.c_void_p]
         _lib.orc_get_mesh.argtypes = [C.c_void_p] + [C.c_void_p] * 4
@@ -86,6 +87,12 @@ class Oracle:
         k = np.ascontiguousarray(k, np.float64)
         assert k.size == self.n_cells
         self.L.orc_set_kcell(self.h, _p(k))
+
+    def set_vertices(self, vx, vy):
+        vx = np.ascontiguousarray(vx, np.float64)
+        vy = np.ascontiguousarray(vy, np.float64)
+        assert vx.size == self.n_vertices and vy.size == self.n_vertices
+        self.L.orc_set_vertices(self.h, _p(vx), _p(vy))
 
     def set_traction(self, tx, ty):
         self.L.orc_set_traction(self.h, tx, ty)

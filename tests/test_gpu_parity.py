@@ -402,3 +402,17 @@ def test_gather_assembly_alternative_matches(el, monkeypatch):
     x = b.solve_time_step()
     x_ref = spla.splu(o.csr(v_ref).tocsc()).solve(r_ref)
     assert np.linalg.norm(x - x_ref) <= TOL_SOL * np.linalg.norm(x_ref)
+
+
+@pytest.mark.parametrize("el,name", [(BR1_WG, "br1"), (CGQ1_WG, "cgq1")])
+def test_local_matrix_equals_exact_rational_derivation_on_a_rectangle(el, name):
+    """The CUDA cell kernel against the exact (sympy) matrices of scripts/derive_biot_kat.py, cell [0,.5] x [0,.25]."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "biot_exact_rectangle.npz"))
+    hx, hy, lam, mu, alpha, c0, dt, k = [float(v) for v in g["params"]]
+    b = pb.BiotSystem(element=el)
+    b.set_mesh([0.0, hx, 0.0, hx], [0.0, 0.0, hy, hy], [[0, 1, 2, 3]])
+    b.time_step = dt
+    b.set_material(lam, mu, alpha, c0, k)
+    A = b.local_matrices(0, 1, t=0.0)[0]
+    assert rel(A, g[name]) < 1e-13

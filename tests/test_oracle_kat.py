@@ -143,3 +143,25 @@ def test_patch_rigid_body_and_pressure_constants():
         p = np.zeros(17)
         p[[16, 9, 11, 13, 15]] = 1.0
         assert np.abs(A[[16, 9, 11, 13, 15]] @ p).max() < 1e-12
+
+
+@pytest.mark.parametrize("el,name", [(BR1_WG, "br1"), (CGQ1_WG, "cgq1")])
+def test_local_matrix_equals_exact_rational_derivation_on_a_rectangle(el, name):
+    """tests/golden/biot_exact_rectangle.npz: all entries of the 17 x 17 / 13 x 13 local matrix on [0,.5] x [0,.25]
+    derived with exact rational arithmetic (scripts/derive_biot_kat.py) following BR1new:811-925 / CGQ1:1194-1358
+    term by term; independent of the oracle's quadrature, mapping and Gauss-Jordan code."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "biot_exact_rectangle.npz"))
+    hx, hy, lam, mu, alpha, c0, dt, k = g["params"]
+    o = Oracle(el, 0)
+    vx, vy, cv, fk = o.mesh()
+    o.set_vertices(vx * hx, vy * hy)
+    o.set_material(lam, mu, alpha, c0, dt)
+    o.set_kcell(np.full(o.n_cells, k))
+    A, _, _, _ = o.local(0, 0.0)
+    assert np.abs(A - g[name]).max() < 1e-13 * np.abs(g[name]).max()
+    if el == BR1_WG:  # SURVEY 8(c)
+        assert np.trace(A) == pytest.approx(3.113722222222e+01, rel=1e-12)
+        assert np.linalg.norm(A) == pytest.approx(2.019813152856e+01, rel=1e-12)
+        assert A.sum() == pytest.approx(9.345833333333e+00, rel=1e-11)
+        assert A[16, 16] == pytest.approx(1.4e-02, rel=1e-12)
