@@ -56,13 +56,13 @@ def _worker(rank, world, port, element, nref, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("element", [0, 1])
-def test_two_rank_partition_views_are_consistent(element):
+@pytest.mark.parametrize("element,world", [(0, 2), (1, 2), (0, 4)])
+def test_partition_views_are_consistent(element, world):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + element
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, element, 4, q)) for r in range(2)]
+    port = 29600 + element + 10 * world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, element, 4, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=180) for _ in procs]
