@@ -416,3 +416,32 @@ def test_local_matrix_equals_exact_rational_derivation_on_a_rectangle(el, name):
     b.set_material(lam, mu, alpha, c0, k)
     A = b.local_matrices(0, 1, t=0.0)[0]
     assert rel(A, g[name]) < 1e-13
+
+
+def test_cfg1_cgq1_default_refinement_time_loop():
+    """BASELINE cfg 1: PoroElasCGQ1_WG general case, refine_global(3) (8 x 8, CGQ1:887), lambda = mu = alpha = 1,
+    c0 = 0, coscos data, all-Dirichlet; dt = 1/1024 as in the reference (CGQ1:824-831) over the first 64 steps of the
+    float-accumulated time loop (CGQ1:2929), the device-resident old_solution carried from step to step.  The final
+    solution against the oracle's own loop (sparse LU every step) and the accumulated error norms to 3 digits."""
+    import scipy.sparse.linalg as spla
+    dt, nref, nsteps = 1.0 / 1024, 3, 64
+    o, b = make_pair(CGQ1_WG, nref, dt=dt)
+    assert (o.n_cells, o.n_dofs) == (64, 370)
+    b.rel_tol = 1e-12
+    old = np.zeros(o.n_dofs)
+    acc_ref, acc = np.zeros(3), np.zeros(3)
+    t, step = dt, 0
+    while step < nsteps:
+        v_ref, r_ref, _ = o.assemble(t, old)
+        old = spla.splu(o.csr(v_ref).tocsc()).solve(r_ref)
+        b.assemble_system(t)
+        b.solve_time_step(want_solution=False)
+        acc_ref += dt * o.step_errors(t, old)
+        acc += dt * b.step_errors(t)
+        t += dt
+        step += 1
+    x = b.solution()
+    nu = o.n_u
+    assert np.linalg.norm(x[:nu] - old[:nu]) <= TOL_SOL * np.linalg.norm(old[:nu])
+    assert np.linalg.norm(x[nu:] - old[nu:]) <= TOL_SOL * np.linalg.norm(old[nu:])
+    assert np.all(np.abs(np.sqrt(acc) - np.sqrt(acc_ref)) <= 5e-4 * np.sqrt(acc_ref))
