@@ -163,12 +163,13 @@ int pe_get_rhs(const pe_handle *h, double *rhs);
  * solution may be NULL (result stays on the device as the next old_solution). */
 int pe_solve_time_step(pe_handle *h, double rel_tol, int max_iterations, double *solution,
                        pe_solve_stats *stats);
-/* preconditioner of the Krylov solve: use_multigrid = 1: block preconditioner with
- * auxiliary-space V-cycles (pe_precond.cu), 2: additive Jacobi + V-cycles, 0: diagonal only (meshes made
- * by pe_make_unit_square); theta scales the diagonal part, omega / nu = Jacobi damping / sweeps.
- * Defaults 1, 1.0, 0.6, 2.  Higher bits of use_multigrid: 16 = warp-per-row SpMV, 32 = colour-ordered
- * deterministic scatter (applies at the next pattern build), 64 = no CUDA graphs, bits 8.. = assembly
- * chunk size in units of 4096 cells. */
+/* preconditioner of the Krylov solve.  use_multigrid bit 0: 1 = block preconditioner of the three-field form with
+ * the vertex-grid and cell-grid V-cycles (meshes made by pe_make_unit_square), 0 = inverse block diagonal only.
+ * omega = weight of the damped block-Jacobi sweeps on the vertex grids (every second sweep uses 1.5 omega), nu =
+ * sweeps before and after each coarse correction; theta is reserved.  Defaults 1, 1.0, 0.6, 2.  Higher bits of
+ * use_multigrid: 16 = warp-per-row SpMV, 32 = colour-ordered deterministic scatter (applies at the next pattern
+ * build), 64 = no CUDA graphs, 128 = CUDA graphs also with NCCL operations (multi-GPU), bits 8.. = assembly chunk
+ * size in units of 4096 cells. */
 int pe_set_solver_options(pe_handle *h, int use_multigrid, double theta, double omega, int nu);
 int pe_get_solution(const pe_handle *h, double *solution);
 int pe_set_solution(pe_handle *h, const double *solution);

@@ -809,7 +809,9 @@ namespace
     else
       {
         // no refinement hierarchy: inverse block diagonal of K3
-        if (k3_make_pinv(k, h->mu, h->d_w[10].n >= n3 ? h->d_w[10].p : (h->d_w[10].alloc(n3), h->d_w[10].p), s) != 0)
+        if (h->d_w[10].n < n3 && h->d_w[10].alloc(n3) != cudaSuccess)
+          return 2;
+        if (k3_make_pinv(k, h->mu, h->d_w[10].p, s) != 0)
           return 1;
         pinv3 = h->d_w[10].p;
       }
