@@ -83,13 +83,14 @@ typedef struct pe_sizes {
 
 typedef struct pe_solve_stats {
   int32_t iterations;
-  int32_t converged;
+  int32_t converged;        /* 0 = no; 1 = ||b - A x|| <= rel_tol ||b||; 2 = rounding floor of the data reached:
+                             * ||b - A x|| <= 64 eps (||A||_inf ||x|| + ||b||), backward stable like the LU solve */
   double  rhs_norm;         /* ||b||_2 (preconditioned norm for MINRES is reported separately) */
   double  residual_norm;    /* true ||b - A x||_2 at exit */
   double  rel_residual;     /* residual_norm / rhs_norm */
   double  seconds;          /* device time of the solve (CUDA events) */
   int32_t spmv_count;
-  int32_t reserved;
+  int32_t restarts;         /* MINRES restarts from the current iterate (recurrence lost the true residual) */
 } pe_solve_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
@@ -141,7 +142,10 @@ int pe_set_lognormal_k(pe_handle *h, double sigma, uint64_t seed);
  * params[5] = {f_lambda, f_mu, f_alpha, s_capacity, s_alpha}: the constants those classes hard-code
  * (BR1new:369-370,400-402); NULL = {1,1,1,0,1}. */
 int pe_set_case(pe_handle *h, int case_id, const double *params);
-/* set_boundary_id loops BR1new:652-666 CGQ1:990-1000 + the Dirichlet/Neumann blocks */
+/* set_boundary_id loops BR1new:652-666 CGQ1:990-1000 + the Dirichlet/Neumann blocks.
+ * The resident old_solution survives this call and pe_set_lognormal_k / pe_set_material (only the device tables are
+ * rebuilt).  Multi-GPU: the rebuild re-runs the halo setup, which is COLLECTIVE -- every rank must make the same
+ * sequence of pe_set_boundary / pe_set_lognormal_k calls before its next pe_assemble_system. */
 int pe_set_boundary(pe_handle *h, int64_t n_bfaces, const uint32_t *cell, const uint8_t *face,
                     const uint8_t *kinds, const double traction[2]);
 
@@ -160,17 +164,28 @@ int pe_get_rhs(const pe_handle *h, double *rhs);
 /* solve_time_step()  BR1new:1177-1187 CGQ1:1732-1742 BR1old:859-870: UMFPACK LU in the reference,
  * here preconditioned MINRES on the pressure-row-negated (symmetric) form to ||r|| <= rel_tol ||b||.
  * solve()  ESM:583-590: SolverCG + PreconditionIdentity, tol = rel_tol*||b|| (1e-8), <= 1000 its.
- * solution may be NULL (result stays on the device as the next old_solution). */
+ * solution may be NULL (result stays on the device as the next old_solution).
+ * Stopping rule of MINRES: the TRUE residual of the reference system decides, ||b - A x||_2 <= rel_tol ||b||_2
+ * (stats.converged = 1).  If the iterate has reached the rounding floor of the data first (e.g. a right-hand side
+ * that vanishes against A x_old), it is accepted when it is backward stable like an LU solution,
+ * ||b - A x||_2 <= 64 eps (||A||_inf ||x||_2 + ||b||_2)  (stats.converged = 2).  Otherwise PE_ERR_NOT_CONVERGED.
+ * Multi-GPU: collective; a failed NCCL call inside the solve is reported as PE_ERR_NCCL. */
 int pe_solve_time_step(pe_handle *h, double rel_tol, int max_iterations, double *solution,
                        pe_solve_stats *stats);
 /* preconditioner of the Krylov solve.  use_multigrid bit 0: 1 = block preconditioner of the three-field form with
  * the vertex-grid and cell-grid V-cycles (meshes made by pe_make_unit_square), 0 = inverse block diagonal only.
  * omega = weight of the damped block-Jacobi sweeps on the vertex grids (every second sweep uses 1.5 omega), nu =
  * sweeps before and after each coarse correction; theta is reserved.  Defaults 1, 1.0, 0.6, 2.  Higher bits of
- * use_multigrid: 16 = warp-per-row SpMV, 32 = colour-ordered deterministic scatter (applies at the next pattern
- * build), 64 = no CUDA graphs, 128 = CUDA graphs also with NCCL operations (multi-GPU), bits 8.. = assembly chunk
- * size in units of 4096 cells. */
+ * use_multigrid: 16 = warp-per-row SpMV, 32 = colour-ordered deterministic scatter (STRUCTURAL: recorded here, applied
+ * by the next pe_make_sparsity_pattern / pe_set_pattern; an existing pattern keeps the mode its tables were built
+ * for), 64 = no CUDA graphs, 128 = CUDA graphs also with NCCL operations (multi-GPU), bits 8.. = assembly chunk
+ * size in units of 4096 cells (0 = keep; the chunk tables are rebuilt before the next assembly). */
 int pe_set_solver_options(pe_handle *h, int use_multigrid, double theta, double omega, int nu);
+/* Initial guess of the Krylov solve (a direct solver has none; the result is the same up to rel_tol):
+ * order 0 = old_solution (BR1new:2241), 1 / 2 = linear / quadratic extrapolation in time from the solutions of the
+ * previous steps kept on the device (default 2; falls back to a lower order until enough steps exist, when the
+ * time does not advance, or after pe_set_solution). */
+int pe_set_initial_guess(pe_handle *h, int order);
 int pe_get_solution(const pe_handle *h, double *solution);
 int pe_set_solution(pe_handle *h, const double *solution);
 

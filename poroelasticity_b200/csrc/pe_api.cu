@@ -32,6 +32,8 @@ namespace pe
   void comm_reduce_rows(void *ctx, const double *in, double *out, int64_t row_len, int n_comp, int64_t comp_stride,
                         const int64_t *bounds);
   void comm_allreduce(void *ctx, double *v, int n);
+  void comm_allreduce_max(void *ctx, double *v, int n);
+  int  comm_status(pe_handle *h);
   void comm_allreduce2(void *ctx, const double *in, double *out, int n);
   int  comm_unique_id(uint8_t id[128]);
 } // namespace pe
@@ -58,6 +60,34 @@ namespace
         return cuda_fail(h, e_, #call);               \
     }                                                 \
   while (0)
+
+  // Every entry point that touches the GPU runs on the handle's device, whatever the calling thread's current
+  // device is (a host program may hold handles on several GPUs); the caller's device is restored on return.
+  struct DeviceGuard
+  {
+    int  prev = -1;
+    bool ok   = true;
+    explicit DeviceGuard(const pe_handle *h)
+    {
+      if (!h || h->device < 0)
+        return;
+      if (cudaGetDevice(&prev) != cudaSuccess)
+        prev = -1;
+      if (prev != h->device)
+        ok = cudaSetDevice(h->device) == cudaSuccess;
+      else
+        prev = -1;
+    }
+    ~DeviceGuard()
+    {
+      if (prev >= 0)
+        cudaSetDevice(prev);
+    }
+  };
+#define PE_DEVICE(h)                                                   \
+  DeviceGuard device_guard_(h);                                        \
+  if (!device_guard_.ok)                                               \
+    return fail(const_cast<pe_handle *>(h), PE_ERR_CUDA, "cudaSetDevice(handle device) failed")
 
   template <class T>
   cudaError_t
@@ -122,6 +152,8 @@ namespace
     h->k3                  = nullptr;
     delete h->cmg;
     h->cmg                 = nullptr;
+    ++h->graph_epoch; // the captured iteration refers to buffers that are rebuilt below
+    h->anorm               = -1.;
     cudaStream_t     s     = h->stream;
     const int        n_loc = h->dofs.n_loc;
     const Partition &pt    = h->part;
@@ -213,8 +245,15 @@ namespace
     }
     PE_CUDA(h->d_values.alloc((size_t)h->nnz));
     PE_CUDA(h->d_rhs.alloc((size_t)(h->L + h->H)));
-    PE_CUDA(h->d_sol.alloc((size_t)(h->L + h->H)));
-    PE_CUDA(cudaMemsetAsync(h->d_sol.p, 0, sizeof(double) * (size_t)(h->L + h->H), s));
+    // the resident old_solution survives a rebuild of the device tables (boundary kinds, permeability field,
+    // chunk size ...) as long as the numbering is the same; it is zeroed on the first upload or a size change
+    if (h->d_sol.n != (size_t)(h->L + h->H) || h->sol_dofs_epoch != h->dofs_epoch)
+      {
+        PE_CUDA(h->d_sol.alloc((size_t)(h->L + h->H)));
+        PE_CUDA(cudaMemsetAsync(h->d_sol.p, 0, sizeof(double) * (size_t)(h->L + h->H), s));
+        h->sol_dofs_epoch = h->dofs_epoch;
+        h->hist_n         = 0;
+      }
     PE_CUDA(h->d_err.alloc(1));
     PE_CUDA(cudaMemsetAsync(h->d_err.p, 0, sizeof(int), s));
 
@@ -342,6 +381,7 @@ namespace
             owner[l] = mn;
           }
         const int64_t blk_end[3] = {pt.local_off[1], pt.local_off[2], h->L};
+            h->chunk_cells = h->pending_chunk_cells;
         for (int64_t c0 = 0; c0 < n_asm; c0 += h->chunk_cells)
           {
             const int64_t c1 = std::min(n_asm, c0 + h->chunk_cells);
@@ -613,6 +653,27 @@ namespace
     h->launches += 2;
   }
 
+  // ||A||_inf of the assembled reference matrix, once per assembled matrix and only when the rounding-floor test
+  // of the solver asks for it
+  double
+  hook_anorm(void *ctx)
+  {
+    pe_handle *h = (pe_handle *)ctx;
+    if (h->anorm >= 0.)
+      return h->anorm;
+    SolverCtx c = make_solver_ctx(h);
+    double   *d = h->d_scal.p + 44;
+    matrix_inf_norm(c, d);
+    ++h->launches;
+    if (h->part.world > 1)
+      comm_allreduce_max(h, d, 1);
+    cudaMemcpyAsync(h->h_scal + 9, d, sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess)
+      return 0.;
+    h->anorm = h->h_scal[9];
+    return h->anorm;
+  }
+
   // the solver operator: second assembly pass A0 = A(lambda0, alpha = 1) into k3.values0, K3 values,
   // block preconditioner data.  Once per assembled matrix.
   int
@@ -626,6 +687,16 @@ namespace
     // lambda = lambda0 + lambda_s with the xi block carrying lambda_s (>= a floor so that 1/lambda_s exists)
     const double lambda_s = std::max(h->lambda, 1e-6 * h->mu);
     const double lambda0  = h->lambda - lambda_s;
+    {
+      // by-value kernel arguments of the captured iteration: a change invalidates the cached graphs
+      const double fp[8] = {lambda_s, h->mu, h->mg_omega, (double)h->mg_nu, (double)h->use_mg, h->alpha, h->mg_theta, 0.};
+      if (std::memcmp(fp, h->graph_fp, sizeof(fp)) != 0)
+        {
+          std::memcpy(h->graph_fp, fp, sizeof(fp));
+          ++h->graph_epoch;
+        }
+    }
+    h->anorm = -1.;
     DevParams    P        = make_params(h, h->last_t, h->last_dt);
     P.lambda              = lambda0;
     P.alpha               = 1.;
@@ -738,11 +809,17 @@ namespace
     const size_t n3 = (size_t)h->k3->n_phys();
     for (int i = 0; i < 10; ++i)
       if (h->d_w[i].n < n3)
-        if (h->d_w[i].alloc(n3) != cudaSuccess)
-          return 2;
+        {
+          if (h->d_w[i].alloc(n3) != cudaSuccess)
+            return 2;
+          ++h->graph_epoch;
+        }
     if (h->d_pinv.n < n3)
-      if (h->d_pinv.alloc(n3) != cudaSuccess)
-        return 2;
+      {
+        if (h->d_pinv.alloc(n3) != cudaSuccess)
+          return 2;
+        ++h->graph_epoch;
+      }
     return 0;
   }
 
@@ -764,6 +841,11 @@ namespace
     c3.precond_ctx    = h;
     if (h->part.world > 1)
       c3.halo = comm_halo_exchange3;
+    c3.graphs    = h->graphs;
+    c3.graph_key = h->graph_epoch;
+    c3.calib     = &h->minres_calib;
+    c3.anorm     = hook_anorm;
+    c3.ev_ring   = h->ev_ring;
     return c3;
   }
 
@@ -792,9 +874,41 @@ namespace
     double *b3 = h->d_w[7].p, *x3 = h->d_w[8].p;
     if (k3_make_rhs(k, h->d_rhs.p, h->d_rowptr.p, h->d_colidx.p, h->d_values.p, b3, s) != 0)
       return 1;
-    // initial guess: the previous solution (old_solution) with its consistent xi
+    // initial guess: old_solution (BR1new:2241: the solution of the previous step), or -- when the solutions of the
+    // last two / three steps are on the device -- their polynomial extrapolation to the new time, with its
+    // consistent xi.  (A direct solver needs no guess; any guess leaves the result of the Krylov solve unchanged
+    // up to the residual tolerance.)
     cudaMemsetAsync(x3, 0, sizeof(double) * n3, s);
-    cudaMemcpyAsync(x3, h->d_sol.p, sizeof(double) * (size_t)h->L, cudaMemcpyDeviceToDevice, s);
+    {
+      const double t = h->last_t, dt = h->last_dt;
+      // d_sol is the state at the end of the previous step
+      if (h->hist_n < 1 || !(h->hist_t[0] < t))
+        {
+          h->hist_n    = 1;
+          h->hist_t[0] = t - dt;
+        }
+      int n = std::min(h->hist_n, h->extrapolate + 1);
+      // usable history: strictly decreasing times, and the new step not much longer than the previous ones
+      if (n >= 2 && !(h->hist_t[1] < h->hist_t[0] && t - h->hist_t[0] <= 2.000001 * (h->hist_t[0] - h->hist_t[1])))
+        n = 1;
+      if (n >= 3 && !(h->hist_t[2] < h->hist_t[1]))
+        n = 2;
+      if (n == 1)
+        cudaMemcpyAsync(x3, h->d_sol.p, sizeof(double) * (size_t)h->L, cudaMemcpyDeviceToDevice, s);
+      else
+        {
+          double w[3] = {0., 0., 0.};
+          for (int i = 0; i < n; ++i)
+            {
+              w[i] = 1.;
+              for (int j = 0; j < n; ++j)
+                if (j != i)
+                  w[i] *= (t - h->hist_t[j]) / (h->hist_t[i] - h->hist_t[j]);
+            }
+          lincomb3(h->L, w[0], h->d_sol.p, w[1], h->d_hist[0].p, w[2], n >= 3 ? h->d_hist[1].p : nullptr, x3, s);
+          ++h->launches;
+        }
+    }
     if (h->part.world > 1)
       comm_halo_exchange(h, x3);
     if (k3_init_xi(k, x3, s) != 0)
@@ -829,6 +943,23 @@ namespace
     }
     double *work[7] = {h->d_w[0].p, h->d_w[1].p, h->d_w[2].p, h->d_w[3].p, h->d_w[4].p, h->d_w[5].p, h->d_w[6].p};
     const int rc    = minres_solve(c3, b3, x3, pinv3, work, (MinresState *)h->d_scal.p, h->h_scal, rel_tol, max_iterations, stats);
+    if (rc == -2)
+      return 3;
+    // history of the solutions for the next initial guess: (d_sol, hist[0], hist[1]) <- (x, d_sol, hist[0])
+    if (h->extrapolate > 0)
+      {
+        const size_t nb = sizeof(double) * (size_t)h->L;
+        for (int k = 0; k < 2; ++k)
+          if (h->d_hist[k].n < (size_t)h->L && h->d_hist[k].alloc((size_t)h->L) != cudaSuccess)
+            return 2;
+        if (h->hist_n >= 2)
+          cudaMemcpyAsync(h->d_hist[1].p, h->d_hist[0].p, nb, cudaMemcpyDeviceToDevice, s);
+        cudaMemcpyAsync(h->d_hist[0].p, h->d_sol.p, nb, cudaMemcpyDeviceToDevice, s);
+        h->hist_t[2] = h->hist_t[1];
+        h->hist_t[1] = h->hist_t[0];
+        h->hist_t[0] = h->last_t;
+        h->hist_n    = std::min(3, h->hist_n + 1);
+      }
     cudaMemcpyAsync(h->d_sol.p, x3, sizeof(double) * (size_t)h->L, cudaMemcpyDeviceToDevice, s);
     return rc == 0 ? 0 : 1;
   }
@@ -870,6 +1001,11 @@ extern "C"
         h->cfg.world_size = 1;
         h->cfg.rank       = 0;
       }
+    if (h->cfg.rank < 0 || h->cfg.rank >= h->cfg.world_size)
+      {
+        delete h;
+        return PE_ERR_ARG;
+      }
     h->part.rank  = h->cfg.rank;
     h->part.world = h->cfg.world_size;
     if (host_only)
@@ -896,7 +1032,15 @@ extern "C"
       }
     for (auto &ev : h->ev)
       cudaEventCreate(&ev);
+    for (auto &ev : h->ev_ring)
+      cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    h->graphs = new (std::nothrow) MinresGraphs;
     cudaMallocHost((void **)&h->h_scal, 64 * sizeof(double));
+    if (!h->graphs || !h->h_scal)
+      {
+        pe_destroy(h);
+        return PE_ERR_ALLOC;
+      }
     *out = h;
     return PE_OK;
   }
@@ -915,6 +1059,11 @@ extern "C"
     comm_destroy(h);
     if (h->stream)
       cudaStreamSynchronize(h->stream);
+    delete h->graphs;
+    h->graphs = nullptr;
+    for (auto &ev : h->ev_ring)
+      if (ev)
+        cudaEventDestroy(ev);
     delete h->mg;
     h->mg = nullptr;
     delete h->bp;
@@ -962,6 +1111,7 @@ extern "C"
     PE_TRY
     make_unit_square(h->mesh, n_refine, distort, seed, boundary_kinds);
     h->have_mesh = true;
+    ++h->dofs_epoch;
     h->have_dofs = h->have_pattern = h->device_ready = false;
     return PE_OK;
     PE_CATCH
@@ -991,6 +1141,7 @@ extern "C"
         return fail(h, PE_ERR_ARG, "pe_set_mesh: vertex index out of range");
     m.face_kinds.assign(4 * (size_t)n_cells, 0);
     h->have_mesh = true;
+    ++h->dofs_epoch;
     h->have_dofs = h->have_pattern = h->device_ready = false;
     return PE_OK;
     PE_CATCH
@@ -1004,6 +1155,7 @@ extern "C"
     PE_TRY
     distribute_dofs(h->mesh, h->cfg.element, h->dofs, h->part);
     h->have_dofs    = true;
+    ++h->dofs_epoch;
     h->have_pattern = h->device_ready = false;
     return PE_OK;
     PE_CATCH
@@ -1041,6 +1193,7 @@ extern "C"
     pt.all_row_begin.assign(pt.row_begin, pt.row_begin + 3);
     pt.all_row_end.assign(pt.row_end, pt.row_end + 3);
     h->have_dofs    = true;
+    ++h->dofs_epoch;
     h->have_pattern = h->device_ready = false;
     return PE_OK;
     PE_CATCH
@@ -1052,6 +1205,7 @@ extern "C"
     if (!h || !h->have_dofs)
       return fail(h, PE_ERR_ARG, "pe_make_sparsity_pattern: distribute dofs first");
     PE_TRY
+    h->part.scatter_mode = h->pending_scatter_mode;
     make_sparsity_pattern(h->mesh, h->dofs, h->part, h->pat);
     h->have_pattern = true;
     h->device_ready = false;
@@ -1081,6 +1235,7 @@ extern "C"
     h->pat.rowptr.assign(rowptr, rowptr + n + 1);
     h->pat.colidx.assign(colidx, colidx + rowptr[n]);
     Partition &pt = h->part;
+    pt.scatter_mode = h->pending_scatter_mode;
     build_row_adjacency(h->mesh, h->dofs, pt);
     color_asm_cells(h->mesh, h->dofs, pt);
     pt.ghost_cols.clear();
@@ -1193,6 +1348,7 @@ extern "C"
   {
     if (!h)
       return PE_ERR_ARG;
+    PE_DEVICE(h);
     PE_TRY
     h->lambda      = lambda;
     h->mu          = mu;
@@ -1278,6 +1434,7 @@ extern "C"
   {
     if (!h)
       return PE_ERR_ARG;
+    PE_DEVICE(h);
     PE_TRY
     return assemble_impl(h, t, time_step, old_solution, true);
     PE_CATCH
@@ -1288,6 +1445,7 @@ extern "C"
   {
     if (!h)
       return PE_ERR_ARG;
+    PE_DEVICE(h);
     PE_TRY
     return assemble_impl(h, t, time_step, old_solution, false);
     PE_CATCH
@@ -1299,6 +1457,7 @@ extern "C"
     pe_handle *h = const_cast<pe_handle *>(hc);
     if (!h || !values || !h->device_ready || !h->matrix_valid)
       return fail(h, PE_ERR_ARG, "pe_get_matrix: nothing assembled");
+    PE_DEVICE(h);
     PE_CUDA(cudaMemcpyAsync(values, h->d_values.p, sizeof(double) * (size_t)h->nnz, cudaMemcpyDeviceToHost, h->stream));
     PE_CUDA(cudaStreamSynchronize(h->stream));
     return PE_OK;
@@ -1310,6 +1469,7 @@ extern "C"
     pe_handle *h = const_cast<pe_handle *>(hc);
     if (!h || !rhs || !h->device_ready)
       return fail(h, PE_ERR_ARG, "pe_get_rhs: nothing assembled");
+    PE_DEVICE(h);
     PE_CUDA(cudaMemcpyAsync(rhs, h->d_rhs.p, sizeof(double) * (size_t)h->L, cudaMemcpyDeviceToHost, h->stream));
     PE_CUDA(cudaStreamSynchronize(h->stream));
     return PE_OK;
@@ -1321,6 +1481,7 @@ extern "C"
     pe_handle *h = const_cast<pe_handle *>(hc);
     if (!h || !solution || !h->device_ready)
       return fail(h, PE_ERR_ARG, "pe_get_solution: no device state");
+    PE_DEVICE(h);
     PE_CUDA(cudaMemcpyAsync(solution, h->d_sol.p, sizeof(double) * (size_t)h->L, cudaMemcpyDeviceToHost, h->stream));
     PE_CUDA(cudaStreamSynchronize(h->stream));
     return PE_OK;
@@ -1331,6 +1492,7 @@ extern "C"
   {
     if (!h || !solution)
       return PE_ERR_ARG;
+    PE_DEVICE(h);
     PE_TRY
     const int rc = ensure_device(h);
     if (rc != PE_OK)
@@ -1339,6 +1501,7 @@ extern "C"
     if (r2 != PE_OK)
       return r2;
     PE_CUDA(cudaStreamSynchronize(h->stream));
+    h->hist_n = 0; // an explicitly set state starts a new trajectory (no extrapolated initial guess across it)
     return PE_OK;
     PE_CATCH
   }
@@ -1348,6 +1511,7 @@ extern "C"
   {
     if (!h || !x || !y || !h->device_ready || !h->matrix_valid)
       return fail(h, PE_ERR_ARG, "pe_spmv: assemble first");
+    PE_DEVICE(h);
     PE_TRY
     const size_t n = (size_t)(h->L + h->H);
     for (int k = 0; k < 2; ++k)
@@ -1373,17 +1537,38 @@ extern "C"
     if (!h || theta <= 0. || omega <= 0. || nu < 1)
       return fail(h, PE_ERR_ARG, "pe_set_solver_options: bad argument");
     h->use_mg      = use_multigrid & 3;
-    // bit 5: colour-ordered first-writer scatter (deterministic) instead of pre-zero + RED atomics;
-    // takes effect at the next pe_make_sparsity_pattern / pe_set_pattern
-    h->part.scatter_mode = (use_multigrid & 32) ? 1 : 0;
-    // bits 8..: chunk size of the atomics mode in units of 4096 cells (0 = default 32768)
+    // bit 5: colour-ordered first-writer scatter (deterministic) instead of pre-zero + RED atomics.  STRUCTURAL: the
+    // colouring, the first-writer flags and the chunk tables are built with the pattern, so the request is only
+    // recorded here and applied by the next pe_make_sparsity_pattern / pe_set_pattern -- the tables of a pattern
+    // that exists keep the mode they were built for (a later call that only tunes omega / nu cannot corrupt them)
+    h->pending_scatter_mode = (use_multigrid & 32) ? 1 : 0;
+    // bits 8..: chunk size of the atomics mode in units of 4096 cells (0 = keep).  The chunk tables are rebuilt
+    // (device tables only; the resident old_solution is kept) before the next assembly.
     if ((use_multigrid >> 8) > 0)
-      h->chunk_cells = (int64_t)(use_multigrid >> 8) * 4096;
-    h->spmv_kernel = (use_multigrid & 16) ? 0 : 1;
-    h->use_graphs  = (use_multigrid & 64) ? 0 : ((use_multigrid & 128) ? 2 : 1); // bit 6: no CUDA graphs; bit 7: also multi-GPU // bit 4: fall back to the warp-per-row SpMV (A/B measurements)
+      {
+        const int64_t cc = (int64_t)(use_multigrid >> 8) * 4096;
+        if (cc != h->pending_chunk_cells)
+          {
+            h->pending_chunk_cells = cc;
+            if (h->device_ready && h->part.scatter_mode == 0)
+              h->device_ready = false;
+          }
+      }
+    h->spmv_kernel = (use_multigrid & 16) ? 0 : 1; // bit 4: warp-per-row SpMV (A/B measurements)
+    h->use_graphs  = (use_multigrid & 64) ? 0 : ((use_multigrid & 128) ? 2 : 1); // bit 6: no CUDA graphs; bit 7: also multi-GPU
     h->mg_theta = theta;
     h->mg_omega = omega;
     h->mg_nu    = nu;
+    ++h->graph_epoch;
+    return PE_OK;
+  }
+
+  int
+  pe_set_initial_guess(pe_handle *h, int order)
+  {
+    if (!h || order < 0 || order > 2)
+      return fail(h, PE_ERR_ARG, "pe_set_initial_guess: order must be 0, 1 or 2");
+    h->extrapolate = order;
     return PE_OK;
   }
 
@@ -1392,6 +1577,7 @@ extern "C"
   {
     if (!h || !tflops || h->device < 0)
       return fail(h, PE_ERR_ARG, "pe_bench_fp64: bad argument");
+    PE_DEVICE(h);
     PE_TRY
     if (h->d_scal.n < 64)
       PE_CUDA(h->d_scal.alloc(64));
@@ -1408,6 +1594,7 @@ extern "C"
   {
     if (!h || repeats <= 0 || !ms_per_launch || !h->device_ready || !h->matrix_valid)
       return fail(h, PE_ERR_ARG, "pe_bench_spmv: assemble first");
+    PE_DEVICE(h);
     PE_TRY
     size_t n = (size_t)(h->L + h->H);
     for (int k = 0; k < 2; ++k)
@@ -1447,6 +1634,7 @@ extern "C"
   {
     if (!h || !h->device_ready || !h->matrix_valid)
       return fail(h, PE_ERR_ARG, "pe_solve_time_step: assemble first");
+    PE_DEVICE(h);
     PE_TRY
     pe_solve_stats local{};
     if (!stats)
@@ -1472,6 +1660,8 @@ extern "C"
     else
       {
         rc = solve_three_field(h, rel_tol, max_iterations, stats);
+        if (rc == 3)
+          return fail(h, PE_ERR_CUDA, "CUDA graph capture of the MINRES iteration failed (pe_set_solver_options bit 6 runs without graphs)");
         if (rc > 0)
           return rc == 1 ? cuda_fail(h, cudaGetLastError(), "three-field solver setup") : PE_ERR_ALLOC;
         if (rc == PE_ERR_PATTERN)
@@ -1481,6 +1671,12 @@ extern "C"
     PE_CUDA(cudaEventSynchronize(h->ev[4]));
     if (rc != 0)
       return cuda_fail(h, cudaGetLastError(), "krylov solve");
+    if (h->part.world > 1)
+      {
+        const int cst = comm_status(h);
+        if (cst != PE_OK)
+          return cst;
+      }
     float ms = 0.f;
     cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]);
     h->solve_ms    = ms;
@@ -1507,6 +1703,7 @@ extern "C"
       return fail(h, PE_ERR_ARG, "pe_local_matrices: one GPU only");
     if (h->device < 0)
       return fail(h, PE_ERR_NO_DEVICE, "no hot path without a GPU");
+    PE_DEVICE(h);
     PE_TRY
     cudaStream_t s     = h->stream;
     const int    n_loc = element_n_loc(h->cfg.element);
@@ -1597,6 +1794,7 @@ extern "C"
       return fail(h, PE_ERR_ARG, "pe_local_matrices_bench: bad argument");
     if (h->device < 0)
       return fail(h, PE_ERR_NO_DEVICE, "no hot path without a GPU");
+    PE_DEVICE(h);
     PE_TRY
     cudaStream_t  s     = h->stream;
     const int     n_loc = element_n_loc(h->cfg.element);
@@ -1678,6 +1876,7 @@ extern "C"
       return PE_ERR_ARG;
     if (h->cfg.element != PE_BR1_WG && h->cfg.element != PE_CGQ1_WG)
       return fail(h, PE_ERR_ARG, "pe_step_errors: element not implemented yet");
+    PE_DEVICE(h);
     PE_TRY
     const int rc = ensure_device(h);
     if (rc != PE_OK)

@@ -47,7 +47,23 @@ namespace pe
     ncclComm_t              comm = nullptr;
     std::vector<PeerPlan>   plan;
     std::vector<HaloPeer>  *peers = nullptr;
+    ncclResult_t            first_err = ncclSuccess; // first failed NCCL call of a hot-path hook (latched)
+    const char             *first_where = "";
+    int                    *d_flag = nullptr;         // device int[2]: agreement of the ranks during setup
   };
+  // The hot-path hooks are void (they run inside the captured iteration): a failed call is latched here and
+  // turned into PE_ERR_NCCL by comm_status() at the synchronisation points of the solve.
+#define PE_NCCL(c, call)                                             \
+  do                                                                 \
+    {                                                                \
+      const ncclResult_t r_ = (call);                                \
+      if (r_ != ncclSuccess && (c)->first_err == ncclSuccess)        \
+        {                                                            \
+          (c)->first_err   = r_;                                     \
+          (c)->first_where = #call;                                  \
+        }                                                            \
+    }                                                                \
+  while (0)
 
   static CommState *
   cs(pe_handle *h)
@@ -81,6 +97,13 @@ namespace pe
         h->err = "ncclCommInitRank failed";
         return PE_ERR_NCCL;
       }
+    if (cudaMalloc((void **)&c->d_flag, 2 * sizeof(int)) != cudaSuccess)
+      {
+        ncclCommDestroy(c->comm);
+        delete c;
+        h->err = "pe_comm_init: cudaMalloc failed";
+        return PE_ERR_ALLOC;
+      }
     h->comm = reinterpret_cast<ncclComm *>(c);
     return PE_OK;
   }
@@ -91,10 +114,51 @@ namespace pe
     if (!h->comm)
       return;
     CommState *c = cs(h);
+    if (c->d_flag)
+      cudaFree(c->d_flag);
     if (c->comm)
       ncclCommDestroy(c->comm);
     delete c;
     h->comm = nullptr;
+  }
+
+  // PE_OK, or PE_ERR_NCCL with the text of the first failed call / the communicator's asynchronous error
+  int
+  comm_status(pe_handle *h)
+  {
+    CommState *c = cs(h);
+    if (!c)
+      return PE_OK;
+    if (c->first_err != ncclSuccess)
+      {
+        h->err = std::string("NCCL call failed: ") + c->first_where + ": " + ncclGetErrorString(c->first_err);
+        return PE_ERR_NCCL;
+      }
+    ncclResult_t async = ncclSuccess;
+    if (ncclCommGetAsyncError(c->comm, &async) != ncclSuccess || async != ncclSuccess)
+      {
+        h->err = std::string("NCCL asynchronous error: ") + ncclGetErrorString(async);
+        return PE_ERR_NCCL;
+      }
+    return PE_OK;
+  }
+
+  // true on every rank iff `mine` is true on every rank (collective; used where one rank must not leave a
+  // collective sequence alone)
+  static bool
+  all_ranks_ok(pe_handle *h, const bool mine)
+  {
+    CommState *c = cs(h);
+    const int  v = mine ? 1 : 0;
+    int        r = 0;
+    if (cudaMemcpyAsync(c->d_flag, &v, sizeof(int), cudaMemcpyHostToDevice, h->stream) != cudaSuccess)
+      return false;
+    if (ncclAllReduce(c->d_flag, c->d_flag + 1, 1, ncclInt, ncclMin, c->comm, h->stream) != ncclSuccess)
+      return false;
+    if (cudaMemcpyAsync(&r, c->d_flag + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+        cudaStreamSynchronize(h->stream) != cudaSuccess)
+      return false;
+    return r == 1;
   }
 
   // Tell every owner which of its rows we need; learn which of ours the others need.
@@ -122,29 +186,40 @@ namespace pe
           need_cnt[(size_t)q * 3 + b] = q == me ? 0 : i1 - i0;
         }
     // all-gather the count matrix: cnt_all[r][q][b] = what r needs from q
+    // COLLECTIVE: every rank of the partition must call this (pe_assemble_system / pe_set_solution after any
+    // change of the mesh, pattern, boundary or permeability field).  No rank leaves the sequence alone: local
+    // failures are agreed on with all_ranks_ok() before the next collective starts.
     DevBuf<int64_t> d_cnt_mine, d_cnt_all;
-    if (d_cnt_mine.alloc((size_t)W * 3) != cudaSuccess || d_cnt_all.alloc((size_t)W * W * 3) != cudaSuccess)
-      return PE_ERR_ALLOC;
+    DevBuf<uint32_t> d_ghost;
+    bool ok = d_cnt_mine.alloc((size_t)W * 3) == cudaSuccess && d_cnt_all.alloc((size_t)W * W * 3) == cudaSuccess &&
+              d_ghost.alloc(pt.ghost_cols.size()) == cudaSuccess;
+    if (!all_ranks_ok(h, ok))
+      {
+        h->err = "halo setup: device allocation failed on a rank";
+        return PE_ERR_ALLOC;
+      }
     cudaMemcpyAsync(d_cnt_mine.p, need_cnt.data(), sizeof(int64_t) * W * 3, cudaMemcpyHostToDevice, s);
-    if (ncclAllGather(d_cnt_mine.p, d_cnt_all.p, (size_t)W * 3, ncclInt64, c->comm, s) != ncclSuccess)
-      return PE_ERR_NCCL;
+    ok = ncclAllGather(d_cnt_mine.p, d_cnt_all.p, (size_t)W * 3, ncclInt64, c->comm, s) == ncclSuccess;
     std::vector<int64_t> cnt_all((size_t)W * W * 3);
-    cudaMemcpyAsync(cnt_all.data(), d_cnt_all.p, sizeof(int64_t) * cnt_all.size(), cudaMemcpyDeviceToHost, s);
-    cudaStreamSynchronize(s);
+    ok = ok && cudaMemcpyAsync(cnt_all.data(), d_cnt_all.p, sizeof(int64_t) * cnt_all.size(), cudaMemcpyDeviceToHost, s) == cudaSuccess;
+    ok = ok && cudaStreamSynchronize(s) == cudaSuccess;
 
     // exchange the index lists (global ids)
-    DevBuf<uint32_t> d_ghost;
-    if (d_ghost.alloc(pt.ghost_cols.size()) != cudaSuccess)
-      return PE_ERR_ALLOC;
     cudaMemcpyAsync(d_ghost.p, pt.ghost_cols.data(), sizeof(uint32_t) * pt.ghost_cols.size(), cudaMemcpyHostToDevice, s);
     std::vector<DevBuf<uint32_t>> d_want((size_t)W);
     std::vector<int64_t>          want_cnt((size_t)W, 0);
-    for (int q = 0; q < W; ++q)
+    if (ok)
+      for (int q = 0; q < W; ++q)
+        {
+          for (int b = 0; b < 3; ++b)
+            want_cnt[q] += cnt_all[((size_t)q * W + me) * 3 + b];
+          if (want_cnt[q] && d_want[q].alloc((size_t)want_cnt[q]) != cudaSuccess)
+            ok = false;
+        }
+    if (!all_ranks_ok(h, ok))
       {
-        for (int b = 0; b < 3; ++b)
-          want_cnt[q] += cnt_all[((size_t)q * W + me) * 3 + b];
-        if (want_cnt[q] && d_want[q].alloc((size_t)want_cnt[q]) != cudaSuccess)
-          return PE_ERR_ALLOC;
+        h->err = "halo setup: count exchange or allocation failed on a rank";
+        return PE_ERR_NCCL;
       }
     ncclGroupStart();
     for (int q = 0; q < W; ++q)
@@ -163,13 +238,13 @@ namespace pe
             off += n;
           }
       }
-    if (ncclGroupEnd() != ncclSuccess)
-      return PE_ERR_NCCL;
-    cudaStreamSynchronize(s);
+    ok = ncclGroupEnd() == ncclSuccess;
+    ok = cudaStreamSynchronize(s) == cudaSuccess && ok;
 
     h->peers.clear();
     c->plan.clear();
-    for (int q = 0; q < W; ++q)
+    const char *why = "halo setup: index exchange failed on a rank";
+    for (int q = 0; q < W && ok; ++q)
       {
         if (q == me)
           continue;
@@ -192,24 +267,40 @@ namespace pe
         if (want_cnt[q])
           {
             std::vector<uint32_t> want((size_t)want_cnt[q]);
-            cudaMemcpy(want.data(), d_want[q].p, sizeof(uint32_t) * want.size(), cudaMemcpyDeviceToHost);
+            if (cudaMemcpy(want.data(), d_want[q].p, sizeof(uint32_t) * want.size(), cudaMemcpyDeviceToHost) != cudaSuccess)
+              {
+                ok = false;
+                break;
+              }
             hp.send_rows.resize(want.size());
             for (size_t k = 0; k < want.size(); ++k)
               {
                 const int64_t l = pt.global_to_owned(want[k]);
                 if (l < 0)
                   {
-                    h->err = "halo setup: a peer asked for a row this rank does not own";
-                    return PE_ERR_NCCL;
+                    why = "halo setup: a peer asked for a row this rank does not own";
+                    ok  = false;
+                    break;
                   }
                 hp.send_rows[k] = (int32_t)l;
               }
+            if (!ok)
+              break;
             if (hp.d_send_rows.alloc(want.size()) != cudaSuccess || hp.d_send_buf.alloc(want.size()) != cudaSuccess ||
-                hp.d_send_buf_xi.alloc((size_t)pl.send_cnt[1]) != cudaSuccess)
-              return PE_ERR_ALLOC;
-            cudaMemcpy(hp.d_send_rows.p, hp.send_rows.data(), sizeof(int32_t) * want.size(), cudaMemcpyHostToDevice);
+                hp.d_send_buf_xi.alloc((size_t)pl.send_cnt[1]) != cudaSuccess ||
+                cudaMemcpy(hp.d_send_rows.p, hp.send_rows.data(), sizeof(int32_t) * want.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+              {
+                why = "halo setup: device allocation failed on a rank";
+                ok  = false;
+                break;
+              }
           }
         c->plan.push_back(pl);
+      }
+    if (!all_ranks_ok(h, ok))
+      {
+        h->err = why;
+        return PE_ERR_NCCL;
       }
     return PE_OK;
   }
@@ -229,7 +320,7 @@ namespace pe
           k_gather<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, hp.d_send_rows.p, x, hp.d_send_buf.p);
           ++h->launches;
         }
-    ncclGroupStart();
+    PE_NCCL(c, ncclGroupStart());
     for (size_t k = 0; k < h->peers.size(); ++k)
       {
         HaloPeer       &hp = h->peers[k];
@@ -238,13 +329,13 @@ namespace pe
         for (int b = 0; b < 3; ++b)
           {
             if (pl.send_cnt[b])
-              ncclSend(hp.d_send_buf.p + so, (size_t)pl.send_cnt[b], ncclDouble, pl.rank, c->comm, s);
+              PE_NCCL(c, ncclSend(hp.d_send_buf.p + so, (size_t)pl.send_cnt[b], ncclDouble, pl.rank, c->comm, s));
             so += pl.send_cnt[b];
             if (pl.recv_cnt[b])
-              ncclRecv(x + h->L + pl.recv_off[b], (size_t)pl.recv_cnt[b], ncclDouble, pl.rank, c->comm, s);
+              PE_NCCL(c, ncclRecv(x + h->L + pl.recv_off[b], (size_t)pl.recv_cnt[b], ncclDouble, pl.rank, c->comm, s));
           }
       }
-    ncclGroupEnd();
+    PE_NCCL(c, ncclGroupEnd());
   }
 
   // three-field vectors (pe_k3.h): the (u, p) part as above plus the xi unknowns of the interior
@@ -276,7 +367,7 @@ namespace pe
             ++h->launches;
           }
       }
-    ncclGroupStart();
+    PE_NCCL(c, ncclGroupStart());
     for (size_t q = 0; q < h->peers.size(); ++q)
       {
         HaloPeer       &hp = h->peers[q];
@@ -285,18 +376,18 @@ namespace pe
         for (int b = 0; b < 3; ++b)
           {
             if (pl.send_cnt[b])
-              ncclSend(hp.d_send_buf.p + so, (size_t)pl.send_cnt[b], ncclDouble, pl.rank, c->comm, s);
+              PE_NCCL(c, ncclSend(hp.d_send_buf.p + so, (size_t)pl.send_cnt[b], ncclDouble, pl.rank, c->comm, s));
             so += pl.send_cnt[b];
             if (pl.recv_cnt[b])
-              ncclRecv(x + h->L + pl.recv_off[b], (size_t)pl.recv_cnt[b], ncclDouble, pl.rank, c->comm, s);
+              PE_NCCL(c, ncclRecv(x + h->L + pl.recv_off[b], (size_t)pl.recv_cnt[b], ncclDouble, pl.rank, c->comm, s));
           }
         if (pl.send_cnt[1])
-          ncclSend(hp.d_send_buf_xi.p, (size_t)pl.send_cnt[1], ncclDouble, pl.rank, c->comm, s);
+          PE_NCCL(c, ncclSend(hp.d_send_buf_xi.p, (size_t)pl.send_cnt[1], ncclDouble, pl.rank, c->comm, s));
         if (pl.recv_cnt[1])
-          ncclRecv(x + k.L + k.H + k.Lx + (h->L + pl.recv_off[1] - k.hu_end), (size_t)pl.recv_cnt[1], ncclDouble, pl.rank,
-                   c->comm, s);
+          PE_NCCL(c, ncclRecv(x + k.L + k.H + k.Lx + (h->L + pl.recv_off[1] - k.hu_end), (size_t)pl.recv_cnt[1], ncclDouble, pl.rank,
+                   c->comm, s));
       }
-    ncclGroupEnd();
+    PE_NCCL(c, ncclGroupEnd());
   }
 
   // ---- row slabs of the multigrid grids (GridComm hooks) ------------------------------------------------
@@ -309,22 +400,22 @@ namespace pe
       return;
     const int    me = h->part.rank, W = h->part.world;
     cudaStream_t s  = h->stream;
-    ncclGroupStart();
+    PE_NCCL(c, ncclGroupStart());
     for (int k = 0; k < n_comp; ++k)
       {
         double *q = p + (size_t)k * comp_stride;
         if (me > 0)
           {
-            ncclSend(q + a * row_len, (size_t)row_len, ncclDouble, me - 1, c->comm, s);
-            ncclRecv(q + (a - 1) * row_len, (size_t)row_len, ncclDouble, me - 1, c->comm, s);
+            PE_NCCL(c, ncclSend(q + a * row_len, (size_t)row_len, ncclDouble, me - 1, c->comm, s));
+            PE_NCCL(c, ncclRecv(q + (a - 1) * row_len, (size_t)row_len, ncclDouble, me - 1, c->comm, s));
           }
         if (me < W - 1)
           {
-            ncclSend(q + (b - 1) * row_len, (size_t)row_len, ncclDouble, me + 1, c->comm, s);
-            ncclRecv(q + b * row_len, (size_t)row_len, ncclDouble, me + 1, c->comm, s);
+            PE_NCCL(c, ncclSend(q + (b - 1) * row_len, (size_t)row_len, ncclDouble, me + 1, c->comm, s));
+            PE_NCCL(c, ncclRecv(q + b * row_len, (size_t)row_len, ncclDouble, me + 1, c->comm, s));
           }
       }
-    ncclGroupEnd();
+    PE_NCCL(c, ncclGroupEnd());
   }
   void
   comm_allgather_rows(void *ctx, double *p, int64_t row_len, int n_comp, int64_t comp_stride, const int64_t *bounds)
@@ -335,16 +426,16 @@ namespace pe
       return;
     const int    W = h->part.world;
     cudaStream_t s = h->stream;
-    ncclGroupStart();
+    PE_NCCL(c, ncclGroupStart());
     for (int q = 0; q < W; ++q)
       for (int k = 0; k < n_comp; ++k)
         {
           double      *x = p + (size_t)k * comp_stride + bounds[q] * row_len;
           const size_t n = (size_t)((bounds[q + 1] - bounds[q]) * row_len);
           if (n)
-            ncclBroadcast(x, x, n, ncclDouble, q, c->comm, s);
+            PE_NCCL(c, ncclBroadcast(x, x, n, ncclDouble, q, c->comm, s));
         }
-    ncclGroupEnd();
+    PE_NCCL(c, ncclGroupEnd());
   }
 
   void
@@ -357,16 +448,16 @@ namespace pe
       return;
     const int    W = h->part.world;
     cudaStream_t s = h->stream;
-    ncclGroupStart();
+    PE_NCCL(c, ncclGroupStart());
     for (int q = 0; q < W; ++q)
       for (int k = 0; k < n_comp; ++k)
         {
           const size_t off = (size_t)k * comp_stride + bounds[q] * row_len;
           const size_t n   = (size_t)((bounds[q + 1] - bounds[q]) * row_len);
           if (n)
-            ncclReduce(in + off, out + off, n, ncclDouble, ncclSum, q, c->comm, s);
+            PE_NCCL(c, ncclReduce(in + off, out + off, n, ncclDouble, ncclSum, q, c->comm, s));
         }
-    ncclGroupEnd();
+    PE_NCCL(c, ncclGroupEnd());
   }
 
   void
@@ -376,7 +467,17 @@ namespace pe
     CommState *c = cs(h);
     if (!c)
       return;
-    ncclAllReduce(in, out, (size_t)n, ncclDouble, ncclSum, c->comm, h->stream);
+    PE_NCCL(c, ncclAllReduce(in, out, (size_t)n, ncclDouble, ncclSum, c->comm, h->stream));
+  }
+
+  void
+  comm_allreduce_max(void *ctx, double *v, int n)
+  {
+    pe_handle *h = (pe_handle *)ctx;
+    CommState *c = cs(h);
+    if (!c)
+      return;
+    PE_NCCL(c, ncclAllReduce(v, v, (size_t)n, ncclDouble, ncclMax, c->comm, h->stream));
   }
 
   void
@@ -386,6 +487,6 @@ namespace pe
     CommState *c = cs(h);
     if (!c)
       return;
-    ncclAllReduce(v, v, (size_t)n, ncclDouble, ncclSum, c->comm, h->stream);
+    PE_NCCL(c, ncclAllReduce(v, v, (size_t)n, ncclDouble, ncclSum, c->comm, h->stream));
   }
 } // namespace pe

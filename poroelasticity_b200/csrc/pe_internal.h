@@ -20,7 +20,7 @@
 #include <vector>
 
 struct ncclComm;
-namespace pe { struct MgHierarchy; struct BlockPrecond; struct K3System; struct CellMg; }
+namespace pe { struct MgHierarchy; struct BlockPrecond; struct K3System; struct CellMg; struct MinresGraphs; }
 
 namespace pe
 {
@@ -127,6 +127,7 @@ struct pe_handle
   pe::HostPattern pat;
   bool            have_mesh = false, have_dofs = false, have_pattern = false, device_ready = false;
   bool            matrix_valid = false;
+  uint64_t        dofs_epoch = 1, sol_dofs_epoch = 0; // numbering generation / the one d_sol belongs to
   double          lambda = 1., mu = 1., alpha = 1., c0 = 0., k_scalar = 1.;
   std::vector<double> k_cell; // empty = scalar
   bool            k_lognormal = false;
@@ -151,6 +152,10 @@ struct pe_handle
   pe::DevBuf<int32_t>  d_rowadj;
   pe::DevBuf<double>   d_T;
   int64_t              chunk_cells = 32768;
+  // requested by pe_set_solver_options; scatter mode takes effect at the next pattern build, the chunk size at the
+  // next (re)build of the chunk tables -- never on tables that were built for another mode
+  int                  pending_scatter_mode = 0;
+  int64_t              pending_chunk_cells  = 32768;
   pe::DevBuf<int32_t>  d_cdofs, d_colidx, d_bnd_list, d_rowblk;
   int64_t              n_rowblk = 0;
   int                  spmv_kernel = 1; // 1 = stream, 0 = warp per row
@@ -176,6 +181,19 @@ struct pe_handle
   double           mg_theta = 1.0, mg_omega = 0.6;
   int              mg_nu = 2;
   double           precond_ms = 0.;
+  // Krylov state kept across solves: captured iteration graphs, calibration of the stopping estimate, ||A||_inf of
+  // the assembled reference matrix (lazy, -1 = not computed), events of the look-ahead convergence test
+  pe::MinresGraphs *graphs = nullptr;
+  uint64_t          graph_epoch = 1; // bumped whenever buffers or by-value kernel arguments of the iteration change
+  double            graph_fp[8] = {};
+  double            minres_calib = 1.;
+  double            anorm = -1.;
+  cudaEvent_t       ev_ring[16] = {};
+  // initial guess by extrapolation in time from the previous solutions (uniform steps only): x_n, x_{n-1}, x_{n-2}
+  pe::DevBuf<double> d_hist[2];
+  double             hist_t[3] = {0., 0., 0.}; // times of d_sol (after a solve), d_hist[0], d_hist[1]
+  int                hist_n = 0;               // number of valid solutions in (d_sol, d_hist[0], d_hist[1])
+  int                extrapolate = 2;          // max order of the extrapolation (0 = plain warm start)
 
   // WG_Q2RT2 (EltStiffMat.cc): boundary dofs of interpolate_boundary_values (ESM:565-571), physical support points
   std::vector<int32_t> esm_bdofs;

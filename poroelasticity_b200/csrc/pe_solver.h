@@ -15,6 +15,19 @@ namespace pe
   {
     int64_t at = INT64_MAX, len = 0;
   };
+  // the two executable CUDA graphs of one MINRES iteration (one per parity of the buffer rotation), kept on the
+  // handle across solves; key = fingerprint of everything baked into them (buffers, by-value kernel arguments)
+  struct MinresGraphs
+  {
+    cudaGraphExec_t exec[2]     = {nullptr, nullptr};
+    int64_t         launches[2] = {0, 0};
+    uint64_t        key         = 0;
+    MinresGraphs()              = default;
+    MinresGraphs(const MinresGraphs &) = delete;
+    MinresGraphs &operator=(const MinresGraphs &) = delete;
+    ~MinresGraphs();
+    void clear();
+  };
   struct SolverCtx
   {
     int64_t        L = 0, H = 0;    // owned rows, halo columns
@@ -40,6 +53,12 @@ namespace pe
     double bnorm2 = -1.;        // >= 0: ||b||^2 the stopping test is relative to (else computed from b)
     // optional: *nrm2_dev += ||true residual(x)||^2 of this rank (else b - A x with the ctx matrix)
     void (*true_residual)(void *ctx, const double *x, double *nrm2_dev) = nullptr;
+    bool          x0_is_zero = false;  // initial guess known to be zero: ||b||_{P^-1} = the initial eta
+    MinresGraphs *graphs     = nullptr; // cache of the captured iteration (null: capture per solve)
+    uint64_t      graph_key  = 0;
+    double       *calib      = nullptr; // calibration factor between the P^-1 norm and the 2-norm, kept across solves
+    double (*anorm)(void *ctx) = nullptr; // lazy ||A||_inf of the reference matrix (rounding-floor test only)
+    cudaEvent_t  *ev_ring    = nullptr; // 16 events (disable-timing) for the look-ahead convergence test
   };
 
   void   build_row_blocks(int64_t n_rows, const int64_t *rowptr, std::vector<int32_t> &blk);
@@ -48,6 +67,10 @@ namespace pe
   // *nrm2_dev += || b - A x ||^2 over the owned rows (plain A: no sign flip); y = A x is scratch (L long)
   void   residual_norm2(const SolverCtx &c, const double *b, const double *x, double *y, double *nrm2_dev);
   void   norm2(const SolverCtx &c, const double *x, double *nrm2_dev);
+  // *out_dev = max row sum of |A| over the owned rows of the ctx matrix (this rank)
+  void   matrix_inf_norm(const SolverCtx &c, double *out_dev);
+  void   lincomb3(int64_t n, double w0, const double *a, double w1, const double *b, double w2, const double *c, double *out,
+                  cudaStream_t s);
   // diag[r] = A(r, r) for the ctx matrix (owned rows)
   void   extract_diagonal(const SolverCtx &c, double *diag);
   int    build_preconditioner(const SolverCtx &c, double *diag_full, double *pinv);
