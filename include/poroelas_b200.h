@@ -208,6 +208,17 @@ int pe_step_errors(pe_handle *h, double t, double e[3]);
 /* run() accumulates dt*e over the steps and prints the square roots: L2L2Error_intp, L2L2Error_u,
  * L2h1semiError_u, L2h1Error_u = sqrt(sum dt (e[1]+e[2]))  (BR1new:2251-2266). */
 
+/* postprocess()  CGQ1:1744-1966 (dilation 1849-1860, |u| 1862-1877, Darcy velocity in DGRT 1881-1964) and
+ * BR1new:1189-1246 + postprocess_darcy_velocity BR1new:1352-1606 / CGQ1:1973-2225, from the device solution, for the
+ * cells this rank owns (deal.II active-cell order, n = cell_end - cell_begin):
+ *   div_displacement[n]        cell average of div u_h              (QGauss(3))
+ *   displacement_magnitude[n]  sqrt of the cell average of |u_h|^2
+ *   darcy_beta[n][4]           RT0 coefficients of the Darcy velocity -K grad_w p_h  (= darcy_velocity of CGQ1)
+ *   velocity_center[n][2]      that velocity at the cell midpoint   (= velocity.txt of BR1new:1598-1602)
+ * Any pointer may be NULL. */
+int pe_postprocess(pe_handle *h, double *div_displacement, double *displacement_magnitude, double *darcy_beta,
+                   double *velocity_center);
+
 /* the solver's SpMV kernel alone, `repeats` back-to-back launches on the handle's stream timed with
  * CUDA events (roofline measurement; x = current solution vector): average ms per launch */
 int pe_bench_spmv(pe_handle *h, int repeats, double *ms_per_launch);

@@ -194,6 +194,18 @@ extern "C"
     std::vector<double> s(solution, solution + P->dofs.n());
     step_errors(*P, t, s, e3);
   }
+  // postprocess (CGQ1:1744-1966, BR1new:1189-1246,1352-1606): div[n_cells], mag[n_cells], beta[n_cells][4], vel[n_cells][2]
+  void
+  orc_postprocess(void *h, const double *solution, double *div, double *mag, double *beta, double *vel)
+  {
+    Problem            *P = (Problem *)h;
+    std::vector<double> s(solution, solution + P->dofs.n()), d, m, b, v;
+    postprocess(*P, s, d, m, b, v);
+    std::copy(d.begin(), d.end(), div);
+    std::copy(m.begin(), m.end(), mag);
+    std::copy(b.begin(), b.end(), beta);
+    std::copy(v.begin(), v.end(), vel);
+  }
   // number of steps the reference's float-accumulated loop runs:
   //   for (n=1, time=dt; time <= t_end; time += dt, ++n)      BR1new:2181, CGQ1:2929
   int

@@ -5,6 +5,8 @@
 //   BR1-WG   assemble_system : PoroElasBR1WG_new.cc:684-1174
 //   CGQ1-WG  assemble_system : PoroElasCGQ1_WG.cc:1030-1729
 //   error norms               : PoroElasBR1WG_new.cc:1251-1349, 2251-2266
+//   postprocess (dilation, |u|, Darcy velocity): PoroElasCGQ1_WG.cc:1744-1966, 1973-2225;
+//                                PoroElasBR1WG_new.cc:1189-1246, 1352-1606
 // on top of the deal.II behaviour restated in dealii_restated.hpp.
 //
 // PARITY UNPINNED: the reference ships no golden vectors and cannot be built here (deal.II 9.1 +
@@ -584,6 +586,111 @@ namespace orc
                      (gh[2] - ge[1][0]) * (gh[2] - ge[1][0]) + (gh[3] - ge[1][1]) * (gh[3] - ge[1][1])) *
                     fv.JxW[q];
           }
+      }
+  }
+  // ------------------------------------------------------------------------------------------
+  // postprocess() of CGQ1 (PoroElasCGQ1_WG.cc:1744-1966) = postprocess() + postprocess_darcy_velocity() of BR1new
+  // (PoroElasBR1WG_new.cc:1189-1246, 1352-1606), per cell:
+  //   div_displacement[c]       = (1/|E|) sum_q sum_i u_i div(phi_i) JxW                      CGQ1:1849-1860
+  //   displacement_magnitude[c] = sqrt( (1/|E|) sum_q |u_h(x_q)|^2 JxW )                       CGQ1:1862-1877
+  //   darcy beta[c][k]          = - sum_j sum_i sol_i C_ij D_kj ,  D = M^-1 E,  E = int K w.w ,  C = F M^-1
+  //                                                                                            CGQ1:1881-1964
+  //   velocity_center[c]        = sum_k beta_k w_k(cell midpoint)   (QMidpoint)                BR1new:1580-1588
+  // ------------------------------------------------------------------------------------------
+  inline void
+  postprocess(const Problem &P, const std::vector<double> &solution, std::vector<double> &div_displacement,
+              std::vector<double> &displacement_magnitude, std::vector<double> &beta, std::vector<double> &velocity_center)
+  {
+    const std::vector<LocalDof> ld    = local_dofs(P.dofs.element);
+    const int                   n     = (int)ld.size();
+    const int                   n_rt  = 4;
+    static const Quad2          quad3 = qgauss_2d(3);
+    static const Quad2          quadm = qgauss_2d(1); // QMidpoint<dim> = the one-point Gauss rule
+    static std::vector<double>  fx, fw;
+    if (fx.empty())
+      qgauss_1d(3, fx, fw);
+    const int nc = P.mesh.n_cells();
+    div_displacement.assign(nc, 0.);
+    displacement_magnitude.assign(nc, 0.);
+    beta.assign((size_t)nc * n_rt, 0.);
+    velocity_center.assign((size_t)nc * 2, 0.);
+    for (int c = 0; c < nc; ++c)
+      {
+        const CellGeom    geom = P.mesh.geom(c);
+        const ShapeTables fv   = fe_values(geom, quad3, ld);
+        const dof_t      *idx  = &P.dofs.cell_dofs[(size_t)c * n];
+        const double      Kc   = P.kcell[c];
+        double            cell_area = 0; // cell->measure()
+        for (int q = 0; q < fv.nq; ++q)
+          cell_area += fv.JxW[q];
+        double d = 0;
+        for (int q = 0; q < fv.nq; ++q)
+          for (int i = 0; i < n; ++i)
+            d += solution[idx[i]] * fv.div(q, i) * fv.JxW[q] / cell_area;
+        div_displacement[c] = d;
+        double m2 = 0;
+        for (int q = 0; q < fv.nq; ++q)
+          {
+            double u[2] = {0, 0};
+            for (int i = 0; i < n; ++i)
+              {
+                u[0] += solution[idx[i]] * fv.u(q, i)[0];
+                u[1] += solution[idx[i]] * fv.u(q, i)[1];
+              }
+            m2 += (u[0] * u[0] + u[1] * u[1]) * fv.JxW[q] / cell_area;
+          }
+        displacement_magnitude[c] = std::sqrt(m2);
+        std::vector<double> M(n_rt * n_rt, 0.), E(n_rt * n_rt, 0.), D(n_rt * n_rt, 0.), F((size_t)n * n_rt, 0.),
+          C((size_t)n * n_rt, 0.);
+        for (int q = 0; q < fv.nq; ++q)
+          for (int i = 0; i < n_rt; ++i)
+            for (int k = 0; k < n_rt; ++k)
+              {
+                const double vv = fv.rt(q, i)[0] * fv.rt(q, k)[0] + fv.rt(q, i)[1] * fv.rt(q, k)[1];
+                E[i * n_rt + k] += Kc * vv * fv.JxW[q];
+                M[i * n_rt + k] += vv * fv.JxW[q];
+              }
+        gauss_jordan(M, n_rt);
+        for (int i = 0; i < n_rt; ++i) // D = M^-1 E (mmult)
+          for (int j = 0; j < n_rt; ++j)
+            {
+              double s = 0;
+              for (int k = 0; k < n_rt; ++k)
+                s += M[i * n_rt + k] * E[k * n_rt + j];
+              D[i * n_rt + j] = s;
+            }
+        for (int q = 0; q < fv.nq; ++q)
+          for (int i = 0; i < n; ++i)
+            for (int k = 0; k < n_rt; ++k)
+              F[i * n_rt + k] -= fv.pint[(size_t)q * n + i] * fv.rtdiv[(size_t)q * 4 + k] * fv.JxW[q];
+        for (int f = 0; f < 4; ++f)
+          {
+            const ShapeTables ff = fe_face_values(geom, f, fx, fw, ld);
+            for (int q = 0; q < ff.nq; ++q)
+              for (int i = 0; i < n; ++i)
+                for (int k = 0; k < n_rt; ++k)
+                  F[i * n_rt + k] += ff.pface[(size_t)q * n + i] *
+                                     (ff.rt(q, k)[0] * ff.nrm[2 * q] + ff.rt(q, k)[1] * ff.nrm[2 * q + 1]) * ff.JxW[q];
+          }
+        for (int i = 0; i < n; ++i) // C = F M^-1
+          for (int j = 0; j < n_rt; ++j)
+            {
+              double s = 0;
+              for (int k = 0; k < n_rt; ++k)
+                s += F[i * n_rt + k] * M[k * n_rt + j];
+              C[i * n_rt + j] = s;
+            }
+        for (int k = 0; k < n_rt; ++k)
+          for (int j = 0; j < n_rt; ++j)
+            for (int i = 0; i < n; ++i)
+              beta[(size_t)c * n_rt + k] += -(solution[idx[i]] * C[i * n_rt + j] * D[k * n_rt + j]);
+        const ShapeTables fm = fe_values(geom, quadm, ld);
+        for (int q = 0; q < fm.nq; ++q)
+          for (int k = 0; k < n_rt; ++k)
+            {
+              velocity_center[(size_t)c * 2] += beta[(size_t)c * n_rt + k] * fm.rt(q, k)[0];
+              velocity_center[(size_t)c * 2 + 1] += beta[(size_t)c * n_rt + k] * fm.rt(q, k)[1];
+            }
       }
   }
 } // namespace orc

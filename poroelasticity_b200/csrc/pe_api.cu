@@ -208,6 +208,13 @@ namespace
           bnd.push_back((int32_t)a);
       }
     h->n_bnd = (int64_t)bnd.size();
+    {
+      // output slot of every assembled cell for the per-cell post-processing: owned cells in deal.II order
+      std::vector<int32_t> slot((size_t)n_asm);
+      for (int64_t a = 0; a < n_asm; ++a)
+        slot[a] = (pt.asm_cells[a] >= pt.cell_begin && pt.asm_cells[a] < pt.cell_end) ? (int32_t)(pt.asm_cells[a] - pt.cell_begin) : -1;
+      PE_CUDA(upload(h->d_out_slot, slot.data(), slot.size(), s));
+    }
     h->d_is_ghost.release();
     if (pt.world > 1)
       {
@@ -1893,6 +1900,44 @@ extern "C"
       comm_allreduce(h, h->d_scal.p + 32, 3);
     PE_CUDA(cudaMemcpyAsync(e, h->d_scal.p + 32, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     PE_CUDA(cudaStreamSynchronize(h->stream));
+    return PE_OK;
+    PE_CATCH
+  }
+
+  int
+  pe_postprocess(pe_handle *h, double *div_displacement, double *displacement_magnitude, double *darcy_beta,
+                 double *velocity_center)
+  {
+    if (!h)
+      return PE_ERR_ARG;
+    if (h->cfg.element != PE_BR1_WG && h->cfg.element != PE_CGQ1_WG)
+      return fail(h, PE_ERR_ARG, "pe_postprocess: Biot elements only (the Darcy element has pe_darcy_errors)");
+    PE_DEVICE(h);
+    PE_TRY
+    const int rc = ensure_device(h);
+    if (rc != PE_OK)
+      return rc;
+    if (h->part.world > 1)
+      comm_halo_exchange(h, h->d_sol.p);
+    const int64_t nc = h->part.cell_end - h->part.cell_begin;
+    DevBuf<double> out;
+    PE_CUDA(out.alloc((size_t)8 * nc));
+    double *d_div = out.p, *d_mag = out.p + nc, *d_beta = out.p + 2 * nc, *d_vel = out.p + 6 * nc;
+    const AsmArgs a = make_args(h, false);
+    PE_CUDA(launch_postprocess(h->cfg.element, a, h->d_out_slot.p, d_div, d_mag, d_beta, d_vel, h->stream));
+    ++h->launches;
+    cudaStream_t s = h->stream;
+    if (div_displacement)
+      PE_CUDA(cudaMemcpyAsync(div_displacement, d_div, sizeof(double) * (size_t)nc, cudaMemcpyDeviceToHost, s));
+    if (displacement_magnitude)
+      PE_CUDA(cudaMemcpyAsync(displacement_magnitude, d_mag, sizeof(double) * (size_t)nc, cudaMemcpyDeviceToHost, s));
+    if (darcy_beta)
+      PE_CUDA(cudaMemcpyAsync(darcy_beta, d_beta, sizeof(double) * (size_t)(4 * nc), cudaMemcpyDeviceToHost, s));
+    if (velocity_center)
+      PE_CUDA(cudaMemcpyAsync(velocity_center, d_vel, sizeof(double) * (size_t)(2 * nc), cudaMemcpyDeviceToHost, s));
+    PE_CUDA(cudaStreamSynchronize(s));
+    if (h->part.world > 1)
+      return comm_status(h);
     return PE_OK;
     PE_CATCH
   }

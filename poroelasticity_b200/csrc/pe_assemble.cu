@@ -659,6 +659,140 @@ namespace pe
     return cudaGetLastError();
   }
 
+  // ---------------------------------------------------------------------------------------------
+  // postprocess() (PoroElasCGQ1_WG.cc:1744-1966; PoroElasBR1WG_new.cc:1189-1246 and
+  // postprocess_darcy_velocity 1352-1606), one thread per assembled cell, results of owned cells only:
+  //   div[c]  = (1/|E|) sum_q div u_h JxW          mag[c] = sqrt((1/|E|) sum_q |u_h|^2 JxW)      QGauss(3)
+  //   beta[c] = RT0 coefficients of the Darcy velocity  -K grad_w p_h = -sum_i p_i C_ij D_kj w_k
+  //   vel[c]  = that velocity at the cell midpoint (QMidpoint)
+  // Lean form of the reference's loops (checked against the literal oracle): on any quadrilateral the RT0
+  // weak-gradient right-hand side F is constant, and for K = k I the matrix D = M^-1 E is k I, so
+  //   beta = -k M^-1 g,   g = (p_int - p_f0, p_f1 - p_int, p_int - p_f2, p_f3 - p_int).
+  // ---------------------------------------------------------------------------------------------
+  template <int EL>
+  __global__ void __launch_bounds__(128)
+  k_postprocess(const AsmArgs a, const int32_t *__restrict__ out_slot, double *__restrict__ div_out,
+                double *__restrict__ mag_out, double *__restrict__ beta_out, double *__restrict__ vel_out)
+  {
+    constexpr int NL = Elem<EL>::NL, NS = Elem<EL>::NS;
+    const int64_t c  = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.n_asm)
+      return;
+    const int32_t o = out_slot[c];
+    if (o < 0)
+      return; // ghost cell
+    double  vx[4], vy[4], sol[NL];
+    int32_t idx[NL];
+    load_cell<EL>(a, c, vx, vy, idx, sol);
+    Geom G;
+    G.set(vx, vy);
+    double area = 0., dsum = 0., m2 = 0., M[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k)
+      M[k] = 0.;
+#pragma unroll 1
+    for (int qi = 0; qi < 9; ++qi)
+      {
+        QPoint<NS> q;
+        eval_qpoint<NS>(G, qi, q);
+        double s[NS];
+        shape_values<NS>(q.xi, q.eta, s);
+        double ux = 0., uy = 0., dv = 0.;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          {
+            ux += sol[2 * k] * s[k];
+            uy += sol[2 * k + 1] * s[k];
+            dv += sol[2 * k] * q.nx[k] + sol[2 * k + 1] * q.ny[k];
+          }
+        if (EL == 0)
+          {
+#pragma unroll
+            for (int f = 0; f < 4; ++f)
+              {
+                const double cf = sol[(8 + 2 * f) % NL];
+                if (f < 2)
+                  {
+                    ux += cf * s[(4 + f) % NS];
+                    dv += cf * q.nx[(4 + f) % NS];
+                  }
+                else
+                  {
+                    uy += cf * s[(4 + f) % NS];
+                    dv += cf * q.ny[(4 + f) % NS];
+                  }
+              }
+          }
+        area += q.jxw;
+        dsum += dv * q.wh; // div = dv / det, JxW = wh det
+        m2 += (ux * ux + uy * uy) * q.jxw;
+        // RT0: w_k = J what_k / det, what = ((1-xi),0), (xi,0), (0,1-eta), (0,eta);  M += w_i . w_j JxW
+        const double c0x = q.j00, c0y = q.j10, c1x = q.j01, c1y = q.j11; // columns of J
+        const double a00 = (c0x * c0x + c0y * c0y) * q.r, a01 = (c0x * c1x + c0y * c1y) * q.r,
+                     a11 = (c1x * c1x + c1y * c1y) * q.r;
+        const double mxi = 1. - q.xi, meta = 1. - q.eta;
+        M[sym4(0, 0)] += mxi * mxi * a00;
+        M[sym4(0, 1)] += mxi * q.xi * a00;
+        M[sym4(1, 1)] += q.xi * q.xi * a00;
+        M[sym4(0, 2)] += mxi * meta * a01;
+        M[sym4(0, 3)] += mxi * q.eta * a01;
+        M[sym4(1, 2)] += q.xi * meta * a01;
+        M[sym4(1, 3)] += q.xi * q.eta * a01;
+        M[sym4(2, 2)] += meta * meta * a11;
+        M[sym4(2, 3)] += meta * q.eta * a11;
+        M[sym4(3, 3)] += q.eta * q.eta * a11;
+      }
+    double Mi[10];
+    spd4_inverse(M, Mi);
+    const double pint = sol[Elem<EL>::PINT];
+    const double g[4] = {pint - sol[Elem<EL>::pface(0)], sol[Elem<EL>::pface(1)] - pint, pint - sol[Elem<EL>::pface(2)],
+                         sol[Elem<EL>::pface(3)] - pint};
+    const double kperm = a.kcell ? a.kcell[c] : a.k_scalar;
+    double       beta[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      {
+        double t = 0.;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          t += Mi[sym4(k, j)] * g[j];
+        beta[k] = -kperm * t;
+      }
+    if (div_out)
+      div_out[o] = dsum / area;
+    if (mag_out)
+      mag_out[o] = sqrt(m2 / area);
+    if (beta_out)
+      {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          beta_out[(size_t)4 * o + k] = beta[k];
+      }
+    if (vel_out)
+      {
+        double j00, j01, j10, j11;
+        G.jac(.5, .5, j00, j01, j10, j11);
+        const double idet = 1. / (j00 * j11 - j01 * j10);
+        const double hx = .5 * (beta[0] + beta[1]), hy = .5 * (beta[2] + beta[3]); // sum_k beta_k what_k(1/2,1/2)
+        vel_out[(size_t)2 * o]     = (j00 * hx + j01 * hy) * idet;
+        vel_out[(size_t)2 * o + 1] = (j10 * hx + j11 * hy) * idet;
+      }
+  }
+
+  cudaError_t
+  launch_postprocess(const int element, const AsmArgs &a, const int32_t *out_slot, double *div_out, double *mag_out,
+                     double *beta_out, double *vel_out, cudaStream_t s)
+  {
+    if (a.n_asm == 0)
+      return cudaSuccess;
+    const unsigned g = (unsigned)((a.n_asm + 127) / 128);
+    if (element == 0)
+      k_postprocess<0><<<g, 128, 0, s>>>(a, out_slot, div_out, mag_out, beta_out, vel_out);
+    else
+      k_postprocess<1><<<g, 128, 0, s>>>(a, out_slot, div_out, mag_out, beta_out, vel_out);
+    return cudaGetLastError();
+  }
+
   // K = exp(sigma Z), Z by Box-Muller from the counter generator keyed on (seed, global cell id)
   __device__ __forceinline__ uint64_t
   d_splitmix64(uint64_t z)

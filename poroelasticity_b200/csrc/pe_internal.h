@@ -156,7 +156,7 @@ struct pe_handle
   // next (re)build of the chunk tables -- never on tables that were built for another mode
   int                  pending_scatter_mode = 0;
   int64_t              pending_chunk_cells  = 32768;
-  pe::DevBuf<int32_t>  d_cdofs, d_colidx, d_bnd_list, d_rowblk;
+  pe::DevBuf<int32_t>  d_cdofs, d_colidx, d_bnd_list, d_rowblk, d_out_slot;
   int64_t              n_rowblk = 0;
   int                  spmv_kernel = 1; // 1 = stream, 0 = warp per row
   pe::DevBuf<int64_t>  d_rowptr;

@@ -43,6 +43,9 @@ namespace pe
                                     double *out, double *rhs_out, cudaStream_t s);
   cudaError_t launch_step_errors(int element, const AsmArgs &a, const DevParams &P, const uint8_t *is_ghost, double *e,
                                  cudaStream_t s);
+  // postprocess(): dilation, |u|, Darcy velocity per owned cell (out_slot[c] = output index, -1 for ghost cells)
+  cudaError_t launch_postprocess(int element, const AsmArgs &a, const int32_t *out_slot, double *div_out, double *mag_out,
+                                 double *beta_out, double *vel_out, cudaStream_t s);
   cudaError_t launch_lognormal(int64_t n, const int64_t *cell_ids, int64_t first, double sigma, uint64_t seed,
                                double *k, cudaStream_t s);
   cudaError_t launch_sum(const double *x, size_t n, double *out, cudaStream_t s);

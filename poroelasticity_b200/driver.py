@@ -245,6 +245,14 @@ class BiotSystem:
         self._ck(self.L.pe_step_errors(self.h, t, ptr(e)))
         return e
 
+    def postprocess(self):
+        """(div_displacement, displacement_magnitude, darcy beta [n][4], cell-centre Darcy velocity [n][2]) of the owned cells"""
+        s = self.sizes()
+        n = s.cell_end - s.cell_begin
+        d, m, b, v = np.zeros(n), np.zeros(n), np.zeros((n, 4)), np.zeros((n, 2))
+        self._ck(self.L.pe_postprocess(self.h, ptr(d), ptr(m), ptr(b), ptr(v)))
+        return d, m, b, v
+
     def timings(self):
         a, k, s, m = C.c_double(), C.c_double(), C.c_double(), C.c_double()
         n = C.c_int64()

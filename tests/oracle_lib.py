@@ -46,6 +46,7 @@ def lib():
         _lib.orc_assemble.restype = C.c_double
         _lib.orc_assemble.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.orc_step_errors.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+        _lib.orc_postprocess.argtypes = [C.c_void_p] + [C.c_void_p] * 5
         _lib.orc_count_steps.restype = C.c_int
         _lib.orc_count_steps.argtypes = [C.c_double, C.c_double]
         _lib.orc_gauss_jordan.argtypes = [C.c_void_p, C.c_int]
@@ -147,6 +148,14 @@ class Oracle:
         e = np.zeros(3)
         self.L.orc_step_errors(self.h, t, _p(sol), _p(e))
         return e
+
+    def postprocess(self, sol):
+        """(div_displacement, displacement_magnitude, darcy beta [n_cells][4], cell-centre velocity [n_cells][2])"""
+        sol = np.ascontiguousarray(sol, np.float64)
+        d, m = np.zeros(self.n_cells), np.zeros(self.n_cells)
+        b, v = np.zeros((self.n_cells, 4)), np.zeros((self.n_cells, 2))
+        self.L.orc_postprocess(self.h, _p(sol), _p(d), _p(m), _p(b), _p(v))
+        return d, m, b, v
 
     def csr(self, values):
         import scipy.sparse as sp

@@ -229,3 +229,52 @@ def test_full_reference_loop_cfg1_quick_variant():
     n_gpu = np.sqrt(np.append(acc, acc[1] + acc[2]))
     assert np.all(np.abs(n_gpu - n_ref) <= 5e-4 * n_ref), (n_gpu, n_ref)
     b.close()
+
+
+@pytest.mark.parametrize("el", [BR1_WG, CGQ1_WG])
+def test_postprocess_dilation_magnitude_darcy_velocity(el):
+    """postprocess() (CGQ1:1744-1966, BR1new:1189-1246, 1352-1606): cell-averaged dilation, |u|, RT0 coefficients of
+    the Darcy velocity and its cell-centre value, on a distorted mesh with per-cell K, against the literal oracle:
+    1e-12 of the largest entry."""
+    rng = np.random.default_rng(5)
+    nref = 4
+    k = np.exp(rng.normal(size=1 << (2 * nref)))
+    o = Oracle(el, nref, distort=0.2)
+    o.set_material(1, 1, 1, 0, 0.1)
+    o.set_kcell(k)
+    o.set_case(CASE_COSCOS)
+    b = pb.BiotSystem(element=el)
+    b.make_grid_and_dofs(nref, distort=0.2)
+    b.time_step = 0.1
+    b.set_material(1, 1, 1, 0, 1.0, k)
+    b.set_case(pb.PE_CASE_COSCOS)
+    sol = rng.normal(size=o.n_dofs)
+    b.set_solution(sol)
+    d_ref, m_ref, beta_ref, v_ref = o.postprocess(sol)
+    d, m, beta, v = b.postprocess()
+    assert rel(d, d_ref) < TOL_MAT
+    assert rel(m, m_ref) < TOL_MAT
+    assert rel(beta, beta_ref) < TOL_MAT
+    assert rel(v, v_ref) < TOL_MAT
+    # and on a solved step: the recovered velocity approximates -K grad p of the manufactured solution
+    o2 = Oracle(el, 5)
+    o2.set_material(1, 1, 1, 0, 0.1)
+    o2.set_case(CASE_COSCOS)
+    b2 = pb.BiotSystem(element=el)
+    b2.make_grid_and_dofs(5)
+    b2.time_step = 0.1
+    b2.set_material(1, 1, 1, 0)
+    b2.set_case(pb.PE_CASE_COSCOS)
+    b2.rel_tol = 1e-12
+    b2.assemble_system(0.1)
+    x = b2.solve_time_step()
+    _, _, _, vc = b2.postprocess()
+    _, _, _, vc_ref = o2.postprocess(x)
+    assert rel(vc, vc_ref) < 1e-10
+    vx, vy, cv, _ = o2.mesh()
+    cx, cy = vx[cv].mean(axis=1), vy[cv].mean(axis=1)
+    st = np.sin(np.pi / 2 * 0.1)
+    exact = np.pi * st * np.stack([np.sin(np.pi * cx) * np.cos(np.pi * cy), np.cos(np.pi * cx) * np.sin(np.pi * cy)], axis=1)
+    assert np.abs(vc - exact).max() < 0.05 * np.abs(exact).max()
+    b.close()
+    b2.close()
