@@ -219,6 +219,7 @@ def run_cfg4(args):
     b.set_case(pb.PE_CASE_COSCOS)
     b.rel_tol = args.rel_tol
     b.set_solver_options(args.solver_options)
+    b.set_krylov(args.krylov, args.gmres_m)
     b.set_solution(np.zeros(s.n_owned_rows))
     times = run_times(0.1)
     hist = []
@@ -234,7 +235,7 @@ def run_cfg4(args):
     line = {"config": 4, "metric": "s per time step (assemble+solve) and MINRES iterations, BR1-WG cfg 4",
             "workload": "PoroElasBR1WG 2D %dx%d, lambda=1e6, mu=1, alpha=1, c0=1e-6, K=exp(2 Z) per cell (seed 12345), coscos "
                         "forcing, dt=0.1" % (N, N),
-            "n_gpus": 1, "rel_tol": args.rel_tol, "steps": hist, "s_per_step_mean": sum(ms) / len(ms) * 1e-3,
+            "n_gpus": 1, "rel_tol": args.rel_tol, "krylov": "FGMRES(%d)" % args.gmres_m if args.krylov == 1 else "MINRES", "steps": hist, "s_per_step_mean": sum(ms) / len(ms) * 1e-3,
             "iterations_mean": sum(h["iterations"] for h in hist) / len(hist),
             "all_converged": all(h["converged"] for h in hist),
             "cells_per_s": s.n_cells / (sum(ms) / len(ms) * 1e-3)}
@@ -339,7 +340,7 @@ def parity_check(pb, torch, dist, rank, world, local_rank):
             "iterations": its, "converged": bad == 0.0, "tolerances": {"matrix": 1e-12, "rhs": 1e-12, "solution": 1e-8}, "ok": ok}
 
 
-def gpu_at_reference_n(pb, torch, n_refine, rel_tol, options, local_rank):
+def gpu_at_reference_n(pb, torch, n_refine, rel_tol, options, local_rank, krylov=(1, 16)):
     """the GPU arm on a mesh the CPU arm can also run: one run() of 10 steps, device-resident and end to end"""
     import numpy as np
     dt = 0.1
@@ -350,6 +351,7 @@ def gpu_at_reference_n(pb, torch, n_refine, rel_tol, options, local_rank):
     b.set_case(pb.PE_CASE_COSCOS)
     b.rel_tol = rel_tol
     b.set_solver_options(options)
+    b.set_krylov(*krylov)
     times = run_times(dt)
     zero = np.zeros(s.n_owned_rows)
     for rep in range(2):          # rep 0 = warm-up
@@ -396,6 +398,8 @@ def main():
     ap.add_argument("--chunk-cells", type=int, default=1 << 20, help="config 5: cells per output chunk")
     ap.add_argument("--solver-options", type=int, default=1, help="pe_set_solver_options bit field")
     ap.add_argument("--initial-guess", type=int, default=2, help="pe_set_initial_guess order")
+    ap.add_argument("--krylov", type=int, default=1, help="pe_set_krylov method: 1 = FGMRES + block-triangular P, 0 = MINRES")
+    ap.add_argument("--gmres-m", type=int, default=16, help="pe_set_krylov restart length")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.n_refine <= 0:
@@ -458,6 +462,7 @@ def main():
     b.rel_tol = args.rel_tol
     b.set_solver_options(args.solver_options)
     b.set_initial_guess(args.initial_guess)
+    b.set_krylov(args.krylov, args.gmres_m)
     n_cells, n_dofs = s.n_cells, s.n_dofs
     N = 1 << args.n_refine
     zero_state = torch.zeros(s.n_owned_rows if world == 1 else n_dofs, dtype=torch.float64).pin_memory().numpy()
@@ -653,7 +658,8 @@ def main():
     # ---- the same arm on the meshes the CPU arm can run (same physics, same tolerance) -----------------------
     at_ref = None
     if world == 1 and not args.no_checks:
-        at_ref = [gpu_at_reference_n(pb, torch, n, args.rel_tol, args.solver_options, local_rank) for n in REF_MESHES]
+        at_ref = [gpu_at_reference_n(pb, torch, n, args.rel_tol, args.solver_options, local_rank, (args.krylov, args.gmres_m))
+                  for n in REF_MESHES]
     if world > 1:
         dist.destroy_process_group()
     if rank != 0:
@@ -681,10 +687,11 @@ def main():
                             "holds among N = 2, 4, 8 (same mesh); the 1-GPU line of the 4096^2 mesh is kept in profiles/",
             "s_per_time_step": dev_s / args.steps, "assemble_ms": sum(asm_ms) / len(asm_ms),
             "assembly_cells_per_s": n_cells / asm_kernel_s, "solve_ms": sum(sol_ms) / len(sol_ms),
-            "solver": {"method": "MINRES on the three-field (u, total pressure, p) form + block preconditioner (bubble Jacobi x Q1 "
-                                 "V-cycle; cell mass; p_int elimination + face V-cycle); preconditioner coefficients stored in "
-                                 "FP32, Krylov vectors / SpMV / true residual in FP64; initial guess = order-%d extrapolation "
-                                 "in time" % args.initial_guess,
+            "solver": {"method": ("FGMRES(%d), block upper-triangular preconditioner" % args.gmres_m if args.krylov == 1 else
+                                  "MINRES, block-diagonal preconditioner") +
+                                 " on the three-field (u, total pressure, p) form; blocks: bubble Jacobi x Q1 V-cycle; cell mass; "
+                                 "p_int elimination + face V-cycle; preconditioner coefficients stored in FP32, Krylov vectors / "
+                                 "SpMV / true residual in FP64; initial guess = order-%d extrapolation in time" % args.initial_guess,
                        "stopping": "true residual of the reference system ||b - A x|| <= rel_tol ||b||",
                        "iterations": iters, "per_step": per_step, "converged": all_converged,
                        "rel_residual_max": max(p["rel_residual"] for p in per_step)},

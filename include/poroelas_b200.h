@@ -181,6 +181,12 @@ int pe_solve_time_step(pe_handle *h, double rel_tol, int max_iterations, double 
  * for), 64 = no CUDA graphs, 128 = CUDA graphs also with NCCL operations (multi-GPU), bits 8.. = assembly chunk
  * size in units of 4096 cells (0 = keep; the chunk tables are rebuilt before the next assembly). */
 int pe_set_solver_options(pe_handle *h, int use_multigrid, double theta, double omega, int nu);
+/* Krylov method of pe_solve_time_step for the Biot elements on meshes with a refinement hierarchy:
+ * method 1 (default) = restarted flexible GMRES(restart) on the row-signed three-field system with the block
+ * upper-triangular preconditioner [P_u -B^T 0; 0 P_xi 0; 0 0 P_p] (2.6x fewer iterations than method 0 at
+ * lambda ~ mu, scripts/krylov_study.py); method 0 = MINRES with the block-diagonal SPD preconditioner.
+ * restart: basis vectors per cycle, 2..24 (0 = keep, default 16).  Same stopping rule for both. */
+int pe_set_krylov(pe_handle *h, int method, int restart);
 /* Initial guess of the Krylov solve (a direct solver has none; the result is the same up to rel_tol):
  * order 0 = old_solution (BR1new:2241), 1 / 2 = linear / quadratic extrapolation in time from the solutions of the
  * previous steps kept on the device (default 2; falls back to a lower order until enough steps exist, when the

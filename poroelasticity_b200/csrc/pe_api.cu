@@ -27,6 +27,7 @@ namespace pe
   int  comm_setup_halo(pe_handle *h);
   void comm_halo_exchange(void *ctx, double *x);
   void comm_halo_exchange3(void *ctx, double *x);
+  void comm_halo_exchange_xi(void *ctx, double *x);
   void comm_exchange_rows(void *ctx, double *p, int64_t row_len, int n_comp, int64_t comp_stride, int64_t a, int64_t b);
   void comm_allgather_rows(void *ctx, double *p, int64_t row_len, int n_comp, int64_t comp_stride, const int64_t *bounds);
   void comm_reduce_rows(void *ctx, const double *in, double *out, int64_t row_len, int n_comp, int64_t comp_stride,
@@ -648,6 +649,18 @@ namespace
     k3_precond_xi(*h->k3, h->mu, r, z, h->stream);
     ++h->launches;
   }
+  // block upper-triangular variant for FGMRES on the row-signed system: z_xi first, then the displacement block on
+  // r_u + B^T z_xi; the pressure block is independent of both (runs on the forked stream)
+  void
+  hook_precond3_tri(void *ctx, const double *r, double *z)
+  {
+    pe_handle *h = (pe_handle *)ctx;
+    k3_precond_xi(*h->k3, h->mu, r, z, h->stream);
+    ++h->launches;
+    if (h->part.world > 1)
+      comm_halo_exchange_xi(h, z);
+    precond_apply(*h->bp, *h->mg, *h->cmg, h->d_pinv.p, r, z, h->stream, &h->launches, z);
+  }
   void
   hook_true_residual(void *ctx, const double *x3, double *nrm2_dev)
   {
@@ -853,6 +866,7 @@ namespace
     c3.calib     = &h->minres_calib;
     c3.anorm     = hook_anorm;
     c3.ev_ring   = h->ev_ring;
+    c3.gmres_graphs = h->gmres_graphs;
     return c3;
   }
 
@@ -949,7 +963,28 @@ namespace
       c3.bnorm2 = h->h_scal[8];
     }
     double *work[7] = {h->d_w[0].p, h->d_w[1].p, h->d_w[2].p, h->d_w[3].p, h->d_w[4].p, h->d_w[5].p, h->d_w[6].p};
-    const int rc    = minres_solve(c3, b3, x3, pinv3, work, (MinresState *)h->d_scal.p, h->h_scal, rel_tol, max_iterations, stats);
+    int     rc;
+    if (block_pc && h->krylov == 1)
+      {
+        // FGMRES(m) + block-triangular preconditioner on the row-signed system (rows >= n_u negated)
+        const int    m      = std::max(2, std::min(h->gmres_m, kGmresMax));
+        const size_t need   = (size_t)(2 * m + 1) * n3;
+        if (h->d_gm.n < need)
+          {
+            if (h->d_gm.alloc(need) != cudaSuccess)
+              return 2;
+            ++h->graph_epoch;
+          }
+        if (h->d_gmres_state.n < gmres_state_bytes() && h->d_gmres_state.alloc(gmres_state_bytes()) != cudaSuccess)
+          return 2;
+        c3.n_pos         = k.n_u;
+        c3.precond_apply = hook_precond3_tri;
+        c3.graph_key     = h->graph_epoch * 64 + (uint64_t)m;
+        rc = fgmres_solve(c3, b3, x3, h->d_gm.p, h->d_gm.p + (size_t)(m + 1) * n3, (int64_t)n3, h->d_w[0].p, m,
+                          h->d_gmres_state.p, h->h_scal, rel_tol, max_iterations, stats);
+      }
+    else
+      rc = minres_solve(c3, b3, x3, pinv3, work, (MinresState *)h->d_scal.p, h->h_scal, rel_tol, max_iterations, stats);
     if (rc == -2)
       return 3;
     // history of the solutions for the next initial guess: (d_sol, hist[0], hist[1]) <- (x, d_sol, hist[0])
@@ -1041,9 +1076,10 @@ extern "C"
       cudaEventCreate(&ev);
     for (auto &ev : h->ev_ring)
       cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-    h->graphs = new (std::nothrow) MinresGraphs;
+    h->graphs       = new (std::nothrow) MinresGraphs;
+    h->gmres_graphs = new (std::nothrow) GmresGraphs;
     cudaMallocHost((void **)&h->h_scal, 64 * sizeof(double));
-    if (!h->graphs || !h->h_scal)
+    if (!h->graphs || !h->gmres_graphs || !h->h_scal)
       {
         pe_destroy(h);
         return PE_ERR_ALLOC;
@@ -1068,6 +1104,8 @@ extern "C"
       cudaStreamSynchronize(h->stream);
     delete h->graphs;
     h->graphs = nullptr;
+    delete h->gmres_graphs;
+    h->gmres_graphs = nullptr;
     for (auto &ev : h->ev_ring)
       if (ev)
         cudaEventDestroy(ev);
@@ -1567,6 +1605,17 @@ extern "C"
     h->mg_omega = omega;
     h->mg_nu    = nu;
     ++h->graph_epoch;
+    return PE_OK;
+  }
+
+  int
+  pe_set_krylov(pe_handle *h, int method, int restart)
+  {
+    if (!h || method < 0 || method > 1 || restart < 0 || restart > kGmresMax)
+      return fail(h, PE_ERR_ARG, "pe_set_krylov: method 0 (MINRES) or 1 (FGMRES), restart <= 24");
+    h->krylov = method;
+    if (restart > 0)
+      h->gmres_m = restart;
     return PE_OK;
   }
 

@@ -390,6 +390,41 @@ namespace pe
     PE_NCCL(c, ncclGroupEnd());
   }
 
+  // only the xi unknowns of the halo (block-triangular preconditioner: B^T z_xi needs the neighbours' xi)
+  void
+  comm_halo_exchange_xi(void *ctx, double *x)
+  {
+    pe_handle *h = (pe_handle *)ctx;
+    CommState *c = cs(h);
+    if (!c || h->peers.empty() || !h->k3)
+      return;
+    const K3System &k = *h->k3;
+    cudaStream_t    s = h->stream;
+    for (size_t q = 0; q < h->peers.size(); ++q)
+      {
+        HaloPeer       &hp = h->peers[q];
+        const PeerPlan &pl = c->plan[q];
+        const int64_t   nx = pl.send_cnt[1];
+        if (hp.send_rows.empty() || nx <= 0)
+          continue;
+        k_gather_shift<<<(unsigned)((nx + 255) / 256), 256, 0, s>>>(nx, hp.d_send_rows.p + pl.send_cnt[0],
+                                                                   k.L + k.H - k.pint_begin, x, hp.d_send_buf_xi.p);
+        ++h->launches;
+      }
+    PE_NCCL(c, ncclGroupStart());
+    for (size_t q = 0; q < h->peers.size(); ++q)
+      {
+        HaloPeer       &hp = h->peers[q];
+        const PeerPlan &pl = c->plan[q];
+        if (pl.send_cnt[1])
+          PE_NCCL(c, ncclSend(hp.d_send_buf_xi.p, (size_t)pl.send_cnt[1], ncclDouble, pl.rank, c->comm, s));
+        if (pl.recv_cnt[1])
+          PE_NCCL(c, ncclRecv(x + k.L + k.H + k.Lx + (h->L + pl.recv_off[1] - k.hu_end), (size_t)pl.recv_cnt[1], ncclDouble,
+                              pl.rank, c->comm, s));
+      }
+    PE_NCCL(c, ncclGroupEnd());
+  }
+
   // ---- row slabs of the multigrid grids (GridComm hooks) ------------------------------------------------
   void
   comm_exchange_rows(void *ctx, double *p, int64_t row_len, int n_comp, int64_t comp_stride, int64_t a, int64_t b)

@@ -20,7 +20,7 @@
 #include <vector>
 
 struct ncclComm;
-namespace pe { struct MgHierarchy; struct BlockPrecond; struct K3System; struct CellMg; struct MinresGraphs; }
+namespace pe { struct MgHierarchy; struct BlockPrecond; struct K3System; struct CellMg; struct MinresGraphs; struct GmresGraphs; }
 
 namespace pe
 {
@@ -184,6 +184,10 @@ struct pe_handle
   // Krylov state kept across solves: captured iteration graphs, calibration of the stopping estimate, ||A||_inf of
   // the assembled reference matrix (lazy, -1 = not computed), events of the look-ahead convergence test
   pe::MinresGraphs *graphs = nullptr;
+  pe::GmresGraphs  *gmres_graphs = nullptr;
+  int               krylov = 1, gmres_m = 16; // 0 = MINRES + block-diagonal P, 1 = FGMRES(m) + block-triangular P
+  pe::DevBuf<double>  d_gm;                    // GMRES basis: (m + 1) v's, m z's
+  pe::DevBuf<uint8_t> d_gmres_state;
   uint64_t          graph_epoch = 1; // bumped whenever buffers or by-value kernel arguments of the iteration change
   double            graph_fp[8] = {};
   double            minres_calib = 1.;

@@ -258,13 +258,21 @@ namespace pe
         pint_rows.push_back(to_local(d.cell_dofs[(size_t)c * n_loc + n_loc - 1]));
         area_of_pint.push_back(0.5 * ((x3 - x0) * (y2 - y1) - (x2 - x1) * (y3 - y0)));
       }
-    auto build = [&](const int row_cls, const int col_mask, SubCsr &out, const int neg_mask = 0) -> bool {
+    // physical index (pe_k3.h) of the xi unknown that belongs to interior-pressure column c (local numbering)
+    const int64_t pint_begin = part.local_off[1], Lx = part.local_off[2] - part.local_off[1];
+    const int64_t hu_end = L + (std::lower_bound(part.ghost_cols.begin(), part.ghost_cols.end(), (uint32_t)d.n_u) -
+                                part.ghost_cols.begin());
+    auto xi_of = [&](const int32_t c) -> int32_t {
+      return (int32_t)(c < L ? LH + (c - pint_begin) : LH + Lx + (c - hu_end));
+    };
+    auto build = [&](const int row_mask, const int col_mask, SubCsr &out, const int neg_mask = 0,
+                     const bool cols_to_xi = false) -> bool {
       std::vector<int32_t>  rows, rp(1, 0), col;
       std::vector<uint32_t> src;
       std::vector<uint8_t>  neg;
       for (int64_t r = 0; r < L; ++r)
         {
-          if (cls[r] != row_cls)
+          if (!((row_mask >> cls[r]) & 1))
             continue;
           rows.push_back((int32_t)r);
           for (int64_t k = pat.rowptr[r]; k < pat.rowptr[r + 1]; ++k)
@@ -272,7 +280,7 @@ namespace pe
               const int32_t cc = to_local((uint32_t)pat.colidx[k]);
               if (cc >= 0 && ((col_mask >> cls[cc]) & 1))
                 {
-                  col.push_back(cc);
+                  col.push_back(cols_to_xi ? xi_of(cc) : cc);
                   src.push_back((uint32_t)k);
                   if (neg_mask)
                     neg.push_back((uint8_t)((neg_mask >> cls[cc]) & 1));
@@ -312,11 +320,15 @@ namespace pe
     };
     bp.has_bubbles = d.element == 0;
     if (bp.has_bubbles)
-      if (!build(CLS_BUBBLE, (1 << CLS_VERTEX) | (1 << CLS_BUBBLE), bp.Abu) ||
-          !build(CLS_VERTEX, 1 << CLS_BUBBLE, bp.Avb))
+      if (!build(1 << CLS_BUBBLE, (1 << CLS_VERTEX) | (1 << CLS_BUBBLE), bp.Abu) ||
+          !build(1 << CLS_VERTEX, 1 << CLS_BUBBLE, bp.Avb))
         return -1;
-    if (!build(CLS_PINT, 1 << CLS_PFACE, bp.Sif) || !build(CLS_PFACE, 1 << CLS_PINT, bp.Sfi) ||
-        !build(CLS_PFACE, (1 << CLS_PINT) | (1 << CLS_PFACE), bp.Spf, 1 << CLS_PINT))
+    if (!build(1 << CLS_PINT, 1 << CLS_PFACE, bp.Sif) || !build(1 << CLS_PFACE, 1 << CLS_PINT, bp.Sfi) ||
+        !build(1 << CLS_PFACE, (1 << CLS_PINT) | (1 << CLS_PFACE), bp.Spf, 1 << CLS_PINT))
+      return -1;
+    // -B^T: displacement rows x interior-pressure columns of A0 (alpha = 1), columns renumbered to the xi unknowns
+    // of the three-field vectors (block-triangular preconditioner of the GMRES solve)
+    if (!build((1 << CLS_VERTEX) | (1 << CLS_BUBBLE), 1 << CLS_PINT, bp.Bt, 0, true))
       return -1;
     if (bp.cls.alloc(cls.size()) != cudaSuccess || bp.pint_rows.alloc(pint_rows.size()) != cudaSuccess ||
         bp.pint_area.alloc(area_of_pint.size()) != cudaSuccess)
@@ -325,8 +337,9 @@ namespace pe
     cudaMemcpyAsync(bp.pint_rows.p, pint_rows.data(), pint_rows.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s);
     cudaMemcpyAsync(bp.pint_area.p, area_of_pint.data(), area_of_pint.size() * sizeof(double), cudaMemcpyHostToDevice, s);
     if (bp.t.alloc((size_t)LH) != cudaSuccess || bp.t2.alloc((size_t)LH) != cudaSuccess || bp.dinv.alloc((size_t)LH) != cudaSuccess ||
-        bp.t3.alloc((size_t)LH) != cudaSuccess || bp.wdinv.alloc((size_t)LH) != cudaSuccess)
+        bp.t3.alloc((size_t)LH) != cudaSuccess || bp.wdinv.alloc((size_t)LH) != cudaSuccess || bp.t4.alloc((size_t)LH) != cudaSuccess)
       return -1;
+    cudaMemsetAsync(bp.t4.p, 0, sizeof(double) * (size_t)LH, s);
     cudaMemsetAsync(bp.t3.p, 0, sizeof(double) * (size_t)LH, s);
     cudaMemsetAsync(bp.wdinv.p, 0, sizeof(double) * (size_t)LH, s);
     cudaMemsetAsync(bp.t.p, 0, sizeof(double) * (size_t)LH, s);
@@ -379,7 +392,7 @@ namespace pe
                  int64_t *launches)
   {
     bp.values = values;
-    for (SubCsr *sc : {&bp.Abu, &bp.Avb, &bp.Sif, &bp.Sfi, &bp.Spf})
+    for (SubCsr *sc : {&bp.Abu, &bp.Avb, &bp.Sif, &bp.Sfi, &bp.Spf, &bp.Bt})
       if (sc->nnz > 0)
         {
           k_sub_gather_values<<<gb(sc->nnz, 256), 256, 0, s>>>(sc->nnz, sc->src.p, sc->neg.p, values, sc->val.p);
@@ -398,9 +411,12 @@ namespace pe
   // ---- z = P^{-1} r ---------------------------------------------------------------------------------
   // Multi-GPU: sub-block products need the neighbours' entries (halo exchange of t and z); the two
   // V-cycles run replicated on every rank on the all-reduced grid right-hand sides.
+  // z_xi: when non-null (physical three-field vector holding the already preconditioned xi part of z), the
+  // displacement block is applied to  r_u + B^T z_xi  instead of r_u: block upper-triangular variant
+  //   P = [ P_u  -B^T  0 ; 0  P_xi  0 ; 0  0  P_p ]   of the row-signed system (pe_solver.cu, FGMRES)
   void
   precond_apply(BlockPrecond &bp, MgHierarchy &mg, CellMg &cm, const double *pinv, const double *r, double *z,
-                cudaStream_t s, int64_t *launches)
+                cudaStream_t s, int64_t *launches, const double *z_xi)
   {
     MgLevel      &L0 = mg.lv[0];
     const int     N  = L0.N, nv = (N + 1) * (N + 1);
@@ -411,8 +427,15 @@ namespace pe
         k_sub_stream<<<(unsigned)S.n_blk, 256, 0, st>>>(S.rowblk.p, S.rows.p, S.rp.p, S.col.p, S.val.p, x, a, m, b, out);
       ++*launches;
     };
+    // block-triangular variant: ru = r_u + B^T z_xi  (the Bt block holds -B^T: ru = r - Bt z_xi), kept in t4
+    const double *ru = r;
+    if (z_xi && bp.Bt.n_blk > 0)
+      {
+        sub(s, bp.Bt, z_xi, nullptr, nullptr, r, bp.t4.p);
+        ru = bp.t4.p;
+      }
     // local Jacobi parts:  u: z = pinv r, t = y1 on bubbles;  p_int: t_i = dinv_i r_i
-    k_pre_u<<<gb(bp.n_u, 256), 256, 0, s>>>(bp.n_u, bp.cls.p, pinv, r, bp.t.p, z);
+    k_pre_u<<<gb(bp.n_u, 256), 256, 0, s>>>(bp.n_u, bp.cls.p, pinv, ru, bp.t.p, z);
     k_pre_p<<<gb(bp.n_pint), 128, 0, s>>>(bp.n_pint, bp.pint_rows.p, bp.dinv.p, r, bp.t.p);
     *launches += 2;
     if (bp.halo)
@@ -431,7 +454,7 @@ namespace pe
     if (bp.has_bubbles)
       sub(s, bp.Avb, bp.t.p, nullptr, nullptr, nullptr, bp.t2.p);
     const int nbox_v = (bp.box.i1 - bp.box.i0 + 1) * (bp.box.j1 - bp.box.j0 + 1);
-    k_gather_u2<<<gb(nbox_v), 128, 0, s>>>(nv, N + 1, bp.box, L, mg.vdof.p, L0.mask_u.p, r, bp.has_bubbles ? bp.t2.p : nullptr,
+    k_gather_u2<<<gb(nbox_v), 128, 0, s>>>(nv, N + 1, bp.box, L, mg.vdof.p, L0.mask_u.p, ru, bp.has_bubbles ? bp.t2.p : nullptr,
                                            bp.allreduce2 ? bp.bu_local.p : L0.bu.p);
     ++*launches;
     PE_MARK(s, "precond: A_vb + vertex gather");
@@ -449,7 +472,7 @@ namespace pe
     k_scatter_u2<<<gb(nbox_v), 128, 0, s>>>(nv, N + 1, bp.box, mg.vdof.p, L0.mask_u.p, L0.wu[2].p, z, bp.t.p);
     ++*launches;
     if (bp.has_bubbles && fork)
-      sub(s, bp.Abu, bp.t.p, bp.t.p, pinv, r, z); // z_b = y1 + pinv_b (r_b - A_bb y1 - A_bv x_v),  t = (x_v, y1)
+      sub(s, bp.Abu, bp.t.p, bp.t.p, pinv, ru, z); // z_b = y1 + pinv_b (r_b - A_bb y1 - A_bv x_v),  t = (x_v, y1)
     // ---- pressure block: interior pressures eliminated exactly; on the face Schur complement
     //      F = S_ff - S_fi D_i^{-1} S_if:  Jacobi, cell-space correction (pe_cmg.h), Jacobi
     // g = r_f - S_fi D_i^{-1} r_i   -> t2 (face entries)
@@ -488,7 +511,7 @@ namespace pe
     // z_f = y2 + omega dinvF (g - F y2)
     sub(sp, bp.Spf, bp.t.p, bp.t.p, bp.wdinv.p, bp.t2.p, z);
     if (bp.has_bubbles && !fork)
-      sub(s, bp.Abu, bp.t.p, bp.t.p, pinv, r, z);
+      sub(s, bp.Abu, bp.t.p, bp.t.p, pinv, ru, z);
     if (bp.halo)
       bp.halo(bp.comm_ctx, z); // face pressures of the neighbours
     // z_i = dinv_i (r_i - S_if z_f)

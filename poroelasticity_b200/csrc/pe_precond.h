@@ -35,9 +35,10 @@ namespace pe
     CellBox         box;                 // cells this rank assembles (all cells on one GPU)
     DevBuf<double>  bu_local, rc_local;  // multi-GPU: this rank's contribution to the grid right-hand sides (zero outside box)
     SubCsr          Abu, Avb, Sif, Sfi, Spf; // Spf: p_face rows x [-S_fi | S_ff]
+    SubCsr          Bt;                      // -B^T: displacement rows x xi columns (three-field physical indices)
     DevBuf<uint8_t> cls;
     DevBuf<int32_t> pint_rows;
-    DevBuf<double>  pint_area, t, t2, t3, dinv, wdinv; // wdinv = omega_F / diag(F) on the face rows
+    DevBuf<double>  pint_area, t, t2, t3, t4, dinv, wdinv; // wdinv = omega_F / diag(F) on the face rows
     double          omega_f = 0.65;
     const double   *values = nullptr;
     // single GPU: the pressure pipeline runs on a forked stream beside the displacement V-cycle
@@ -50,5 +51,5 @@ namespace pe
   int  precond_update(BlockPrecond &bp, const double *values, const double *diag, double gamma, cudaStream_t s,
                       int64_t *launches);
   void precond_apply(BlockPrecond &bp, MgHierarchy &mg, CellMg &cm, const double *pinv, const double *r, double *z,
-                     cudaStream_t s, int64_t *launches);
+                     cudaStream_t s, int64_t *launches, const double *z_xi = nullptr);
 } // namespace pe

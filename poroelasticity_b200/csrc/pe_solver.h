@@ -28,6 +28,19 @@ namespace pe
     ~MinresGraphs();
     void clear();
   };
+  constexpr int kGmresMax = 24; // longest GMRES cycle (basis vectors kept)
+  struct GmresGraphs
+  {
+    cudaGraphExec_t exec[kGmresMax]     = {};
+    int64_t         launches[kGmresMax] = {};
+    uint64_t        key                 = 0;
+    int             m                   = 0;
+    GmresGraphs()                       = default;
+    GmresGraphs(const GmresGraphs &)    = delete;
+    GmresGraphs &operator=(const GmresGraphs &) = delete;
+    ~GmresGraphs();
+    void clear();
+  };
   struct SolverCtx
   {
     int64_t        L = 0, H = 0;    // owned rows, halo columns
@@ -55,6 +68,7 @@ namespace pe
     void (*true_residual)(void *ctx, const double *x, double *nrm2_dev) = nullptr;
     bool          x0_is_zero = false;  // initial guess known to be zero: ||b||_{P^-1} = the initial eta
     MinresGraphs *graphs     = nullptr; // cache of the captured iteration (null: capture per solve)
+    GmresGraphs  *gmres_graphs = nullptr;
     uint64_t      graph_key  = 0;
     double       *calib      = nullptr; // calibration factor between the P^-1 norm and the 2-norm, kept across solves
     double (*anorm)(void *ctx) = nullptr; // lazy ||A||_inf of the reference matrix (rounding-floor test only)
@@ -76,6 +90,10 @@ namespace pe
   int    build_preconditioner(const SolverCtx &c, double *diag_full, double *pinv);
   int    minres_solve(const SolverCtx &c, const double *b, double *x, const double *pinv, double *work[7],
                       MinresState *st, double *h_pinned, double rel_tol, int max_it, pe_solve_stats *stats);
+  // restarted flexible GMRES on the row-signed system (c.n_pos = first negated row); c.precond_apply = P^-1
+  int    fgmres_solve(const SolverCtx &c, const double *b, double *x, double *V, double *Z, int64_t stride, double *w, int m,
+                      void *st_dev, double *h_pinned, double rel_tol, int max_it, pe_solve_stats *stats);
+  size_t gmres_state_bytes();
   int    cg_solve(const SolverCtx &c, const double *b, double *x, double *work[3], void *st_dev, double *h_pinned,
                   double rel_tol, int max_it, pe_solve_stats *stats);
   size_t minres_state_bytes();

@@ -195,6 +195,10 @@ class BiotSystem:
     def set_solver_options(self, use_multigrid=1, theta=1.0, omega=0.6, nu=2):
         self._ck(self.L.pe_set_solver_options(self.h, use_multigrid, theta, omega, nu))
 
+    def set_krylov(self, method=1, restart=0):
+        """1 = FGMRES(restart) + block-triangular preconditioner (default), 0 = MINRES + block-diagonal"""
+        self._ck(self.L.pe_set_krylov(self.h, method, restart))
+
     def set_initial_guess(self, order):
         """0 = old_solution, 1 / 2 = linear / quadratic extrapolation in time (default 2)"""
         self._ck(self.L.pe_set_initial_guess(self.h, order))

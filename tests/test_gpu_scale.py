@@ -96,8 +96,9 @@ def test_changing_options_after_setup_cannot_corrupt_the_matrix(oracle128):
     b.close()
 
 
-def test_bench_tolerance_gives_1e8_solution_parity():
-    """The tolerance bench.py times with (DEFAULT_REL_TOL), warm starts and extrapolated initial guesses included,
+@pytest.mark.parametrize("krylov", [1, 0])
+def test_bench_tolerance_gives_1e8_solution_parity(krylov):
+    """Both Krylov methods (1 = FGMRES + block-triangular preconditioner, the default; 0 = MINRES).  The tolerance bench.py times with (DEFAULT_REL_TOL), warm starts and extrapolated initial guesses included,
     on 256^2 (three un-fused multigrid levels, 16 chunks of 4096 cells): per-step u and p within 1e-8 relative L2
     of the sparse LU solution of the oracle's system, over four steps of the reference loop."""
     import bench
@@ -112,6 +113,7 @@ def test_bench_tolerance_gives_1e8_solution_parity():
     b.set_material(1, 1, 1, 0)
     b.set_case(pb.PE_CASE_COSCOS)
     b.rel_tol = bench.DEFAULT_REL_TOL
+    b.set_krylov(krylov)
     old = np.zeros(o.n_dofs)
     its = []
     for k, t in enumerate(bench.run_times(dt)[:4]):
