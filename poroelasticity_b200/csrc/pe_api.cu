@@ -736,7 +736,9 @@ namespace
     if (build_preconditioner(c0, k.diag0.p, h->d_pinv.p) != 0)
       return 1;
     h->launches += 2;
-    if (k3_fill_values(k, lambda_s, h->alpha, s, &h->launches) != 0)
+    // GMRES works on the row-signed system with the xi rows scaled (pe_k3.cu); MINRES needs the symmetric K3
+    const bool gmres = h->krylov == 1 && h->use_mg && h->mg && h->mg->ready && h->bp && h->bp->ready && h->cmg && h->cmg->ready;
+    if (k3_fill_values(k, lambda_s, h->alpha, gmres, s, &h->launches) != 0)
       return 1;
     if (h->use_mg && h->mg && h->mg->ready && h->bp && h->bp->ready && h->cmg && h->cmg->ready)
       {
@@ -1613,6 +1615,8 @@ extern "C"
   {
     if (!h || method < 0 || method > 1 || restart < 0 || restart > kGmresMax)
       return fail(h, PE_ERR_ARG, "pe_set_krylov: method 0 (MINRES) or 1 (FGMRES), restart <= 24");
+    if (h->krylov != method && h->k3)
+      h->k3->values_valid = false; // the xi rows of the solver matrix are scaled for GMRES only
     h->krylov = method;
     if (restart > 0)
       h->gmres_m = restart;

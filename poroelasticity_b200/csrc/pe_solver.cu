@@ -1286,7 +1286,7 @@ namespace pe
     const double tol_abs = rel_tol * bnorm;
     double       f       = (c.calib && *c.calib > 0.) ? *c.calib : 1.;
     double       target  = f * tol_abs;
-    int          it = 0, converged = 0, checks = 0, cycles = 0, stall = 0;
+    int          it = 0, converged = 0, checks = 0, cycles = 0, stall = 0, slow = 0;
     double       rn = -1., rn_prev_cycle = -1.;
     bool         give_up = false;
     double       beta    = start_cycle();
@@ -1383,7 +1383,36 @@ namespace pe
           }
         if (it >= max_it)
           break;
-        beta = start_cycle();
+        const double beta_old = beta;
+        beta                  = start_cycle();
+        // stagnation: whole cycles that do not reduce the true residual of K3 (rounding floor of the data, or a target
+        // below it): decide on the true residual of the reference system, accept a backward stable iterate
+        if (beta > 0.7 * beta_old)
+          {
+            if (++slow >= 3)
+              {
+                rn = true_residual();
+                if (rn <= tol_abs)
+                  converged = 1;
+                else
+                  {
+                    cudaMemsetAsync(&st->scratch[1], 0, sizeof(double), s);
+                    k_norm2<<<g, 256, 0, s>>>(L, x, &st->scratch[1], c.gap);
+                    if (c.allreduce)
+                      c.allreduce(c.halo_ctx, &st->scratch[1], 1);
+                    cudaMemcpyAsync(h_pinned + 5, &st->scratch[1], sizeof(double), cudaMemcpyDeviceToHost, s);
+                    cudaStreamSynchronize(s);
+                    const double xnorm = std::sqrt(std::fmax(h_pinned[5], 0.));
+                    const double anorm = c.anorm ? c.anorm(c.precond_ctx) : 0.;
+                    if (anorm > 0. && rn <= 64. * 2.220446049250313e-16 * (anorm * xnorm + bnorm))
+                      converged = 2;
+                    else
+                      give_up = true;
+                  }
+              }
+          }
+        else
+          slow = 0;
       }
     cudaStreamSynchronize(s);
     if (!(converged && rn >= 0.))
