@@ -8,6 +8,7 @@
 #include "pe_mg.h"
 #include "pe_precond.h"
 #include "pe_solver.h"
+#include "pe_timer.h"
 
 #include <algorithm>
 #include <cmath>
@@ -726,10 +727,12 @@ namespace
     a.sol                 = nullptr;
     int nl                = 0;
     cudaError_t e;
+    PE_MARK(s, "setup: (start)");
     e = run_assembly(h, a, P, &nl);
     h->launches += nl;
     if (e != cudaSuccess)
       return 1;
+    PE_MARK(s, "setup: second assembly pass A0");
     // diagonal of A0 (with the halo part), Jacobi inverse for the u block
     SolverCtx c0 = make_solver_ctx(h);
     c0.values    = k.values0.p;
@@ -738,8 +741,9 @@ namespace
     h->launches += 2;
     // GMRES works on the row-signed system with the xi rows scaled (pe_k3.cu); MINRES needs the symmetric K3
     const bool gmres = h->krylov == 1 && h->use_mg && h->mg && h->mg->ready && h->bp && h->bp->ready && h->cmg && h->cmg->ready;
-    if (k3_fill_values(k, lambda_s, h->alpha, gmres, s, &h->launches) != 0)
+    if (k3_fill_values(k, lambda_s, h->alpha, h->mu, gmres, s, &h->launches) != 0)
       return 1;
+    PE_MARK(s, "setup: diagonal + K3 values");
     if (h->use_mg && h->mg && h->mg->ready && h->bp && h->bp->ready && h->cmg && h->cmg->ready)
       {
         // damped (block-)Jacobi sweeps alternate between two weights (a degree-2 Chebyshev-like smoother at the cost
@@ -767,6 +771,7 @@ namespace
           return 1;
         if (precond_update(*h->bp, k.values0.p, k.diag0.p, extra, s, &h->launches) != 0)
           return 1;
+        PE_MARK(s, "setup: multigrid levels + sub-block values");
       }
     return 0;
   }
@@ -966,6 +971,7 @@ namespace
     }
     double *work[7] = {h->d_w[0].p, h->d_w[1].p, h->d_w[2].p, h->d_w[3].p, h->d_w[4].p, h->d_w[5].p, h->d_w[6].p};
     int     rc;
+    PE_MARK(s, "setup: rhs, initial guess, ||b||");
     if (block_pc && h->krylov == 1)
       {
         // FGMRES(m) + block-triangular preconditioner on the row-signed system (rows >= n_u negated)

@@ -134,17 +134,20 @@ namespace pe
       val[pos[3 * Lx + i]] = alpha * wl;
     }
 
-    // GMRES path: the xi rows are scaled by T_i = lambda_s / sqrt(w_i), so that the 2-norm of the Krylov residual
-    // weighs the xi equation like its effect on the residual of the reference system,
-    //     r_u(two-field) = r_u - lambda B^T W^-1 r_xi     (pe_k3.h), ||B^T W^-1/2|| = O(1)
+    // GMRES path: the xi rows are scaled by T_i = tau / sqrt(w_i), tau = 1 / (1/lambda_s + 1/(2 mu)) (= the xi block of
+    // the preconditioner times sqrt(w)), so that the 2-norm of the Krylov residual weighs the xi equation like its
+    // effect on the residual of the reference system,
+    //     r_u(two-field) = r_u - lambda B^T W^-1 r_xi = r_u - (1 + lambda / 2 mu) (B^T W^-1/2) (T r_xi),   ||B^T W^-1/2|| = O(1)
+    // and the scaled row keeps O(mu) entries for every lambda (tau -> lambda for lambda << mu, -> 2 mu for lambda >> mu;
+    // scaling by lambda itself makes the xi - u coupling of the preconditioned operator O(lambda): GMRES stalls).
     __global__ void
     k_k3_scale_xi_rows(const int64_t L, const int64_t Lx, const int64_t *__restrict__ rowptr3, const double *__restrict__ w,
-                       const double lambda_s, double *__restrict__ val)
+                       const double tau, double *__restrict__ val)
     {
       const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
       if (i >= Lx)
         return;
-      const double T = lambda_s * rsqrt(w[i]);
+      const double T = tau * rsqrt(w[i]);
       for (int64_t k = rowptr3[L + i]; k < rowptr3[L + i + 1]; ++k)
         val[k] *= T;
     }
@@ -198,7 +201,7 @@ namespace pe
     __global__ void
     k_k3_init_xi(const Ranges R, const int64_t *__restrict__ rowptr3, const int32_t *__restrict__ colidx3,
                  const double *__restrict__ val, const double *__restrict__ w, const double lambda_s, const double alpha,
-                 const int xi_scaled, double *__restrict__ x3)
+                 const double xi_tau /* 0: rows not scaled */, double *__restrict__ x3)
     {
       const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
       if (i >= R.Lx)
@@ -207,17 +210,17 @@ namespace pe
       double        s = 0.;
       for (int64_t k = b; k < e; ++k)
         s += val[k] * x3[colidx3[k]];
-      // rows scaled by T = lambda_s / sqrt(w): (lambda_s / w) / T = 1 / sqrt(w)
-      x3[R.L + R.H + i] = (xi_scaled ? rsqrt(w[i]) : lambda_s / w[i]) * s + alpha * x3[R.pint_begin + i];
+      // rows scaled by T = tau / sqrt(w): (lambda_s / w) / T = (lambda_s / tau) / sqrt(w)
+      x3[R.L + R.H + i] = (xi_tau > 0. ? (lambda_s / xi_tau) * rsqrt(w[i]) : lambda_s / w[i]) * s + alpha * x3[R.pint_begin + i];
     }
     __global__ void
     k_k3_precond_xi(const int64_t Lx, const double *__restrict__ w, const double scale, const int xi_scaled,
-                    const double lambda_s, const double *__restrict__ r, double *__restrict__ z)
+                    const double *__restrict__ r, double *__restrict__ z)
     {
       const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
       if (i < Lx)
-        // scaled rows: z = P_xi^-1 T^-1 r,  T = lambda_s / sqrt(w)
-        z[i] = xi_scaled ? r[i] * (scale / lambda_s) * rsqrt(w[i]) : r[i] * (scale / w[i]);
+        // scaled rows: z = P_xi^-1 T^-1 r = r / sqrt(w)   (T = scale / sqrt(w), P_xi = w / scale)
+        z[i] = xi_scaled ? r[i] * rsqrt(w[i]) : r[i] * (scale / w[i]);
     }
 
     inline unsigned
@@ -355,12 +358,13 @@ namespace pe
   }
 
   int
-  k3_fill_values(K3System &k, const double lambda_s, const double alpha, const bool scale_xi_rows, cudaStream_t s,
-                 int64_t *launches)
+  k3_fill_values(K3System &k, const double lambda_s, const double alpha, const double mu, const bool scale_xi_rows,
+                 cudaStream_t s, int64_t *launches)
   {
     k.lambda_s  = lambda_s;
     k.alpha     = alpha;
     k.xi_scaled = scale_xi_rows;
+    k.xi_tau    = scale_xi_rows ? 1. / (1. / lambda_s + 1. / (2. * mu)) : 0.;
     if (k.nnz > 0)
       k_k3_gather<<<gb(k.nnz), 256, 0, s>>>(k.nnz, k.nnz_u, k.src.p, k.values0.p, k.val.p);
     if (k.Lx > 0)
@@ -368,7 +372,7 @@ namespace pe
     *launches += 2;
     if (scale_xi_rows && k.Lx > 0)
       {
-        k_k3_scale_xi_rows<<<gb(k.Lx), 256, 0, s>>>(k.L, k.Lx, k.rowptr.p, k.w.p, lambda_s, k.val.p);
+        k_k3_scale_xi_rows<<<gb(k.Lx), 256, 0, s>>>(k.L, k.Lx, k.rowptr.p, k.w.p, k.xi_tau, k.val.p);
         ++*launches;
       }
     k.values_valid = true;
@@ -400,7 +404,7 @@ namespace pe
   {
     if (k.Lx > 0)
       k_k3_init_xi<<<gb(k.Lx, 128), 128, 0, s>>>(ranges_of(k), k.rowptr.p, k.colidx.p, k.val.p, k.w.p, k.lambda_s, k.alpha,
-                                                 k.xi_scaled ? 1 : 0, x3);
+                                                 k.xi_tau, x3);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
   }
 
@@ -409,8 +413,7 @@ namespace pe
   {
     const double scale = 1. / (1. / k.lambda_s + 1. / (2. * mu));
     if (k.Lx > 0)
-      k_k3_precond_xi<<<gb(k.Lx), 256, 0, s>>>(k.Lx, k.w.p, scale, k.xi_scaled ? 1 : 0, k.lambda_s, r3 + k.L + k.H,
-                                               z3 + k.L + k.H);
+      k_k3_precond_xi<<<gb(k.Lx), 256, 0, s>>>(k.Lx, k.w.p, scale, k.xi_scaled ? 1 : 0, r3 + k.L + k.H, z3 + k.L + k.H);
     return 0;
   }
 } // namespace pe

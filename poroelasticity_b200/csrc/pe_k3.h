@@ -27,7 +27,8 @@ namespace pe
   struct K3System
   {
     bool    built = false, values_valid = false;
-    bool    xi_scaled = false; // xi rows of val multiplied by lambda_s / sqrt(w) (GMRES path; MINRES needs the symmetric K3)
+    bool    xi_scaled = false; // xi rows of val multiplied by xi_tau / sqrt(w) (GMRES path; MINRES needs the symmetric K3)
+    double  xi_tau = 0.;       // 1 / (1/lambda_s + 1/(2 mu)), 0 when the rows are not scaled
     int64_t L = 0, H = 0, Lx = 0, Hx = 0;
     int64_t n_u = 0, pint_begin = 0, pint_end = 0, hu_end = 0, hpi_end = 0;
     int64_t nnz = 0, nnz_u = 0, n_rowblk = 0, n_con = 0;
@@ -44,7 +45,8 @@ namespace pe
   int k3_build_structure(K3System &k, const HostMesh &mesh, const HostDofs &dofs, const Partition &part,
                          const int64_t *d_rowptr, const int32_t *d_colidx, cudaStream_t s);
   // values: once per assembled matrix.  values0 = A0 (same CSR as the reference pattern).
-  int k3_fill_values(K3System &k, double lambda_s, double alpha, bool scale_xi_rows, cudaStream_t s, int64_t *launches);
+  int k3_fill_values(K3System &k, double lambda_s, double alpha, double mu, bool scale_xi_rows, cudaStream_t s,
+                     int64_t *launches);
   // b3 = (b_u [constrained rows rescaled to the A0 diagonal] | -b_p | 0)
   int k3_make_rhs(const K3System &k, const double *rhs, const int64_t *rowptr, const int32_t *colidx, const double *values_a,
                   double *b3, cudaStream_t s);
