@@ -34,6 +34,11 @@ namespace pe
   void comm_reduce_rows(void *ctx, const double *in, double *out, int64_t row_len, int n_comp, int64_t comp_stride,
                         const int64_t *bounds);
   void comm_allreduce(void *ctx, double *v, int n);
+  void comm_boxes_to_slabs(void *ctx, const double *in, double *out, int64_t row_len, int n_comp, int64_t comp_stride,
+                           const int64_t *bounds, int kind);
+  void comm_slabs_to_boxes(void *ctx, double *p, int64_t row_len, int n_comp, int64_t comp_stride, const int64_t *bounds,
+                           int kind);
+  int  comm_set_box(pe_handle *h, const CellBox &box);
   void comm_allreduce_max(void *ctx, double *v, int n);
   int  comm_status(pe_handle *h);
   void comm_allreduce2(void *ctx, const double *in, double *out, int n);
@@ -815,6 +820,11 @@ namespace
             gc.exchange_rows  = comm_exchange_rows;
             gc.allgather_rows = comm_allgather_rows;
             gc.reduce_rows    = comm_reduce_rows;
+            if (!getenv("PE_MG_WHOLE_SLABS")) // A/B: round-1 transfers of whole slabs (reduce / all-gather)
+              {
+                gc.boxes_to_slabs = comm_boxes_to_slabs;
+                gc.slabs_to_boxes = comm_slabs_to_boxes;
+              }
             mg_set_comm(*h->mg, gc);
             if (h->cmg->ready)
               cmg_set_comm(*h->cmg, gc);
@@ -827,6 +837,8 @@ namespace
           return 1;
         if (h->part.world > 1)
           {
+            if (comm_set_box(h, h->bp->box) != PE_OK)
+              return 1;
             h->bp->halo       = comm_halo_exchange;
             h->bp->allreduce  = comm_allreduce;
             h->bp->allreduce2 = comm_allreduce2;
@@ -872,6 +884,7 @@ namespace
     c3.graph_key = h->graph_epoch;
     c3.calib     = &h->minres_calib;
     c3.anorm     = hook_anorm;
+    c3.floor_rows = k.L;
     c3.ev_ring   = h->ev_ring;
     c3.gmres_graphs = h->gmres_graphs;
     return c3;

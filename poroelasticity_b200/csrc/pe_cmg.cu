@@ -648,7 +648,9 @@ namespace pe
         *launches += nu;
         if (dist)
           {
-            if (l == 0)
+            if (l == 0 && cm.gc.slabs_to_boxes)
+              cm.gc.slabs_to_boxes(cm.gc.ctx, x0, L.N, 1, 0, cm.bounds[0].data(), 1);
+            else if (l == 0)
               cm.gc.allgather_rows(cm.gc.ctx, x0, L.N, 1, 0, cm.bounds[0].data());
             else
               exchange(x0); // the finer level corrects from my rows and one halo row on each side

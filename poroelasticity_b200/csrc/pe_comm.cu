@@ -34,6 +34,66 @@ namespace pe
         buf[i] = x[rows[i] + shift];
     }
 
+    // rectangle [c0, c1) x [r0, r1) of a lexicographic grid with rows of row_len entries, n_comp components
+    // comp_stride apart  <->  contiguous buffer [comp][row][col]
+    __global__ void
+    k_rect_pack(const double *__restrict__ grid, const int64_t row_len, const int64_t comp_stride, const int n_comp,
+                const int c0, const int c1, const int r0, const int r1, double *__restrict__ buf)
+    {
+      const int64_t w = c1 - c0, n = w * (r1 - r0), t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      if (t >= n * n_comp)
+        return;
+      const int64_t k = t / n, q = t % n;
+      buf[t]          = grid[k * comp_stride + (r0 + q / w) * row_len + c0 + q % w];
+    }
+    template <bool ADD>
+    __global__ void
+    k_rect_unpack(double *__restrict__ grid, const int64_t row_len, const int64_t comp_stride, const int n_comp, const int c0,
+                  const int c1, const int r0, const int r1, const double *__restrict__ buf)
+    {
+      const int64_t w = c1 - c0, n = w * (r1 - r0), t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      if (t >= n * n_comp)
+        return;
+      const int64_t k = t / n, q = t % n;
+      double       *d = grid + k * comp_stride + (r0 + q / w) * row_len + c0 + q % w;
+      *d              = ADD ? *d + buf[t] : buf[t];
+    }
+    // zero rows [r0, r1) of every component
+    __global__ void
+    k_rows_zero(double *__restrict__ grid, const int64_t row_len, const int64_t comp_stride, const int n_comp, const int64_t r0,
+                const int64_t r1)
+    {
+      const int64_t n = (r1 - r0) * row_len, t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      if (t >= n * n_comp)
+        return;
+      grid[(t / n) * comp_stride + r0 * row_len + t % n] = 0.;
+    }
+
+    struct Rect
+    {
+      int c0 = 0, c1 = 0, r0 = 0, r1 = 0;
+      int64_t
+      count() const
+      {
+        return (c1 > c0 && r1 > r0) ? (int64_t)(c1 - c0) * (r1 - r0) : 0;
+      }
+    };
+    inline Rect
+    clip_rows(Rect b, const int64_t ra, const int64_t rb)
+    {
+      b.r0 = (int)std::max<int64_t>(b.r0, ra);
+      b.r1 = (int)std::min<int64_t>(b.r1, rb);
+      return b;
+    }
+    // box <-> slab transfer plan of one grid (vertex or cell grid of one size)
+    struct BoxPlan
+    {
+      int64_t            row_len = 0;
+      int                n_comp  = 0;
+      std::vector<Rect>  send, recv; // per rank (self included: local copy)
+      std::vector<DevBuf<double>> sbuf, rbuf;
+    };
+
     struct PeerPlan
     {
       int     rank;
@@ -47,6 +107,8 @@ namespace pe
     ncclComm_t              comm = nullptr;
     std::vector<PeerPlan>   plan;
     std::vector<HaloPeer>  *peers = nullptr;
+    std::vector<int>        all_boxes;                // asm cell bounding box (i0, i1, j0, j1) of every rank
+    std::vector<BoxPlan>    box_plans;                // [2 * kind + direction], built at first use
     ncclResult_t            first_err = ncclSuccess; // first failed NCCL call of a hot-path hook (latched)
     const char             *first_where = "";
     int                    *d_flag = nullptr;         // device int[2]: agreement of the ranks during setup
@@ -493,6 +555,190 @@ namespace pe
             PE_NCCL(c, ncclReduce(in + off, out + off, n, ncclDouble, ncclSum, q, c->comm, s));
         }
     PE_NCCL(c, ncclGroupEnd());
+  }
+
+  // ---- box <-> slab transfers: the Biot vectors live on Morton blocks of cells (boxes), the fine multigrid levels
+  // on row slabs.  Each rank sends / receives only the rectangles box x slab that overlap (round 1 reduced / all-
+  // gathered the WHOLE grid on every rank: 268 MB per V-cycle on the 4096^2 vertex grid).
+  // kind 0: vertex grid (row_len = N + 1; the box of cells [i0,i1) x [j0,j1) holds vertices [i0,i1] x [j0,j1]),
+  // kind 1: cell grid (row_len = N).  `grow`: the box is widened by one entry on every side (the grid -> Biot
+  // transfer of the cell grid reads the cells next to the box).
+  int
+  comm_set_box(pe_handle *h, const CellBox &box)
+  {
+    CommState *c = cs(h);
+    if (!c)
+      return PE_OK;
+    const int W = h->part.world;
+    DevBuf<int> d_mine, d_all;
+    if (d_mine.alloc(4) != cudaSuccess || d_all.alloc((size_t)4 * W) != cudaSuccess)
+      return PE_ERR_ALLOC;
+    const int mine[4] = {box.i0, box.i1, box.j0, box.j1};
+    cudaMemcpyAsync(d_mine.p, mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream);
+    if (ncclAllGather(d_mine.p, d_all.p, 4, ncclInt, c->comm, h->stream) != ncclSuccess)
+      return PE_ERR_NCCL;
+    c->all_boxes.assign((size_t)4 * W, 0);
+    cudaMemcpyAsync(c->all_boxes.data(), d_all.p, sizeof(int) * 4 * W, cudaMemcpyDeviceToHost, h->stream);
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess)
+      return PE_ERR_CUDA;
+    c->box_plans.clear();
+    c->box_plans.resize(4);
+    return PE_OK;
+  }
+
+  static BoxPlan *
+  box_plan(pe_handle *h, const int kind, const int dir /* 0: boxes -> slabs, 1: slabs -> boxes */, const int64_t row_len,
+           const int n_comp, const int64_t *bounds)
+  {
+    CommState *c = cs(h);
+    if (c->all_boxes.empty() || c->box_plans.size() != 4)
+      return nullptr;
+    BoxPlan &P = c->box_plans[(size_t)(2 * kind + dir)];
+    if (P.row_len == row_len && P.n_comp == n_comp && !P.send.empty())
+      return &P;
+    const int W = h->part.world, me = h->part.rank;
+    const int n_rows = (int)bounds[W];
+    auto box_of = [&](const int q) {
+      const int *b = &c->all_boxes[(size_t)4 * q];
+      Rect r;
+      const int ext = kind == 0 ? 1 : 0; // vertices of the cell box
+      const int grow = dir == 1 ? 1 : 0;
+      r.c0 = std::max(0, b[0] - grow);
+      r.c1 = (int)std::min<int64_t>(row_len, b[1] + ext + grow);
+      r.r0 = std::max(0, b[2] - grow);
+      r.r1 = std::min(n_rows, b[3] + ext + grow);
+      if (b[1] <= b[0] || b[3] <= b[2])
+        r = Rect{};
+      return r;
+    };
+    P.row_len = row_len;
+    P.n_comp  = n_comp;
+    P.send.assign((size_t)W, Rect{});
+    P.recv.assign((size_t)W, Rect{});
+    P.sbuf.clear();
+    P.rbuf.clear();
+    P.sbuf.resize((size_t)W);
+    P.rbuf.resize((size_t)W);
+    for (int q = 0; q < W; ++q)
+      {
+        if (dir == 0)
+          {
+            P.send[(size_t)q] = clip_rows(box_of(me), bounds[q], bounds[q + 1]); // my box x slab of q
+            P.recv[(size_t)q] = clip_rows(box_of(q), bounds[me], bounds[me + 1]); // box of q x my slab
+          }
+        else
+          {
+            P.send[(size_t)q] = clip_rows(box_of(q), bounds[me], bounds[me + 1]);
+            P.recv[(size_t)q] = clip_rows(box_of(me), bounds[q], bounds[q + 1]);
+          }
+        if (q != me)
+          {
+            if (P.sbuf[(size_t)q].alloc((size_t)(P.send[(size_t)q].count() * n_comp)) != cudaSuccess ||
+                P.rbuf[(size_t)q].alloc((size_t)(P.recv[(size_t)q].count() * n_comp)) != cudaSuccess)
+              return nullptr;
+          }
+      }
+    return &P;
+  }
+
+  static void
+  box_transfer(pe_handle *h, BoxPlan &P, const double *in, double *out, const int64_t comp_stride, const bool add)
+  {
+    CommState   *c  = cs(h);
+    const int    W  = h->part.world, me = h->part.rank;
+    cudaStream_t s  = h->stream;
+    auto grid_of = [](const int64_t n) { return (unsigned)((n + 255) / 256); };
+    for (int q = 0; q < W; ++q)
+      {
+        const Rect   &r = P.send[(size_t)q];
+        const int64_t n = r.count() * P.n_comp;
+        if (q == me || n == 0)
+          continue;
+        k_rect_pack<<<grid_of(n), 256, 0, s>>>(in, P.row_len, comp_stride, P.n_comp, r.c0, r.c1, r.r0, r.r1, P.sbuf[(size_t)q].p);
+        ++h->launches;
+      }
+    PE_NCCL(c, ncclGroupStart());
+    for (int q = 0; q < W; ++q)
+      {
+        if (q == me)
+          continue;
+        const int64_t ns = P.send[(size_t)q].count() * P.n_comp, nr = P.recv[(size_t)q].count() * P.n_comp;
+        if (ns)
+          PE_NCCL(c, ncclSend(P.sbuf[(size_t)q].p, (size_t)ns, ncclDouble, q, c->comm, s));
+        if (nr)
+          PE_NCCL(c, ncclRecv(P.rbuf[(size_t)q].p, (size_t)nr, ncclDouble, q, c->comm, s));
+      }
+    PE_NCCL(c, ncclGroupEnd());
+    // own part: in -> out directly (in and out may be the same array: then nothing to do)
+    {
+      const Rect   &r = P.send[(size_t)me];
+      const int64_t n = r.count() * P.n_comp;
+      if (n && in != out)
+        {
+          // pack + unpack through a temporary is avoided: one kernel reads `in` and writes / adds into `out`
+          if (P.sbuf[(size_t)me].n < (size_t)n)
+            P.sbuf[(size_t)me].alloc((size_t)n);
+          k_rect_pack<<<grid_of(n), 256, 0, s>>>(in, P.row_len, comp_stride, P.n_comp, r.c0, r.c1, r.r0, r.r1, P.sbuf[(size_t)me].p);
+          if (add)
+            k_rect_unpack<true><<<grid_of(n), 256, 0, s>>>(out, P.row_len, comp_stride, P.n_comp, r.c0, r.c1, r.r0, r.r1, P.sbuf[(size_t)me].p);
+          else
+            k_rect_unpack<false><<<grid_of(n), 256, 0, s>>>(out, P.row_len, comp_stride, P.n_comp, r.c0, r.c1, r.r0, r.r1, P.sbuf[(size_t)me].p);
+          h->launches += 2;
+        }
+    }
+    for (int q = 0; q < W; ++q)
+      {
+        const Rect   &r = P.recv[(size_t)q];
+        const int64_t n = r.count() * P.n_comp;
+        if (q == me || n == 0)
+          continue;
+        if (add)
+          k_rect_unpack<true><<<grid_of(n), 256, 0, s>>>(out, P.row_len, comp_stride, P.n_comp, r.c0, r.c1, r.r0, r.r1, P.rbuf[(size_t)q].p);
+        else
+          k_rect_unpack<false><<<grid_of(n), 256, 0, s>>>(out, P.row_len, comp_stride, P.n_comp, r.c0, r.c1, r.r0, r.r1, P.rbuf[(size_t)q].p);
+        ++h->launches;
+      }
+  }
+
+  // out[my slab] = sum over the ranks of in[their box]  (in: this rank's contribution, valid on its box)
+  void
+  comm_boxes_to_slabs(void *ctx, const double *in, double *out, int64_t row_len, int n_comp, int64_t comp_stride,
+                      const int64_t *bounds, int kind)
+  {
+    pe_handle *h = (pe_handle *)ctx;
+    CommState *c = cs(h);
+    if (!c)
+      return;
+    BoxPlan *P = box_plan(h, kind, 0, row_len, n_comp, bounds);
+    if (!P)
+      {
+        comm_reduce_rows(ctx, in, out, row_len, n_comp, comp_stride, bounds); // no box information: whole slabs
+        return;
+      }
+    const int     me = h->part.rank;
+    const int64_t n  = (bounds[me + 1] - bounds[me]) * row_len * n_comp;
+    if (n > 0)
+      {
+        k_rows_zero<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(out, row_len, comp_stride, n_comp, bounds[me], bounds[me + 1]);
+        ++h->launches;
+      }
+    box_transfer(h, *P, in, out, comp_stride, true);
+  }
+  // p[my box, widened by one] = the slab owners' values  (p: my slab rows valid on entry)
+  void
+  comm_slabs_to_boxes(void *ctx, double *p, int64_t row_len, int n_comp, int64_t comp_stride, const int64_t *bounds, int kind)
+  {
+    pe_handle *h = (pe_handle *)ctx;
+    CommState *c = cs(h);
+    if (!c)
+      return;
+    BoxPlan *P = box_plan(h, kind, 1, row_len, n_comp, bounds);
+    if (!P)
+      {
+        comm_allgather_rows(ctx, p, row_len, n_comp, comp_stride, bounds);
+        return;
+      }
+    box_transfer(h, *P, p, p, comp_stride, false);
   }
 
   void

@@ -85,6 +85,12 @@ namespace pe
     // an all-reduce: a distributed level only needs its own rows of the right-hand side)
     void (*reduce_rows)(void *ctx, const double *in, double *out, int64_t row_len, int n_comp, int64_t comp_stride,
                         const int64_t *bounds) = nullptr;
+    // box <-> slab transfers (pe_comm.cu): only the overlapping rectangles travel.  kind 0 = vertex grid, 1 = cell grid.
+    //   boxes_to_slabs: out[my slab] = sum over ranks of in[their box];  slabs_to_boxes: p[my box + 1] from the owners
+    void (*boxes_to_slabs)(void *ctx, const double *in, double *out, int64_t row_len, int n_comp, int64_t comp_stride,
+                           const int64_t *bounds, int kind) = nullptr;
+    void (*slabs_to_boxes)(void *ctx, double *p, int64_t row_len, int n_comp, int64_t comp_stride, const int64_t *bounds,
+                           int kind) = nullptr;
   };
 
   // bounding box (cell indices, half open) of the cells a rank assembles on a structured mesh: the grid <-> Biot

@@ -870,8 +870,10 @@ namespace pe
                       cudaMemcpyDeviceToDevice, s);
     if (dist)
       {
-        if (l == 0)
-          mg.gc.allgather_rows(mg.gc.ctx, out, V, NC, nv, mg.bounds[0].data()); // every rank scatters its own vertices
+        if (l == 0 && mg.gc.slabs_to_boxes)
+          mg.gc.slabs_to_boxes(mg.gc.ctx, out, V, NC, nv, mg.bounds[0].data(), 0); // every rank scatters the vertices of its box
+        else if (l == 0)
+          mg.gc.allgather_rows(mg.gc.ctx, out, V, NC, nv, mg.bounds[0].data());
         else
           exchange(out); // the finer level prolongates from my rows and one halo row on each side
       }

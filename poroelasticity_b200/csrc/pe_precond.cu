@@ -461,7 +461,9 @@ namespace pe
     if (bp.allreduce2)
       {
         // a distributed finest level only needs its own rows: reduce to the slab owners (half the traffic)
-        if (mg.n_dist > 0 && mg.gc.reduce_rows)
+        if (mg.n_dist > 0 && mg.gc.boxes_to_slabs)
+          mg.gc.boxes_to_slabs(mg.gc.ctx, bp.bu_local.p, L0.bu.p, N + 1, 2, nv, mg.bounds[0].data(), 0);
+        else if (mg.n_dist > 0 && mg.gc.reduce_rows)
           mg.gc.reduce_rows(mg.gc.ctx, bp.bu_local.p, L0.bu.p, N + 1, 2, nv, mg.bounds[0].data());
         else
           bp.allreduce2(bp.comm_ctx, bp.bu_local.p, L0.bu.p, 2 * nv);
@@ -496,7 +498,9 @@ namespace pe
     PE_MARK(sp, "precond: face Schur products");
     if (bp.allreduce2)
       {
-        if (cm.n_dist > 0 && cm.gc.reduce_rows)
+        if (cm.n_dist > 0 && cm.gc.boxes_to_slabs)
+          cm.gc.boxes_to_slabs(cm.gc.ctx, bp.rc_local.p, cm.lv[0].b.p, N, 1, 0, cm.bounds[0].data(), 1);
+        else if (cm.n_dist > 0 && cm.gc.reduce_rows)
           cm.gc.reduce_rows(cm.gc.ctx, bp.rc_local.p, cm.lv[0].b.p, N, 1, 0, cm.bounds[0].data());
         else
           bp.allreduce2(bp.comm_ctx, bp.rc_local.p, cm.lv[0].b.p, N * N);

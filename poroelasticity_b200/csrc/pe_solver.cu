@@ -866,7 +866,7 @@ namespace pe
           {
             // rounding floor of the data?  accept a backward stable iterate like an LU solution
             cudaMemsetAsync(&st->d2, 0, sizeof(double), s);
-            k_norm2<<<g, 256, 0, s>>>(L, x, &st->d2, c.gap);
+            k_norm2<<<g, 256, 0, s>>>(c.floor_rows > 0 ? c.floor_rows : L, x, &st->d2, c.gap);
             if (c.allreduce)
               c.allreduce(c.halo_ctx, &st->d2, 1);
             cudaMemcpyAsync(h_pinned + 5, &st->d2, sizeof(double), cudaMemcpyDeviceToHost, s);
@@ -1357,7 +1357,7 @@ namespace pe
               {
                 ++stall;
                 cudaMemsetAsync(&st->scratch[1], 0, sizeof(double), s);
-                k_norm2<<<g, 256, 0, s>>>(L, x, &st->scratch[1], c.gap);
+                k_norm2<<<g, 256, 0, s>>>(c.floor_rows > 0 ? c.floor_rows : L, x, &st->scratch[1], c.gap);
                 if (c.allreduce)
                   c.allreduce(c.halo_ctx, &st->scratch[1], 1);
                 cudaMemcpyAsync(h_pinned + 5, &st->scratch[1], sizeof(double), cudaMemcpyDeviceToHost, s);
@@ -1397,7 +1397,7 @@ namespace pe
                 else
                   {
                     cudaMemsetAsync(&st->scratch[1], 0, sizeof(double), s);
-                    k_norm2<<<g, 256, 0, s>>>(L, x, &st->scratch[1], c.gap);
+                    k_norm2<<<g, 256, 0, s>>>(c.floor_rows > 0 ? c.floor_rows : L, x, &st->scratch[1], c.gap);
                     if (c.allreduce)
                       c.allreduce(c.halo_ctx, &st->scratch[1], 1);
                     cudaMemcpyAsync(h_pinned + 5, &st->scratch[1], sizeof(double), cudaMemcpyDeviceToHost, s);

@@ -72,6 +72,8 @@ namespace pe
     uint64_t      graph_key  = 0;
     double       *calib      = nullptr; // calibration factor between the P^-1 norm and the 2-norm, kept across solves
     double (*anorm)(void *ctx) = nullptr; // lazy ||A||_inf of the reference matrix (rounding-floor test only)
+    int64_t       floor_rows = 0;       // leading logical rows whose ||x|| enters the floor test (0 = all; three-field
+                                        // vectors: the (u, p) part only -- xi = O(lambda) is not an unknown of the reference)
     cudaEvent_t  *ev_ring    = nullptr; // 16 events (disable-timing) for the look-ahead convergence test
   };
 
