@@ -28,6 +28,8 @@ namespace pe
   int  comm_setup_halo(pe_handle *h);
   void comm_halo_exchange(void *ctx, double *x);
   void comm_halo_exchange3(void *ctx, double *x);
+  void comm_halo_exchange_p(void *ctx, double *x);
+  int  comm_has_lanes(pe_handle *h);
   void comm_halo_exchange_xi(void *ctx, double *x);
   void comm_exchange_rows(void *ctx, double *p, int64_t row_len, int n_comp, int64_t comp_stride, int64_t a, int64_t b);
   void comm_allgather_rows(void *ctx, double *p, int64_t row_len, int n_comp, int64_t comp_stride, const int64_t *bounds);
@@ -155,6 +157,8 @@ namespace
     h->mg                  = nullptr;
     delete h->bp;
     h->bp                  = nullptr;
+    h->stream2             = nullptr; // owned by the block preconditioner
+    h->cur_lane            = 0;
     delete h->k3;
     h->k3                  = nullptr;
     delete h->cmg;
@@ -655,6 +659,11 @@ namespace
     k3_precond_xi(*h->k3, h->mu, r, z, h->stream);
     ++h->launches;
   }
+  void
+  hook_set_lane(void *ctx, int lane)
+  {
+    ((pe_handle *)ctx)->cur_lane = lane;
+  }
   // block upper-triangular variant for FGMRES on the row-signed system: z_xi first, then the displacement block on
   // r_u + B^T z_xi; the pressure block is independent of both (runs on the forked stream)
   void
@@ -840,6 +849,10 @@ namespace
             if (comm_set_box(h, h->bp->box) != PE_OK)
               return 1;
             h->bp->halo       = comm_halo_exchange;
+            h->bp->halo_p     = comm_halo_exchange_p;
+            h->stream2        = h->bp->s2;
+            if (comm_has_lanes(h))
+              h->bp->set_lane = hook_set_lane; // pressure pipeline on its own stream + communicator
             h->bp->allreduce  = comm_allreduce;
             h->bp->allreduce2 = comm_allreduce2;
             h->bp->comm_ctx  = h;
@@ -1134,6 +1147,7 @@ extern "C"
     h->mg = nullptr;
     delete h->bp;
     h->bp = nullptr;
+    h->stream2 = nullptr;
     delete h->k3;
     h->k3 = nullptr;
     delete h->cmg;

@@ -105,6 +105,7 @@ namespace pe
   struct CommState
   {
     ncclComm_t              comm = nullptr;
+    ncclComm_t              comm2 = nullptr;          // duplicate communicator of lane 1 (pressure pipeline of the preconditioner)
     std::vector<PeerPlan>   plan;
     std::vector<HaloPeer>  *peers = nullptr;
     std::vector<int>        all_boxes;                // asm cell bounding box (i0, i1, j0, j1) of every rank
@@ -133,6 +134,27 @@ namespace pe
     return reinterpret_cast<CommState *>(h->comm);
   }
 
+  // Lanes: the displacement and the pressure pipeline of the preconditioner run concurrently on two streams; NCCL
+  // operations of one communicator are serialised, so lane 1 has its own communicator (ncclCommSplit duplicate).
+  // The host enqueues one lane at a time (h->cur_lane), in the same order on every rank.
+  static inline cudaStream_t
+  lane_stream(pe_handle *h)
+  {
+    return (h->cur_lane == 1 && h->stream2) ? h->stream2 : h->stream;
+  }
+  static inline ncclComm_t
+  lane_comm(pe_handle *h)
+  {
+    CommState *c = cs(h);
+    return (h->cur_lane == 1 && h->stream2 && c->comm2) ? c->comm2 : c->comm;
+  }
+  int
+  comm_has_lanes(pe_handle *h)
+  {
+    CommState *c = cs(h);
+    return c && c->comm2 && h->stream2;
+  }
+
   int
   comm_unique_id(uint8_t id[128])
   {
@@ -159,6 +181,9 @@ namespace pe
         h->err = "ncclCommInitRank failed";
         return PE_ERR_NCCL;
       }
+    // second lane: a duplicate communicator (all ranks, same order).  Failure is not fatal: one lane only.
+    if (!getenv("PE_ONE_LANE") && ncclCommSplit(c->comm, 0, h->cfg.rank, &c->comm2, nullptr) != ncclSuccess)
+      c->comm2 = nullptr;
     if (cudaMalloc((void **)&c->d_flag, 2 * sizeof(int)) != cudaSuccess)
       {
         ncclCommDestroy(c->comm);
@@ -178,6 +203,8 @@ namespace pe
     CommState *c = cs(h);
     if (c->d_flag)
       cudaFree(c->d_flag);
+    if (c->comm2)
+      ncclCommDestroy(c->comm2);
     if (c->comm)
       ncclCommDestroy(c->comm);
     delete c;
@@ -367,21 +394,47 @@ namespace pe
     return PE_OK;
   }
 
+  static void halo_exchange_blocks(pe_handle *h, double *x, int block_mask);
   void
   comm_halo_exchange(void *ctx, double *x)
   {
-    pe_handle *h = (pe_handle *)ctx;
+    halo_exchange_blocks((pe_handle *)ctx, x, 7);
+  }
+  // interior and face pressures only (lane 1 of the preconditioner must not read displacement entries that lane 0
+  // is still writing)
+  void
+  comm_halo_exchange_p(void *ctx, double *x)
+  {
+    halo_exchange_blocks((pe_handle *)ctx, x, 6);
+  }
+  static void
+  halo_exchange_blocks(pe_handle *h, double *x, const int block_mask)
+  {
     CommState *c = cs(h);
     if (!c || h->peers.empty())
       return;
-    cudaStream_t s = h->stream;
-    for (HaloPeer &hp : h->peers)
-      if (!hp.send_rows.empty())
-        {
-          const int64_t n = (int64_t)hp.send_rows.size();
-          k_gather<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, hp.d_send_rows.p, x, hp.d_send_buf.p);
-          ++h->launches;
-        }
+    cudaStream_t s = lane_stream(h);
+    for (size_t k = 0; k < h->peers.size(); ++k)
+      {
+        HaloPeer       &hp = h->peers[k];
+        const PeerPlan &pl = c->plan[k];
+        if (hp.send_rows.empty())
+          continue;
+        // send rows are ordered by block [u | p_int | p_face]: gather the contiguous run of the wanted blocks
+        int64_t o0 = 0, n = 0;
+        for (int b = 0; b < 3; ++b)
+          {
+            if ((block_mask >> b) & 1)
+              n += pl.send_cnt[b];
+            else if (n == 0)
+              o0 += pl.send_cnt[b];
+          }
+        if (n > 0)
+          {
+            k_gather<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, hp.d_send_rows.p + o0, x, hp.d_send_buf.p + o0);
+            ++h->launches;
+          }
+      }
     PE_NCCL(c, ncclGroupStart());
     for (size_t k = 0; k < h->peers.size(); ++k)
       {
@@ -390,11 +443,12 @@ namespace pe
         int64_t         so = 0;
         for (int b = 0; b < 3; ++b)
           {
-            if (pl.send_cnt[b])
-              PE_NCCL(c, ncclSend(hp.d_send_buf.p + so, (size_t)pl.send_cnt[b], ncclDouble, pl.rank, c->comm, s));
+            const bool on = (block_mask >> b) & 1;
+            if (on && pl.send_cnt[b])
+              PE_NCCL(c, ncclSend(hp.d_send_buf.p + so, (size_t)pl.send_cnt[b], ncclDouble, pl.rank, lane_comm(h), s));
             so += pl.send_cnt[b];
-            if (pl.recv_cnt[b])
-              PE_NCCL(c, ncclRecv(x + h->L + pl.recv_off[b], (size_t)pl.recv_cnt[b], ncclDouble, pl.rank, c->comm, s));
+            if (on && pl.recv_cnt[b])
+              PE_NCCL(c, ncclRecv(x + h->L + pl.recv_off[b], (size_t)pl.recv_cnt[b], ncclDouble, pl.rank, lane_comm(h), s));
           }
       }
     PE_NCCL(c, ncclGroupEnd());
@@ -410,7 +464,7 @@ namespace pe
     if (!c || h->peers.empty() || !h->k3)
       return;
     const K3System &k = *h->k3;
-    cudaStream_t    s = h->stream;
+    cudaStream_t    s = lane_stream(h);
     for (size_t q = 0; q < h->peers.size(); ++q)
       {
         HaloPeer       &hp = h->peers[q];
@@ -438,16 +492,16 @@ namespace pe
         for (int b = 0; b < 3; ++b)
           {
             if (pl.send_cnt[b])
-              PE_NCCL(c, ncclSend(hp.d_send_buf.p + so, (size_t)pl.send_cnt[b], ncclDouble, pl.rank, c->comm, s));
+              PE_NCCL(c, ncclSend(hp.d_send_buf.p + so, (size_t)pl.send_cnt[b], ncclDouble, pl.rank, lane_comm(h), s));
             so += pl.send_cnt[b];
             if (pl.recv_cnt[b])
-              PE_NCCL(c, ncclRecv(x + h->L + pl.recv_off[b], (size_t)pl.recv_cnt[b], ncclDouble, pl.rank, c->comm, s));
+              PE_NCCL(c, ncclRecv(x + h->L + pl.recv_off[b], (size_t)pl.recv_cnt[b], ncclDouble, pl.rank, lane_comm(h), s));
           }
         if (pl.send_cnt[1])
-          PE_NCCL(c, ncclSend(hp.d_send_buf_xi.p, (size_t)pl.send_cnt[1], ncclDouble, pl.rank, c->comm, s));
+          PE_NCCL(c, ncclSend(hp.d_send_buf_xi.p, (size_t)pl.send_cnt[1], ncclDouble, pl.rank, lane_comm(h), s));
         if (pl.recv_cnt[1])
           PE_NCCL(c, ncclRecv(x + k.L + k.H + k.Lx + (h->L + pl.recv_off[1] - k.hu_end), (size_t)pl.recv_cnt[1], ncclDouble, pl.rank,
-                   c->comm, s));
+                   lane_comm(h), s));
       }
     PE_NCCL(c, ncclGroupEnd());
   }
@@ -461,7 +515,7 @@ namespace pe
     if (!c || h->peers.empty() || !h->k3)
       return;
     const K3System &k = *h->k3;
-    cudaStream_t    s = h->stream;
+    cudaStream_t    s = lane_stream(h);
     for (size_t q = 0; q < h->peers.size(); ++q)
       {
         HaloPeer       &hp = h->peers[q];
@@ -479,10 +533,10 @@ namespace pe
         HaloPeer       &hp = h->peers[q];
         const PeerPlan &pl = c->plan[q];
         if (pl.send_cnt[1])
-          PE_NCCL(c, ncclSend(hp.d_send_buf_xi.p, (size_t)pl.send_cnt[1], ncclDouble, pl.rank, c->comm, s));
+          PE_NCCL(c, ncclSend(hp.d_send_buf_xi.p, (size_t)pl.send_cnt[1], ncclDouble, pl.rank, lane_comm(h), s));
         if (pl.recv_cnt[1])
           PE_NCCL(c, ncclRecv(x + k.L + k.H + k.Lx + (h->L + pl.recv_off[1] - k.hu_end), (size_t)pl.recv_cnt[1], ncclDouble,
-                              pl.rank, c->comm, s));
+                              pl.rank, lane_comm(h), s));
       }
     PE_NCCL(c, ncclGroupEnd());
   }
@@ -496,20 +550,20 @@ namespace pe
     if (!c)
       return;
     const int    me = h->part.rank, W = h->part.world;
-    cudaStream_t s  = h->stream;
+    cudaStream_t s  = lane_stream(h);
     PE_NCCL(c, ncclGroupStart());
     for (int k = 0; k < n_comp; ++k)
       {
         double *q = p + (size_t)k * comp_stride;
         if (me > 0)
           {
-            PE_NCCL(c, ncclSend(q + a * row_len, (size_t)row_len, ncclDouble, me - 1, c->comm, s));
-            PE_NCCL(c, ncclRecv(q + (a - 1) * row_len, (size_t)row_len, ncclDouble, me - 1, c->comm, s));
+            PE_NCCL(c, ncclSend(q + a * row_len, (size_t)row_len, ncclDouble, me - 1, lane_comm(h), s));
+            PE_NCCL(c, ncclRecv(q + (a - 1) * row_len, (size_t)row_len, ncclDouble, me - 1, lane_comm(h), s));
           }
         if (me < W - 1)
           {
-            PE_NCCL(c, ncclSend(q + (b - 1) * row_len, (size_t)row_len, ncclDouble, me + 1, c->comm, s));
-            PE_NCCL(c, ncclRecv(q + b * row_len, (size_t)row_len, ncclDouble, me + 1, c->comm, s));
+            PE_NCCL(c, ncclSend(q + (b - 1) * row_len, (size_t)row_len, ncclDouble, me + 1, lane_comm(h), s));
+            PE_NCCL(c, ncclRecv(q + b * row_len, (size_t)row_len, ncclDouble, me + 1, lane_comm(h), s));
           }
       }
     PE_NCCL(c, ncclGroupEnd());
@@ -522,7 +576,7 @@ namespace pe
     if (!c)
       return;
     const int    W = h->part.world;
-    cudaStream_t s = h->stream;
+    cudaStream_t s = lane_stream(h);
     PE_NCCL(c, ncclGroupStart());
     for (int q = 0; q < W; ++q)
       for (int k = 0; k < n_comp; ++k)
@@ -530,7 +584,7 @@ namespace pe
           double      *x = p + (size_t)k * comp_stride + bounds[q] * row_len;
           const size_t n = (size_t)((bounds[q + 1] - bounds[q]) * row_len);
           if (n)
-            PE_NCCL(c, ncclBroadcast(x, x, n, ncclDouble, q, c->comm, s));
+            PE_NCCL(c, ncclBroadcast(x, x, n, ncclDouble, q, lane_comm(h), s));
         }
     PE_NCCL(c, ncclGroupEnd());
   }
@@ -544,7 +598,7 @@ namespace pe
     if (!c)
       return;
     const int    W = h->part.world;
-    cudaStream_t s = h->stream;
+    cudaStream_t s = lane_stream(h);
     PE_NCCL(c, ncclGroupStart());
     for (int q = 0; q < W; ++q)
       for (int k = 0; k < n_comp; ++k)
@@ -552,7 +606,7 @@ namespace pe
           const size_t off = (size_t)k * comp_stride + bounds[q] * row_len;
           const size_t n   = (size_t)((bounds[q + 1] - bounds[q]) * row_len);
           if (n)
-            PE_NCCL(c, ncclReduce(in + off, out + off, n, ncclDouble, ncclSum, q, c->comm, s));
+            PE_NCCL(c, ncclReduce(in + off, out + off, n, ncclDouble, ncclSum, q, lane_comm(h), s));
         }
     PE_NCCL(c, ncclGroupEnd());
   }
@@ -575,7 +629,7 @@ namespace pe
       return PE_ERR_ALLOC;
     const int mine[4] = {box.i0, box.i1, box.j0, box.j1};
     cudaMemcpyAsync(d_mine.p, mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream);
-    if (ncclAllGather(d_mine.p, d_all.p, 4, ncclInt, c->comm, h->stream) != ncclSuccess)
+    if (ncclAllGather(d_mine.p, d_all.p, 4, ncclInt, lane_comm(h), lane_stream(h)) != ncclSuccess)
       return PE_ERR_NCCL;
     c->all_boxes.assign((size_t)4 * W, 0);
     cudaMemcpyAsync(c->all_boxes.data(), d_all.p, sizeof(int) * 4 * W, cudaMemcpyDeviceToHost, h->stream);
@@ -646,7 +700,7 @@ namespace pe
   {
     CommState   *c  = cs(h);
     const int    W  = h->part.world, me = h->part.rank;
-    cudaStream_t s  = h->stream;
+    cudaStream_t s  = lane_stream(h);
     auto grid_of = [](const int64_t n) { return (unsigned)((n + 255) / 256); };
     for (int q = 0; q < W; ++q)
       {
@@ -664,9 +718,9 @@ namespace pe
           continue;
         const int64_t ns = P.send[(size_t)q].count() * P.n_comp, nr = P.recv[(size_t)q].count() * P.n_comp;
         if (ns)
-          PE_NCCL(c, ncclSend(P.sbuf[(size_t)q].p, (size_t)ns, ncclDouble, q, c->comm, s));
+          PE_NCCL(c, ncclSend(P.sbuf[(size_t)q].p, (size_t)ns, ncclDouble, q, lane_comm(h), s));
         if (nr)
-          PE_NCCL(c, ncclRecv(P.rbuf[(size_t)q].p, (size_t)nr, ncclDouble, q, c->comm, s));
+          PE_NCCL(c, ncclRecv(P.rbuf[(size_t)q].p, (size_t)nr, ncclDouble, q, lane_comm(h), s));
       }
     PE_NCCL(c, ncclGroupEnd());
     // own part: in -> out directly (in and out may be the same array: then nothing to do)
@@ -719,7 +773,7 @@ namespace pe
     const int64_t n  = (bounds[me + 1] - bounds[me]) * row_len * n_comp;
     if (n > 0)
       {
-        k_rows_zero<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(out, row_len, comp_stride, n_comp, bounds[me], bounds[me + 1]);
+        k_rows_zero<<<(unsigned)((n + 255) / 256), 256, 0, lane_stream(h)>>>(out, row_len, comp_stride, n_comp, bounds[me], bounds[me + 1]);
         ++h->launches;
       }
     box_transfer(h, *P, in, out, comp_stride, true);
@@ -748,7 +802,7 @@ namespace pe
     CommState *c = cs(h);
     if (!c)
       return;
-    PE_NCCL(c, ncclAllReduce(in, out, (size_t)n, ncclDouble, ncclSum, c->comm, h->stream));
+    PE_NCCL(c, ncclAllReduce(in, out, (size_t)n, ncclDouble, ncclSum, lane_comm(h), lane_stream(h)));
   }
 
   void
@@ -758,7 +812,7 @@ namespace pe
     CommState *c = cs(h);
     if (!c)
       return;
-    PE_NCCL(c, ncclAllReduce(v, v, (size_t)n, ncclDouble, ncclMax, c->comm, h->stream));
+    PE_NCCL(c, ncclAllReduce(v, v, (size_t)n, ncclDouble, ncclMax, lane_comm(h), lane_stream(h)));
   }
 
   void
@@ -768,6 +822,6 @@ namespace pe
     CommState *c = cs(h);
     if (!c)
       return;
-    PE_NCCL(c, ncclAllReduce(v, v, (size_t)n, ncclDouble, ncclSum, c->comm, h->stream));
+    PE_NCCL(c, ncclAllReduce(v, v, (size_t)n, ncclDouble, ncclSum, lane_comm(h), lane_stream(h)));
   }
 } // namespace pe

@@ -216,6 +216,8 @@ struct pe_handle
   ncclComm                 *comm = nullptr;
   std::vector<pe::HaloPeer> peers;
   cudaStream_t              comm_stream = nullptr;
+  cudaStream_t              stream2 = nullptr; // lane 1: pressure pipeline of the preconditioner (own NCCL communicator)
+  int                       cur_lane = 0;      // lane the host is enqueuing on (pe_comm.cu: lane_stream / lane_comm)
 
   // timings
   double  assemble_ms = 0., assemble_kernel_ms = 0., solve_ms = 0., spmv_ms_avg = 0.;

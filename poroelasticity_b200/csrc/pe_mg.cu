@@ -57,11 +57,11 @@ namespace pe
     k_mg_assemble(const int N, const double *__restrict__ vx, const double *__restrict__ vy,
                   const double *__restrict__ kc, const double k_scalar, const uint8_t *__restrict__ mask,
                   const double c_a /* mu | dt */, const double c_b /* lambda | gamma */, stencil_t *__restrict__ st,
-                  double *__restrict__ dinv)
+                  double *__restrict__ dinv, const int v_begin, const int v_end)
     {
       const int V = N + 1, nv = V * V;
-      const int v = blockIdx.x * blockDim.x + threadIdx.x;
-      if (v >= nv)
+      const int v = v_begin + blockIdx.x * blockDim.x + threadIdx.x;
+      if (v >= v_end)
         return;
       const int i = v % V, j = v / V;
       double    acc[9][NC * NC];
@@ -735,8 +735,14 @@ namespace pe
     for (size_t l = 0; l < mg.lv.size(); ++l)
       {
         MgLevel  &L  = mg.lv[l];
-        const int nv = (L.N + 1) * (L.N + 1);
-        k_mg_assemble<2><<<g1(nv), 128, 0, s>>>(L.N, L.x.p, L.y.p, nullptr, 1., L.mask_u.p, mu, lambda, L.st_u.p, L.dinv_u.p);
+        const int V  = L.N + 1;
+        // a distributed level only smooths its own rows: stencils of the slab (round 1 built the whole level on every rank)
+        const bool dist = (int)l < mg.n_dist;
+        const int  v0   = dist ? (int)(mg.bounds[l][(size_t)mg.gc.rank] * V) : 0;
+        const int  v1   = dist ? (int)(mg.bounds[l][(size_t)mg.gc.rank + 1] * V) : V * V;
+        if (v1 > v0)
+          k_mg_assemble<2><<<g1(v1 - v0), 128, 0, s>>>(L.N, L.x.p, L.y.p, nullptr, 1., L.mask_u.p, mu, lambda, L.st_u.p, L.dinv_u.p,
+                                                       v0, v1);
         ++*launches;
       }
     {

@@ -373,7 +373,7 @@ namespace pe
           cudaStreamSynchronize(s);
         }
     }
-    if (part.world == 1 && !bp.s2)
+    if (!bp.s2)
       {
         cudaStreamCreateWithFlags(&bp.s2, cudaStreamNonBlocking);
         cudaEventCreateWithFlags(&bp.ev_fork, cudaEventDisableTiming);
@@ -443,8 +443,13 @@ namespace pe
     PE_MARK(s, "precond: local Jacobi + halo");
     // The displacement and the pressure part touch disjoint entries of t, t2, z: on one GPU the pressure
     // pipeline is forked onto a second stream (inside the captured CUDA graph: a parallel branch).
-    const bool   fork = bp.s2 != nullptr && !bp.halo;
+    // one GPU: always; several GPUs: when the communication layer has a second lane (stream + NCCL communicator)
+    const bool   fork = bp.s2 != nullptr && (!bp.halo || bp.set_lane);
     cudaStream_t sp   = fork ? bp.s2 : s;
+    auto         halo_p = [&](double *x) {
+      if (bp.halo)
+        (fork && bp.halo_p ? bp.halo_p : bp.halo)(bp.comm_ctx, x);
+    };
     if (fork)
       {
         cudaEventRecord(bp.ev_fork, s);
@@ -477,6 +482,8 @@ namespace pe
       sub(s, bp.Abu, bp.t.p, bp.t.p, pinv, ru, z); // z_b = y1 + pinv_b (r_b - A_bb y1 - A_bv x_v),  t = (x_v, y1)
     // ---- pressure block: interior pressures eliminated exactly; on the face Schur complement
     //      F = S_ff - S_fi D_i^{-1} S_if:  Jacobi, cell-space correction (pe_cmg.h), Jacobi
+    if (fork && bp.set_lane)
+      bp.set_lane(bp.comm_ctx, 1); // communication of the pressure pipeline: lane 1
     // g = r_f - S_fi D_i^{-1} r_i   -> t2 (face entries)
     sub(sp, bp.Sfi, bp.t.p, nullptr, nullptr, r, bp.t2.p);
     // y1 = omega dinvF g            -> t (face entries)
@@ -484,11 +491,9 @@ namespace pe
     ++*launches;
     // F y = S_ff y - S_fi q,  q = D_i^{-1} S_if y  (q on the p_int entries of t, y on its face entries)
     auto apply_q = [&]() {
-      if (bp.halo)
-        bp.halo(bp.comm_ctx, bp.t.p);
+      halo_p(bp.t.p);
       sub(sp, bp.Sif, bp.t.p, nullptr, bp.dinv.p, nullptr, bp.t.p);
-      if (bp.halo)
-        bp.halo(bp.comm_ctx, bp.t.p);
+      halo_p(bp.t.p);
     };
     apply_q();
     // res = g - F y1                -> t3 (face entries)
@@ -516,11 +521,12 @@ namespace pe
     sub(sp, bp.Spf, bp.t.p, bp.t.p, bp.wdinv.p, bp.t2.p, z);
     if (bp.has_bubbles && !fork)
       sub(s, bp.Abu, bp.t.p, bp.t.p, pinv, ru, z);
-    if (bp.halo)
-      bp.halo(bp.comm_ctx, z); // face pressures of the neighbours
+    halo_p(z); // face pressures of the neighbours
     // z_i = dinv_i (r_i - S_if z_f)
     sub(sp, bp.Sif, z, nullptr, bp.dinv.p, r, z);
     PE_MARK(sp, "precond: face Schur products");
+    if (fork && bp.set_lane)
+      bp.set_lane(bp.comm_ctx, 0);
     if (fork)
       {
         cudaEventRecord(bp.ev_join, sp);

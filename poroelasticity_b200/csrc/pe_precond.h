@@ -32,6 +32,8 @@ namespace pe
     void (*allreduce)(void *ctx, double *v, int n) = nullptr;
     void (*allreduce2)(void *ctx, const double *in, double *out, int n) = nullptr; // out of place
     void *comm_ctx                                 = nullptr;
+    void (*halo_p)(void *ctx, double *x)           = nullptr; // pressure blocks only
+    void (*set_lane)(void *ctx, int lane)          = nullptr; // non-null: the pressure pipeline runs on lane 1 (own stream + communicator)
     CellBox         box;                 // cells this rank assembles (all cells on one GPU)
     DevBuf<double>  bu_local, rc_local;  // multi-GPU: this rank's contribution to the grid right-hand sides (zero outside box)
     SubCsr          Abu, Avb, Sif, Sfi, Spf; // Spf: p_face rows x [-S_fi | S_ff]

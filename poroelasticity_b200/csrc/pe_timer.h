@@ -68,7 +68,8 @@ namespace pe
           acc[marks[k].second] += ms;
           cnt[marks[k].second] += 1;
         }
-      if (rank == 0)
+      const char *env_rank = getenv("RANK"); // one process per GPU under torchrun: only rank 0 prints
+      if (rank == 0 && (!env_rank || atoi(env_rank) == 0))
         {
           double tot = 0.;
           for (auto &kv : acc)
