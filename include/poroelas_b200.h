@@ -181,6 +181,12 @@ int pe_solve_time_step(pe_handle *h, double rel_tol, int max_iterations, double 
  * for), 64 = no CUDA graphs, 128 = CUDA graphs also with NCCL operations (multi-GPU), bits 8.. = assembly chunk
  * size in units of 4096 cells (0 = keep; the chunk tables are rebuilt before the next assembly). */
 int pe_set_solver_options(pe_handle *h, int use_multigrid, double theta, double omega, int nu);
+/* Tuning / A-B switches (the hot path reads no environment variables; PE_TIMING=1 only switches the phase tracer on).
+ * Keys: "mg_omega2", "cmg_omega", "cmg_omega2", "face_omega" (smoother weights); "mg_fused_n" (largest level of the
+ * single-CTA multigrid kernel); "asm_gather" (1: gather assembly instead of the RED scatter); multi-GPU: "mg_replicated",
+ * "mg_whole_slabs", "one_lane" (1: the round-1 communication schemes, kept for A/B runs), "mg_dist_min_n" (smallest grid
+ * level distributed over the ranks).  Structural keys rebuild the device tables before the next assembly. */
+int pe_set_tuning(pe_handle *h, const char *key, double value);
 /* Krylov method of pe_solve_time_step for the Biot elements on meshes with a refinement hierarchy:
  * method 1 (default) = restarted flexible GMRES(restart) on the row-signed three-field system with the block
  * upper-triangular preconditioner [P_u -B^T 0; 0 P_xi 0; 0 0 P_p] (2.6x fewer iterations than method 0 at
@@ -194,6 +200,10 @@ int pe_set_krylov(pe_handle *h, int method, int restart);
 int pe_set_initial_guess(pe_handle *h, int order);
 int pe_get_solution(const pe_handle *h, double *solution);
 int pe_set_solution(pe_handle *h, const double *solution);
+/* the owned part of the device solution written into a vector of n_dofs doubles in GLOBAL deal.II order (the three
+ * owned row ranges of pe_get_owned_ranges): what a host program with one old_solution vector shared by all ranks of
+ * the node wants (one process per GPU; every rank fills its own ranges). */
+int pe_get_solution_global(const pe_handle *h, double *solution_global);
 
 /* y = system_matrix * x (the SpMV the solver is built on), host in / host out: parity hook */
 int pe_spmv(pe_handle *h, const double *x, double *y);

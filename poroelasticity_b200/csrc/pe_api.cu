@@ -262,6 +262,14 @@ namespace
       PE_CUDA(upload(h->d_rowblk, blk.data(), blk.size(), s));
     }
     PE_CUDA(h->d_values.alloc((size_t)h->nnz));
+    {
+      // position of the diagonal entry of every owned row: the diagonal of an assembled matrix is then one gather
+      h->d_diag_pos.release();
+      SolverCtx c0 = make_solver_ctx(h);
+      PE_CUDA(h->d_diag_pos.alloc((size_t)h->L));
+      diagonal_positions(c0, h->d_diag_pos.p);
+      ++h->launches;
+    }
     PE_CUDA(h->d_rhs.alloc((size_t)(h->L + h->H)));
     // the resident old_solution survives a rebuild of the device tables (boundary kinds, permeability field,
     // chunk size ...) as long as the numbering is the same; it is zeroed on the first upload or a size change
@@ -331,7 +339,7 @@ namespace
       DevBuf<int> d_bad;
       // measured slower than the RED scatter (4.15 ms against 2.23 ms at N = 1024: both move 193 M eight-byte
       // contributions through L2 one 32-byte sector at a time), kept as an opt-in alternative: PE_ASM_GATHER=1
-      const bool  want_gather = pt.scatter_mode == 0 && h->dofs.element != PE_WG_Q2RT2 && getenv("PE_ASM_GATHER");
+      const bool  want_gather = pt.scatter_mode == 0 && h->dofs.element != PE_WG_Q2RT2 && h->tune.asm_gather;
       if (want_gather)
         {
           bool ok = true;
@@ -636,6 +644,7 @@ namespace
     c.stream     = h->stream;
     c.launch_counter = &h->launches;
     c.use_graphs     = h->use_graphs;
+    c.diag_pos       = h->d_diag_pos.n == (size_t)h->L ? h->d_diag_pos.p : nullptr;
     if (h->spmv_kernel == 1)
       {
         c.rowblk   = h->d_rowblk.p;
@@ -767,15 +776,16 @@ namespace
         h->mg->omega2 = 1.5 * h->mg_omega;
         h->mg->nu     = h->mg_nu;
         h->cmg->nu    = h->mg_nu;
-        // tuning hooks: weights of the alternating smoothing sweeps
-        if (const char *e = getenv("PE_MG_OMEGA2"))
-          h->mg->omega2 = atof(e);
-        if (const char *e = getenv("PE_CMG_OMEGA"))
-          h->cmg->omega = atof(e);
-        if (const char *e = getenv("PE_CMG_OMEGA2"))
-          h->cmg->omega2 = atof(e);
-        if (const char *e = getenv("PE_FACE_OMEGA"))
-          h->bp->omega_f = atof(e);
+        // tuning (pe_set_tuning): weights of the alternating smoothing sweeps
+        if (h->tune.mg_omega2 > 0.)
+          h->mg->omega2 = h->tune.mg_omega2;
+        if (h->tune.cmg_omega > 0.)
+          h->cmg->omega = h->tune.cmg_omega;
+        if (h->tune.cmg_omega2 > 0.)
+          h->cmg->omega2 = h->tune.cmg_omega2;
+        if (h->tune.face_omega > 0.)
+          h->bp->omega_f = h->tune.face_omega;
+        h->mg->fused_n = h->tune.mg_fused_n;
         // pressure block of the preconditioner: C + alpha^2/lambda_s W_int (C already holds c0 M)
         const double extra = h->alpha * h->alpha / lambda_s;
         if (mg_assemble(*h->mg, h->d_k_morton.p, h->k_scalar, lambda0, h->mu, h->last_dt, h->c0 + extra, s, &h->launches) != 0)
@@ -820,16 +830,17 @@ namespace
           return 1;
         // multi-GPU: the fine grid levels are distributed in row slabs (PE_MG_REPLICATED=1: every rank runs the
         // complete V-cycles, the first multi-GPU version, kept for A/B measurements)
-        if (h->part.world > 1 && !getenv("PE_MG_REPLICATED"))
+        if (h->part.world > 1 && !h->tune.mg_replicated)
           {
             GridComm gc;
             gc.rank           = h->part.rank;
             gc.world          = h->part.world;
             gc.ctx            = h;
+            gc.dist_min_n     = h->tune.mg_dist_min_n;
             gc.exchange_rows  = comm_exchange_rows;
             gc.allgather_rows = comm_allgather_rows;
             gc.reduce_rows    = comm_reduce_rows;
-            if (!getenv("PE_MG_WHOLE_SLABS")) // A/B: round-1 transfers of whole slabs (reduce / all-gather)
+            if (!h->tune.mg_whole_slabs) // A/B: round-1 transfers of whole slabs (reduce / all-gather)
               {
                 gc.boxes_to_slabs = comm_boxes_to_slabs;
                 gc.slabs_to_boxes = comm_slabs_to_boxes;
@@ -851,7 +862,7 @@ namespace
             h->bp->halo       = comm_halo_exchange;
             h->bp->halo_p     = comm_halo_exchange_p;
             h->stream2        = h->bp->s2;
-            if (comm_has_lanes(h))
+            if (comm_has_lanes(h) && !h->tune.one_lane)
               h->bp->set_lane = hook_set_lane; // pressure pipeline on its own stream + communicator
             h->bp->allreduce  = comm_allreduce;
             h->bp->allreduce2 = comm_allreduce2;
@@ -1568,6 +1579,22 @@ extern "C"
   }
 
   int
+  pe_get_solution_global(const pe_handle *hc, double *solution_global)
+  {
+    pe_handle *h = const_cast<pe_handle *>(hc);
+    if (!h || !solution_global || !h->device_ready)
+      return fail(h, PE_ERR_ARG, "pe_get_solution_global: no device state");
+    PE_DEVICE(h);
+    const Partition &pt = h->part;
+    for (int b = 0; b < 3; ++b)
+      if (pt.row_end[b] > pt.row_begin[b])
+        PE_CUDA(cudaMemcpyAsync(solution_global + pt.row_begin[b], h->d_sol.p + pt.local_off[b],
+                                sizeof(double) * (size_t)(pt.row_end[b] - pt.row_begin[b]), cudaMemcpyDeviceToHost, h->stream));
+    PE_CUDA(cudaStreamSynchronize(h->stream));
+    return PE_OK;
+  }
+
+  int
   pe_set_solution(pe_handle *h, const double *solution)
   {
     if (!h || !solution)
@@ -1639,6 +1666,44 @@ extern "C"
     h->mg_theta = theta;
     h->mg_omega = omega;
     h->mg_nu    = nu;
+    ++h->graph_epoch;
+    return PE_OK;
+  }
+
+  int
+  pe_set_tuning(pe_handle *h, const char *key, double value)
+  {
+    if (!h || !key)
+      return PE_ERR_ARG;
+    const std::string k(key);
+    Tuning           &t = h->tune;
+    if (k == "asm_gather")
+      t.asm_gather = value != 0.;
+    else if (k == "mg_omega2")
+      t.mg_omega2 = value;
+    else if (k == "cmg_omega")
+      t.cmg_omega = value;
+    else if (k == "cmg_omega2")
+      t.cmg_omega2 = value;
+    else if (k == "face_omega")
+      t.face_omega = value;
+    else if (k == "mg_replicated")
+      t.mg_replicated = value != 0.;
+    else if (k == "mg_whole_slabs")
+      t.mg_whole_slabs = value != 0.;
+    else if (k == "one_lane")
+      t.one_lane = value != 0.;
+    else if (k == "mg_fused_n")
+      t.mg_fused_n = (int)value;
+    else if (k == "mg_dist_min_n")
+      t.mg_dist_min_n = (int)value;
+    else
+      return fail(h, PE_ERR_ARG, "pe_set_tuning: unknown key " + k);
+    // structural switches take effect when the device tables / hierarchies are rebuilt
+    if (k == "asm_gather" || k == "mg_replicated" || k == "mg_whole_slabs" || k == "one_lane" || k == "mg_dist_min_n")
+      h->device_ready = false;
+    if (h->k3)
+      h->k3->values_valid = false;
     ++h->graph_epoch;
     return PE_OK;
   }

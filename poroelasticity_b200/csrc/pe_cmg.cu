@@ -555,7 +555,7 @@ namespace pe
         const int N = cm.lv[(size_t)l].N;
         // a distributed level pays ~6 NCCL row exchanges (~45 us each, measured on 8 GPUs); below ~1024^2 the
         // replicated sweep is cheaper than that latency
-        if (N % (2 * W) != 0 || N / W < 8 || N < dist_min_n())
+        if (N % (2 * W) != 0 || N / W < 8 || N < gc.dist_min_n)
           break;
         std::vector<int64_t> bd((size_t)W + 1);
         for (int r = 0; r <= W; ++r)

@@ -182,7 +182,7 @@ namespace pe
         return PE_ERR_NCCL;
       }
     // second lane: a duplicate communicator (all ranks, same order).  Failure is not fatal: one lane only.
-    if (!getenv("PE_ONE_LANE") && ncclCommSplit(c->comm, 0, h->cfg.rank, &c->comm2, nullptr) != ncclSuccess)
+    if (ncclCommSplit(c->comm, 0, h->cfg.rank, &c->comm2, nullptr) != ncclSuccess)
       c->comm2 = nullptr;
     if (cudaMalloc((void **)&c->d_flag, 2 * sizeof(int)) != cudaSuccess)
       {

@@ -77,6 +77,7 @@ namespace pe
   {
     int   rank = 0, world = 1;
     void *ctx  = nullptr;
+    int   dist_min_n = 1024; // smallest level (cells per side) distributed over the ranks
     // send my first / last owned row (a, b-1) down / up, receive rows a-1 and b; n_comp arrays comp_stride apart
     void (*exchange_rows)(void *ctx, double *p, int64_t row_len, int n_comp, int64_t comp_stride, int64_t a, int64_t b) = nullptr;
     // every rank receives the slabs [bounds[q], bounds[q+1]) of all ranks q (in place)
@@ -100,13 +101,20 @@ namespace pe
     int i0 = 0, i1 = 0, j0 = 0, j1 = 0;
   };
 
-  // smallest grid level (cells per side) that is distributed over the ranks; PE_MG_DIST_MIN_N overrides (tuning / tests)
-  inline int
-  dist_min_n()
+  // Tuning / A-B switches of the library, set through pe_set_tuning (no environment variables are read by the hot path)
+  struct Tuning
   {
-    const char *e = getenv("PE_MG_DIST_MIN_N");
-    return e ? atoi(e) : 1024;
-  }
+    int    asm_gather     = 0;    // gather assembly instead of RED scatter (measured slower, kept as a tested alternative)
+    double mg_omega2      = -1.;  // weight of every second vertex-grid sweep (< 0: 1.5 omega)
+    double cmg_omega      = -1.;  // weights of the cell-grid sweeps (< 0: built-in 0.6 / 1.2)
+    double cmg_omega2     = -1.;
+    double face_omega     = -1.;  // damped Jacobi on the face Schur complement (< 0: 0.65)
+    int    mg_replicated  = 0;    // multi-GPU: every rank runs the complete V-cycles (first multi-GPU version)
+    int    mg_whole_slabs = 0;    // multi-GPU: reduce / all-gather whole slabs instead of box x slab rectangles
+    int    one_lane       = 0;    // multi-GPU: no second stream + communicator for the pressure pipeline
+    int    mg_fused_n     = -1;   // largest level handled by the single-CTA multigrid kernel (< 0: built-in)
+    int    mg_dist_min_n  = 1024; // smallest grid level (cells per side) that is distributed over the ranks
+  };
 
   struct HaloPeer
   {
@@ -165,7 +173,7 @@ struct pe_handle
   pe::DevBuf<int32_t>  d_cdofs, d_colidx, d_bnd_list, d_rowblk, d_out_slot;
   int64_t              n_rowblk = 0;
   int                  spmv_kernel = 1; // 1 = stream, 0 = warp per row
-  pe::DevBuf<int64_t>  d_rowptr;
+  pe::DevBuf<int64_t>  d_rowptr, d_diag_pos;
   pe::DevBuf<uint8_t>  d_off, d_is_ghost; // d_is_ghost: 1 for ghost cells (multi-GPU only, else unallocated)
   pe::DevBuf<int>      d_err;
   // solver work vectors (each L+H long so that any of them can be the SpMV input)
@@ -217,7 +225,8 @@ struct pe_handle
   std::vector<pe::HaloPeer> peers;
   cudaStream_t              comm_stream = nullptr;
   cudaStream_t              stream2 = nullptr; // lane 1: pressure pipeline of the preconditioner (own NCCL communicator)
-  int                       cur_lane = 0;      // lane the host is enqueuing on (pe_comm.cu: lane_stream / lane_comm)
+  int                       cur_lane = 0;
+  pe::Tuning                tune;      // lane the host is enqueuing on (pe_comm.cu: lane_stream / lane_comm)
 
   // timings
   double  assemble_ms = 0., assemble_kernel_ms = 0., solve_ms = 0., spmv_ms_avg = 0.;

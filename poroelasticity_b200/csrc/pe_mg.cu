@@ -773,10 +773,7 @@ namespace pe
     double       *x0   = L.wu[0].p;
     double       *x1   = L.wu[1].p;
     const bool    last = l + 1 == mg.lv.size();
-    static const int fused_n = [] {
-      const char *e = getenv("PE_MG_FUSED_N"); // tuning hook: largest level handled by the single-CTA kernel
-      return e ? std::min(kFusedN, atoi(e)) : kFusedN;
-    }();
+    const int fused_n = mg.fused_n > 0 ? std::min(kFusedN, mg.fused_n) : kFusedN;
     if (L.N <= fused_n && !last)
       {
         FusedArgs a{};
@@ -900,7 +897,7 @@ namespace pe
         // distributed while every rank keeps >= 8 cell rows and the level is above the fused single-CTA levels
         // a distributed level pays ~6 NCCL row exchanges (~45 us each, measured on 8 GPUs); below ~1024^2 the
         // replicated sweep is cheaper than that latency
-        if (N % (2 * W) != 0 || N / W < 8 || N < dist_min_n())
+        if (N % (2 * W) != 0 || N / W < 8 || N < gc.dist_min_n)
           break;
         std::vector<int64_t> bd((size_t)W + 1);
         for (int r = 0; r < W; ++r)

@@ -26,6 +26,7 @@ namespace pe
     double               omega = 0.6, theta = 1.0;
     double               omega2 = 0.; // weight of every second smoothing sweep (<= 0: same as omega)
     int                  nu    = 2;
+    int                  fused_n = -1; // largest level of the single-CTA kernel (< 0: built-in)
     // multi-GPU: the first n_dist levels are distributed in row slabs (bounds[l][r] = first vertex row of
     // rank r on level l), the coarser ones run replicated on every rank
     GridComm                          gc;

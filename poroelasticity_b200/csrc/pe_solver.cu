@@ -230,6 +230,26 @@ namespace pe
         d = values[k];
     diag[r] = d;
   }
+  // position of the diagonal entry of every owned row (once per pattern), -1 if the pattern has none
+  __global__ void
+  k_diag_pos(const int64_t n, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx, int64_t *__restrict__ pos)
+  {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n)
+      return;
+    int64_t p = -1;
+    for (int64_t k = rowptr[r]; k < rowptr[r + 1]; ++k)
+      if (colidx[k] == r)
+        p = k;
+    pos[r] = p;
+  }
+  __global__ void
+  k_diag_gather(const int64_t n, const int64_t *__restrict__ pos, const double *__restrict__ values, double *__restrict__ diag)
+  {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n)
+      diag[r] = pos[r] >= 0 ? values[pos[r]] : 0.;
+  }
   // SPD diagonal preconditioner (stored inverted).  u rows and p_face rows: |A_rr|.  p_int rows:
   // A_rr + sum_{c in u} A_rc^2 / A_cc  (diagonal estimate of the Schur complement
   // c0 M + dt S + a^2 B A_uu^{-1} B^T).  diag must hold the halo part too (exchanged by the caller).
@@ -569,6 +589,12 @@ namespace pe
     k_norm2<<<vec_grid(c.L), 256, 0, c.stream>>>(c.L, x, nrm2_dev, c.gap);
   }
   void
+  diagonal_positions(const SolverCtx &c, int64_t *pos)
+  {
+    if (c.L > 0)
+      k_diag_pos<<<(unsigned)((c.L + 255) / 256), 256, 0, c.stream>>>(c.L, c.rowptr, c.colidx, pos);
+  }
+  void
   matrix_inf_norm(const SolverCtx &c, double *out_dev)
   {
     cudaMemsetAsync(out_dev, 0, sizeof(double), c.stream);
@@ -595,7 +621,10 @@ namespace pe
     const unsigned g = (unsigned)((c.L + 255) / 256);
     if (c.L == 0)
       return 0;
-    k_diag<<<g, 256, 0, c.stream>>>(c.L, c.rowptr, c.colidx, c.values, diag_full);
+    if (c.diag_pos)
+      k_diag_gather<<<g, 256, 0, c.stream>>>(c.L, c.diag_pos, c.values, diag_full);
+    else
+      k_diag<<<g, 256, 0, c.stream>>>(c.L, c.rowptr, c.colidx, c.values, diag_full);
     if (c.halo)
       c.halo(c.halo_ctx, diag_full);
     k_precond<<<g, 256, 0, c.stream>>>(c.L, c.n_pos, c.pint_begin, c.pint_end, c.n_pos, c.rowptr, c.colidx, c.values,

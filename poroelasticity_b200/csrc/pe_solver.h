@@ -49,6 +49,7 @@ namespace pe
     const int64_t *rowptr = nullptr;
     const int32_t *colidx = nullptr;
     const double  *values = nullptr;
+    const int64_t *diag_pos = nullptr; // position of the diagonal entry of every owned row (null: search the row)
     const int32_t *rowblk = nullptr; // row runs of the stream SpMV (n_rowblk + 1 entries), null = warp-per-row
     int64_t        n_rowblk = 0;
     const uint8_t *col_is_u = nullptr; // per local column (L+H): 1 if displacement dof (multi-GPU only)
@@ -83,6 +84,8 @@ namespace pe
   // *nrm2_dev += || b - A x ||^2 over the owned rows (plain A: no sign flip); y = A x is scratch (L long)
   void   residual_norm2(const SolverCtx &c, const double *b, const double *x, double *y, double *nrm2_dev);
   void   norm2(const SolverCtx &c, const double *x, double *nrm2_dev);
+  // pos[r] = index of A(r, r) in the CSR arrays of the ctx matrix (once per pattern)
+  void   diagonal_positions(const SolverCtx &c, int64_t *pos);
   // *out_dev = max row sum of |A| over the owned rows of the ctx matrix (this rank)
   void   matrix_inf_norm(const SolverCtx &c, double *out_dev);
   void   lincomb3(int64_t n, double w0, const double *a, double w1, const double *b, double w2, const double *c, double *out,

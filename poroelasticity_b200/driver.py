@@ -195,6 +195,9 @@ class BiotSystem:
     def set_solver_options(self, use_multigrid=1, theta=1.0, omega=0.6, nu=2):
         self._ck(self.L.pe_set_solver_options(self.h, use_multigrid, theta, omega, nu))
 
+    def set_tuning(self, key, value):
+        self._ck(self.L.pe_set_tuning(self.h, key.encode(), float(value)))
+
     def set_krylov(self, method=1, restart=0):
         """1 = FGMRES(restart) + block-triangular preconditioner (default), 0 = MINRES + block-diagonal"""
         self._ck(self.L.pe_set_krylov(self.h, method, restart))
@@ -207,6 +210,11 @@ class BiotSystem:
         s = np.zeros(self.sizes().n_owned_rows)
         self._ck(self.L.pe_get_solution(self.h, ptr(s)))
         return s
+
+    def solution_global(self, out):
+        """owned part of the device solution into `out` (n_dofs doubles, global deal.II order)"""
+        self._ck(self.L.pe_get_solution_global(self.h, ptr(out)))
+        return out
 
     def set_solution(self, sol):
         s = np.ascontiguousarray(sol, np.float64)

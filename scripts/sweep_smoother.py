@@ -1,4 +1,4 @@
-"""Smoother-weight sweep (tuning hooks PE_MG_OMEGA2 / PE_CMG_OMEGA / PE_CMG_OMEGA2 / PE_FACE_OMEGA):
+"""Smoother-weight sweep (pe_set_tuning keys mg_omega2 / cmg_omega / cmg_omega2 / face_omega):
 iterations and solve time on cfg 2 (N from argv) and on a cfg-4 like case."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -20,8 +20,7 @@ for name, lam, c0, sigma in cases:
         b.set_lognormal_k(sigma, 12345)
     for v in variants:
         for k in ("PE_MG_OMEGA2", "PE_CMG_OMEGA", "PE_CMG_OMEGA2", "PE_FACE_OMEGA"):
-            os.environ.pop(k, None)
-        os.environ.update(v)
+            b.set_tuning(k[3:].lower(), float(v.get(k, -1.0)))
         b.set_solution(np.zeros(s.n_dofs))
         b.assemble_system(0.1)
         b.rel_tol = 1e-10; b.max_iterations = 2000

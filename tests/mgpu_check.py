@@ -72,14 +72,11 @@ def main():
     # ---- distributed grid levels (row slabs) against the replicated V-cycles: the two are the same operator, so
     # MINRES must take the same number of iterations and return the same solution (N = 256: two distributed levels)
     nref2 = int(sys.argv[2]) if len(sys.argv) > 2 else 8
-    os.environ["PE_MG_DIST_MIN_N"] = "128"   # distribute the 256^2 and 128^2 levels of this small mesh
     sols, its = [], []
     for replicated in (True, False):
-        if replicated:
-            os.environ["PE_MG_REPLICATED"] = "1"
-        else:
-            os.environ.pop("PE_MG_REPLICATED", None)
         b = pb.BiotSystem(element=BR1_WG, device=local, rank=rank, world_size=world)
+        b.set_tuning("mg_dist_min_n", 128)   # distribute the 256^2 and 128^2 levels of this small mesh
+        b.set_tuning("mg_replicated", 1 if replicated else 0)
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             idt = torch.frombuffer(bytearray(pb.comm_unique_id()), dtype=torch.uint8).cuda()

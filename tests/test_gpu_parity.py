@@ -387,14 +387,14 @@ def test_rhs_only_mode_reuses_matrix_and_solver_operator():
 
 
 @pytest.mark.parametrize("el", [BR1_WG, CGQ1_WG])
-def test_gather_assembly_alternative_matches(el, monkeypatch):
-    """PE_ASM_GATHER=1: staged local entries + one warp per row instead of RED scatter (measured slower, kept as
+def test_gather_assembly_alternative_matches(el):
+    """pe_set_tuning("asm_gather", 1): staged local entries + one warp per row instead of RED scatter (measured slower, kept as
     an alternative like the colour-ordered mode): same matrix and right-hand side."""
     import scipy.sparse.linalg as spla
     o, b0 = make_pair(el, 5, distort=0.1, lam=2.0, c0=0.01)
     v_ref, r_ref, _ = o.assemble(0.3)
-    monkeypatch.setenv("PE_ASM_GATHER", "1")
     b = make_pair(el, 5, distort=0.1, lam=2.0, c0=0.01)[1]
+    b.set_tuning("asm_gather", 1)
     b.assemble_system(0.3)
     assert rel(b.system_matrix(), v_ref) < TOL_MAT
     assert rel(b.system_rhs(), r_ref) < TOL_MAT

@@ -49,15 +49,12 @@ def oracle128():
 
 @pytest.mark.parametrize("el", [BR1_WG, CGQ1_WG])
 @pytest.mark.parametrize("mode", ["atomics", "colour", "gather"])
-def test_assembly_over_several_chunks(el, mode, oracle128, monkeypatch):
+def test_assembly_over_several_chunks(el, mode, oracle128):
     """128^2 = 16384 cells in chunks of 4096: four chunks, k_zero_ranges between them, REDs across chunk
     boundaries -- in all three scatter modes, matrix and rhs to 1e-12 of the oracle."""
     o, old, v_ref, r_ref = oracle128[el]
-    if mode == "gather":
-        monkeypatch.setenv("PE_ASM_GATHER", "1")
-    else:
-        monkeypatch.delenv("PE_ASM_GATHER", raising=False)
     b = pb.BiotSystem(element=el)
+    b.set_tuning("asm_gather", 1 if mode == "gather" else 0)
     b.set_solver_options(1 | (32 if mode == "colour" else 0) | (1 << 8))   # chunk = 1 x 4096 cells
     b.make_grid_and_dofs(7, distort=0.15)
     b.time_step = 0.1
