@@ -265,7 +265,11 @@ namespace
     {
       // position of the diagonal entry of every owned row: the diagonal of an assembled matrix is then one gather
       h->d_diag_pos.release();
-      SolverCtx c0 = make_solver_ctx(h);
+      SolverCtx c0;
+      c0.L      = h->L;
+      c0.rowptr = h->d_rowptr.p;
+      c0.colidx = h->d_colidx.p;
+      c0.stream = s;
       PE_CUDA(h->d_diag_pos.alloc((size_t)h->L));
       diagonal_positions(c0, h->d_diag_pos.p);
       ++h->launches;
