@@ -428,6 +428,55 @@ namespace
               }
           }
         h->chunk_cell_begin.push_back(n_asm);
+        // tiles of the gather assembly: rows first touched by every run of kTileCells cells, and the cells outside
+        // the tile (inside the same chunk) that are adjacent to those rows
+        h->d_tile_rows.release();
+        h->d_tile_ghost_ptr.release();
+        h->d_tile_ghost.release();
+        if (h->gather_ok)
+          {
+            const int64_t        n_tiles = (n_asm + kTileCells - 1) / kTileCells;
+            std::vector<int64_t> trow((size_t)6 * n_tiles);
+            std::vector<int32_t> gptr((size_t)n_tiles + 1, 0), glist;
+            bool                 ok = h->chunk_cells % kTileCells == 0;
+            std::vector<int32_t> tmp;
+            for (int64_t t = 0; t < n_tiles && ok; ++t)
+              {
+                const int64_t c0 = t * kTileCells, c1 = std::min(n_asm, c0 + kTileCells);
+                const int64_t ch0 = (c0 / h->chunk_cells) * h->chunk_cells, ch1 = std::min(n_asm, ch0 + h->chunk_cells);
+                tmp.clear();
+                for (int b = 0; b < 3; ++b)
+                  {
+                    auto          bb = owner.begin() + pt.local_off[b], be = owner.begin() + blk_end[b];
+                    const int64_t ra = std::lower_bound(bb, be, (int32_t)c0) - owner.begin();
+                    const int64_t rb = std::lower_bound(bb, be, (int32_t)c1) - owner.begin();
+                    trow[(size_t)6 * t + 2 * b]     = ra;
+                    trow[(size_t)6 * t + 2 * b + 1] = rb;
+                    for (int64_t l = ra; l < rb; ++l)
+                      for (int64_t k = pt.adj_ptr[l]; k < pt.adj_ptr[l + 1]; ++k)
+                        {
+                          const int32_t ac = pos[pt.adj[k]];
+                          if ((ac < c0 || ac >= c1) && ac >= ch0 && ac < ch1)
+                            tmp.push_back(ac);
+                        }
+                  }
+                std::sort(tmp.begin(), tmp.end());
+                tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+                if ((int)tmp.size() > kTileGhostMax)
+                  ok = false;
+                glist.insert(glist.end(), tmp.begin(), tmp.end());
+                gptr[(size_t)t + 1] = (int32_t)glist.size();
+              }
+            if (ok)
+              {
+                PE_CUDA(upload(h->d_tile_rows, trow.data(), trow.size(), s));
+                PE_CUDA(upload(h->d_tile_ghost_ptr, gptr.data(), gptr.size(), s));
+                if (glist.empty())
+                  glist.push_back(0);
+                PE_CUDA(upload(h->d_tile_ghost, glist.data(), glist.size(), s));
+                PE_CUDA(cudaStreamSynchronize(s));
+              }
+          }
       }
     if (pt.world > 1)
       {
@@ -510,8 +559,13 @@ namespace
         const size_t nT = (size_t)nz * h->chunk_cells;
         if (h->d_T.n < nT && h->d_T.alloc(nT) != cudaSuccess)
           return cudaErrorMemoryAllocation;
+        GatherTiles tiles;
+        tiles.tile_rows      = h->d_tile_rows.p;
+        tiles.tile_ghost_ptr = h->d_tile_ghost_ptr.p;
+        tiles.tile_ghost     = h->d_tile_ghost.p;
         return launch_assemble_gather(h->cfg.element, a, P, n_chunks, h->chunk_cell_begin.data(), h->chunk_rows.data(),
-                                      h->d_T.p, h->chunk_cells, h->d_gsrc.p, h->d_rowadj.p, s, nl);
+                                      h->d_T.p, h->chunk_cells, h->d_gsrc.p, h->d_rowadj.p,
+                                      h->d_tile_rows.p ? &tiles : nullptr, s, nl);
       }
     return launch_assemble_chunked(h->cfg.element, a, P, n_chunks, h->chunk_cell_begin.data(), h->chunk_zero.data(), s, nl);
   }

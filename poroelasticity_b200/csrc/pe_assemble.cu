@@ -289,6 +289,11 @@ namespace pe
     int64_t        row_begin[3], row_end[3]; // local rows first touched by this chunk, per block (u | p_int | p_face)
     const uint8_t *gsrc;     // [nnz][4]
     const int32_t *rowadj;   // [L][4] asm indices of the cells adjacent to a row, -1 padded
+    // tiled phase B (k_assemble_gatherB2): tiles of kTileCells consecutive cells of the chunk
+    const int64_t *tile_rows;      // [n_tiles][6] local rows first touched by the tile, per block
+    const int32_t *tile_ghost_ptr; // [n_tiles + 1]
+    const int32_t *tile_ghost;     // asm indices of the cells OUTSIDE the tile (same chunk) adjacent to its rows
+    int64_t        tile_first;     // index of the first tile of this chunk
   };
 
   template <int EL, int NL>
@@ -417,6 +422,79 @@ namespace pe
               v += g.T[(size_t)nz * g.chunk_stride + cell[q]];
           }
         a.values[k] = v;
+      }
+  }
+
+  // phase B, tiled: one CTA per tile of kTileCells Morton-consecutive cells.  The staged entries of the tile's cells
+  // (coalesced: 32 consecutive cells per slot) and of the few cells outside the tile that touch its rows are loaded
+  // into shared memory once; every CSR entry of the rows first touched by the tile is then summed from shared memory
+  // (<= 4 contributions, one table word per entry) and stored -- each matrix value is written exactly once, coalesced,
+  // with no atomics and in a fixed order (bitwise reproducible).  Replaces the warp-per-row phase B whose read-back
+  // cost one 32-byte L2 sector per 8-byte contribution.
+  template <int NZ>
+  __global__ void __launch_bounds__(256)
+  k_assemble_gatherB2(const AsmArgs a, const GatherArgs g)
+  {
+    extern __shared__ double S[]; // [kTileCells + kTileGhostMax][NZ]
+    __shared__ int32_t       ghost[kTileGhostMax];
+    const int64_t tile = g.tile_first + blockIdx.x;
+    const int64_t c0   = a.a_begin + (int64_t)blockIdx.x * kTileCells;
+    const int     nown = (int)min((int64_t)kTileCells, a.a_end - c0);
+    const int     g0 = g.tile_ghost_ptr[tile], ng = g.tile_ghost_ptr[tile + 1] - g0;
+    if (threadIdx.x < ng)
+      ghost[threadIdx.x] = g.tile_ghost[g0 + threadIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // own cells: warp <-> slot, lane <-> cell (256 B coalesced per slot)
+    const int64_t t0 = c0 - a.a_begin; // column of the first own cell in T
+    for (int nz = warp; nz < NZ; nz += 8)
+      if (lane < nown)
+        S[lane * NZ + nz] = g.T[(size_t)nz * g.chunk_stride + t0 + lane];
+    __syncthreads();
+    // cells outside the tile: lane <-> slot
+    for (int q = warp; q < ng; q += 8)
+      {
+        const int64_t tc = (int64_t)ghost[q] - a.a_begin;
+        for (int nz = lane; nz < NZ; nz += 32)
+          S[(kTileCells + q) * NZ + nz] = g.T[(size_t)nz * g.chunk_stride + tc];
+      }
+    __syncthreads();
+    // rows of the tile: warp per row
+    const int64_t *tr = g.tile_rows + 6 * tile;
+    const int64_t  n0 = tr[1] - tr[0], n1 = tr[3] - tr[2], n2 = tr[5] - tr[4], nr = n0 + n1 + n2;
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(g.gsrc);
+    for (int64_t w = warp; w < nr; w += 8)
+      {
+        const int64_t r = w < n0 ? tr[0] + w : (w < n0 + n1 ? tr[2] + (w - n0) : tr[4] + (w - n0 - n1));
+        int           cs[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          {
+            const int32_t ac = __ldg(g.rowadj + 4 * r + q);
+            int           sl = -1;
+            if (ac >= c0 && ac < c0 + nown)
+              sl = (int)(ac - c0);
+            else if (ac >= a.a_begin && ac < a.a_end)
+              {
+                for (int z = 0; z < ng; ++z)
+                  if (ghost[z] == ac)
+                    sl = kTileCells + z;
+              }
+            cs[q] = sl; // -1: no cell / a cell of a later chunk (adds its share with RED when its chunk runs)
+          }
+        const int64_t b = __ldg(a.rowptr + r), e = __ldg(a.rowptr + r + 1);
+        for (int64_t k = b + lane; k < e; k += 32)
+          {
+            const uint32_t wq = __ldg(src + k);
+            double         v  = 0.;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              {
+                const uint32_t nz = (wq >> (8 * q)) & 255u;
+                if (nz != 255u && cs[q] >= 0)
+                  v += S[cs[q] * NZ + nz];
+              }
+            a.values[k] = v;
+          }
       }
   }
 
@@ -990,8 +1068,8 @@ namespace pe
   cudaError_t
   launch_assemble_gather(const int element, const AsmArgs &a0, const DevParams &P, const int n_chunks,
                          const int64_t *chunk_cell_begin, const int64_t *chunk_rows /* [n_chunks][6] */, double *T,
-                         const int64_t chunk_stride, const uint8_t *gsrc, const int32_t *rowadj, cudaStream_t s,
-                         int *n_launches)
+                         const int64_t chunk_stride, const uint8_t *gsrc, const int32_t *rowadj, const GatherTiles *tiles,
+                         cudaStream_t s, int *n_launches)
   {
     for (int ch = 0; ch < n_chunks; ++ch)
       {
@@ -1020,7 +1098,40 @@ namespace pe
               k_assemble_gatherA<1><<<grid, 128, 0, s>>>(a, P, g);
             ++*n_launches;
           }
-        if (n_rows > 0)
+        if (n_rows > 0 && tiles && tiles->tile_rows)
+          {
+            g.tile_rows      = tiles->tile_rows;
+            g.tile_ghost_ptr = tiles->tile_ghost_ptr;
+            g.tile_ghost     = tiles->tile_ghost;
+            g.tile_first     = a.a_begin / kTileCells;
+            const unsigned nt = (unsigned)((n + kTileCells - 1) / kTileCells);
+            if (element == 0)
+              {
+                constexpr int    NZ   = NzCount<0>::value;
+                constexpr size_t smem = sizeof(double) * (size_t)(kTileCells + kTileGhostMax) * NZ;
+                static bool      attr = false;
+                if (!attr)
+                  {
+                    cudaFuncSetAttribute(k_assemble_gatherB2<NZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    attr = true;
+                  }
+                k_assemble_gatherB2<NZ><<<nt, 256, smem, s>>>(a, g);
+              }
+            else
+              {
+                constexpr int    NZ   = NzCount<1>::value;
+                constexpr size_t smem = sizeof(double) * (size_t)(kTileCells + kTileGhostMax) * NZ;
+                static bool      attr = false;
+                if (!attr)
+                  {
+                    cudaFuncSetAttribute(k_assemble_gatherB2<NZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    attr = true;
+                  }
+                k_assemble_gatherB2<NZ><<<nt, 256, smem, s>>>(a, g);
+              }
+            ++*n_launches;
+          }
+        else if (n_rows > 0)
           {
             k_assemble_gatherB<<<grid_for(n_rows * 32, 256), 256, 0, s>>>(a, g);
             ++*n_launches;

@@ -163,7 +163,8 @@ struct pe_handle
   // the staging buffer T[NZ][chunk_cells]; opt-in (PE_ASM_GATHER=1), measured slower than the default RED scatter
   bool                 gather_ok = false;
   pe::DevBuf<uint8_t>  d_gsrc;
-  pe::DevBuf<int32_t>  d_rowadj;
+  pe::DevBuf<int32_t>  d_rowadj, d_tile_ghost_ptr, d_tile_ghost;
+  pe::DevBuf<int64_t>  d_tile_rows;
   pe::DevBuf<double>   d_T;
   int64_t              chunk_cells = 32768;
   // requested by pe_set_solver_options; scatter mode takes effect at the next pattern build, the chunk size at the

@@ -34,11 +34,19 @@ namespace pe
   cudaError_t launch_assemble_chunked(int element, const AsmArgs &a, const DevParams &P, int n_chunks,
                                       const int64_t *chunk_cell_begin, const int64_t *chunk_zero, cudaStream_t s,
                                       int *n_launches);
-  // gather assembly (pe_assemble.cu): staged local entries + one warp per row, atomics only across chunk boundaries
+  // gather assembly (pe_assemble.cu): staged local entries, then one CTA per tile of kTileCells cells sums the CSR
+  // entries of the rows first touched by the tile from shared memory; atomics only across chunk boundaries
+  constexpr int kTileCells = 32, kTileGhostMax = 32;
+  struct GatherTiles
+  {
+    const int64_t *tile_rows      = nullptr; // [n_tiles][6]
+    const int32_t *tile_ghost_ptr = nullptr; // [n_tiles + 1]
+    const int32_t *tile_ghost     = nullptr;
+  };
   cudaError_t launch_assemble_gather(int element, const AsmArgs &a, const DevParams &P, int n_chunks,
                                      const int64_t *chunk_cell_begin, const int64_t *chunk_rows, double *T,
-                                     int64_t chunk_stride, const uint8_t *gsrc, const int32_t *rowadj, cudaStream_t s,
-                                     int *n_launches);
+                                     int64_t chunk_stride, const uint8_t *gsrc, const int32_t *rowadj,
+                                     const GatherTiles *tiles, cudaStream_t s, int *n_launches);
   cudaError_t launch_local_matrices(int element, const AsmArgs &a, const DevParams &P, int64_t first, int64_t n,
                                     double *out, double *rhs_out, cudaStream_t s);
   cudaError_t launch_step_errors(int element, const AsmArgs &a, const DevParams &P, const uint8_t *is_ghost, double *e,
