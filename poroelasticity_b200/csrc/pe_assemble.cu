@@ -6,6 +6,8 @@
 #include "pe_internal.h"
 #include "pe_kernels.h"
 
+#include <cuda_pipeline.h>
+
 #include <algorithm>
 #include <cstdlib>
 
@@ -432,69 +434,110 @@ namespace pe
   // with no atomics and in a fixed order (bitwise reproducible).  Replaces the warp-per-row phase B whose read-back
   // cost one 32-byte L2 sector per 8-byte contribution.
   template <int NZ>
-  __global__ void __launch_bounds__(256)
+  __global__ void __launch_bounds__(kTileThreads)
   k_assemble_gatherB2(const AsmArgs a, const GatherArgs g)
   {
+    constexpr int            NT = kTileThreads, NW = NT / 32;
     extern __shared__ double S[]; // [kTileCells + kTileGhostMax][NZ]
+    constexpr int            kRowsMax = 320; // rows of one tile (all three blocks); longer tiles run in batches
     __shared__ int32_t       ghost[kTileGhostMax];
+    __shared__ int64_t       rs_sh[3][kRowsMax + 1];
+    __shared__ int8_t        cs_sh[3][kRowsMax][4];
     const int64_t tile = g.tile_first + blockIdx.x;
     const int64_t c0   = a.a_begin + (int64_t)blockIdx.x * kTileCells;
     const int     nown = (int)min((int64_t)kTileCells, a.a_end - c0);
     const int     g0 = g.tile_ghost_ptr[tile], ng = g.tile_ghost_ptr[tile + 1] - g0;
+    const int     lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // ---- all global -> shared copies of the tile are issued asynchronously (cp.async, 8 bytes each) before anything
+    // waits: own cells warp <-> slot, lane <-> cell (256 B coalesced per slot); cells outside the tile lane <-> slot
+    const int64_t t0 = c0 - a.a_begin; // column of the first own cell in T
+    for (int nz = warp; nz < NZ; nz += NW)
+      if (lane < nown)
+        __pipeline_memcpy_async(&S[lane * NZ + nz], &g.T[(size_t)nz * g.chunk_stride + t0 + lane], sizeof(double));
+    for (int q = warp; q < ng; q += NW)
+      {
+        const int64_t tc = (int64_t)__ldg(g.tile_ghost + g0 + q) - a.a_begin;
+        for (int nz = lane; nz < NZ; nz += 32)
+          __pipeline_memcpy_async(&S[(kTileCells + q) * NZ + nz], &g.T[(size_t)nz * g.chunk_stride + tc], sizeof(double));
+      }
+    __pipeline_commit();
     if (threadIdx.x < ng)
       ghost[threadIdx.x] = g.tile_ghost[g0 + threadIdx.x];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // own cells: warp <-> slot, lane <-> cell (256 B coalesced per slot)
-    const int64_t t0 = c0 - a.a_begin; // column of the first own cell in T
-    for (int nz = warp; nz < NZ; nz += 8)
-      if (lane < nown)
-        S[lane * NZ + nz] = g.T[(size_t)nz * g.chunk_stride + t0 + lane];
-    __syncthreads();
-    // cells outside the tile: lane <-> slot
-    for (int q = warp; q < ng; q += 8)
-      {
-        const int64_t tc = (int64_t)ghost[q] - a.a_begin;
-        for (int nz = lane; nz < NZ; nz += 32)
-          S[(kTileCells + q) * NZ + nz] = g.T[(size_t)nz * g.chunk_stride + tc];
-      }
-    __syncthreads();
-    // rows of the tile: warp per row
-    const int64_t *tr = g.tile_rows + 6 * tile;
-    const int64_t  n0 = tr[1] - tr[0], n1 = tr[3] - tr[2], n2 = tr[5] - tr[4], nr = n0 + n1 + n2;
+    const int64_t  *tr  = g.tile_rows + 6 * tile;
     const uint32_t *src = reinterpret_cast<const uint32_t *>(g.gsrc);
-    for (int64_t w = warp; w < nr; w += 8)
+    int64_t         done[3] = {tr[0], tr[2], tr[4]};
+    bool            first   = true;
+    while (done[0] < tr[1] || done[1] < tr[3] || done[2] < tr[5])
       {
-        const int64_t r = w < n0 ? tr[0] + w : (w < n0 + n1 ? tr[2] + (w - n0) : tr[4] + (w - n0 - n1));
-        int           cs[4];
+        // row starts of the three blocks (contiguous CSR ranges)
+        int nrow[3];
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+        for (int blk = 0; blk < 3; ++blk)
           {
-            const int32_t ac = __ldg(g.rowadj + 4 * r + q);
-            int           sl = -1;
-            if (ac >= c0 && ac < c0 + nown)
-              sl = (int)(ac - c0);
-            else if (ac >= a.a_begin && ac < a.a_end)
-              {
+            nrow[blk] = (int)min((int64_t)kRowsMax, tr[2 * blk + 1] - done[blk]);
+            for (int t = threadIdx.x; t <= nrow[blk]; t += NT)
+              rs_sh[blk][t] = __ldg(a.rowptr + done[blk] + t);
+          }
+        __syncthreads(); // ghost[] visible
+#pragma unroll
+        for (int blk = 0; blk < 3; ++blk)
+          for (int t = threadIdx.x; t < nrow[blk] * 4; t += NT)
+            {
+              const int32_t ac = __ldg(g.rowadj + 4 * done[blk] + t);
+              int           sl = -1;
+              if (ac >= c0 && ac < c0 + nown)
+                sl = (int)(ac - c0);
+              else if (ac >= a.a_begin && ac < a.a_end)
                 for (int z = 0; z < ng; ++z)
                   if (ghost[z] == ac)
                     sl = kTileCells + z;
-              }
-            cs[q] = sl; // -1: no cell / a cell of a later chunk (adds its share with RED when its chunk runs)
-          }
-        const int64_t b = __ldg(a.rowptr + r), e = __ldg(a.rowptr + r + 1);
-        for (int64_t k = b + lane; k < e; k += 32)
-          {
-            const uint32_t wq = __ldg(src + k);
-            double         v  = 0.;
+              cs_sh[blk][t >> 2][t & 3] = (int8_t)sl; // -1: no cell / a cell of a later chunk (RED when its chunk runs)
+            }
+        if (first)
+          __pipeline_wait_prior(0);
+        first = false;
+        __syncthreads();
+        // one thread per CSR entry; the table words of four entries are loaded before any is used
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+        for (int blk = 0; blk < 3; ++blk)
+          {
+            const int64_t k0 = rs_sh[blk][0], k1 = rs_sh[blk][nrow[blk]];
+            for (int64_t kb = k0 + threadIdx.x; kb < k1; kb += 4 * NT)
               {
-                const uint32_t nz = (wq >> (8 * q)) & 255u;
-                if (nz != 255u && cs[q] >= 0)
-                  v += S[cs[q] * NZ + nz];
+                uint32_t wq[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  wq[u] = kb + u * NT < k1 ? __ldg(src + kb + u * NT) : 0xffffffffu;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  {
+                    const int64_t k = kb + u * NT;
+                    if (k >= k1)
+                      break;
+                    int lo = 0, hi = nrow[blk];
+                    while (hi - lo > 1)
+                      {
+                        const int mid = (lo + hi) >> 1;
+                        if (rs_sh[blk][mid] <= k)
+                          lo = mid;
+                        else
+                          hi = mid;
+                      }
+                    double v = 0.;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                      {
+                        const uint32_t nz = (wq[u] >> (8 * q)) & 255u;
+                        const int      sl = cs_sh[blk][lo][q];
+                        if (nz != 255u && sl >= 0)
+                          v += S[sl * NZ + nz];
+                      }
+                    a.values[k] = v;
+                  }
               }
-            a.values[k] = v;
+            done[blk] += nrow[blk];
           }
+        __syncthreads();
       }
   }
 
@@ -1115,7 +1158,7 @@ namespace pe
                     cudaFuncSetAttribute(k_assemble_gatherB2<NZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                     attr = true;
                   }
-                k_assemble_gatherB2<NZ><<<nt, 256, smem, s>>>(a, g);
+                k_assemble_gatherB2<NZ><<<nt, kTileThreads, smem, s>>>(a, g);
               }
             else
               {
@@ -1127,7 +1170,7 @@ namespace pe
                     cudaFuncSetAttribute(k_assemble_gatherB2<NZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                     attr = true;
                   }
-                k_assemble_gatherB2<NZ><<<nt, 256, smem, s>>>(a, g);
+                k_assemble_gatherB2<NZ><<<nt, kTileThreads, smem, s>>>(a, g);
               }
             ++*n_launches;
           }

@@ -36,7 +36,7 @@ namespace pe
                                       int *n_launches);
   // gather assembly (pe_assemble.cu): staged local entries, then one CTA per tile of kTileCells cells sums the CSR
   // entries of the rows first touched by the tile from shared memory; atomics only across chunk boundaries
-  constexpr int kTileCells = 32, kTileGhostMax = 32;
+  constexpr int kTileCells = 32, kTileGhostMax = 24, kTileThreads = 512;
   struct GatherTiles
   {
     const int64_t *tile_rows      = nullptr; // [n_tiles][6]

@@ -969,7 +969,7 @@ namespace pe
   // least-squares problem by one thread on the device.  The basis vectors are kept UNNORMALISED with their
   // scales s_i = 1/||v~_i|| on the device (no normalisation pass).  Right preconditioning makes the recurrence
   // residual the true 2-norm residual of K' (= of K3); the decision is still taken on the residual of the
-  // reference system.  A cycle ends after m iterations or when the residual has dropped by 1e-6 within the cycle
+  // reference system.  A cycle ends after m iterations or when the residual has dropped by 1e-7 within the cycle
   // (classical Gram-Schmidt loses orthogonality like (||r_0|| / ||r_j||)^2 eps).
   // =============================================================================================
   struct GmresState
@@ -1359,8 +1359,9 @@ namespace pe
                 give_up = true;
                 break;
               }
-            // end the cycle: target reached, or deep enough for classical Gram-Schmidt
-            if (res <= target || res <= 1e-6 * beta)
+            // end the cycle: target reached, or deep enough for classical Gram-Schmidt (loss of orthogonality
+            // ~ (||r_0|| / ||r_j||)^2 eps: 1e-2 at a reduction of 1e-7; the true residual is recomputed at every restart)
+            if (res <= target || res <= 1e-7 * beta)
               hit = true;
           }
         if (give_up)
