@@ -15,7 +15,7 @@ main(int argc, char **argv)
       poroelas::PoroElas_CGQ1_WG<2> prog(T, dt, 1., 1., 1., 0.);
       prog.refinement = refinement;
       prog.run();
-      std::printf("last solve: %d MINRES iterations, relative residual %.3e\n", prog.last_solve().iterations,
+      std::printf("last solve: %d Krylov iterations, relative residual %.3e\n", prog.last_solve().iterations,
                   prog.last_solve().rel_residual);
     }
   catch (const std::exception &e)

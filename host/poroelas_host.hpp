@@ -1,11 +1,19 @@
 // Host-side C++ mirror of the reference's classes for the hot path, on top of the C ABI
 // (include/poroelas_b200.h).  Same member names as PoroElasBR1WG / PoroElas_CGQ1_WG
-// (PoroElasBR1WG_new.cc:62-137): make_grid_and_dofs(), assemble_system(t), solve_time_step(), run(),
-// same stdout lines (BR1new:599-610, 2183-2185).  No numerics live here.
+// (PoroElasBR1WG_new.cc:62-137): make_grid_and_dofs(), assemble_system(t), solve_time_step(), postprocess(),
+// postprocess_errors(t, n), postprocess_darcy_velocity(n), run(); same stdout lines (BR1new:599-610, 2183-2185,
+// 2263-2266).  No numerics live here.
+//
+// Defaults: the default constructors carry the reference's commented "general case" blocks (manufactured coscos
+// solution, BR1new:532-539 / CGQ1:824-831), which is what BASELINE configs 1-4 run; the values the files SHIP with
+// (cantilever bracket BR1new:551-558, 3-D sandwich CGQ1:859-866) are selected with `cantilever = true` /
+// the six-argument constructors.
 #pragma once
 #include "../include/poroelas_b200.h"
 
+#include <cmath>
 #include <cstdio>
+#include <fstream>
 #include <iostream>
 #include <stdexcept>
 #include <string>
@@ -47,6 +55,8 @@ namespace poroelas
     double rel_tol       = 1e-10;
     int    max_iterations = 100000;
     bool   cantilever    = false; // BR1new as shipped: u = 0 on x = 0, traction (0,-1) on y = 1, K = 1e-7
+    bool   with_errors   = false; // postprocess_errors every step + the final l2-in-time line (BR1new:2193, 2251-2266)
+    int    velocity_step = -1;    // postprocess_darcy_velocity writes velocity.txt at this step (BR1new:1356: t == 10)
 
     void
     run()
@@ -59,9 +69,22 @@ namespace poroelas
           std::cout << "Time step " << timestep_number << " at t=" << time << " time_step " << time_step << std::endl;
           assemble_system(time);
           solve_time_step();
+          postprocess();
+          if (with_errors)
+            postprocess_errors(time, timestep_number);
+          postprocess_darcy_velocity(timestep_number);
           // old_solution = solution (BR1new:2241): stays on the device
         }
+      if (with_errors)
+        std::cout << "L2L2Error_intp " << std::sqrt(err_acc[0]) << ", "
+                  << "L2L2Error_u " << std::sqrt(err_acc[1]) << ", "
+                  << "L2h1semiError_u " << std::sqrt(err_acc[2]) << ", "
+                  << "L2h1Error_u " << std::sqrt(err_acc[1] + err_acc[2]) << std::endl;
     }
+
+    // numerical dilation and |u| per cell of the last step (BR1new:1189-1246, CGQ1:1849-1877)
+    const std::vector<double> &dilation() const { return div_displacement; }
+    const std::vector<double> &magnitude() const { return displacement_magnitude; }
 
     const pe_solve_stats &last_solve() const { return stats; }
     pe_handle            *handle() { return h; }
@@ -135,6 +158,40 @@ namespace poroelas
     {
       check(pe_solve_time_step(h, rel_tol, max_iterations, nullptr, &stats), "pe_solve_time_step");
     }
+    // postprocess()  BR1new:1189-1246 / CGQ1:1744-1879: cell averages of div u_h and |u_h|
+    void
+    postprocess()
+    {
+      pe_sizes s;
+      pe_get_sizes(h, &s);
+      div_displacement.resize((size_t)s.n_cells);
+      displacement_magnitude.resize((size_t)s.n_cells);
+      check(pe_postprocess(h, div_displacement.data(), displacement_magnitude.data(), nullptr, nullptr), "pe_postprocess");
+    }
+    // postprocess_errors(t, n)  BR1new:1251-1349: squared errors of this step times dt, summed over the steps
+    void
+    postprocess_errors(const double t, const unsigned int /*n*/)
+    {
+      double e[3];
+      check(pe_step_errors(h, t, e), "pe_step_errors");
+      for (int k = 0; k < 3; ++k)
+        err_acc[k] += time_step * e[k];
+    }
+    // postprocess_darcy_velocity(n)  BR1new:1352-1606: cell-centre Darcy velocities -> velocity.txt
+    void
+    postprocess_darcy_velocity(const unsigned int n)
+    {
+      if ((int)n != velocity_step)
+        return;
+      std::cout << "run the final time " << std::endl;
+      pe_sizes s;
+      pe_get_sizes(h, &s);
+      std::vector<double> vel((size_t)2 * s.n_cells);
+      check(pe_postprocess(h, nullptr, nullptr, nullptr, vel.data()), "pe_postprocess");
+      std::ofstream out("velocity.txt");
+      for (int64_t i = 0; i < s.n_cells; ++i)
+        out << vel[2 * i] << " " << vel[2 * i + 1] << " " << 0 << std::endl;
+    }
     void
     check(const int rc, const char *what) const
     {
@@ -144,6 +201,8 @@ namespace poroelas
 
     pe_handle     *h = nullptr;
     pe_solve_stats stats{};
+    std::vector<double> div_displacement, displacement_magnitude;
+    double              err_acc[3] = {0., 0., 0.};
     double         total_time, time = 0., time_step;
     unsigned int   number_timestep, timestep_number;
     const double   lambda, mu, alpha, capacity;

@@ -222,6 +222,24 @@ def test_cpp_host_driver_runs():
     assert out.returncode == 0, out.stdout + out.stderr
     assert "Number of degrees of freedom: 1922 (1122+256+544)" in out.stdout
     assert out.stdout.count("Time step") == 4
+    # the final l2-in-time error line of run() (BR1new:2263-2266) against the oracle loop, 3 significant digits
+    import re
+    import scipy.sparse.linalg as spla
+    m = re.search(r"L2L2Error_intp ([\d.e+-]+), L2L2Error_u ([\d.e+-]+), L2h1semiError_u ([\d.e+-]+), L2h1Error_u ([\d.e+-]+)",
+                  out.stdout)
+    assert m, out.stdout
+    got = np.array([float(m.group(k)) for k in range(1, 5)])
+    o = Oracle(BR1_WG, 4)
+    o.set_material(1, 1, 1, 0, 0.25)
+    o.set_case(CASE_COSCOS)
+    old, acc, t = np.zeros(o.n_dofs), np.zeros(3), 0.25
+    while t <= 1.0:
+        v, r, _ = o.assemble(t, old)
+        old = spla.splu(o.csr(v).tocsc()).solve(r)
+        acc += 0.25 * o.step_errors(t, old)
+        t += 0.25
+    ref = np.sqrt(np.append(acc, acc[1] + acc[2]))
+    assert np.all(np.abs(got - ref) <= 2e-3 * ref), (got, ref)   # cout prints 6 significant digits
 
 
 @pytest.mark.parametrize("el", [BR1_WG, CGQ1_WG])
