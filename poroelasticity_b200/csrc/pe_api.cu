@@ -743,6 +743,16 @@ namespace
       comm_halo_exchange_xi(h, z);
     precond_apply(*h->bp, *h->mg, *h->cmg, h->d_pinv.p, r, z, h->stream, &h->launches, z);
   }
+  // xi := -lambda W^-1 B u + alpha p_int from the (u, p) part of the iterate
+  void
+  hook_consistent_xi(void *ctx, double *x3)
+  {
+    pe_handle *h = (pe_handle *)ctx;
+    if (h->part.world > 1)
+      comm_halo_exchange(h, x3);
+    k3_init_xi(*h->k3, x3, h->stream);
+    ++h->launches;
+  }
   void
   hook_true_residual(void *ctx, const double *x3, double *nrm2_dev)
   {
@@ -1085,6 +1095,27 @@ namespace
         c3.graph_key     = h->graph_epoch * 64 + (uint64_t)m;
         rc = fgmres_solve(c3, b3, x3, h->d_gm.p, h->d_gm.p + (size_t)(m + 1) * n3, (int64_t)n3, h->d_w[0].p, m,
                           h->d_gmres_state.p, h->h_scal, rel_tol, max_iterations, stats);
+        if (rc == 0 && !stats->converged && stats->residual_norm == stats->residual_norm && stats->iterations < max_iterations)
+          {
+            // Safety net for lambda >> mu on small meshes: the 2-norm GMRES on the three-field system weighs the xi
+            // equation less than its effect on the reference residual (amplified by lambda / 2 mu), so its attainable
+            // reference residual is ~ eps lambda / mu times a constant that MINRES (energy norm) does not pay.
+            // Continue from the GMRES iterate with MINRES on the symmetric (unscaled) K3.
+            const pe_solve_stats g = *stats;
+            if (k3_fill_values(k, k.lambda_s, k.alpha, h->mu, false, s, &h->launches) != 0)
+              return 1;
+            SolverCtx cm     = make_solver_ctx3(h);
+            cm.true_residual = hook_true_residual;
+            cm.precond_apply = hook_precond3;
+            cm.bnorm2        = c3.bnorm2;
+            cm.calib         = nullptr;
+            rc = minres_solve(cm, b3, x3, nullptr, work, (MinresState *)h->d_scal.p, h->h_scal, rel_tol,
+                              max_iterations - g.iterations, stats);
+            stats->iterations += g.iterations;
+            stats->spmv_count += g.spmv_count;
+            stats->restarts += g.restarts + 1;
+            k.values_valid = false; // the next solve refills the GMRES (row-scaled) operator
+          }
       }
     else
       rc = minres_solve(c3, b3, x3, pinv3, work, (MinresState *)h->d_scal.p, h->h_scal, rel_tol, max_iterations, stats);

@@ -1213,6 +1213,12 @@ namespace pe
     cudaMemsetAsync(st, 0, sizeof(GmresState), s);
     // r_0 = D (b - K x) into V[0], ||r_0||^2 into beta2
     auto start_cycle = [&]() {
+      // three-field system: make the auxiliary unknown consistent with (u, p) first.  Its equation is then satisfied
+      // exactly and the residual of K' IS the residual of the reference system: every cycle starts from, and is
+      // measured against, the quantity the stopping rule is about (the xi equation enters the reference residual
+      // amplified by lambda: without this the attainable accuracy is eps * lambda / mu times a large constant).
+      if (c.on_restart)
+        c.on_restart(c.precond_ctx, x);
       if (c.halo)
         c.halo(c.halo_ctx, x);
       spmv_signed(c, x, w, nullptr);

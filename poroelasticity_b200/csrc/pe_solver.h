@@ -67,6 +67,7 @@ namespace pe
     double bnorm2 = -1.;        // >= 0: ||b||^2 the stopping test is relative to (else computed from b)
     // optional: *nrm2_dev += ||true residual(x)||^2 of this rank (else b - A x with the ctx matrix)
     void (*true_residual)(void *ctx, const double *x, double *nrm2_dev) = nullptr;
+    void (*on_restart)(void *ctx, double *x) = nullptr; // GMRES: called on the iterate before every cycle
     bool          x0_is_zero = false;  // initial guess known to be zero: ||b||_{P^-1} = the initial eta
     MinresGraphs *graphs     = nullptr; // cache of the captured iteration (null: capture per solve)
     GmresGraphs  *gmres_graphs = nullptr;
