@@ -235,6 +235,11 @@ int pe_step_errors(pe_handle *h, double t, double e[3]);
 int pe_postprocess(pe_handle *h, double *div_displacement, double *displacement_magnitude, double *darcy_beta,
                    double *velocity_center);
 
+/* postprocess() of EltStiffMat.cc (ESM:662-919) for the WG(Q2,Q2;RT[2]) Darcy element, from the device solution:
+ * e[0] = L2_error_vel^2  = sum_cells int |u_h - u|^2,  u_h = -K grad_w p_h in RT[2], u = Velocity::value (ESM:200-211)
+ * e[1] = L2_error_flux^2 = sum_cells sum_faces (|E| / |f|) int_f ((u_h - u).n)^2     (the program prints the square roots) */
+int pe_darcy_errors(pe_handle *h, double e[2]);
+
 /* the solver's SpMV kernel alone, `repeats` back-to-back launches on the handle's stream timed with
  * CUDA events (roofline measurement; x = current solution vector): average ms per launch */
 int pe_bench_spmv(pe_handle *h, int repeats, double *ms_per_launch);

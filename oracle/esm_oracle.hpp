@@ -372,5 +372,138 @@ namespace orc
         apply_boundary_values(boundary_values(P), P.pattern, mat.val, solution, rhs);
       val = mat.val;
     }
+    // Velocity::value  ESM:200-211: exact Darcy velocity -K grad p of p = cos(pi x) cos(pi y), K = I
+    inline void
+    exact_velocity(const double x, const double y, double v[2])
+    {
+      v[0] = M_PI * std::sin(M_PI * x) * std::cos(M_PI * y);
+      v[1] = M_PI * std::cos(M_PI * x) * std::sin(M_PI * y);
+    }
+
+    // postprocess()  ESM:662-919: e[0] = L2_error_vel^2 = sum_cells int |u_h - u|^2,  u_h = sum_k beta_k w_k,
+    //   beta_k = - sum_j sum_i sol_i C_ij D_kj,  D = M^-1 E,  E = int K w.w   (ESM:730-818)
+    // e[1] = L2_error_flux^2 = sum_cells sum_faces (|E| / |f|) int_f ((u_h - u).n)^2   (ESM:840-905)
+    inline void
+    postprocess(const Problem &P, const std::vector<double> &solution, double e[2])
+    {
+      static const Quad2         q2 = qgauss_2d(4);
+      static std::vector<double> fx, fw;
+      if (fx.empty())
+        qgauss_1d(4, fx, fw);
+      const int nq = (int)q2.p.size();
+      e[0] = e[1] = 0.;
+      for (int c = 0; c < P.mesh.n_cells(); ++c)
+        {
+          const CellGeom geom = P.mesh.geom(c);
+          const double   K    = P.kcell[c];
+          const dof_t   *idx  = &P.cell_dofs[(size_t)c * kNLoc];
+          std::vector<double> M(kNRt * kNRt, 0.), E(kNRt * kNRt, 0.), D(kNRt * kNRt, 0.), F(kNLoc * kNRt, 0.),
+            C(kNLoc * kNRt, 0.), beta(kNRt, 0.);
+          std::vector<double> rt((size_t)nq * kNRt * 2), rtdiv((size_t)nq * kNRt), pv((size_t)nq * kNLoc), JxW(nq), px(nq), py(nq);
+          double cell_area = 0.;
+          for (int q = 0; q < nq; ++q)
+            {
+              const MapPoint m = map_at(geom, q2.p[q].x, q2.p[q].y);
+              JxW[q]           = m.det * q2.w[q];
+              cell_area += JxW[q];
+              px[q] = m.x[0];
+              py[q] = m.x[1];
+              double w[kNRt][2], dv[kNRt];
+              rt2_ref(q2.p[q].x, q2.p[q].y, w, dv);
+              for (int k = 0; k < kNRt; ++k)
+                {
+                  rt[((size_t)q * kNRt + k) * 2 + 0] = (m.J[0][0] * w[k][0] + m.J[0][1] * w[k][1]) / m.det;
+                  rt[((size_t)q * kNRt + k) * 2 + 1] = (m.J[1][0] * w[k][0] + m.J[1][1] * w[k][1]) / m.det;
+                  rtdiv[(size_t)q * kNRt + k]        = dv[k] / m.det;
+                }
+              interior_values(q2.p[q].x, q2.p[q].y, &pv[(size_t)q * kNLoc]);
+            }
+          for (int q = 0; q < nq; ++q)
+            for (int i = 0; i < kNRt; ++i)
+              for (int j = 0; j < kNRt; ++j)
+                {
+                  const double ww = rt[((size_t)q * kNRt + i) * 2] * rt[((size_t)q * kNRt + j) * 2] +
+                                    rt[((size_t)q * kNRt + i) * 2 + 1] * rt[((size_t)q * kNRt + j) * 2 + 1];
+                  E[i * kNRt + j] += K * ww * JxW[q];
+                  M[i * kNRt + j] += ww * JxW[q];
+                }
+          gauss_jordan(M, kNRt);
+          for (int i = 0; i < kNRt; ++i)
+            for (int j = 0; j < kNRt; ++j)
+              {
+                double s = 0;
+                for (int k = 0; k < kNRt; ++k)
+                  s += M[i * kNRt + k] * E[k * kNRt + j];
+                D[i * kNRt + j] = s;
+              }
+          for (int q = 0; q < nq; ++q)
+            for (int i = 0; i < kNLoc; ++i)
+              for (int k = 0; k < kNRt; ++k)
+                F[i * kNRt + k] -= pv[(size_t)q * kNLoc + i] * rtdiv[(size_t)q * kNRt + k] * JxW[q];
+          for (int f = 0; f < 4; ++f)
+            for (size_t q = 0; q < fx.size(); ++q)
+              {
+                const FacePoint fp = face_point(geom, f, fx[q], fw[q]);
+                const Point2    r  = project_to_face(f, fx[q]);
+                double          w[kNRt][2], dv[kNRt], fv[kNLoc];
+                rt2_ref(r.x, r.y, w, dv);
+                face_values(f, fx[q], fv);
+                for (int i = 0; i < kNLoc; ++i)
+                  for (int k = 0; k < kNRt; ++k)
+                    {
+                      const double wx = (fp.m.J[0][0] * w[k][0] + fp.m.J[0][1] * w[k][1]) / fp.m.det;
+                      const double wy = (fp.m.J[1][0] * w[k][0] + fp.m.J[1][1] * w[k][1]) / fp.m.det;
+                      F[i * kNRt + k] += fv[i] * (wx * fp.n[0] + wy * fp.n[1]) * fp.JxW;
+                    }
+              }
+          for (int i = 0; i < kNLoc; ++i)
+            for (int k = 0; k < kNRt; ++k)
+              {
+                double s = 0;
+                for (int l = 0; l < kNRt; ++l)
+                  s += F[i * kNRt + l] * M[l * kNRt + k];
+                C[i * kNRt + k] = s;
+              }
+          for (int k = 0; k < kNRt; ++k)
+            for (int j = 0; j < kNRt; ++j)
+              for (int i = 0; i < kNLoc; ++i)
+                beta[k] += -(solution[idx[i]] * C[i * kNRt + j] * D[k * kNRt + j]);
+          // velocity error on the cell                                                  ESM:822-838
+          for (int q = 0; q < nq; ++q)
+            {
+              double vh[2] = {0, 0}, ve[2];
+              for (int k = 0; k < kNRt; ++k)
+                {
+                  vh[0] += beta[k] * rt[((size_t)q * kNRt + k) * 2];
+                  vh[1] += beta[k] * rt[((size_t)q * kNRt + k) * 2 + 1];
+                }
+              exact_velocity(px[q], py[q], ve);
+              e[0] += ((vh[0] - ve[0]) * (vh[0] - ve[0]) + (vh[1] - ve[1]) * (vh[1] - ve[1])) * JxW[q];
+            }
+          // normal flux error on the faces                                              ESM:840-905
+          for (int f = 0; f < 4; ++f)
+            {
+              const int    v0 = face_vertices[f][0], v1 = face_vertices[f][1];
+              const double face_length = std::hypot(geom.vx[v1] - geom.vx[v0], geom.vy[v1] - geom.vy[v0]);
+              double       local = 0.;
+              for (size_t q = 0; q < fx.size(); ++q)
+                {
+                  const FacePoint fp = face_point(geom, f, fx[q], fw[q]);
+                  const Point2    r  = project_to_face(f, fx[q]);
+                  double          w[kNRt][2], dv[kNRt], vh[2] = {0, 0}, ve[2];
+                  rt2_ref(r.x, r.y, w, dv);
+                  for (int k = 0; k < kNRt; ++k)
+                    {
+                      vh[0] += beta[k] * (fp.m.J[0][0] * w[k][0] + fp.m.J[0][1] * w[k][1]) / fp.m.det;
+                      vh[1] += beta[k] * (fp.m.J[1][0] * w[k][0] + fp.m.J[1][1] * w[k][1]) / fp.m.det;
+                    }
+                  exact_velocity(fp.m.x[0], fp.m.x[1], ve);
+                  const double dn = (vh[0] - ve[0]) * fp.n[0] + (vh[1] - ve[1]) * fp.n[1];
+                  local += dn * dn * fp.JxW;
+                }
+              e[1] += local / face_length * cell_area;
+            }
+        }
+    }
   } // namespace esm
 } // namespace orc

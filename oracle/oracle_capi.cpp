@@ -316,4 +316,12 @@ extern "C"
     std::copy(s.begin(), s.end(), solution);
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   }
+  // postprocess() ESM:662-919: e[0] = L2_error_vel^2, e[1] = L2_error_flux^2
+  void
+  orc_esm_postprocess(void *h, const double *solution, double *e2)
+  {
+    esm::Problem       *P = (esm::Problem *)h;
+    std::vector<double> s(solution, solution + P->n_dofs);
+    esm::postprocess(*P, s, e2);
+  }
 }

@@ -40,7 +40,7 @@ EXPORTS = [
     "pe_get_mesh", "pe_get_dofs", "pe_get_pattern", "pe_get_dealii_block_order", "pe_set_material",
     "pe_set_lognormal_k", "pe_set_case", "pe_set_boundary", "pe_assemble_system", "pe_assemble_rhs_only",
     "pe_get_matrix", "pe_get_rhs", "pe_solve_time_step", "pe_set_solver_options", "pe_set_initial_guess", "pe_set_krylov", "pe_set_tuning", "pe_get_solution", "pe_get_solution_global", "pe_set_solution", "pe_spmv",
-    "pe_bench_spmv", "pe_bench_fp64", "pe_local_matrices", "pe_local_matrices_bench", "pe_step_errors", "pe_postprocess", "pe_comm_unique_id", "pe_comm_init",
+    "pe_bench_spmv", "pe_bench_fp64", "pe_local_matrices", "pe_local_matrices_bench", "pe_step_errors", "pe_postprocess", "pe_darcy_errors", "pe_comm_unique_id", "pe_comm_init",
     "pe_get_timings",
 ]
 
@@ -100,6 +100,7 @@ def load():
         "pe_local_matrices_bench": [vp, dbl, dbl, i64, i32, C.POINTER(dbl), C.POINTER(dbl)],
         "pe_step_errors": [vp, dbl, vp],
         "pe_postprocess": [vp, vp, vp, vp, vp],
+        "pe_darcy_errors": [vp, vp],
         "pe_comm_unique_id": [vp],
         "pe_comm_init": [vp, vp],
         "pe_get_timings": [vp, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(dbl), C.POINTER(dbl), C.POINTER(i64)],

@@ -2183,6 +2183,29 @@ extern "C"
   }
 
   int
+  pe_darcy_errors(pe_handle *h, double *e)
+  {
+    if (!h || !e)
+      return PE_ERR_ARG;
+    if (h->cfg.element != PE_WG_Q2RT2)
+      return fail(h, PE_ERR_ARG, "pe_darcy_errors: the WG(Q2,Q2;RT[2]) Darcy element only (Biot elements: pe_postprocess)");
+    PE_DEVICE(h);
+    PE_TRY
+    const int rc = ensure_device(h);
+    if (rc != PE_OK)
+      return rc;
+    if (h->d_scal.n < 64)
+      PE_CUDA(h->d_scal.alloc(64));
+    const AsmArgs a = make_args(h, false);
+    PE_CUDA(launch_esm_postprocess(a, h->d_sol.p, h->d_scal.p + 36, h->stream));
+    ++h->launches;
+    PE_CUDA(cudaMemcpyAsync(e, h->d_scal.p + 36, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    PE_CUDA(cudaStreamSynchronize(h->stream));
+    return PE_OK;
+    PE_CATCH
+  }
+
+  int
   pe_comm_unique_id(uint8_t id[128])
   {
     return comm_unique_id(id);

@@ -394,7 +394,200 @@ namespace pe
       rhs[d] = diag * vals[t];
       sol[d] = vals[t];
     }
+
+    // ---- postprocess()  EltStiffMat.cc:662-919 ------------------------------------------------------------
+    // One thread per cell (a diagnostic, not a hot kernel): beta = -k M^-1 F^T p_cell are the RT[2] coefficients of the
+    // Darcy velocity -K grad_w p_h (for K = k I the matrix D = M^-1 E of ESM:757-758 is k I), M by Cholesky in
+    // thread-local memory.  e[0] += int |u_h - u|^2 (QGauss(4)),  e[1] += sum_f (|E|/|f|) int_f ((u_h - u).n)^2.
+    __device__ __forceinline__ void
+    d_legendre01(const double x, double P[4])
+    {
+      const double t = 2. * x - 1.;
+      P[0] = 1.;
+      P[1] = t;
+      P[2] = .5 * (3. * t * t - 1.);
+      P[3] = .5 * (5. * t * t * t - 3. * t);
+    }
+    // reference velocity sum_k beta_k w^_k at (xi, eta)
+    __device__ __forceinline__ void
+    d_rt2_combine(const double *beta, const double xi, const double eta, double &hx, double &hy)
+    {
+      double Px[4], Py[4];
+      d_legendre01(xi, Px);
+      d_legendre01(eta, Py);
+      hx = hy = 0.;
+      for (int k = 0; k < 12; ++k)
+        {
+          hx += beta[k] * Px[k % 4] * Py[k / 4];
+          hy += beta[12 + k] * Px[k % 3] * Py[k / 3];
+        }
+    }
+    __global__ void __launch_bounds__(64)
+    k_esm_postprocess(const EsmArgs a, const double *__restrict__ sol, double *__restrict__ e2)
+    {
+      const int64_t c  = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      double        ev = 0., ef = 0.;
+      if (c < a.n_asm)
+        {
+          double vx[4], vy[4];
+#pragma unroll
+          for (int v = 0; v < 4; ++v)
+            {
+              const uint32_t vi = a.cv[(size_t)v * a.n_asm + c];
+              vx[v]             = a.vx[vi];
+              vy[v]             = a.vy[vi];
+            }
+          Geom G;
+          G.set(vx, vy);
+          const double kperm = a.kcell ? a.kcell[c] : a.k_scalar;
+          double       g[kRt], M[kRt * kRt];
+          for (int k = 0; k < kRt; ++k)
+            g[k] = 0.;
+          for (int i = 0; i < kLoc; ++i)
+            {
+              const double si = sol[a.cdofs[(size_t)i * a.n_asm + c]];
+              for (int k = 0; k < kRt; ++k)
+                g[k] += cT.F[i * kRt + k] * si;
+            }
+          for (int k = 0; k < kRt * kRt; ++k)
+            M[k] = 0.;
+          double area = 0.;
+          for (int q = 0; q < kQ; ++q)
+            {
+              double j00, j01, j10, j11;
+              G.jac(cT.qx[q], cT.qy[q], j00, j01, j10, j11);
+              const double det = j00 * j11 - j01 * j10, r = cT.qw[q] / det;
+              area += cT.qw[q] * det;
+              // w_k = J w^_k / det: x-carriers use column 0 of J, y-carriers column 1
+              const double a00 = (j00 * j00 + j10 * j10) * r, a01 = (j00 * j01 + j10 * j11) * r, a11 = (j01 * j01 + j11 * j11) * r;
+              for (int i = 0; i < kRt; ++i)
+                {
+                  const double pi = i < 12 ? cT.px[q * 12 + i] : cT.py[q * 12 + i - 12];
+                  for (int j = 0; j <= i; ++j)
+                    {
+                      const double pj = j < 12 ? cT.px[q * 12 + j] : cT.py[q * 12 + j - 12];
+                      const double cc = i < 12 ? a00 : (j < 12 ? a01 : a11);
+                      M[i * kRt + j] += pi * pj * cc;
+                    }
+                }
+            }
+          // Cholesky M = L L^T (lower triangle in place), then L L^T y = g
+          for (int j = 0; j < kRt; ++j)
+            {
+              double d = M[j * kRt + j];
+              for (int k = 0; k < j; ++k)
+                d -= M[j * kRt + k] * M[j * kRt + k];
+              d              = sqrt(d);
+              M[j * kRt + j] = d;
+              for (int i = j + 1; i < kRt; ++i)
+                {
+                  double t = M[i * kRt + j];
+                  for (int k = 0; k < j; ++k)
+                    t -= M[i * kRt + k] * M[j * kRt + k];
+                  M[i * kRt + j] = t / d;
+                }
+            }
+          for (int i = 0; i < kRt; ++i)
+            {
+              double t = g[i];
+              for (int k = 0; k < i; ++k)
+                t -= M[i * kRt + k] * g[k];
+              g[i] = t / M[i * kRt + i];
+            }
+          for (int i = kRt - 1; i >= 0; --i)
+            {
+              double t = g[i];
+              for (int k = i + 1; k < kRt; ++k)
+                t -= M[k * kRt + i] * g[k];
+              g[i] = t / M[i * kRt + i];
+            }
+          for (int k = 0; k < kRt; ++k)
+            g[k] = -kperm * g[k]; // beta
+          // velocity error, QGauss<2>(4)
+          for (int q = 0; q < kQ; ++q)
+            {
+              double j00, j01, j10, j11, hx = 0., hy = 0., px, py, sx, cx, sy, cy;
+              G.jac(cT.qx[q], cT.qy[q], j00, j01, j10, j11);
+              const double det = j00 * j11 - j01 * j10;
+              for (int k = 0; k < 12; ++k)
+                {
+                  hx += g[k] * cT.px[q * 12 + k];
+                  hy += g[12 + k] * cT.py[q * 12 + k];
+                }
+              const double ux = (j00 * hx + j01 * hy) / det, uy = (j10 * hx + j11 * hy) / det;
+              G.point(cT.qx[q], cT.qy[q], px, py);
+              sincospi(px, &sx, &cx);
+              sincospi(py, &sy, &cy);
+              const double dx = ux - M_PI * sx * cy, dy = uy - M_PI * cx * sy; // Velocity::value, ESM:200-211
+              ev += (dx * dx + dy * dy) * cT.qw[q] * det;
+            }
+          // normal flux error per face, QGauss<1>(4); face f: 0 x^=0, 1 x^=1, 2 y^=0, 3 y^=1
+          const double gw0 = sqrt(cT.qw[0]);
+          for (int f = 0; f < 4; ++f)
+            {
+              const int    v0 = f == 0 ? 0 : (f == 1 ? 1 : (f == 2 ? 0 : 2)), v1 = f == 0 ? 2 : (f == 1 ? 3 : (f == 2 ? 1 : 3));
+              const double flen = hypot(vx[v1] - vx[v0], vy[v1] - vy[v0]);
+              double       loc  = 0.;
+              for (int q = 0; q < 4; ++q)
+                {
+                  const double t = cT.qx[q], w1 = cT.qw[q] / gw0; // 1-D Gauss point / weight
+                  const double xi = f == 0 ? 0. : (f == 1 ? 1. : t), eta = f == 2 ? 0. : (f == 3 ? 1. : t);
+                  double       j00, j01, j10, j11, hx, hy, px, py, sx, cx, sy, cy;
+                  G.jac(xi, eta, j00, j01, j10, j11);
+                  const double det = j00 * j11 - j01 * j10;
+                  d_rt2_combine(g, xi, eta, hx, hy);
+                  const double ux = (j00 * hx + j01 * hy) / det, uy = (j10 * hx + j11 * hy) / det;
+                  // tangent = column of J along the face; outward normal = rotated tangent
+                  const double tx = f < 2 ? j01 : j00, ty = f < 2 ? j11 : j10, tl = sqrt(tx * tx + ty * ty);
+                  double       nx = ty / tl, ny = -tx / tl; // right of the tangent
+                  if (f == 0 || f == 3)
+                    {
+                      nx = -nx;
+                      ny = -ny;
+                    }
+                  G.point(xi, eta, px, py);
+                  sincospi(px, &sx, &cx);
+                  sincospi(py, &sy, &cy);
+                  const double dn = (ux - M_PI * sx * cy) * nx + (uy - M_PI * cx * sy) * ny;
+                  loc += dn * dn * tl * w1;
+                }
+              ef += loc / flen * area;
+            }
+        }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+        {
+          ev += __shfl_xor_sync(0xffffffffu, ev, o);
+          ef += __shfl_xor_sync(0xffffffffu, ef, o);
+        }
+      if ((threadIdx.x & 31) == 0)
+        {
+          atomicAdd(e2, ev);
+          atomicAdd(e2 + 1, ef);
+        }
+    }
   } // namespace
+
+  cudaError_t
+  launch_esm_postprocess(const AsmArgs &a, const double *sol, double *e2, cudaStream_t s)
+  {
+    cudaError_t e = upload_tables();
+    if (e != cudaSuccess)
+      return e;
+    cudaMemsetAsync(e2, 0, 2 * sizeof(double), s);
+    if (a.n_asm == 0)
+      return cudaSuccess;
+    EsmArgs x{};
+    x.n_asm    = a.n_asm;
+    x.vx       = a.vx;
+    x.vy       = a.vy;
+    x.kcell    = a.kcell;
+    x.k_scalar = a.k_scalar;
+    x.cv       = a.cv;
+    x.cdofs    = a.cdofs;
+    k_esm_postprocess<<<(unsigned)((a.n_asm + 63) / 64), 64, 0, s>>>(x, sol, e2);
+    return cudaGetLastError();
+  }
 
   cudaError_t
   launch_esm_assemble(const AsmArgs &a, const int case_id, cudaStream_t s, int *n_launches)

@@ -64,6 +64,8 @@ namespace pe
   cudaError_t launch_esm_assemble(const AsmArgs &a, int case_id, cudaStream_t s, int *n_launches);
   cudaError_t launch_esm_local_matrices(const AsmArgs &a, int case_id, int64_t first, int64_t n, double *out, double *rhs_out,
                                         cudaStream_t s);
+  // postprocess() ESM:662-919: e2[0] = L2_error_vel^2, e2[1] = L2_error_flux^2 of the solution `sol`
+  cudaError_t launch_esm_postprocess(const AsmArgs &a, const double *sol, double *e2, cudaStream_t s);
   cudaError_t launch_esm_boundary_values(int n, const int32_t *dofs, const double *vals, const uint8_t *is_bnd,
                                          const int64_t *rowptr, const int32_t *colidx, double *values, double *rhs,
                                          double *sol, cudaStream_t s);

@@ -340,6 +340,12 @@ class WGDarcyEquation(BiotSystem):
     def solve(self, want_solution=True, check=True):
         return self.solve_time_step(want_solution=want_solution, check=check)
 
+    def postprocess(self):
+        """(L2_error_vel, L2_error_flux) as EltStiffMat.cc prints them (ESM:915-917)"""
+        e = np.zeros(2)
+        self._ck(self.L.pe_darcy_errors(self.h, ptr(e)))
+        return np.sqrt(e)
+
     def run(self, n_refine=1):
         self.make_grid(n_refine)
         self.setup_system()

@@ -181,6 +181,7 @@ class EsmOracle:
         L.orc_esm_local_matrices.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_esm_assemble.restype = C.c_double
         L.orc_esm_assemble.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_esm_postprocess.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         self.h = L.orc_esm_create(n_refine, distort, seed)
         s = np.zeros(5, np.int64)
         L.orc_esm_sizes(self.h, _p(s))
@@ -224,6 +225,13 @@ class EsmOracle:
         v, r, s = np.zeros(self.nnz), np.zeros(self.n_dofs), np.zeros(self.n_dofs)
         sec = self.L.orc_esm_assemble(self.h, _p(v), _p(r), _p(s), 1 if with_boundary_values else 0)
         return v, r, s, sec
+
+    def postprocess(self, sol):
+        """(L2_error_vel^2, L2_error_flux^2) of EltStiffMat.cc postprocess(), ESM:662-919"""
+        sol = np.ascontiguousarray(sol, np.float64)
+        e = np.zeros(2)
+        self.L.orc_esm_postprocess(self.h, _p(sol), _p(e))
+        return e
 
     def csr(self, values):
         import scipy.sparse as sp

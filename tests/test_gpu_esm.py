@@ -123,3 +123,31 @@ def test_local_matrix_equals_exact_rational_derivation():
     b2 = pb.WGDarcyEquation()
     b2.make_grid(5)
     assert rel(b2.local_matrices(777, 1)[0], A) < 1e-12
+
+
+@pytest.mark.parametrize("nref,distort", [(1, 0.0), (3, 0.0), (3, 0.2)])
+def test_postprocess_velocity_and_flux_errors(nref, distort):
+    """postprocess() of EltStiffMat.cc (ESM:662-919): L2_error_vel and L2_error_flux of the Darcy velocity recovered
+    from the discrete weak gradient, CUDA vs the literal oracle on the SAME solution vector (1e-10 relative: sums of
+    squares over all cells), and on the solved system 3 significant digits of what the program prints."""
+    import scipy.sparse.linalg as spla
+    o, b = make(nref, distort)
+    k = np.exp(0.5 * np.random.default_rng(3).normal(size=o.n_cells))
+    o.set_kcell(k)
+    b.set_material(1, 1, 1, 0, 1.0, k)
+    rng = np.random.default_rng(4)
+    x = rng.normal(size=o.n_dofs)
+    b.assemble_system()
+    b.set_solution(x)
+    e_ref = np.sqrt(o.postprocess(x))
+    e = b.postprocess()
+    assert np.all(np.abs(e - e_ref) <= 1e-10 * e_ref), (e, e_ref)
+    # the program as shipped: K = I, solve, print
+    o2, b2 = make(nref, distort)
+    v, r, s, _ = o2.assemble()
+    x_ref = spla.splu(o2.csr(v).tocsc()).solve(r)
+    b2.assemble_system()
+    b2.solve()
+    e2 = b2.postprocess()
+    e2_ref = np.sqrt(o2.postprocess(x_ref))
+    assert np.all(np.abs(e2 - e2_ref) <= 1e-3 * e2_ref), (e2, e2_ref)
