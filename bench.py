@@ -398,6 +398,7 @@ def main():
     ap.add_argument("--chunk-cells", type=int, default=1 << 20, help="config 5: cells per output chunk")
     ap.add_argument("--solver-options", type=int, default=1, help="pe_set_solver_options bit field")
     ap.add_argument("--initial-guess", type=int, default=2, help="pe_set_initial_guess order")
+    ap.add_argument("--recycle", type=int, default=3, help="pe_set_recycling: previous corrections kept (0 = off)")
     ap.add_argument("--krylov", type=int, default=1, help="pe_set_krylov method: 1 = FGMRES + block-triangular P, 0 = MINRES")
     ap.add_argument("--gmres-m", type=int, default=16, help="pe_set_krylov restart length")
     args = ap.parse_args()
@@ -463,6 +464,7 @@ def main():
     b.set_solver_options(args.solver_options)
     b.set_initial_guess(args.initial_guess)
     b.set_krylov(args.krylov, args.gmres_m)
+    b.set_recycling(args.recycle)
     n_cells, n_dofs = s.n_cells, s.n_dofs
     N = 1 << args.n_refine
     zero_state = torch.zeros(s.n_owned_rows if world == 1 else n_dofs, dtype=torch.float64).pin_memory().numpy()

@@ -39,7 +39,7 @@ EXPORTS = [
     "pe_distribute_dofs", "pe_set_dofs", "pe_make_sparsity_pattern", "pe_set_pattern", "pe_get_sizes", "pe_get_owned_ranges",
     "pe_get_mesh", "pe_get_dofs", "pe_get_pattern", "pe_get_dealii_block_order", "pe_set_material",
     "pe_set_lognormal_k", "pe_set_case", "pe_set_boundary", "pe_assemble_system", "pe_assemble_rhs_only",
-    "pe_get_matrix", "pe_get_rhs", "pe_solve_time_step", "pe_set_solver_options", "pe_set_initial_guess", "pe_set_krylov", "pe_set_tuning", "pe_get_solution", "pe_get_solution_global", "pe_set_solution", "pe_spmv",
+    "pe_get_matrix", "pe_get_rhs", "pe_solve_time_step", "pe_set_solver_options", "pe_set_initial_guess", "pe_set_recycling", "pe_set_krylov", "pe_set_tuning", "pe_get_solution", "pe_get_solution_global", "pe_set_solution", "pe_spmv",
     "pe_bench_spmv", "pe_bench_fp64", "pe_local_matrices", "pe_local_matrices_bench", "pe_step_errors", "pe_postprocess", "pe_darcy_errors", "pe_comm_unique_id", "pe_comm_init",
     "pe_get_timings",
 ]
@@ -89,6 +89,7 @@ def load():
         "pe_solve_time_step": [vp, dbl, i32, vp, C.POINTER(pe_solve_stats)],
         "pe_set_solver_options": [vp, i32, dbl, dbl, i32],
         "pe_set_initial_guess": [vp, i32],
+        "pe_set_recycling": [vp, i32],
         "pe_set_krylov": [vp, i32, i32],
         "pe_set_tuning": [vp, C.c_char_p, dbl],
         "pe_get_solution": [vp, vp],

@@ -1019,6 +1019,8 @@ namespace
         {
           h->hist_n    = 1;
           h->hist_t[0] = t - dt;
+          if (h->recycle)
+            h->recycle->k = 0; // a new trajectory (time does not advance): nothing is carried over from the old one
         }
       int n = std::min(h->hist_n, h->extrapolate + 1);
       // usable history: strictly decreasing times, and the new step not much longer than the previous ones
@@ -1092,6 +1094,48 @@ namespace
           return 2;
         c3.n_pos         = k.n_u;
         c3.precond_apply = hook_precond3_tri;
+        // projection space of the previous solves: valid as long as the operator is the same matrix
+        if (h->recycle_k > 0)
+          {
+            const int    kr  = std::min(h->recycle_k, 4);
+            const size_t nr  = (size_t)(2 * kr + 2) * n3;
+            if (!h->recycle)
+              h->recycle = new (std::nothrow) Recycle;
+            if (h->recycle && (h->d_recycle.n < nr || h->recycle->k_max != kr || h->recycle->stride != (int64_t)n3))
+              {
+                if (h->d_recycle.alloc(nr) != cudaSuccess)
+                  return 2;
+                Recycle &R = *h->recycle;
+                R          = Recycle{};
+                R.k_max    = kr;
+                R.stride   = (int64_t)n3;
+                R.D        = h->d_recycle.p;
+                R.Q        = h->d_recycle.p + (size_t)kr * n3;
+                R.x0       = h->d_recycle.p + (size_t)(2 * kr) * n3;
+                R.r0       = h->d_recycle.p + (size_t)(2 * kr + 1) * n3;
+              }
+            if (h->recycle)
+              {
+                // fingerprint of the matrix: data that enter its values (the mesh / pattern generation is in graph_epoch)
+                uint64_t key = 1469598103934665603ull;
+                auto     mix = [&key](const void *p, const size_t n) {
+                  const unsigned char *b = (const unsigned char *)p;
+                  for (size_t i = 0; i < n; ++i)
+                    key = (key ^ b[i]) * 1099511628211ull;
+                };
+                const double fp[7] = {h->lambda, h->mu, h->alpha, h->c0, h->k_scalar, h->last_dt, h->k_sigma};
+                mix(fp, sizeof(fp));
+                mix(&h->k_seed, sizeof(h->k_seed));
+                mix(&h->dofs_epoch, sizeof(h->dofs_epoch));
+                mix(&h->data_epoch, sizeof(h->data_epoch));
+                if (h->recycle->matrix_key != key)
+                  {
+                    h->recycle->k          = 0;
+                    h->recycle->matrix_key = key;
+                  }
+                c3.recycle = h->recycle;
+              }
+          }
         c3.graph_key     = h->graph_epoch * 64 + (uint64_t)m;
         rc = fgmres_solve(c3, b3, x3, h->d_gm.p, h->d_gm.p + (size_t)(m + 1) * n3, (int64_t)n3, h->d_w[0].p, m,
                           h->d_gmres_state.p, h->h_scal, rel_tol, max_iterations, stats);
@@ -1240,6 +1284,8 @@ extern "C"
     h->graphs = nullptr;
     delete h->gmres_graphs;
     h->gmres_graphs = nullptr;
+    delete h->recycle;
+    h->recycle = nullptr;
     for (auto &ev : h->ev_ring)
       if (ev)
         cudaEventDestroy(ev);
@@ -1536,6 +1582,7 @@ extern "C"
     h->c0          = c0;
     h->k_scalar    = k_scalar;
     h->k_lognormal = false;
+    ++h->data_epoch;
     h->matrix_valid = false; // the assembled matrix (and the solver operator built from it) belongs to the old data
     if (k_cell)
       {
@@ -1572,6 +1619,7 @@ extern "C"
   {
     if (!h)
       return PE_ERR_ARG;
+    ++h->data_epoch;
     h->k_lognormal  = true;
     h->k_sigma      = sigma;
     h->k_seed       = seed;
@@ -1603,6 +1651,7 @@ extern "C"
           return fail(h, PE_ERR_ARG, "pe_set_boundary: cell/face out of range");
         h->mesh.face_kinds[4 * (size_t)cell[k] + face[k]] = kinds[k] & 7;
       }
+    ++h->data_epoch;
     h->mesh.traction[0] = traction ? traction[0] : 0.;
     h->mesh.traction[1] = traction ? traction[1] : 0.;
     h->device_ready     = false;
@@ -1698,6 +1747,8 @@ extern "C"
       return r2;
     PE_CUDA(cudaStreamSynchronize(h->stream));
     h->hist_n = 0; // an explicitly set state starts a new trajectory (no extrapolated initial guess across it)
+    if (h->recycle)
+      h->recycle->k = 0;
     return PE_OK;
     PE_CATCH
   }
@@ -1816,6 +1867,17 @@ extern "C"
     if (!h || order < 0 || order > 2)
       return fail(h, PE_ERR_ARG, "pe_set_initial_guess: order must be 0, 1 or 2");
     h->extrapolate = order;
+    return PE_OK;
+  }
+
+  int
+  pe_set_recycling(pe_handle *h, int pairs)
+  {
+    if (!h || pairs < 0 || pairs > 4)
+      return fail(h, PE_ERR_ARG, "pe_set_recycling: 0 .. 4 pairs");
+    h->recycle_k = pairs;
+    if (h->recycle)
+      h->recycle->k = 0;
     return PE_OK;
   }
 

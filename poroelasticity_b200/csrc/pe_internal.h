@@ -20,7 +20,7 @@
 #include <vector>
 
 struct ncclComm;
-namespace pe { struct MgHierarchy; struct BlockPrecond; struct K3System; struct CellMg; struct MinresGraphs; struct GmresGraphs; }
+namespace pe { struct MgHierarchy; struct BlockPrecond; struct K3System; struct CellMg; struct MinresGraphs; struct GmresGraphs; struct Recycle; }
 
 namespace pe
 {
@@ -141,6 +141,7 @@ struct pe_handle
   pe::HostPattern pat;
   bool            have_mesh = false, have_dofs = false, have_pattern = false, device_ready = false;
   bool            matrix_valid = false;
+  uint64_t        data_epoch = 1; // bumped when permeability / boundary data that enter the matrix change
   uint64_t        dofs_epoch = 1, sol_dofs_epoch = 0; // numbering generation / the one d_sol belongs to
   double          lambda = 1., mu = 1., alpha = 1., c0 = 0., k_scalar = 1.;
   std::vector<double> k_cell; // empty = scalar
@@ -202,6 +203,9 @@ struct pe_handle
   pe::GmresGraphs  *gmres_graphs = nullptr;
   int               krylov = 1, gmres_m = 16; // 0 = MINRES + block-diagonal P, 1 = FGMRES(m) + block-triangular P
   pe::DevBuf<double>  d_gm;                    // GMRES basis: (m + 1) v's, m z's
+  pe::DevBuf<double>  d_recycle;               // projection space carried between solves: 2 k_max + 2 vectors
+  pe::Recycle        *recycle = nullptr;
+  int                 recycle_k = 3;           // pairs kept (0 = off)
   pe::DevBuf<uint8_t> d_gmres_state;
   uint64_t          graph_epoch = 1; // bumped whenever buffers or by-value kernel arguments of the iteration change
   double            graph_fp[8] = {};

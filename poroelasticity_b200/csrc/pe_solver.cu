@@ -1069,6 +1069,108 @@ namespace pe
         x[i] = t;
       }
   }
+  // projection onto the recycled pairs: alpha_i = <r0, q_i> (q orthonormal): c = y = alpha
+  __global__ void
+  k_recycle_coeffs(GmresState *st, const int k)
+  {
+    for (int i = 0; i < k; ++i)
+      {
+        st->c[i] = st->d[i];
+        st->y[i] = st->d[i];
+        st->d[i] = 0.;
+      }
+    st->n2 = 0.;
+  }
+  // r -= sum_k c_k q_k in place ; n2 += ||r||^2
+  template <int NV>
+  __global__ void __launch_bounds__(256)
+  k_project_out(const int64_t n, double *r, const double *Q, const int64_t stride, const double *c, double *n2, const Gap gap)
+  {
+    double ck[NV > 0 ? NV : 1];
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+      ck[k] = c[k];
+    double s = 0.;
+    for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < n; l += (int64_t)gridDim.x * blockDim.x)
+      {
+        const int64_t i = phys(l, gap);
+        double        t = r[i];
+#pragma unroll
+        for (int k = 0; k < NV; ++k)
+          t -= ck[k] * Q[(size_t)k * stride + i];
+        r[i] = t;
+        s += t * t;
+      }
+    s = block_sum(s);
+    if (threadIdx.x == 0)
+      atomicAdd(n2, s);
+  }
+  __global__ void
+  k_gmres_beta_from_n2(GmresState *st)
+  {
+    st->beta2 = st->n2;
+    st->n2    = 0.;
+  }
+  // new pair: d = (x - x0 - sum h_i D_i) / nrm, q = (r0 - sum h_i Q_i) / nrm  with h = c (set by k_recycle_new_coeffs)
+  __global__ void
+  k_recycle_new_coeffs(GmresState *st, const int k)
+  {
+    for (int i = 0; i < k; ++i)
+      {
+        st->c[i] = st->d[i];
+        st->d[i] = 0.;
+      }
+    st->n2 = 0.;
+  }
+  template <int NV>
+  __global__ void __launch_bounds__(256)
+  k_recycle_orth(const int64_t n, const double *__restrict__ x, const double *__restrict__ x0, const double *__restrict__ r0,
+                 const double *__restrict__ D, const double *__restrict__ Q, const int64_t stride, const double *__restrict__ c,
+                 double *__restrict__ d_out, double *__restrict__ q_out, double *__restrict__ n2, const Gap gap)
+  {
+    double ck[NV > 0 ? NV : 1];
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+      ck[k] = c[k];
+    double s = 0.;
+    for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < n; l += (int64_t)gridDim.x * blockDim.x)
+      {
+        const int64_t i = phys(l, gap);
+        double        dv = x[i] - x0[i], qv = r0[i];
+#pragma unroll
+        for (int k = 0; k < NV; ++k)
+          {
+            dv -= ck[k] * D[(size_t)k * stride + i];
+            qv -= ck[k] * Q[(size_t)k * stride + i];
+          }
+        d_out[i] = dv;
+        q_out[i] = qv;
+        s += qv * qv;
+      }
+    s = block_sum(s);
+    if (threadIdx.x == 0)
+      atomicAdd(n2, s);
+  }
+  __global__ void
+  k_recycle_scale(const int64_t n, double *__restrict__ d, double *__restrict__ q, const GmresState *__restrict__ st, const Gap gap)
+  {
+    const double inv = st->scratch[2];
+    for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < n; l += (int64_t)gridDim.x * blockDim.x)
+      {
+        const int64_t i = phys(l, gap);
+        d[i] *= inv;
+        q[i] *= inv;
+      }
+  }
+  __global__ void
+  k_recycle_norm(GmresState *st)
+  {
+    const double nv = sqrt(fmax(st->n2, 0.));
+    st->scratch[2]  = nv > 0. ? 1. / nv : 0.;
+    st->scratch[3]  = nv;
+    st->n2          = 0.;
+  }
+
   // start of a cycle: s_0 = 1/||r_0||, g = (||r_0||, 0, ...)
   __global__ void
   k_gmres_begin(GmresState *st)
@@ -1166,6 +1268,37 @@ namespace pe
       else
         GmresLaunch<NV - 1>::xupd(nv, g, s, n, Z, stride, y, x, gap);
     }
+  };
+  constexpr int kRecycleMax = 4;
+  template <int NV>
+  struct RecycleLaunch
+  {
+    static void
+    project(const int nv, const unsigned g, cudaStream_t s, const int64_t n, double *r, const double *Q, const int64_t stride,
+            const double *c, double *n2, const Gap gap)
+    {
+      if (nv == NV)
+        k_project_out<NV><<<g, 256, 0, s>>>(n, r, Q, stride, c, n2, gap);
+      else
+        RecycleLaunch<NV - 1>::project(nv, g, s, n, r, Q, stride, c, n2, gap);
+    }
+    static void
+    orth(const int nv, const unsigned g, cudaStream_t s, const int64_t n, const double *x, const double *x0, const double *r0,
+         const double *D, const double *Q, const int64_t stride, const double *c, double *d_out, double *q_out, double *n2,
+         const Gap gap)
+    {
+      if (nv == NV)
+        k_recycle_orth<NV><<<g, 256, 0, s>>>(n, x, x0, r0, D, Q, stride, c, d_out, q_out, n2, gap);
+      else
+        RecycleLaunch<NV - 1>::orth(nv, g, s, n, x, x0, r0, D, Q, stride, c, d_out, q_out, n2, gap);
+    }
+  };
+  template <>
+  struct RecycleLaunch<-1>
+  {
+    static void project(int, unsigned, cudaStream_t, int64_t, double *, const double *, int64_t, const double *, double *, Gap) {}
+    static void orth(int, unsigned, cudaStream_t, int64_t, const double *, const double *, const double *, const double *,
+                     const double *, int64_t, const double *, double *, double *, double *, Gap) {}
   };
   template <>
   struct GmresLaunch<0>
@@ -1325,6 +1458,28 @@ namespace pe
     double       rn = -1., rn_prev_cycle = -1.;
     bool         give_up = false;
     double       beta    = start_cycle();
+    // ---- projection onto the corrections of the previous solves with this matrix (V[0] = r_0 on entry):
+    // x += sum_i <r_0, q_i> d_i, then the residual is recomputed exactly (the stored q_i equal K d_i only to the
+    // accuracy the previous solves were converged to)
+    Recycle *R = c.recycle;
+    if (R && R->k_max > 0 && beta > 0.)
+      {
+        const size_t nb = sizeof(double) * (size_t)(L + c.H);
+        if (R->k > 0)
+          {
+            GmresLaunch<kGmresMax>::dots(R->k, g, s, L, V, R->Q, R->stride, st->d, c.gap);
+            if (c.allreduce)
+              c.allreduce(c.halo_ctx, st->d, R->k);
+            k_recycle_coeffs<<<1, 1, 0, s>>>(st, R->k);
+            GmresLaunch<kGmresMax>::xupd(R->k, g, s, L, R->D, R->stride, st->y, x, c.gap);
+            if (c.launch_counter)
+              *c.launch_counter += 3;
+            beta = start_cycle();
+          }
+        cudaMemcpyAsync(R->x0, x, nb, cudaMemcpyDeviceToDevice, s);
+        cudaMemcpyAsync(R->r0, V, nb, cudaMemcpyDeviceToDevice, s);
+      }
+    const double beta_first = beta;
     while (!converged && !give_up)
       {
         ++cycles;
@@ -1461,6 +1616,42 @@ namespace pe
         if (converged == 1 && checks == 1 && rn < 0.35 * tol_abs)
           fn = std::min(8., f * 1.4);
         *c.calib = fn;
+      }
+    // ---- the correction of this solve joins the projection space: d = x - x0, q = K d ~ r0 (the final residual is
+    // rel_tol-small against it), orthonormalised against the pairs held
+    if (R && R->k_max > 0 && converged && it > 0 && beta_first > 0.)
+      {
+        // full: drop the oldest pair (slot 0) by shifting the others down -- a subset of orthonormal q_i stays orthonormal
+        if (R->k == R->k_max)
+          {
+            const size_t nb = sizeof(double) * (size_t)(L + c.H);
+            for (int i = 1; i < R->k; ++i)
+              {
+                cudaMemcpyAsync(R->D + (size_t)(i - 1) * R->stride, R->D + (size_t)i * R->stride, nb, cudaMemcpyDeviceToDevice, s);
+                cudaMemcpyAsync(R->Q + (size_t)(i - 1) * R->stride, R->Q + (size_t)i * R->stride, nb, cudaMemcpyDeviceToDevice, s);
+              }
+            R->k -= 1;
+          }
+        double *dn = R->D + (size_t)R->k * R->stride, *qn = R->Q + (size_t)R->k * R->stride;
+        if (R->k > 0)
+          {
+            GmresLaunch<kGmresMax>::dots(R->k, g, s, L, R->r0, R->Q, R->stride, st->d, c.gap);
+            if (c.allreduce)
+              c.allreduce(c.halo_ctx, st->d, R->k);
+          }
+        k_recycle_new_coeffs<<<1, 1, 0, s>>>(st, R->k);
+        RecycleLaunch<kRecycleMax>::orth(R->k, g, s, L, x, R->x0, R->r0, R->D, R->Q, R->stride, st->c, dn, qn, &st->n2, c.gap);
+        if (c.allreduce)
+          c.allreduce(c.halo_ctx, &st->n2, 1);
+        k_recycle_norm<<<1, 1, 0, s>>>(st);
+        cudaMemcpyAsync(h_pinned + 6, &st->scratch[3], sizeof(double), cudaMemcpyDeviceToHost, s);
+        k_recycle_scale<<<g, 256, 0, s>>>(L, dn, qn, st, c.gap);
+        if (c.launch_counter)
+          *c.launch_counter += 5;
+        cudaStreamSynchronize(s);
+        // keep the pair unless it is (numerically) inside the span already
+        if (h_pinned[6] > 1e-8 * beta_first)
+          R->k += 1;
       }
     stats->residual_norm = rn;
     stats->rel_residual  = bnorm > 0. ? rn / bnorm : 0.;

@@ -41,6 +41,17 @@ namespace pe
     ~GmresGraphs();
     void clear();
   };
+  // Projection onto the corrections of the previous solves with the SAME matrix (Fischer 1998: successive right-hand
+  // sides): pairs (d_i, q_i = K d_i) with orthonormal q_i.  Before the first GMRES cycle the initial residual is
+  // projected, x += sum <r0, q_i> d_i; after the solve the new correction is appended (oldest pair dropped).
+  struct Recycle
+  {
+    int      k_max = 0, k = 0, next = 0; // capacity, pairs held, slot of the next pair
+    double  *D = nullptr, *Q = nullptr;  // k_max vectors each, `stride` apart
+    double  *x0 = nullptr, *r0 = nullptr; // iterate / residual after the projection (for the new pair)
+    int64_t  stride = 0;
+    uint64_t matrix_key = 0;             // fingerprint of the operator the pairs belong to
+  };
   struct SolverCtx
   {
     int64_t        L = 0, H = 0;    // owned rows, halo columns
@@ -67,6 +78,7 @@ namespace pe
     double bnorm2 = -1.;        // >= 0: ||b||^2 the stopping test is relative to (else computed from b)
     // optional: *nrm2_dev += ||true residual(x)||^2 of this rank (else b - A x with the ctx matrix)
     void (*true_residual)(void *ctx, const double *x, double *nrm2_dev) = nullptr;
+    Recycle *recycle = nullptr;       // GMRES: projection space carried from solve to solve (null: none)
     void (*on_restart)(void *ctx, double *x) = nullptr; // GMRES: called on the iterate before every cycle
     bool          x0_is_zero = false;  // initial guess known to be zero: ||b||_{P^-1} = the initial eta
     MinresGraphs *graphs     = nullptr; // cache of the captured iteration (null: capture per solve)

@@ -202,6 +202,10 @@ class BiotSystem:
         """1 = FGMRES(restart) + block-triangular preconditioner (default), 0 = MINRES + block-diagonal"""
         self._ck(self.L.pe_set_krylov(self.h, method, restart))
 
+    def set_recycling(self, pairs):
+        """pairs (0..4) of previous corrections the next solves project onto (same matrix only); 0 = off"""
+        self._ck(self.L.pe_set_recycling(self.h, pairs))
+
     def set_initial_guess(self, order):
         """0 = old_solution, 1 / 2 = linear / quadratic extrapolation in time (default 2)"""
         self._ck(self.L.pe_set_initial_guess(self.h, order))
