@@ -398,7 +398,7 @@ def main():
     ap.add_argument("--chunk-cells", type=int, default=1 << 20, help="config 5: cells per output chunk")
     ap.add_argument("--solver-options", type=int, default=1, help="pe_set_solver_options bit field")
     ap.add_argument("--initial-guess", type=int, default=2, help="pe_set_initial_guess order")
-    ap.add_argument("--recycle", type=int, default=3, help="pe_set_recycling: previous corrections kept (0 = off)")
+    ap.add_argument("--recycle", type=int, default=4, help="pe_set_recycling: previous corrections kept (0 = off)")
     ap.add_argument("--krylov", type=int, default=1, help="pe_set_krylov method: 1 = FGMRES + block-triangular P, 0 = MINRES")
     ap.add_argument("--gmres-m", type=int, default=16, help="pe_set_krylov restart length")
     args = ap.parse_args()

@@ -199,8 +199,10 @@ int pe_set_krylov(pe_handle *h, int method, int restart);
  * time does not advance, or after pe_set_solution). */
 int pe_set_initial_guess(pe_handle *h, int order);
 /* Projection onto the corrections of the previous solves with the same matrix (Fischer, successive right-hand sides):
- * `pairs` (0 .. 4, default 3; 0 = off) pairs (d_i, K d_i) are kept on the device; the space is dropped whenever a
- * quantity that enters the matrix changes (mesh, material, time step, permeability, boundary kinds).  GMRES path. */
+ * `pairs` (0 .. 8, default 4; 0 = off) pairs (d_i, K d_i) are kept on the device (when full, the pair that contributed
+ * least to the latest projection is replaced); the space is dropped whenever a quantity that enters the matrix changes
+ * (mesh, material, time step, permeability, boundary kinds) and when a new trajectory starts (pe_set_solution, or the
+ * time does not advance).  GMRES path. */
 int pe_set_recycling(pe_handle *h, int pairs);
 int pe_get_solution(const pe_handle *h, double *solution);
 int pe_set_solution(pe_handle *h, const double *solution);

@@ -1097,7 +1097,7 @@ namespace
         // projection space of the previous solves: valid as long as the operator is the same matrix
         if (h->recycle_k > 0)
           {
-            const int    kr  = std::min(h->recycle_k, 4);
+            const int    kr  = std::min(h->recycle_k, 8);
             const size_t nr  = (size_t)(2 * kr + 2) * n3;
             if (!h->recycle)
               h->recycle = new (std::nothrow) Recycle;
@@ -1873,8 +1873,8 @@ extern "C"
   int
   pe_set_recycling(pe_handle *h, int pairs)
   {
-    if (!h || pairs < 0 || pairs > 4)
-      return fail(h, PE_ERR_ARG, "pe_set_recycling: 0 .. 4 pairs");
+    if (!h || pairs < 0 || pairs > 8)
+      return fail(h, PE_ERR_ARG, "pe_set_recycling: 0 .. 8 pairs");
     h->recycle_k = pairs;
     if (h->recycle)
       h->recycle->k = 0;

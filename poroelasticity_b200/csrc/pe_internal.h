@@ -205,7 +205,7 @@ struct pe_handle
   pe::DevBuf<double>  d_gm;                    // GMRES basis: (m + 1) v's, m z's
   pe::DevBuf<double>  d_recycle;               // projection space carried between solves: 2 k_max + 2 vectors
   pe::Recycle        *recycle = nullptr;
-  int                 recycle_k = 3;           // pairs kept (0 = off)
+  int                 recycle_k = 4;           // pairs kept (0 = off)
   pe::DevBuf<uint8_t> d_gmres_state;
   uint64_t          graph_epoch = 1; // bumped whenever buffers or by-value kernel arguments of the iteration change
   double            graph_fp[8] = {};

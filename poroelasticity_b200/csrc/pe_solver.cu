@@ -1269,7 +1269,7 @@ namespace pe
         GmresLaunch<NV - 1>::xupd(nv, g, s, n, Z, stride, y, x, gap);
     }
   };
-  constexpr int kRecycleMax = 4;
+  constexpr int kRecycleMax = 8;
   template <int NV>
   struct RecycleLaunch
   {
@@ -1471,10 +1471,14 @@ namespace pe
             if (c.allreduce)
               c.allreduce(c.halo_ctx, st->d, R->k);
             k_recycle_coeffs<<<1, 1, 0, s>>>(st, R->k);
+            cudaMemcpyAsync(h_pinned + 24, st->y, sizeof(double) * (size_t)R->k, cudaMemcpyDeviceToHost, s);
             GmresLaunch<kGmresMax>::xupd(R->k, g, s, L, R->D, R->stride, st->y, x, c.gap);
             if (c.launch_counter)
               *c.launch_counter += 3;
-            beta = start_cycle();
+            beta = start_cycle(); // synchronises: the coefficients are on the host
+            for (int i = 0; i < R->k; ++i)
+              R->alpha[i] = std::fabs(h_pinned[24 + i]);
+            R->have_alpha = true;
           }
         cudaMemcpyAsync(R->x0, x, nb, cudaMemcpyDeviceToDevice, s);
         cudaMemcpyAsync(R->r0, V, nb, cudaMemcpyDeviceToDevice, s);
@@ -1621,14 +1625,21 @@ namespace pe
     // rel_tol-small against it), orthonormalised against the pairs held
     if (R && R->k_max > 0 && converged && it > 0 && beta_first > 0.)
       {
-        // full: drop the oldest pair (slot 0) by shifting the others down -- a subset of orthonormal q_i stays orthonormal
+        // full: drop the pair that contributed least to the projection of this solve (smallest |<r_0, q_i>|) by moving
+        // the last pair into its slot -- any subset of the orthonormal q_i stays orthonormal
         if (R->k == R->k_max)
           {
-            const size_t nb = sizeof(double) * (size_t)(L + c.H);
-            for (int i = 1; i < R->k; ++i)
+            int victim = 0;
+            if (R->have_alpha)
+              for (int i = 1; i < R->k; ++i)
+                if (R->alpha[i] < R->alpha[victim])
+                  victim = i;
+            const int    last = R->k - 1;
+            const size_t nb   = sizeof(double) * (size_t)(L + c.H);
+            if (victim != last)
               {
-                cudaMemcpyAsync(R->D + (size_t)(i - 1) * R->stride, R->D + (size_t)i * R->stride, nb, cudaMemcpyDeviceToDevice, s);
-                cudaMemcpyAsync(R->Q + (size_t)(i - 1) * R->stride, R->Q + (size_t)i * R->stride, nb, cudaMemcpyDeviceToDevice, s);
+                cudaMemcpyAsync(R->D + (size_t)victim * R->stride, R->D + (size_t)last * R->stride, nb, cudaMemcpyDeviceToDevice, s);
+                cudaMemcpyAsync(R->Q + (size_t)victim * R->stride, R->Q + (size_t)last * R->stride, nb, cudaMemcpyDeviceToDevice, s);
               }
             R->k -= 1;
           }

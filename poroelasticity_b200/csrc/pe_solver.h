@@ -51,6 +51,8 @@ namespace pe
     double  *x0 = nullptr, *r0 = nullptr; // iterate / residual after the projection (for the new pair)
     int64_t  stride = 0;
     uint64_t matrix_key = 0;             // fingerprint of the operator the pairs belong to
+    double   alpha[8]   = {};            // |<r_0, q_i>| of the latest projection: the least used pair is replaced
+    bool     have_alpha = false;
   };
   struct SolverCtx
   {

@@ -365,7 +365,7 @@ def test_shipped_cantilever_configuration():
     b.time_step = dt
     b.set_material(lam, mu, alpha, c0, kperm)
     b.set_case(pb.PE_CASE_ZERO)
-    b.rel_tol, b.max_iterations = 1e-11, 4000
+    b.rel_tol, b.max_iterations = 1e-12, 4000
     old = np.zeros(o.n_dofs)
     for step in range(2):
         t = dt * (step + 1)
