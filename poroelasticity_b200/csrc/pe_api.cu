@@ -741,7 +741,15 @@ namespace
     ++h->launches;
     if (h->part.world > 1)
       comm_halo_exchange_xi(h, z);
-    precond_apply(*h->bp, *h->mg, *h->cmg, h->d_pinv.p, r, z, h->stream, &h->launches, z);
+    // the pressure rows of the GMRES operator are scaled: P^-1 acts on the unscaled residual
+    const double *rp = nullptr;
+    if (h->k3->p_scaled)
+      {
+        k3_p_vec_scale(*h->k3, true, r, h->bp->t5.p, h->stream);
+        ++h->launches;
+        rp = h->bp->t5.p;
+      }
+    precond_apply(*h->bp, *h->mg, *h->cmg, h->d_pinv.p, r, z, h->stream, &h->launches, z, rp);
   }
   // xi := -lambda W^-1 B u + alpha p_int from the (u, p) part of the iterate
   void
@@ -862,6 +870,8 @@ namespace
                          &h->launches) != 0)
           return 1;
         if (precond_update(*h->bp, k.values0.p, k.diag0.p, extra, s, &h->launches) != 0)
+          return 1;
+        if (gmres && k3_scale_p_rows(k, h->bp->dinv.p, h->mu, s, &h->launches) != 0)
           return 1;
         PE_MARK(s, "setup: multigrid levels + sub-block values");
       }
@@ -1007,6 +1017,11 @@ namespace
     double *b3 = h->d_w[7].p, *x3 = h->d_w[8].p;
     if (k3_make_rhs(k, h->d_rhs.p, h->d_rowptr.p, h->d_colidx.p, h->d_values.p, b3, s) != 0)
       return 1;
+    if (k.p_scaled)
+      {
+        k3_p_vec_scale(k, false, b3, b3, s); // the right-hand side of the row-scaled operator
+        ++h->launches;
+      }
     // initial guess: old_solution (BR1new:2241: the solution of the previous step), or -- when the solutions of the
     // last two / three steps are on the device -- their polynomial extrapolation to the new time, with its
     // consistent xi.  (A direct solver needs no guess; any guess leaves the result of the Krylov solve unchanged
@@ -1147,6 +1162,8 @@ namespace
             // Continue from the GMRES iterate with MINRES on the symmetric (unscaled) K3.
             const pe_solve_stats g = *stats;
             if (k3_fill_values(k, k.lambda_s, k.alpha, h->mu, false, s, &h->launches) != 0)
+              return 1;
+            if (k3_make_rhs(k, h->d_rhs.p, h->d_rowptr.p, h->d_colidx.p, h->d_values.p, b3, s) != 0)
               return 1;
             SolverCtx cm     = make_solver_ctx3(h);
             cm.true_residual = hook_true_residual;

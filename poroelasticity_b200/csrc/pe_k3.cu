@@ -151,6 +151,42 @@ namespace pe
       for (int64_t k = rowptr3[L + i]; k < rowptr3[L + i + 1]; ++k)
         val[k] *= T;
     }
+    // GMRES path: pressure row r (interior and face) scaled by S_r = sqrt(2 mu * dinv_r), dinv_r = 1 / (diagonal of the
+    // pressure block of the preconditioner).  With the xi rows scaled by tau / sqrt(w) every row of the Krylov operator
+    // is then measured in the units of the displacement rows (the 2-norm GMRES minimises approximates the P^-1 norm of
+    // MINRES).  Without it the pressure rows of a stiff, nearly impermeable medium (mu ~ 1e5, dt K ~ 1e-9) are 1e12
+    // times smaller than the rows they couple to and GMRES(m) stagnates on residuals that live in them.
+    __global__ void
+    k_k3_p_scale(const int64_t n, const int64_t pint_begin, const double *__restrict__ dinv, const double two_mu,
+                 double *__restrict__ ps)
+    {
+      const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      if (i < n)
+        {
+          const double d = dinv[pint_begin + i];
+          ps[i]          = d > 0. ? sqrt(two_mu * d) : 1.;
+        }
+    }
+    __global__ void
+    k_k3_scale_p_rows(const int64_t n, const int64_t pint_begin, const int64_t *__restrict__ rowptr3,
+                      const double *__restrict__ ps, double *__restrict__ val)
+    {
+      const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      if (i >= n)
+        return;
+      const double S = ps[i];
+      for (int64_t k = rowptr3[pint_begin + i]; k < rowptr3[pint_begin + i + 1]; ++k)
+        val[k] *= S;
+    }
+    // v[p rows] *= ps  (inverse = 1: v /= ps, written to out)
+    __global__ void
+    k_k3_p_vec_scale(const int64_t n, const int64_t pint_begin, const double *__restrict__ ps, const int inverse,
+                     const double *v, double *out)
+    {
+      const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      if (i < n)
+        out[pint_begin + i] = inverse ? v[pint_begin + i] / ps[i] : v[pint_begin + i] * ps[i];
+    }
     __global__ void
     k_k3_rhs(const Ranges R, const double *__restrict__ rhs, double *__restrict__ b3)
     {
@@ -364,6 +400,7 @@ namespace pe
     k.lambda_s  = lambda_s;
     k.alpha     = alpha;
     k.xi_scaled = scale_xi_rows;
+    k.p_scaled  = false;
     k.xi_tau    = scale_xi_rows ? 1. / (1. / lambda_s + 1. / (2. * mu)) : 0.;
     if (k.nnz > 0)
       k_k3_gather<<<gb(k.nnz), 256, 0, s>>>(k.nnz, k.nnz_u, k.src.p, k.values0.p, k.val.p);
@@ -389,6 +426,30 @@ namespace pe
     if (k.n_con > 0)
       k_k3_rhs_con<<<gb(k.n_con), 256, 0, s>>>(k.n_con, k.con_rows.p, rhs, rowptr, colidx, values_a, k.diag0.p, b3);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  }
+
+  int
+  k3_scale_p_rows(K3System &k, const double *dinv, const double mu, cudaStream_t s, int64_t *launches)
+  {
+    const int64_t n = k.L - k.pint_begin;
+    k.p_scaled      = false;
+    if (n <= 0)
+      return 0;
+    if (k.p_scale.n < (size_t)n && k.p_scale.alloc((size_t)n) != cudaSuccess)
+      return -1;
+    k_k3_p_scale<<<gb(n), 256, 0, s>>>(n, k.pint_begin, dinv, 2. * mu, k.p_scale.p);
+    k_k3_scale_p_rows<<<gb(n), 256, 0, s>>>(n, k.pint_begin, k.rowptr.p, k.p_scale.p, k.val.p);
+    *launches += 2;
+    k.p_scaled = true;
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  }
+  // out[p rows] = v[p rows] * S (inverse: / S); other entries of out are not touched
+  void
+  k3_p_vec_scale(const K3System &k, const bool inverse, const double *v, double *out, cudaStream_t s)
+  {
+    const int64_t n = k.L - k.pint_begin;
+    if (n > 0 && k.p_scaled)
+      k_k3_p_vec_scale<<<gb(n), 256, 0, s>>>(n, k.pint_begin, k.p_scale.p, inverse ? 1 : 0, v, out);
   }
 
   int

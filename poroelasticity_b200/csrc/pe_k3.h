@@ -29,6 +29,8 @@ namespace pe
     bool    built = false, values_valid = false;
     bool    xi_scaled = false; // xi rows of val multiplied by xi_tau / sqrt(w) (GMRES path; MINRES needs the symmetric K3)
     double  xi_tau = 0.;       // 1 / (1/lambda_s + 1/(2 mu)), 0 when the rows are not scaled
+    bool    p_scaled = false;  // pressure rows of val multiplied by p_scale (GMRES path)
+    DevBuf<double> p_scale;    // [L - pint_begin]
     int64_t L = 0, H = 0, Lx = 0, Hx = 0;
     int64_t n_u = 0, pint_begin = 0, pint_end = 0, hu_end = 0, hpi_end = 0;
     int64_t nnz = 0, nnz_u = 0, n_rowblk = 0, n_con = 0;
@@ -47,6 +49,10 @@ namespace pe
   // values: once per assembled matrix.  values0 = A0 (same CSR as the reference pattern).
   int k3_fill_values(K3System &k, double lambda_s, double alpha, double mu, bool scale_xi_rows, cudaStream_t s,
                      int64_t *launches);
+  // GMRES path: scale the pressure rows of val by sqrt(2 mu dinv) (dinv: inverse diagonal of the pressure block of the
+  // preconditioner, local row index); the right-hand side / preconditioner input are scaled with k3_p_vec_scale
+  int  k3_scale_p_rows(K3System &k, const double *dinv, double mu, cudaStream_t s, int64_t *launches);
+  void k3_p_vec_scale(const K3System &k, bool inverse, const double *v, double *out, cudaStream_t s);
   // b3 = (b_u [constrained rows rescaled to the A0 diagonal] | -b_p | 0)
   int k3_make_rhs(const K3System &k, const double *rhs, const int64_t *rowptr, const int32_t *colidx, const double *values_a,
                   double *b3, cudaStream_t s);

@@ -337,7 +337,7 @@ namespace pe
     cudaMemcpyAsync(bp.pint_rows.p, pint_rows.data(), pint_rows.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s);
     cudaMemcpyAsync(bp.pint_area.p, area_of_pint.data(), area_of_pint.size() * sizeof(double), cudaMemcpyHostToDevice, s);
     if (bp.t.alloc((size_t)LH) != cudaSuccess || bp.t2.alloc((size_t)LH) != cudaSuccess || bp.dinv.alloc((size_t)LH) != cudaSuccess ||
-        bp.t3.alloc((size_t)LH) != cudaSuccess || bp.wdinv.alloc((size_t)LH) != cudaSuccess || bp.t4.alloc((size_t)LH) != cudaSuccess)
+        bp.t3.alloc((size_t)LH) != cudaSuccess || bp.wdinv.alloc((size_t)LH) != cudaSuccess || bp.t4.alloc((size_t)LH) != cudaSuccess || bp.t5.alloc((size_t)LH) != cudaSuccess)
       return -1;
     cudaMemsetAsync(bp.t4.p, 0, sizeof(double) * (size_t)LH, s);
     cudaMemsetAsync(bp.t3.p, 0, sizeof(double) * (size_t)LH, s);
@@ -416,8 +416,9 @@ namespace pe
   //   P = [ P_u  -B^T  0 ; 0  P_xi  0 ; 0  0  P_p ]   of the row-signed system (pe_solver.cu, FGMRES)
   void
   precond_apply(BlockPrecond &bp, MgHierarchy &mg, CellMg &cm, const double *pinv, const double *r, double *z,
-                cudaStream_t s, int64_t *launches, const double *z_xi)
+                cudaStream_t s, int64_t *launches, const double *z_xi, const double *rp_in)
   {
+    const double *rp = rp_in ? rp_in : r; // pressure part of the input (row-scaled GMRES operator: unscaled copy)
     MgLevel      &L0 = mg.lv[0];
     const int     N  = L0.N, nv = (N + 1) * (N + 1);
     const int64_t L  = bp.n;
@@ -436,7 +437,7 @@ namespace pe
       }
     // local Jacobi parts:  u: z = pinv r, t = y1 on bubbles;  p_int: t_i = dinv_i r_i
     k_pre_u<<<gb(bp.n_u, 256), 256, 0, s>>>(bp.n_u, bp.cls.p, pinv, ru, bp.t.p, z);
-    k_pre_p<<<gb(bp.n_pint), 128, 0, s>>>(bp.n_pint, bp.pint_rows.p, bp.dinv.p, r, bp.t.p);
+    k_pre_p<<<gb(bp.n_pint), 128, 0, s>>>(bp.n_pint, bp.pint_rows.p, bp.dinv.p, rp, bp.t.p);
     *launches += 2;
     if (bp.halo)
       bp.halo(bp.comm_ctx, bp.t.p);
@@ -485,7 +486,7 @@ namespace pe
     if (fork && bp.set_lane)
       bp.set_lane(bp.comm_ctx, 1); // communication of the pressure pipeline: lane 1
     // g = r_f - S_fi D_i^{-1} r_i   -> t2 (face entries)
-    sub(sp, bp.Sfi, bp.t.p, nullptr, nullptr, r, bp.t2.p);
+    sub(sp, bp.Sfi, bp.t.p, nullptr, nullptr, rp, bp.t2.p);
     // y1 = omega dinvF g            -> t (face entries)
     k_face_scale<<<gb(bp.Sfi.n_rows), 128, 0, sp>>>(bp.Sfi.n_rows, bp.Sfi.rows.p, bp.wdinv.p, bp.t2.p, bp.t.p);
     ++*launches;
@@ -523,7 +524,7 @@ namespace pe
       sub(s, bp.Abu, bp.t.p, bp.t.p, pinv, ru, z);
     halo_p(z); // face pressures of the neighbours
     // z_i = dinv_i (r_i - S_if z_f)
-    sub(sp, bp.Sif, z, nullptr, bp.dinv.p, r, z);
+    sub(sp, bp.Sif, z, nullptr, bp.dinv.p, rp, z);
     PE_MARK(sp, "precond: face Schur products");
     if (fork && bp.set_lane)
       bp.set_lane(bp.comm_ctx, 0);

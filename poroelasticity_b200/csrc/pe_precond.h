@@ -40,7 +40,7 @@ namespace pe
     SubCsr          Bt;                      // -B^T: displacement rows x xi columns (three-field physical indices)
     DevBuf<uint8_t> cls;
     DevBuf<int32_t> pint_rows;
-    DevBuf<double>  pint_area, t, t2, t3, t4, dinv, wdinv; // wdinv = omega_F / diag(F) on the face rows
+    DevBuf<double>  pint_area, t, t2, t3, t4, t5, dinv, wdinv; // wdinv = omega_F / diag(F) on the face rows
     double          omega_f = 0.65;
     const double   *values = nullptr;
     // single GPU: the pressure pipeline runs on a forked stream beside the displacement V-cycle
@@ -53,5 +53,5 @@ namespace pe
   int  precond_update(BlockPrecond &bp, const double *values, const double *diag, double gamma, cudaStream_t s,
                       int64_t *launches);
   void precond_apply(BlockPrecond &bp, MgHierarchy &mg, CellMg &cm, const double *pinv, const double *r, double *z,
-                     cudaStream_t s, int64_t *launches, const double *z_xi = nullptr);
+                     cudaStream_t s, int64_t *launches, const double *z_xi = nullptr, const double *rp = nullptr);
 } // namespace pe

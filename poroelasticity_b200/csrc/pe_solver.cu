@@ -15,6 +15,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 namespace pe
@@ -1484,6 +1485,10 @@ namespace pe
         cudaMemcpyAsync(R->r0, V, nb, cudaMemcpyDeviceToDevice, s);
       }
     const double beta_first = beta;
+    static const bool dbg = getenv("PE_DEBUG_SOLVER") != nullptr; // tracing aid only
+    if (dbg)
+      std::fprintf(stderr, "[fgmres] start: beta %.3e bnorm %.3e tol_abs %.3e f %.3e recycle k %d\n", beta, bnorm, tol_abs, f,
+                   R ? R->k : -1);
     while (!converged && !give_up)
       {
         ++cycles;
@@ -1538,9 +1543,13 @@ namespace pe
         if (c.launch_counter)
           *c.launch_counter += 2;
         const double est = h_eta[(it - 1) % kRing];
+        if (dbg)
+          std::fprintf(stderr, "[fgmres] cycle %d: j %d it %d beta %.3e est %.3e target %.3e\n", cycles, j, it, beta, est, target);
         if (est <= target)
           {
             rn = true_residual();
+            if (dbg)
+              std::fprintf(stderr, "[fgmres]   true residual %.3e (tol_abs %.3e)\n", rn, tol_abs);
             ++checks;
             if (rn <= tol_abs)
               {
@@ -1559,14 +1568,11 @@ namespace pe
                 cudaStreamSynchronize(s);
                 const double xnorm = std::sqrt(std::fmax(h_pinned[5], 0.));
                 const double anorm = c.anorm ? c.anorm(c.precond_ctx) : 0.;
-                if (anorm > 0. && rn <= 64. * 2.220446049250313e-16 * (anorm * xnorm + bnorm))
-                  {
-                    converged = 2;
-                    break;
-                  }
+                (void)xnorm;
+                (void)anorm;
                 if (stall >= 3)
                   {
-                    give_up = true;
+                    give_up = true; // the caller continues with MINRES, which owns the rounding-floor decision
                     break;
                   }
               }
@@ -1599,10 +1605,9 @@ namespace pe
                     cudaStreamSynchronize(s);
                     const double xnorm = std::sqrt(std::fmax(h_pinned[5], 0.));
                     const double anorm = c.anorm ? c.anorm(c.precond_ctx) : 0.;
-                    if (anorm > 0. && rn <= 64. * 2.220446049250313e-16 * (anorm * xnorm + bnorm))
-                      converged = 2;
-                    else
-                      give_up = true;
+                    (void)xnorm;
+                    (void)anorm;
+                    give_up = true; // the caller continues with MINRES, which owns the rounding-floor decision
                   }
               }
           }
@@ -1614,6 +1619,8 @@ namespace pe
       rn = true_residual();
     if (converged == 0 && rn <= tol_abs)
       converged = 1;
+    if (!converged && R)
+      R->k = 0; // a stagnating solve leaves nothing worth projecting onto
     if (c.calib)
       {
         double fn = f;
