@@ -1344,6 +1344,8 @@ namespace pe
       return -1;
     double *h_eta = h_pinned + 8;
     constexpr int kRing = 16;
+    const int64_t n_err = c.floor_rows > 0 ? c.floor_rows : L; // unknowns of the reference system: (u, p)
+    double        xnorm = 0.;
     cudaMemsetAsync(st, 0, sizeof(GmresState), s);
     // r_0 = D (b - K x) into V[0], ||r_0||^2 into beta2
     auto start_cycle = [&]() {
@@ -1362,9 +1364,16 @@ namespace pe
         c.allreduce(c.halo_ctx, &st->beta2, 1);
       cudaMemcpyAsync(h_pinned + 1, &st->beta2, sizeof(double), cudaMemcpyDeviceToHost, s);
       k_gmres_begin<<<1, 1, 0, s>>>(st);
+      // ||x|| of the unknowns of the reference system (error-estimate test below)
+      cudaMemsetAsync(&st->scratch[1], 0, sizeof(double), s);
+      k_norm2<<<g, 256, 0, s>>>(n_err, x, &st->scratch[1], c.gap);
+      if (c.allreduce)
+        c.allreduce(c.halo_ctx, &st->scratch[1], 1);
+      cudaMemcpyAsync(h_pinned + 5, &st->scratch[1], sizeof(double), cudaMemcpyDeviceToHost, s);
       if (c.launch_counter)
-        *c.launch_counter += 3;
+        *c.launch_counter += 4;
       cudaStreamSynchronize(s);
+      xnorm = std::sqrt(std::fmax(h_pinned[5], 0.));
       return std::sqrt(std::fmax(h_pinned[1], 0.));
     };
     const double bnorm = c.bnorm2 >= 0. ? std::sqrt(c.bnorm2) : 0.;
@@ -1453,6 +1462,8 @@ namespace pe
           }
       }
     const double tol_abs = rel_tol * bnorm;
+    const double tol_x   = 10. * rel_tol;
+    double       err_start = 0., err_target_res = 1e300;
     double       f       = (c.calib && *c.calib > 0.) ? *c.calib : 1.;
     double       target  = f * tol_abs;
     int          it = 0, converged = 0, checks = 0, cycles = 0, stall = 0, slow = 0;
@@ -1513,6 +1524,18 @@ namespace pe
                   }
                 else
                   iteration(j);
+                if (j == 0)
+                  {
+                    // ||P^-1 r_start|| over the (u, p) unknowns: P^-1 ~ K^-1, so this estimates the ERROR of the
+                    // iterate the cycle starts from (z~_0 = P^-1 v~_0 with the unnormalised v~_0 = r_start)
+                    cudaMemsetAsync(&st->scratch[2], 0, sizeof(double), s);
+                    k_norm2<<<g, 256, 0, s>>>(n_err, Z, &st->scratch[2], c.gap);
+                    if (c.allreduce)
+                      c.allreduce(c.halo_ctx, &st->scratch[2], 1);
+                    cudaMemcpyAsync(h_pinned + 7, &st->scratch[2], sizeof(double), cudaMemcpyDeviceToHost, s);
+                    if (c.launch_counter)
+                      *c.launch_counter += 1;
+                  }
                 cudaMemcpyAsync(h_eta + (it % kRing), &st->res, sizeof(double), cudaMemcpyDeviceToHost, s);
                 cudaEventRecord(c.ev_ring[it % kRing], s);
                 ++j;
@@ -1523,6 +1546,17 @@ namespace pe
             if (cudaEventSynchronize(c.ev_ring[(it0 + tested) % kRing]) != cudaSuccess)
               return -1;
             const double res = h_eta[(it0 + tested) % kRing];
+            if (tested == 0)
+              {
+                // error-estimate target of this cycle: a residual reduction by rho reduces the error by ~ rho (the
+                // preconditioned operator is well conditioned), so the cycle must reach
+                //     ||P^-1 r_start|| * res / beta <= tol_x ||x||,   tol_x = 10 rel_tol
+                // (north_star: per-step u and p within 1e-8 of the direct solve -- a small TRUE RESIDUAL alone does not
+                // bound the error of smooth components: sigma_min(A) ~ 1e-7 on 4096^2)
+                err_start = std::sqrt(std::fmax(h_pinned[7], 0.));
+                const double xn = xnorm > 0. ? xnorm : err_start;
+                err_target_res = err_start > 0. ? beta * (0.5 * tol_x * xn / err_start) : 1e300;
+              }
             ++tested;
             if (!(res == res))
               {
@@ -1531,7 +1565,7 @@ namespace pe
               }
             // end the cycle: target reached, or deep enough for classical Gram-Schmidt (loss of orthogonality
             // ~ (||r_0|| / ||r_j||)^2 eps: 1e-2 at a reduction of 1e-7; the true residual is recomputed at every restart)
-            if (res <= target || res <= 1e-7 * beta)
+            if (res <= std::min(target, err_target_res) || res <= 1e-7 * beta)
               hit = true;
           }
         if (give_up)
@@ -1545,7 +1579,11 @@ namespace pe
         const double est = h_eta[(it - 1) % kRing];
         if (dbg)
           std::fprintf(stderr, "[fgmres] cycle %d: j %d it %d beta %.3e est %.3e target %.3e\n", cycles, j, it, beta, est, target);
-        if (est <= target)
+        const bool err_ok = est <= err_target_res * 2.; // error estimate within tol_x ||x|| (0.5 margin above)
+        if (dbg)
+          std::fprintf(stderr, "[fgmres]   error estimate %.3e of ||x|| %.3e (needs <= %.1e)\n",
+                       err_start * est / (beta > 0. ? beta : 1.), xnorm, tol_x);
+        if (est <= target && err_ok)
           {
             rn = true_residual();
             if (dbg)
@@ -1630,7 +1668,7 @@ namespace pe
       }
     // ---- the correction of this solve joins the projection space: d = x - x0, q = K d ~ r0 (the final residual is
     // rel_tol-small against it), orthonormalised against the pairs held
-    if (R && R->k_max > 0 && converged && it > 0 && beta_first > 0.)
+    if (R && R->k_max > 0 && converged && it >= 3 && beta_first > 0.)
       {
         // full: drop the pair that contributed least to the projection of this solve (smallest |<r_0, q_i>|) by moving
         // the last pair into its slot -- any subset of the orthonormal q_i stays orthonormal
