@@ -826,6 +826,7 @@ namespace
     a.sol                 = nullptr;
     int nl                = 0;
     cudaError_t e;
+    NvtxRange nvtx("solver operator: A0, K3, preconditioner");
     PE_MARK(s, "setup: (start)");
     e = run_assembly(h, a, P, &nl);
     h->launches += nl;
@@ -1678,6 +1679,7 @@ extern "C"
   int
   pe_assemble_system(pe_handle *h, double t, double time_step, const double *old_solution)
   {
+    NvtxRange nvtx("pe_assemble_system");
     if (!h)
       return PE_ERR_ARG;
     PE_DEVICE(h);
@@ -1958,6 +1960,7 @@ extern "C"
   int
   pe_solve_time_step(pe_handle *h, double rel_tol, int max_iterations, double *solution, pe_solve_stats *stats)
   {
+    NvtxRange nvtx("pe_solve_time_step");
     if (!h || !h->device_ready || !h->matrix_valid)
       return fail(h, PE_ERR_ARG, "pe_solve_time_step: assemble first");
     PE_DEVICE(h);

@@ -3,6 +3,7 @@
 // graph (multi-GPU default, or solver option bit 6).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h> // header-only NVTX v3: ranges show up in nsys / ncu --nvtx timelines, no-ops otherwise
 
 #include <cstdio>
 #include <cstdlib>
@@ -87,4 +88,10 @@ namespace pe
     }
   };
 #define PE_MARK(stream, name) ::pe::PhaseTimer::get().mark(stream, name)
+  // NVTX range over one C-ABI call (assemble_system, solve_time_step, ...)
+  struct NvtxRange
+  {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+  };
 } // namespace pe
