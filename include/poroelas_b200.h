@@ -58,7 +58,7 @@ enum {
 
 typedef struct pe_config {
   int32_t element;    /* pe_element */
-  int32_t dim;        /* 2 (3-D is SURVEY 8(f) "next") */
+  int32_t dim;        /* 2; 3 = CGQ1-WG on hexahedra, cell loop only (pe_make_unit_cube, pe_set_mesh3, pe_local_matrices3) */
   int32_t device;     /* CUDA device ordinal; -1 = current device */
   int32_t rank;       /* this process's rank in the mesh partition (0 if world_size == 1) */
   int32_t world_size; /* number of GPUs / processes the mesh is partitioned over */
@@ -109,6 +109,21 @@ int pe_make_unit_square(pe_handle *h, int n_refine, double distort, uint64_t see
  * AoS (xy_stride = 1 or 2) and cell->vertex_index(v), 4 per cell, active-cell order. */
 int pe_set_mesh(pe_handle *h, int64_t n_vertices, const double *x, const double *y, int64_t xy_stride,
                 int64_t n_cells, const uint32_t *cell_vertices);
+
+/* ---- three dimensions (first step): the shipped main() of PoroElasCGQ1_WG.cc is the 3-D program
+ * (CGQ1:3029; hyper_cube + refine_global(3), CGQ1:886-887).  A dim = 3 handle holds a hexahedral mesh (active cells in
+ * deal.II's 3-D Morton order, cell vertex v at offset (v & 1, (v >> 1) & 1, v >> 2)) and runs the CELL LOOP of
+ * assemble_system (CGQ1:1165-1453): dense 31 x 31 local matrices out[n][31][31] and right-hand sides rhs_out[n][31]
+ * for f = s = 0 (the sandwich problem), local dof order 3 v + c | 24 + face | 30 = p_int; cell_old = the 31 old-solution
+ * values of every cell (may be NULL).  Numbering, scatter and solve in 3-D are not built yet: every other hot-path
+ * call on a dim = 3 handle fails with PE_ERR_ARG. */
+int pe_make_unit_cube(pe_handle *h, int n_refine, double distort, uint64_t seed);
+int pe_set_mesh3(pe_handle *h, int64_t n_vertices, const double *x, const double *y, const double *z, int64_t n_cells,
+                 const uint32_t *cell_vertices);
+int pe_get_mesh3(const pe_handle *h, int64_t *n_vertices, int64_t *n_cells, double *x, double *y, double *z,
+                 uint32_t *cell_vertices);
+int pe_local_matrices3(pe_handle *h, int64_t first_cell, int64_t n, double time_step, const double *cell_old, double *out,
+                       double *rhs_out);
 
 /* ---- S2: DoFs.  distribute_dofs + DoFRenumbering::component_wise  BR1new:586-597 CGQ1:902-919 */
 int pe_distribute_dofs(pe_handle *h);

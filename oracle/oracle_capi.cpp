@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE ONLY -- C entry points onto the oracle for ctypes (tests/, smoke(), bench.py
 // cpu_baseline / --impl reference).  Never linked into or loaded by poroelasticity_b200.
 #include "esm_oracle.hpp"
+#include "poro_oracle_3d.hpp"
 #include "poro_oracle.hpp"
 
 #include <chrono>
@@ -323,5 +324,61 @@ extern "C"
     esm::Problem       *P = (esm::Problem *)h;
     std::vector<double> s(solution, solution + P->n_dofs);
     esm::postprocess(*P, s, e2);
+  }
+  // ---- 3-D CGQ1-WG cell loop (poro_oracle_3d.hpp)
+  void *
+  orc3_create(int n_refine, double distort, std::uint64_t seed)
+  {
+    d3::Problem3 *P = new d3::Problem3;
+    P->mesh         = d3::make_unit_cube(n_refine, distort, seed);
+    P->kcell.assign(P->mesh.n_cells(), 1.);
+    return P;
+  }
+  void
+  orc3_destroy(void *h)
+  {
+    delete (d3::Problem3 *)h;
+  }
+  void
+  orc3_sizes(void *h, std::int64_t *s)
+  {
+    d3::Problem3 *P = (d3::Problem3 *)h;
+    s[0]            = P->mesh.n_cells();
+    s[1]            = (std::int64_t)P->mesh.x.size();
+  }
+  void
+  orc3_get_mesh(void *h, double *x, double *y, double *z, std::uint32_t *cv)
+  {
+    d3::Problem3 *P = (d3::Problem3 *)h;
+    std::copy(P->mesh.x.begin(), P->mesh.x.end(), x);
+    std::copy(P->mesh.y.begin(), P->mesh.y.end(), y);
+    std::copy(P->mesh.z.begin(), P->mesh.z.end(), z);
+    std::copy(P->mesh.cell_vertices.begin(), P->mesh.cell_vertices.end(), cv);
+  }
+  void
+  orc3_set_material(void *h, double lambda, double mu, double alpha, double c0, double dt)
+  {
+    d3::Problem3 *P = (d3::Problem3 *)h;
+    P->lambda       = lambda;
+    P->mu           = mu;
+    P->alpha        = alpha;
+    P->capacity     = c0;
+    P->time_step    = dt;
+  }
+  void
+  orc3_set_kcell(void *h, const double *k)
+  {
+    d3::Problem3 *P = (d3::Problem3 *)h;
+    P->kcell.assign(k, k + P->mesh.n_cells());
+  }
+  // local matrix [31][31] and rhs [31] of cell c; cell_old = the 31 old-solution values of the cell
+  void
+  orc3_local(void *h, int c, const double *cell_old, double *A, double *b)
+  {
+    d3::Problem3       *P = (d3::Problem3 *)h;
+    std::vector<double> o(cell_old, cell_old + d3::kNLoc), Av, bv;
+    d3::assemble_cell(*P, c, o, Av, bv);
+    std::copy(Av.begin(), Av.end(), A);
+    std::copy(bv.begin(), bv.end(), b);
   }
 }

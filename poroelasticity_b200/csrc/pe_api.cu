@@ -1217,7 +1217,8 @@ extern "C"
     if (!out || !cfg)
       return PE_ERR_ARG;
     *out = nullptr;
-    if (cfg->element < 0 || cfg->element > 2 || (cfg->dim != 2 && cfg->dim != 0))
+    // dim 3: CGQ1-WG on hexahedra, local matrices only (pe_make_unit_cube / pe_set_mesh3 / pe_local_matrices3)
+    if (cfg->element < 0 || cfg->element > 2 || (cfg->dim != 2 && cfg->dim != 0 && !(cfg->dim == 3 && cfg->element == PE_CGQ1_WG)))
       return PE_ERR_ARG;
     const bool  host_only = (cfg->flags & PE_CFG_HOST_SETUP_ONLY) != 0;
     int         n_dev     = 0;
@@ -1345,6 +1346,164 @@ extern "C"
   catch (const std::exception &ex)                                   \
   {                                                                  \
     return fail(h, PE_ERR_ARG, ex.what());                           \
+  }
+
+  int
+  pe_make_unit_cube(pe_handle *h, int n_refine, double distort, uint64_t seed)
+  {
+    if (!h || h->cfg.dim != 3 || n_refine < 0 || n_refine > 8)
+      return fail(h, PE_ERR_ARG, "pe_make_unit_cube: needs a dim = 3 handle, 0 <= n_refine <= 8");
+    PE_TRY
+    // GridGenerator::hyper_cube(0,1) + refine_global(n) (CGQ1:886-887): active cells in 3-D Morton order (child c of a
+    // cell at (c & 1, (c >> 1) & 1, c >> 2)), vertices lexicographic, cell vertex v at offset (v & 1, (v >> 1) & 1, v >> 2)
+    auto        &m = h->mesh3;
+    const int    N = 1 << n_refine, V = N + 1;
+    const double hh = 1. / N;
+    m.x.resize((size_t)V * V * V);
+    m.y.resize(m.x.size());
+    m.z.resize(m.x.size());
+    for (int k = 0; k < V; ++k)
+      for (int j = 0; j < V; ++j)
+        for (int i = 0; i < V; ++i)
+          {
+            const size_t id = ((size_t)k * V + j) * V + i;
+            double       x = i * hh, y = j * hh, z = k * hh;
+            if (distort > 0. && i > 0 && i < N && j > 0 && j < N && k > 0 && k < N)
+              {
+                x += distort * hh * (2. * u01(seed, id, 0) - 1.);
+                y += distort * hh * (2. * u01(seed, id, 1) - 1.);
+                z += distort * hh * (2. * u01(seed, id, 2) - 1.);
+              }
+            m.x[id] = x;
+            m.y[id] = y;
+            m.z[id] = z;
+          }
+    m.n_cells = (int64_t)N * N * N;
+    m.cell_vertices.resize((size_t)8 * m.n_cells);
+    for (int64_t c = 0; c < m.n_cells; ++c)
+      {
+        uint32_t ix = 0, iy = 0, iz = 0;
+        for (int b = 0; b < 10; ++b)
+          {
+            ix |= (uint32_t)((c >> (3 * b)) & 1) << b;
+            iy |= (uint32_t)((c >> (3 * b + 1)) & 1) << b;
+            iz |= (uint32_t)((c >> (3 * b + 2)) & 1) << b;
+          }
+        for (int v = 0; v < 8; ++v)
+          m.cell_vertices[(size_t)8 * c + v] =
+            (uint32_t)((((size_t)iz + (v >> 2)) * V + iy + ((v >> 1) & 1)) * V + ix + (v & 1));
+      }
+    return PE_OK;
+    PE_CATCH
+  }
+
+  int
+  pe_set_mesh3(pe_handle *h, int64_t n_vertices, const double *x, const double *y, const double *z, int64_t n_cells,
+               const uint32_t *cell_vertices)
+  {
+    if (!h || h->cfg.dim != 3 || !x || !y || !z || !cell_vertices || n_vertices <= 0 || n_cells <= 0)
+      return fail(h, PE_ERR_ARG, "pe_set_mesh3: bad argument");
+    PE_TRY
+    auto &m = h->mesh3;
+    m.x.assign(x, x + n_vertices);
+    m.y.assign(y, y + n_vertices);
+    m.z.assign(z, z + n_vertices);
+    m.cell_vertices.assign(cell_vertices, cell_vertices + 8 * (size_t)n_cells);
+    for (const uint32_t v : m.cell_vertices)
+      if ((int64_t)v >= n_vertices)
+        return fail(h, PE_ERR_ARG, "pe_set_mesh3: vertex index out of range");
+    m.n_cells = n_cells;
+    return PE_OK;
+    PE_CATCH
+  }
+
+  int
+  pe_get_mesh3(const pe_handle *h, int64_t *n_vertices, int64_t *n_cells, double *x, double *y, double *z, uint32_t *cell_vertices)
+  {
+    if (!h || h->cfg.dim != 3)
+      return PE_ERR_ARG;
+    const auto &m = h->mesh3;
+    if (n_vertices)
+      *n_vertices = (int64_t)m.x.size();
+    if (n_cells)
+      *n_cells = m.n_cells;
+    if (x)
+      std::copy(m.x.begin(), m.x.end(), x);
+    if (y)
+      std::copy(m.y.begin(), m.y.end(), y);
+    if (z)
+      std::copy(m.z.begin(), m.z.end(), z);
+    if (cell_vertices)
+      std::copy(m.cell_vertices.begin(), m.cell_vertices.end(), cell_vertices);
+    return PE_OK;
+  }
+
+  int
+  pe_local_matrices3(pe_handle *h, int64_t first_cell, int64_t n, double time_step, const double *cell_old, double *out,
+                     double *rhs_out)
+  {
+    if (!h || h->cfg.dim != 3 || !out || n <= 0 || first_cell < 0 || first_cell + n > h->mesh3.n_cells)
+      return fail(h, PE_ERR_ARG, "pe_local_matrices3: bad argument (dim = 3 handle with a mesh)");
+    if (h->device < 0)
+      return fail(h, PE_ERR_NO_DEVICE, "no hot path without a GPU");
+    PE_DEVICE(h);
+    PE_TRY
+    cudaStream_t     s  = h->stream;
+    const auto      &m  = h->mesh3;
+    const int64_t    nc = m.n_cells;
+    DevBuf<double>   x, y, z, kc, o, ro, old;
+    DevBuf<uint32_t> cv;
+    PE_CUDA(upload(x, m.x.data(), m.x.size(), s));
+    PE_CUDA(upload(y, m.y.data(), m.y.size(), s));
+    PE_CUDA(upload(z, m.z.data(), m.z.size(), s));
+    {
+      std::vector<uint32_t> cvh((size_t)8 * nc);
+      for (int64_t c = 0; c < nc; ++c)
+        for (int v = 0; v < 8; ++v)
+          cvh[(size_t)v * nc + c] = m.cell_vertices[(size_t)8 * c + v];
+      PE_CUDA(upload(cv, cvh.data(), cvh.size(), s));
+      PE_CUDA(cudaStreamSynchronize(s));
+    }
+    const double *kp = nullptr;
+    if (!h->k_cell.empty())
+      {
+        if ((int64_t)h->k_cell.size() != nc)
+          return fail(h, PE_ERR_ARG, "pe_local_matrices3: k_cell was set for another mesh");
+        PE_CUDA(upload(kc, h->k_cell.data(), h->k_cell.size(), s));
+        kp = kc.p;
+      }
+    if (cell_old)
+      {
+        std::vector<double> oh((size_t)31 * n);
+        for (int64_t c = 0; c < n; ++c)
+          for (int i = 0; i < 31; ++i)
+            oh[(size_t)i * n + c] = cell_old[(size_t)c * 31 + i];
+        PE_CUDA(upload(old, oh.data(), oh.size(), s));
+        PE_CUDA(cudaStreamSynchronize(s));
+      }
+    PE_CUDA(o.alloc((size_t)961 * n));
+    if (rhs_out)
+      PE_CUDA(ro.alloc((size_t)31 * n));
+    PE_CUDA(launch_local_matrices_3d(nc, first_cell, n, x.p, y.p, z.p, cv.p, kp, h->k_scalar, h->lambda, h->mu, h->alpha, h->c0,
+                                     time_step, cell_old ? old.p : nullptr, o.p, rhs_out ? ro.p : nullptr, s));
+    ++h->launches;
+    std::vector<double> tmp((size_t)961 * n);
+    PE_CUDA(cudaMemcpyAsync(tmp.data(), o.p, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, s));
+    PE_CUDA(cudaStreamSynchronize(s));
+    for (int64_t c = 0; c < n; ++c)
+      for (size_t e = 0; e < 961; ++e)
+        out[(size_t)c * 961 + e] = tmp[e * (size_t)n + c];
+    if (rhs_out)
+      {
+        std::vector<double> tr((size_t)31 * n);
+        PE_CUDA(cudaMemcpyAsync(tr.data(), ro.p, sizeof(double) * tr.size(), cudaMemcpyDeviceToHost, s));
+        PE_CUDA(cudaStreamSynchronize(s));
+        for (int64_t c = 0; c < n; ++c)
+          for (int i = 0; i < 31; ++i)
+            rhs_out[(size_t)c * 31 + i] = tr[(size_t)i * n + c];
+      }
+    return PE_OK;
+    PE_CATCH
   }
 
   int
@@ -1604,6 +1763,13 @@ extern "C"
     h->matrix_valid = false; // the assembled matrix (and the solver operator built from it) belongs to the old data
     if (k_cell)
       {
+        if (h->cfg.dim == 3)
+          {
+            if (h->mesh3.n_cells <= 0)
+              return fail(h, PE_ERR_ARG, "pe_set_material: per-cell K needs the mesh first");
+            h->k_cell.assign(k_cell, k_cell + h->mesh3.n_cells);
+            return PE_OK;
+          }
         if (!h->have_mesh)
           return fail(h, PE_ERR_ARG, "pe_set_material: per-cell K needs the mesh first");
         h->k_cell.assign(k_cell, k_cell + h->mesh.n_cells);

@@ -135,6 +135,13 @@ struct pe_handle
   cudaEvent_t  ev[8]  = {};
 
   // ---- host side
+  // dim == 3 (CGQ1-WG on hexahedra, first step: local matrices): vertices and 8 vertex ids per cell, deal.II order
+  struct Mesh3
+  {
+    std::vector<double>   x, y, z;
+    std::vector<uint32_t> cell_vertices; // [n_cells][8]
+    int64_t               n_cells = 0;
+  } mesh3;
   pe::HostMesh    mesh;
   pe::HostDofs    dofs;
   pe::Partition   part;

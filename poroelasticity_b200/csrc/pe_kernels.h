@@ -70,6 +70,12 @@ namespace pe
                                          const int64_t *rowptr, const int32_t *colidx, double *values, double *rhs,
                                          double *sol, cudaStream_t s);
 
+  // ---- CGQ1-WG on hexahedra (pe_cell3d.cu): dense local matrices entry-major [31*31][n], rhs [31][n]
+  cudaError_t launch_local_matrices_3d(int64_t n_cells, int64_t first, int64_t n, const double *x, const double *y, const double *z,
+                                       const uint32_t *cv, const double *kcell, double k_scalar, double lambda, double mu,
+                                       double alpha, double c0, double dt, const double *cell_old, double *out, double *rhs_out,
+                                       cudaStream_t s);
+
   // ---- solver kernels (pe_solver.cu)
   cudaError_t launch_spmv(int64_t n_rows, const int64_t *rowptr, const int32_t *colidx, const double *values,
                           const double *x, double *y, cudaStream_t s);

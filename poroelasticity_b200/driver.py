@@ -21,11 +21,11 @@ class BiotSystem:
 
     element = PE_BR1_WG
 
-    def __init__(self, element=None, device=-1, rank=0, world_size=1, host_setup_only=False):
+    def __init__(self, element=None, device=-1, rank=0, world_size=1, host_setup_only=False, dim=2):
         self.L = capi.load()
         if element is not None:
             self.element = element
-        cfg = pe_config(self.element, 2, device, rank, world_size, 1 if host_setup_only else 0)
+        cfg = pe_config(self.element, dim, device, rank, world_size, 1 if host_setup_only else 0)
         h = C.c_void_p()
         rc = self.L.pe_create(C.byref(h), C.byref(cfg))
         if rc != 0:
@@ -318,6 +318,38 @@ class PoroElas_CGQ1_WG(BiotSystem):
     def __init__(self, **kw):
         super().__init__(**kw)
         self.time_step = 1.0 / 1024  # CGQ1:825
+
+
+class PoroElas_CGQ1_WG_3D(BiotSystem):
+    """PoroElas_CGQ1_WG<3> (the shipped main(), CGQ1:3029): first step -- the cell loop on hexahedra."""
+    element = PE_CGQ1_WG
+
+    def __init__(self, **kw):
+        super().__init__(dim=3, **kw)
+        self.time_step = 1e-3  # CGQ1:863
+
+    def make_grid(self, n_refine=3, distort=0.0, seed=12345):
+        self._ck(self.L.pe_make_unit_cube(self.h, n_refine, distort, seed))
+
+    def set_mesh3(self, x, y, z, cell_vertices):
+        x, y, z = (np.ascontiguousarray(a, np.float64) for a in (x, y, z))
+        cv = np.ascontiguousarray(cell_vertices, np.uint32)
+        self._ck(self.L.pe_set_mesh3(self.h, x.size, ptr(x), ptr(y), ptr(z), cv.shape[0], ptr(cv)))
+
+    def mesh3(self):
+        nv, nc = C.c_int64(), C.c_int64()
+        self._ck(self.L.pe_get_mesh3(self.h, C.byref(nv), C.byref(nc), None, None, None, None))
+        x, y, z = np.zeros(nv.value), np.zeros(nv.value), np.zeros(nv.value)
+        cv = np.zeros((nc.value, 8), np.uint32)
+        self._ck(self.L.pe_get_mesh3(self.h, None, None, ptr(x), ptr(y), ptr(z), ptr(cv)))
+        return x, y, z, cv
+
+    def local_matrices3(self, first, n, cell_old=None, want_rhs=True):
+        out = np.zeros((n, 31, 31))
+        rhs = np.zeros((n, 31)) if want_rhs else None
+        o = None if cell_old is None else np.ascontiguousarray(cell_old, np.float64)
+        self._ck(self.L.pe_local_matrices3(self.h, first, n, self.time_step, ptr(o), ptr(out), ptr(rhs)))
+        return (out, rhs) if want_rhs else out
 
 
 class WGDarcyEquation(BiotSystem):

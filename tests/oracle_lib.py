@@ -237,3 +237,51 @@ class EsmOracle:
         import scipy.sparse as sp
         rp, ci = self.pattern()
         return sp.csr_matrix((values, ci, rp), shape=(self.n_dofs, self.n_dofs))
+
+
+class Oracle3D:
+    """CGQ1-WG cell loop on hexahedra (oracle/poro_oracle_3d.hpp): unit cube, refine_global(n), 31 dofs per cell."""
+
+    n_loc = 31
+
+    def __init__(self, n_refine, distort=0.0, seed=12345):
+        self.L = lib()
+        L = self.L
+        L.orc3_create.restype = C.c_void_p
+        L.orc3_create.argtypes = [C.c_int, C.c_double, C.c_uint64]
+        L.orc3_destroy.argtypes = [C.c_void_p]
+        L.orc3_sizes.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc3_get_mesh.argtypes = [C.c_void_p] * 5
+        L.orc3_set_material.argtypes = [C.c_void_p] + [C.c_double] * 5
+        L.orc3_set_kcell.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc3_local.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        self.h = L.orc3_create(n_refine, distort, seed)
+        s = np.zeros(2, np.int64)
+        L.orc3_sizes(self.h, _p(s))
+        self.n_cells, self.n_vertices = int(s[0]), int(s[1])
+
+    def __del__(self):
+        try:
+            self.L.orc3_destroy(self.h)
+        except Exception:
+            pass
+
+    def mesh(self):
+        x, y, z = np.zeros(self.n_vertices), np.zeros(self.n_vertices), np.zeros(self.n_vertices)
+        cv = np.zeros((self.n_cells, 8), np.uint32)
+        self.L.orc3_get_mesh(self.h, _p(x), _p(y), _p(z), _p(cv))
+        return x, y, z, cv
+
+    def set_material(self, lam, mu, alpha, c0, dt):
+        self.L.orc3_set_material(self.h, lam, mu, alpha, c0, dt)
+
+    def set_kcell(self, k):
+        k = np.ascontiguousarray(k, np.float64)
+        assert k.size == self.n_cells
+        self.L.orc3_set_kcell(self.h, _p(k))
+
+    def local(self, cell, cell_old=None):
+        o = np.zeros(31) if cell_old is None else np.ascontiguousarray(cell_old, np.float64)
+        A, b = np.zeros((31, 31)), np.zeros(31)
+        self.L.orc3_local(self.h, cell, _p(o), _p(A), _p(b))
+        return A, b

@@ -1,0 +1,68 @@
+"""3-D (first step): the CGQ1-WG cell loop on hexahedra (PoroElasCGQ1_WG.cc:1165-1453 with dim = 3, the
+shipped main() of that file) through the C ABI against the literal 3-D oracle: 31 x 31 local matrices and local
+right-hand sides to 1e-12, on the shipped 8^3 mesh with the sandwich permeability (CGQ1:176-189) and on distorted
+hexahedra."""
+import numpy as np
+import pytest
+
+import poroelasticity_b200 as pb
+from oracle_lib import Oracle3D
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def sandwich_k(o):
+    """Coefficient::value_list of the shipped program: K = 1e-8 for 1/4 <= z <= 3/4, else 1 (evaluated at the cell centre)"""
+    x, y, z, cv = o.mesh()
+    zc = z[cv].mean(axis=1)
+    return np.where((zc >= 0.25) & (zc <= 0.75), 1e-8, 1.0)
+
+
+def test_unit_cube_mesh_matches_the_oracle():
+    o = Oracle3D(3, distort=0.15, seed=7)
+    b = pb.PoroElas_CGQ1_WG_3D()
+    b.make_grid(3, distort=0.15, seed=7)
+    x, y, z, cv = b.mesh3()
+    xo, yo, zo, cvo = o.mesh()
+    assert np.array_equal(cv, cvo)
+    assert np.array_equal(x, xo) and np.array_equal(y, yo) and np.array_equal(z, zo)
+    b.close()
+
+
+@pytest.mark.parametrize("distort", [0.0, 0.2])
+def test_local_matrices_3d(distort):
+    rng = np.random.default_rng(3)
+    nref = 3   # refine_global(3): the shipped 8 x 8 x 8 mesh (CGQ1:887)
+    o = Oracle3D(nref, distort=distort)
+    lam, mu, alpha, c0, dt = 1.0, 1.0, 1.0, 0.0, 1e-3   # CGQ1:863-866
+    if distort > 0:
+        lam, mu, alpha, c0, dt = 3.0, 0.7, 0.93, 0.1, 0.05
+    k = sandwich_k(o) if distort == 0 else np.exp(rng.normal(size=o.n_cells))
+    o.set_material(lam, mu, alpha, c0, dt)
+    o.set_kcell(k)
+    b = pb.PoroElas_CGQ1_WG_3D()
+    b.set_mesh3(*o.mesh())
+    b.time_step = dt
+    b.set_material(lam, mu, alpha, c0, 1.0, k)
+    old = rng.normal(size=(o.n_cells, 31))
+    A, r = b.local_matrices3(0, o.n_cells, cell_old=old)
+    for c in range(0, o.n_cells, 7):
+        A_ref, b_ref = o.local(c, old[c])
+        assert np.abs(A[c] - A_ref).max() <= 1e-12 * np.abs(A_ref).max(), c
+        assert np.abs(r[c] - b_ref).max() <= 1e-12 * max(np.abs(b_ref).max(), 1e-300), c
+    # a sub-range gives the same matrices
+    A2 = b.local_matrices3(100, 50, want_rhs=False)
+    assert np.array_equal(A2, A[100:150])
+    b.close()
+
+
+def test_other_hot_path_calls_say_not_built_in_3d():
+    b = pb.PoroElas_CGQ1_WG_3D()
+    b.make_grid(1)
+    with pytest.raises(pb.PoroElasError):
+        b.assemble_system(0.1)
+    b.close()
