@@ -220,6 +220,8 @@ def run_cfg4(args):
     b.rel_tol = args.rel_tol
     b.set_solver_options(args.solver_options)
     b.set_krylov(args.krylov, args.gmres_m)
+    if args.rebuild_operator:
+        b.set_tuning("reuse_operator", 0)
     b.set_solution(np.zeros(s.n_owned_rows))
     times = run_times(0.1)
     hist = []
@@ -401,6 +403,9 @@ def main():
     ap.add_argument("--recycle", type=int, default=4, help="pe_set_recycling: previous corrections kept (0 = off)")
     ap.add_argument("--krylov", type=int, default=1, help="pe_set_krylov method: 1 = FGMRES + block-triangular P, 0 = MINRES")
     ap.add_argument("--gmres-m", type=int, default=16, help="pe_set_krylov restart length")
+    ap.add_argument("--rebuild-operator", action="store_true",
+                    help="pe_set_tuning reuse_operator=0: rebuild the solver operator + preconditioner in every step although "
+                         "the matrix inputs did not change (A/B measurement; the matrix itself is assembled every step either way)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.n_refine <= 0:
@@ -465,6 +470,8 @@ def main():
     b.set_initial_guess(args.initial_guess)
     b.set_krylov(args.krylov, args.gmres_m)
     b.set_recycling(args.recycle)
+    if args.rebuild_operator:
+        b.set_tuning("reuse_operator", 0)
     n_cells, n_dofs = s.n_cells, s.n_dofs
     N = 1 << args.n_refine
     zero_state = torch.zeros(s.n_owned_rows if world == 1 else n_dofs, dtype=torch.float64).pin_memory().numpy()
@@ -692,7 +699,10 @@ def main():
                                   "MINRES, block-diagonal preconditioner") +
                                  " on the three-field (u, total pressure, p) form; blocks: bubble Jacobi x Q1 V-cycle; cell mass; "
                                  "p_int elimination + face V-cycle; preconditioner coefficients stored in FP32, Krylov vectors / "
-                                 "SpMV / true residual in FP64; initial guess = order-%d extrapolation in time" % args.initial_guess,
+                                 "SpMV / true residual in FP64; initial guess = order-%d extrapolation in time" % args.initial_guess +
+                                 ("; solver operator + preconditioner rebuilt every step" if args.rebuild_operator else
+                                  "; solver operator + preconditioner rebuilt only when the matrix inputs (material, dt, K, "
+                                  "boundary, mesh) change -- the system matrix and rhs are assembled in every step"),
                        "stopping": "true residual of the reference system ||b - A x|| <= rel_tol ||b||",
                        "iterations": iters, "per_step": per_step, "converged": all_converged,
                        "rel_residual_max": max(p["rel_residual"] for p in per_step)},

@@ -381,4 +381,22 @@ extern "C"
     std::copy(Av.begin(), Av.end(), A);
     std::copy(bv.begin(), bv.end(), b);
   }
+  // 3-D numbering and sparsity: sizes[4] = n_u, n_pint, n_pface, nnz; arrays may be NULL (sizes only)
+  void
+  orc3_dofs_pattern(void *h, std::int64_t *sizes, std::uint32_t *cell_dofs, std::int64_t *rowptr, std::int32_t *colidx)
+  {
+    d3::Problem3   *P = (d3::Problem3 *)h;
+    const d3::Dofs3 d = d3::distribute_dofs3(P->mesh);
+    const Pattern   p = d3::make_sparsity_pattern3(d, P->mesh.n_cells());
+    sizes[0]          = d.n_u;
+    sizes[1]          = d.n_pint;
+    sizes[2]          = d.n_pface;
+    sizes[3]          = (std::int64_t)p.colidx.size();
+    if (cell_dofs)
+      std::copy(d.cell_dofs.begin(), d.cell_dofs.end(), cell_dofs);
+    if (rowptr)
+      std::copy(p.rowptr.begin(), p.rowptr.end(), rowptr);
+    if (colidx)
+      std::copy(p.colidx.begin(), p.colidx.end(), colidx);
+  }
 }

@@ -19,6 +19,10 @@
 #pragma once
 #include "dealii_restated.hpp"
 
+#include <array>
+#include <map>
+#include <set>
+
 namespace orc
 {
   namespace d3
@@ -345,6 +349,101 @@ namespace orc
         for (int i = 0; i < n; ++i)
           b[i] += P.alpha * div_old * fr.pint[i] * fr.JxW;
       }
+    }
+    // ------------------------------------------------------------------------------------------
+    // DoFHandler::distribute_dofs(fe) + DoFRenumbering::component_wise(dof_handler, block_component) with
+    // block_component = {0,0,0,1,2} (CGQ1:902-919) on hexahedra [deal.II-memory]: first pass walks the active cells in
+    // order and numbers, per cell, the not yet numbered vertices 0..7 (3 displacement dofs each, consecutively), then
+    // the lines (FE_Q(1), FE_DGQ(0), FE_FaceQ(0) have no line dofs in 3-D), then the quads = faces 0..5 (one FE_FaceQ(0)
+    // dof each), then the hex (one FE_DGQ(0) dof); component_wise is a stable sort into [u | p_int | p_face].
+    // Face vertex sets: 0 {0,2,4,6}, 1 {1,3,5,7}, 2 {0,1,4,5}, 3 {2,3,6,7}, 4 {0,1,2,3}, 5 {4,5,6,7}.
+    // ------------------------------------------------------------------------------------------
+    struct Dofs3
+    {
+      std::int64_t       n_u = 0, n_pint = 0, n_pface = 0;
+      std::vector<dof_t> cell_dofs; // [n_cells][31]
+      std::int64_t
+      n() const
+      {
+        return n_u + n_pint + n_pface;
+      }
+    };
+    inline Dofs3
+    distribute_dofs3(const Mesh3 &m)
+    {
+      static const int face_v[6][4] = {{0, 2, 4, 6}, {1, 3, 5, 7}, {0, 1, 4, 5}, {2, 3, 6, 7}, {0, 1, 2, 3}, {4, 5, 6, 7}};
+      const int        nc = m.n_cells();
+      const dof_t      inval = 0xffffffffu;
+      std::vector<dof_t> vdof(m.x.size(), inval);
+      std::map<std::array<std::uint32_t, 4>, dof_t> fdof;
+      std::vector<int>   block;
+      Dofs3              d;
+      d.cell_dofs.resize((size_t)nc * kNLoc);
+      dof_t next = 0;
+      for (int c = 0; c < nc; ++c)
+        {
+          const std::uint32_t *cv = &m.cell_vertices[8 * (size_t)c];
+          dof_t               *cd = &d.cell_dofs[(size_t)c * kNLoc];
+          for (int v = 0; v < 8; ++v)
+            {
+              if (vdof[cv[v]] == inval)
+                {
+                  vdof[cv[v]] = next;
+                  next += 3;
+                  block.insert(block.end(), {0, 0, 0});
+                }
+              for (int k = 0; k < 3; ++k)
+                cd[3 * v + k] = vdof[cv[v]] + k;
+            }
+          for (int f = 0; f < 6; ++f)
+            {
+              std::array<std::uint32_t, 4> key = {cv[face_v[f][0]], cv[face_v[f][1]], cv[face_v[f][2]], cv[face_v[f][3]]};
+              std::sort(key.begin(), key.end());
+              auto it = fdof.find(key);
+              if (it == fdof.end())
+                {
+                  it = fdof.emplace(key, next++).first;
+                  block.push_back(2);
+                }
+              cd[kPFace0 + f] = it->second;
+            }
+          cd[kPInt] = next++;
+          block.push_back(1);
+        }
+      std::int64_t cnt[3] = {0, 0, 0};
+      for (const int b : block)
+        ++cnt[b];
+      d.n_u     = cnt[0];
+      d.n_pint  = cnt[1];
+      d.n_pface = cnt[2];
+      std::int64_t       run[3] = {0, cnt[0], cnt[0] + cnt[1]};
+      std::vector<dof_t> renum(next);
+      for (dof_t i = 0; i < next; ++i)
+        renum[i] = (dof_t)run[block[i]]++;
+      for (auto &g : d.cell_dofs)
+        g = renum[g];
+      return d;
+    }
+    // make_sparsity_pattern(dof_handler, dsp, constraints(empty), false) (CGQ1:934-943): full coupling, one global CSR
+    // with ascending columns
+    inline Pattern
+    make_sparsity_pattern3(const Dofs3 &d, const int n_cells)
+    {
+      const std::int64_t            n = d.n();
+      std::vector<std::set<dof_t>>  rows((size_t)n);
+      for (int c = 0; c < n_cells; ++c)
+        for (int i = 0; i < kNLoc; ++i)
+          for (int j = 0; j < kNLoc; ++j)
+            rows[d.cell_dofs[(size_t)c * kNLoc + i]].insert(d.cell_dofs[(size_t)c * kNLoc + j]);
+      Pattern p;
+      p.rowptr.assign((size_t)n + 1, 0);
+      for (std::int64_t r = 0; r < n; ++r)
+        p.rowptr[r + 1] = p.rowptr[r] + (std::int64_t)rows[r].size();
+      p.colidx.reserve((size_t)p.rowptr[n]);
+      for (std::int64_t r = 0; r < n; ++r)
+        for (const dof_t c : rows[r])
+          p.colidx.push_back((std::int32_t)c);
+      return p;
     }
   } // namespace d3
 } // namespace orc

@@ -287,6 +287,114 @@ namespace pe
   }
 
   // ---------------------------------------------------------------------------------------------
+  // Hexahedra: DoFHandler::distribute_dofs + DoFRenumbering::component_wise for FESystem(FE_Q(1)^3, FE_DGQ(0),
+  // FE_FaceQ(0)) (CGQ1:902-919 with dim = 3).  Per cell, in active-cell order: vertices 0..7 not numbered yet get three
+  // consecutive displacement dofs, then the six quads one FE_FaceQ(0) dof each (a quad is identified by its four
+  // vertex ids, so any conforming hexahedral mesh works), then the hex its FE_DGQ(0) dof; stable block sort.
+  // ---------------------------------------------------------------------------------------------
+  void
+  distribute_dofs3(const int64_t n_vertices, const int64_t n_cells, const uint32_t *cv8, HostDofs &d, Partition &part)
+  {
+    if (part.world != 1)
+      throw std::invalid_argument("distribute_dofs3: one rank only");
+    constexpr int  n_loc = 31;
+    const uint32_t inval = 0xffffffffu;
+    static const int face_v[6][4] = {{0, 2, 4, 6}, {1, 3, 5, 7}, {0, 1, 4, 5}, {2, 3, 6, 7}, {0, 1, 2, 3}, {4, 5, 6, 7}};
+    d.element = 1;
+    d.n_loc   = n_loc;
+    d.cell_dofs.resize((size_t)n_cells * n_loc);
+    std::vector<uint32_t> vdof((size_t)n_vertices, inval);
+    std::vector<uint8_t>  block_of;
+    block_of.reserve((size_t)n_vertices * 3 + (size_t)n_cells * 4);
+    // quad table: key = the three smallest vertex ids of the face (unique for conforming hexahedra) packed into 96
+    // bits -> hashed open addressing over (a, b, c)
+    struct Key
+    {
+      uint32_t a, b, c, dof;
+    };
+    size_t cap = 16;
+    while (cap < (size_t)n_cells * 8)
+      cap <<= 1;
+    std::vector<Key> table(cap, Key{inval, inval, inval, inval});
+    auto find_or_insert = [&](uint32_t v[4], bool &ins) -> uint32_t & {
+      std::sort(v, v + 4);
+      uint64_t hsh = splitmix64(((uint64_t)v[0] << 32) ^ v[1]) ^ splitmix64(((uint64_t)v[2] << 32) ^ v[3]);
+      size_t   i   = (size_t)hsh & (cap - 1);
+      while (true)
+        {
+          Key &k = table[i];
+          if (k.a == inval)
+            {
+              k   = Key{v[0], v[1], v[2], inval};
+              ins = true;
+              return k.dof;
+            }
+          if (k.a == v[0] && k.b == v[1] && k.c == v[2])
+            {
+              ins = false;
+              return k.dof;
+            }
+          i = (i + 1) & (cap - 1);
+        }
+    };
+    uint32_t next = 0;
+    for (int64_t c = 0; c < n_cells; ++c)
+      {
+        const uint32_t *cv = cv8 + 8 * (size_t)c;
+        uint32_t       *cd = &d.cell_dofs[(size_t)c * n_loc];
+        for (int v = 0; v < 8; ++v)
+          {
+            uint32_t &vd = vdof[cv[v]];
+            if (vd == inval)
+              {
+                vd = next;
+                next += 3;
+                block_of.insert(block_of.end(), 3, (uint8_t)0);
+              }
+            cd[3 * v] = vd, cd[3 * v + 1] = vd + 1, cd[3 * v + 2] = vd + 2;
+          }
+        for (int f = 0; f < 6; ++f)
+          {
+            uint32_t  fv[4] = {cv[face_v[f][0]], cv[face_v[f][1]], cv[face_v[f][2]], cv[face_v[f][3]]};
+            bool      ins;
+            uint32_t &e = find_or_insert(fv, ins);
+            if (ins)
+              {
+                e = next++;
+                block_of.push_back(2);
+              }
+            cd[24 + f] = e;
+          }
+        cd[30] = next++;
+        block_of.push_back(1);
+      }
+    int64_t cnt[3] = {0, 0, 0};
+    for (uint32_t i = 0; i < next; ++i)
+      ++cnt[block_of[i]];
+    d.n_u     = cnt[0];
+    d.n_pint  = cnt[1];
+    d.n_pface = cnt[2];
+    int64_t               run[3] = {0, cnt[0], cnt[0] + cnt[1]};
+    std::vector<uint32_t> renum(next);
+    for (uint32_t i = 0; i < next; ++i)
+      renum[i] = (uint32_t)run[block_of[i]]++;
+    for (auto &g : d.cell_dofs)
+      g = renum[g];
+    part.cell_begin = 0;
+    part.cell_end   = n_cells;
+    part.n_owned    = d.n();
+    const int64_t st[4] = {0, d.n_u, d.n_u + d.n_pint, d.n()};
+    for (int b = 0; b < 3; ++b)
+      {
+        part.row_begin[b] = st[b];
+        part.row_end[b]   = st[b + 1];
+        part.local_off[b] = st[b];
+      }
+    part.all_row_begin.assign(part.row_begin, part.row_begin + 3);
+    part.all_row_end.assign(part.row_end, part.row_end + 3);
+  }
+
+  // ---------------------------------------------------------------------------------------------
   // Sparsity: for every owned row, the sorted union of the dofs of all cells containing the row.
   // ---------------------------------------------------------------------------------------------
   namespace

@@ -79,6 +79,9 @@ namespace pe
   void make_unit_square(HostMesh &m, int n_refine, double distort, uint64_t seed, int boundary_kinds);
   // first-touch numbering + component-wise renumbering; also fills the partition's row ranges
   void distribute_dofs(const HostMesh &m, int element, HostDofs &d, Partition &part);
+  // hexahedra (dim = 3, CGQ1-WG, one rank): first-touch numbering of 8 vertices x 3, 6 FE_FaceQ(0) quads, 1 FE_DGQ(0)
+  // hex per cell + component_wise; cell_vertices8 = [n_cells][8] in deal.II order
+  void distribute_dofs3(int64_t n_vertices, int64_t n_cells, const uint32_t *cell_vertices8, HostDofs &d, Partition &part);
   // rows owned by the partition; ghost cells; halo columns
   void make_sparsity_pattern(const HostMesh &m, const HostDofs &d, Partition &part, HostPattern &p);
   // after pe_set_pattern: ghost cells / halo columns from a user pattern

@@ -114,6 +114,7 @@ namespace pe
     int    one_lane       = 0;    // multi-GPU: no second stream + communicator for the pressure pipeline
     int    mg_fused_n     = -1;   // largest level handled by the single-CTA multigrid kernel (< 0: built-in)
     int    mg_dist_min_n  = 1024; // smallest grid level (cells per side) that is distributed over the ranks
+    int    reuse_operator = 1;    // keep the solver operator + preconditioner while the inputs of the matrix are unchanged
   };
 
   struct HaloPeer
@@ -174,6 +175,9 @@ struct pe_handle
   pe::DevBuf<int32_t>  d_rowadj, d_tile_ghost_ptr, d_tile_ghost;
   pe::DevBuf<int64_t>  d_tile_rows;
   pe::DevBuf<double>   d_T;
+  uint64_t             op_key       = 0;     // fingerprint of the matrix inputs the solver operator was built from
+  bool                 op_key_valid = false; // false: the next solve rebuilds operator + preconditioner unconditionally
+  int64_t              op_builds    = 0;     // update_solver_operator() calls so far (tests / tracing)
   int64_t              chunk_cells = 32768;
   // requested by pe_set_solver_options; scatter mode takes effect at the next pattern build, the chunk size at the
   // next (re)build of the chunk tables -- never on tables that were built for another mode

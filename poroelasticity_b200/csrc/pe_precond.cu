@@ -445,7 +445,8 @@ namespace pe
     // The displacement and the pressure part touch disjoint entries of t, t2, z: on one GPU the pressure
     // pipeline is forked onto a second stream (inside the captured CUDA graph: a parallel branch).
     // one GPU: always; several GPUs: when the communication layer has a second lane (stream + NCCL communicator)
-    const bool   fork = bp.s2 != nullptr && (!bp.halo || bp.set_lane);
+    // (PE_TIMING serialises the two pipelines so that the phase marks, all on one stream then, add up)
+    const bool   fork = bp.s2 != nullptr && (!bp.halo || bp.set_lane) && !PhaseTimer::get().on;
     cudaStream_t sp   = fork ? bp.s2 : s;
     auto         halo_p = [&](double *x) {
       if (bp.halo)

@@ -280,6 +280,17 @@ class Oracle3D:
         assert k.size == self.n_cells
         self.L.orc3_set_kcell(self.h, _p(k))
 
+    def dofs_pattern(self):
+        """(n_u, n_pint, n_pface), cell_dofs [n_cells][31], rowptr, colidx of the 3-D numbering / full-coupling pattern"""
+        self.L.orc3_dofs_pattern.argtypes = [C.c_void_p] * 5
+        s = np.zeros(4, np.int64)
+        self.L.orc3_dofs_pattern(self.h, _p(s), None, None, None)
+        cd = np.zeros((self.n_cells, 31), np.uint32)
+        rp = np.zeros(int(s[:3].sum()) + 1, np.int64)
+        ci = np.zeros(int(s[3]), np.int32)
+        self.L.orc3_dofs_pattern(self.h, _p(s), _p(cd), _p(rp), _p(ci))
+        return tuple(int(v) for v in s[:3]), cd, rp, ci
+
     def local(self, cell, cell_old=None):
         o = np.zeros(31) if cell_old is None else np.ascontiguousarray(cell_old, np.float64)
         A, b = np.zeros((31, 31)), np.zeros(31)

@@ -277,3 +277,48 @@ def test_postprocess_dilation_magnitude_darcy_velocity(el):
     assert np.abs(vc - exact).max() < 0.05 * np.abs(exact).max()
     b.close()
     b2.close()
+
+
+@pytest.mark.parametrize("reuse", [1, 0])
+def test_operator_is_rebuilt_when_the_matrix_inputs_change(reuse):
+    """The solver operator + preconditioner are kept across steps while material, time step, permeability, boundary
+    and mesh stay the same (tuning key reuse_operator, default 1).  Two steps on one matrix, then a new time step
+    length, then new material data, then a new permeability field: every step within 1e-8 of the sparse LU solution
+    of the oracle's system -- a stale operator would converge to the wrong system and fail the true-residual test."""
+    nref = 7
+    o = Oracle(BR1_WG, nref)
+    b = pb.PoroElasBR1WG()
+    b.set_tuning("reuse_operator", reuse)
+    b.make_grid_and_dofs(nref)
+    b.set_case(pb.PE_CASE_COSCOS)
+    o.set_case(CASE_COSCOS)
+    b.rel_tol = 1e-10
+    rng = np.random.default_rng(3)
+    kcell = np.exp(rng.normal(size=o.n_cells))
+    old = np.zeros(o.n_dofs)
+    t = 0.0
+    #        lambda mu  alpha c0    dt    k field
+    plan = [(1.0, 1.0, 1.0, 0.0, 0.1, None), (1.0, 1.0, 1.0, 0.0, 0.1, None), (1.0, 1.0, 1.0, 0.0, 0.05, None),
+            (50.0, 2.0, 0.7, 0.01, 0.05, None), (50.0, 2.0, 0.7, 0.01, 0.05, kcell), (50.0, 2.0, 0.7, 0.01, 0.05, kcell)]
+    last = None
+    for k, (lam, mu, al, c0, dt, kc) in enumerate(plan):
+        t += dt
+        if (lam, mu, al, c0, kc is None) != last:
+            o.set_material(lam, mu, al, c0, dt)
+            b.set_material(lam, mu, al, c0, k_cell=kc)
+            if kc is not None:
+                o.set_kcell(kc)
+            last = (lam, mu, al, c0, kc is None)
+        else:
+            o.set_material(lam, mu, al, c0, dt)
+        b.time_step = dt
+        v_ref, r_ref, _ = o.assemble(t, old)
+        x_ref = lu(o, v_ref, r_ref)
+        b.assemble_system(t)
+        assert rel(b.system_matrix(), v_ref) < TOL_MAT
+        x = b.solve_time_step()
+        assert b.stats.converged == 1, (k, b.stats.rel_residual)
+        eu, ep = rel_l2_blocks(x, x_ref, o.n_u)
+        assert eu < TOL_SOL and ep < TOL_SOL, (k, eu, ep)
+        old = x_ref
+    b.close()

@@ -85,3 +85,37 @@ def test_coupling_and_storage_entries():
     o.set_material(0.0, mu, alpha, c0, dt)
     A0, _ = o.local(0, old)
     assert np.abs((A - A0)[:24, :24] - lam * vol * np.outer(div_c, div_c)).max() < 1e-13
+
+
+def test_dof_numbering_3d_counts_and_first_cell():
+    """distribute_dofs + component_wise on hexahedra: block sizes, and the first cell's dofs written out by hand
+    (vertices 0..7 x 3 -> u 0..23; after the block sort the hex dof is the first p_int, the six quads the first
+    six p_face numbers in face order)."""
+    for n in (0, 1, 2):
+        o = Oracle3D(n)
+        N = 1 << n
+        (n_u, n_pint, n_pface), cd, rp, ci = o.dofs_pattern()
+        assert n_u == 3 * (N + 1) ** 3 and n_pint == N ** 3 and n_pface == 3 * N * N * (N + 1)
+        assert list(cd[0, :24]) == list(range(24))
+        assert cd[0, 30] == n_u and list(cd[0, 24:30]) == [n_u + n_pint + f for f in range(6)]
+        # every dof appears, the pattern is symmetric with sorted rows and holds the diagonal
+        n = n_u + n_pint + n_pface
+        assert set(cd.ravel()) == set(range(n))
+        import scipy.sparse as sp
+        P = sp.csr_matrix((np.ones(ci.size), ci, rp), shape=(n, n))
+        assert (P != P.T).nnz == 0 and np.all(P.diagonal() == 1)
+        assert all(np.all(np.diff(ci[rp[r]:rp[r + 1]]) > 0) for r in range(n))
+
+
+def test_dof_numbering_3d_shared_entities():
+    """cell 1 (the +x neighbour of cell 0) reuses the four vertices and the quad of the common face"""
+    o = Oracle3D(1)
+    _, cd, _, _ = o.dofs_pattern()
+    for a, b in ((1, 0), (3, 2), (5, 4), (7, 6)):  # vertex a of cell 0 == vertex b of cell 1
+        assert list(cd[0, 3 * a:3 * a + 3]) == list(cd[1, 3 * b:3 * b + 3])
+    assert cd[0, 25] == cd[1, 24]  # face x=1 of cell 0 is face x=0 of cell 1
+    assert cd[0, 30] + 1 == cd[1, 30]
+    # a row of an interior-face dof couples exactly the two cells' dofs: 31 + 31 - (12 + 1) shared
+    (n_u, n_pint, n_pface), cd, rp, ci = o.dofs_pattern()
+    r = cd[0, 25]
+    assert rp[r + 1] - rp[r] == 31 + 31 - 13
