@@ -531,6 +531,7 @@ namespace
     a.vy        = h->d_vy.p;
     a.kcell     = h->d_k.p;
     a.k_scalar  = h->k_scalar;
+    a.esm_variant = h->tune.esm_dfma;
     a.sol       = h->d_sol.p;
     a.cv        = h->d_cv.p;
     a.flags     = h->d_flags.p;
@@ -2068,6 +2069,8 @@ extern "C"
       t.mg_dist_min_n = (int)value;
     else if (k == "reuse_operator")
       t.reuse_operator = value != 0.;
+    else if (k == "esm_dfma")
+      t.esm_dfma = value != 0.;
     else
       return fail(h, PE_ERR_ARG, "pe_set_tuning: unknown key " + k);
     // structural switches take effect when the device tables / hierarchies are rebuilt

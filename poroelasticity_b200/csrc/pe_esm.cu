@@ -347,6 +347,261 @@ namespace pe
         }
     }
 
+    // ---- FP64 tensor-core version ------------------------------------------------------------------------------
+    // D (8 x 8) += A (8 x 4, row) B (4 x 8, col), mma.sync m8n8k4 f64: with g = lane / 4, k = lane % 4 a lane holds
+    // A[g][k], B[k][g] and D[g][2 k], D[g][2 k + 1].
+    __device__ __forceinline__ void
+    dmma(double &d0, double &d1, const double a, const double b)
+    {
+      asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+    }
+
+    constexpr int kMs = kRt + 1; // row stride of the Gram matrix in shared memory: lane-per-row reads hit 16 distinct banks
+    constexpr int kYs = 28;      // row stride of Y: the 4 x 8 fragment loads of a half warp fall into distinct banks
+
+    // One warp per cell, the two GEMM-shaped parts on the FP64 tensor cores:
+    //   Gram matrix   M = U W^T, U_i(q,b) = w_i(q) G_{type(i) b}(q), W_j(q,b) = w_j(q) [type(j) = b]   (24 x 32 x 24; the
+    //                 k-steps in which W vanishes for a whole column tile are skipped: 32 DMMA for the 6 lower tiles);
+    //                 the B fragments and the carrier part of the A fragments are per-lane CONSTANTS (12 registers),
+    //                 the geometry enters through 12 values G(q) per lane
+    //   Cholesky      lane i = row i in registers, as in the first version (shuffle broadcasts)
+    //   L Y = F^T     column-oriented: as soon as Y_q is known all later rows are updated (24 independent FMAs) --
+    //                 the row-oriented loop of the first version was one dependent chain of 276 FMAs per cell
+    //   A = k Y^T Y   fragments of Y serve as A and B operand alike: 18 loads, 36 DMMA for the 6 lower tiles
+    // (ESM:413-429 Gram + inverse, 478 C = F M^-1, 483-502 the q,i,j,k,l loop, 505-513 rhs).
+    template <bool DENSE>
+    __global__ void __launch_bounds__(kWarps * 32, 4)
+    k_esm_cell_mma(const EsmArgs a)
+    {
+      __shared__ double sG[kWarps][kQ * 4];
+      __shared__ __align__(16) double sM[kWarps][kRt * kMs];  // Gram matrix (stride 25), then L^T (stride 24), then A (21 x 21)
+      __shared__ __align__(16) double sYs[kWarps][kRt * kYs]; // Y, columns 21..23 zero
+      __shared__ int64_t sRow[kWarps][kLoc];
+      __shared__ double  sFt[kRt * kLoc];
+      for (int e = threadIdx.x; e < kRt * kLoc; e += blockDim.x)
+        sFt[e] = cT.F[(e % kLoc) * kRt + e / kLoc]; // F^T (24 x 21)
+      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, k4 = lane & 3;
+      // carrier values of this lane's fragment entries: cv[t][sq] = w_{8 t + g}(q = 4 sq + k4)
+      double cv[3][4];
+#pragma unroll
+      for (int t = 0; t < 3; ++t)
+#pragma unroll
+        for (int sq = 0; sq < 4; ++sq)
+          {
+            const int i = 8 * t + g, q = 4 * sq + k4;
+            cv[t][sq]   = i < 12 ? cT.px[q * 12 + i] : cT.py[q * 12 + i - 12];
+          }
+      __syncthreads();
+      const int64_t t = (int64_t)blockIdx.x * kWarps + warp;
+      if (t >= a.n)
+        return;
+      constexpr unsigned FULL = 0xffffffffu;
+      const int64_t      c    = a.first + t;
+      double            *G    = sG[warp];
+      double vx[4], vy[4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+        {
+          const uint32_t vi = a.cv[(size_t)v * a.n_asm + c];
+          vx[v]             = __ldg(a.vx + vi);
+          vy[v]             = __ldg(a.vy + vi);
+        }
+      Geom geo;
+      geo.set(vx, vy);
+      double fq = 0.;
+      if (lane < kQ)
+        {
+          double j00, j01, j10, j11;
+          geo.jac(cT.qx[lane], cT.qy[lane], j00, j01, j10, j11);
+          const double det = j00 * j11 - j01 * j10, r = cT.qw[lane] / det;
+          G[lane * 4 + 0]  = r * (j00 * j00 + j10 * j10);
+          G[lane * 4 + 1]  = r * (j00 * j01 + j10 * j11);
+          G[lane * 4 + 2]  = r * (j01 * j01 + j11 * j11);
+          if (a.case_id == PE_CASE_DARCY_COSCOS)
+            {
+              double px, py;
+              geo.point(cT.qx[lane], cT.qy[lane], px, py);
+              fq = 2. * M_PI * M_PI * cospi(px) * cospi(py) * det * cT.qw[lane]; // RightHandSide, ESM:167
+            }
+        }
+      if (!DENSE && lane < kLoc)
+        sRow[warp][lane] = a.rowptr[a.cdofs[(size_t)lane * a.n_asm + c]];
+      __syncwarp();
+      // ---- Gram matrix on the tensor cores                                                       ESM:413-426
+      double *Ms = sM[warp];
+      {
+        // metric at this lane's four Gauss points q = 4 sq + k4: (g00, g01, g11)
+        double Gq[4][3];
+#pragma unroll
+        for (int sq = 0; sq < 4; ++sq)
+#pragma unroll
+          for (int e = 0; e < 3; ++e)
+            Gq[sq][e] = G[(4 * sq + k4) * 4 + e];
+        // basis functions 0..11 carry the x component, 12..23 the y component: tile 0 all x, tile 1 mixed, tile 2 all y
+        const bool isx[3] = {true, g < 4, false};
+        // A fragments: U_i(q, b) for b = x (k-steps 0..3) and b = y (k-steps 4..7)
+        double af[3][8];
+#pragma unroll
+        for (int ti = 0; ti < 3; ++ti)
+#pragma unroll
+          for (int s = 0; s < 8; ++s)
+            {
+              const int b = s >> 2, sq = s & 3;
+              af[ti][s]   = cv[ti][sq] * (isx[ti] ? Gq[sq][b] : Gq[sq][b + 1]);
+            }
+        // lower tiles; a column tile of pure x (y) functions only sees the k-steps of b = x (y)
+#pragma unroll
+        for (int tj = 0; tj < 3; ++tj)
+#pragma unroll
+          for (int ti = tj; ti < 3; ++ti)
+            {
+              double d0 = 0., d1 = 0.;
+#pragma unroll
+              for (int s = 0; s < 8; ++s)
+                {
+                  const int b = s >> 2, sq = s & 3;
+                  if ((tj == 0 && b == 1) || (tj == 2 && b == 0))
+                    continue;
+                  const bool   match = b == 0 ? isx[tj] : !isx[tj];
+                  const double bf    = match ? cv[tj][sq] : 0.;
+                  dmma(d0, d1, af[ti][s], bf);
+                }
+              double *o = &Ms[(8 * ti + g) * kMs + 8 * tj + 2 * k4];
+              o[0]      = d0;
+              o[1]      = d1;
+            }
+      }
+      __syncwarp();
+      // ---- Cholesky M = L L^T: lane i holds row i (lanes >= 24 a harmless copy of row 23); the entries above the
+      //      diagonal tiles were never written and are never used
+      const int li = lane < kRt ? lane : kRt - 1;
+      double    M[kRt];
+#pragma unroll
+      for (int j = 0; j < kRt; ++j)
+        M[j] = Ms[li * kMs + j];
+      __syncwarp();
+      // Column k of L goes to shared memory as row k of L^T (the layout the substitution below wants) and comes back
+      // as broadcast reads, two entries per LDS.128: 24 STS + 138 LDS instead of the 552 SHFL of the first version.
+      double *Lt = Ms; // every lane holds its row of M in registers by now
+      double  invd[kRt];
+#pragma unroll
+      for (int k = 0; k < kRt; ++k)
+        {
+          const double dkk = __shfl_sync(FULL, M[k], k);
+          invd[k]          = rsqrt(dkk);
+          const double lik = M[k] * invd[k]; // L_ik for lanes i > k, L_kk = sqrt(M_kk) on lane k
+          if (lane < kRt)
+            Lt[k * kRt + lane] = lik;
+          __syncwarp();
+          if ((k + 1) & 1) // k + 1 odd (and < 24): a single entry, the pairs start at the next even row
+            M[k + 1] -= lik * Lt[k * kRt + k + 1];
+#pragma unroll
+          for (int j = k + 1 + ((k + 1) & 1); j + 1 < kRt; j += 2)
+            {
+              const double2 l2 = *reinterpret_cast<const double2 *>(&Lt[k * kRt + j]);
+              M[j] -= lik * l2.x; // meaningful for i >= j; the upper triangle is never read
+              M[j + 1] -= lik * l2.y;
+            }
+        }
+      __syncwarp();
+      // ---- L Y = F^T, column-oriented; lane = column of Y (one local dof)
+      double *Ys = sYs[warp];
+      {
+        const int lc = lane < kLoc ? lane : kLoc - 1;
+        double    acc[kRt];
+#pragma unroll
+        for (int r = 0; r < kRt; ++r)
+          acc[r] = sFt[r * kLoc + lc];
+#pragma unroll
+        for (int q = 0; q < kRt; ++q)
+          {
+            const double yq = acc[q] * invd[q];
+            if (lane < kRt)
+              Ys[q * kYs + lane] = lane < kLoc ? yq : 0.;
+            // rows r > q: pairs (r, r + 1) with r even come back as one LDS.128
+            if ((q + 1) & 1)
+              acc[q + 1] -= Lt[q * kRt + q + 1] * yq;
+#pragma unroll
+            for (int r = q + 1 + ((q + 1) & 1); r + 1 < kRt; r += 2)
+              {
+                const double2 l2 = *reinterpret_cast<const double2 *>(&Lt[q * kRt + r]);
+                acc[r] -= l2.x * yq;
+                acc[r + 1] -= l2.y * yq;
+              }
+          }
+      }
+      __syncwarp();
+      // ---- A = k Y^T Y on the tensor cores                                                       ESM:478-502
+      const double kperm = a.kcell ? a.kcell[c] : a.k_scalar;
+      double       yf[3][6];
+#pragma unroll
+      for (int tt = 0; tt < 3; ++tt)
+#pragma unroll
+        for (int s = 0; s < 6; ++s)
+          yf[tt][s] = Ys[(4 * s + k4) * kYs + 8 * tt + g];
+      double *A = Ms; // L^T is dead
+      __syncwarp();
+#pragma unroll
+      for (int ti = 0; ti < 3; ++ti)
+#pragma unroll
+        for (int tj = 0; tj <= ti; ++tj)
+          {
+            double d0 = 0., d1 = 0.;
+#pragma unroll
+            for (int s = 0; s < 6; ++s)
+              dmma(d0, d1, yf[ti][s], yf[tj][s]);
+            const int row = 8 * ti + g, col = 8 * tj + 2 * k4;
+            d0 *= kperm;
+            d1 *= kperm;
+            if (row < kLoc)
+              {
+                if (col < kLoc)
+                  {
+                    A[row * kLoc + col] = d0;
+                    if (ti != tj)
+                      A[col * kLoc + row] = d0;
+                  }
+                if (col + 1 < kLoc)
+                  {
+                    A[row * kLoc + col + 1] = d1;
+                    if (ti != tj)
+                      A[(col + 1) * kLoc + row] = d1;
+                  }
+              }
+          }
+      // ---- right-hand side (ESM:505-513)
+      double bi = 0.;
+      for (int q = 0; q < kQ; ++q)
+        {
+          const double f = __shfl_sync(FULL, fq, q);
+          if (lane < 9)
+            bi += f * cT.pv[q * 9 + lane];
+        }
+      __syncwarp();
+      for (int e = lane; e < kLoc * kLoc; e += 32)
+        {
+          if (DENSE)
+            a.out[(size_t)t * kLoc * kLoc + e] = A[e];
+          else
+            {
+              const uint32_t o = a.off[((size_t)(e >> 2) * a.n_asm + c) * 4 + (e & 3)];
+              atomicAdd(a.values + sRow[warp][e / kLoc] + (o & 127u), A[e]);
+            }
+        }
+      const double bsh = __shfl_sync(FULL, bi, lane >= 12 ? lane - 12 : 0);
+      if (DENSE)
+        {
+          if (a.rhs_out && lane < kLoc)
+            a.rhs_out[(size_t)t * kLoc + lane] = lane >= 12 ? bsh : 0.;
+        }
+      else if (lane < 9)
+        {
+          const int32_t r2 = a.cdofs[(size_t)(12 + lane) * a.n_asm + c];
+          if (bi != 0.)
+            atomicAdd(a.rhs + r2, bi);
+        }
+    }
+
     // ---- MatrixTools::apply_boundary_values (ESM:572-575), two passes ------------------------------------
     // pass 1: eliminate the column of every boundary dof d:  rhs_r -= a_rd g_d (free rows r), a_rd = 0
     __global__ void
@@ -610,7 +865,10 @@ namespace pe
     x.values   = a.values;
     x.rhs      = a.rhs;
     x.case_id  = case_id;
-    k_esm_cell<false><<<(unsigned)((x.n + kWarps - 1) / kWarps), kWarps * 32, 0, s>>>(x);
+    if (a.esm_variant == 0)
+      k_esm_cell_mma<false><<<(unsigned)((x.n + kWarps - 1) / kWarps), kWarps * 32, 0, s>>>(x);
+    else
+      k_esm_cell<false><<<(unsigned)((x.n + kWarps - 1) / kWarps), kWarps * 32, 0, s>>>(x);
     ++*n_launches;
     return cudaGetLastError();
   }
@@ -634,7 +892,10 @@ namespace pe
     x.out      = out;
     x.rhs_out  = rhs_out;
     x.case_id  = case_id;
-    k_esm_cell<true><<<(unsigned)((n + kWarps - 1) / kWarps), kWarps * 32, 0, s>>>(x);
+    if (a.esm_variant == 0)
+      k_esm_cell_mma<true><<<(unsigned)((n + kWarps - 1) / kWarps), kWarps * 32, 0, s>>>(x);
+    else
+      k_esm_cell<true><<<(unsigned)((n + kWarps - 1) / kWarps), kWarps * 32, 0, s>>>(x);
     return cudaGetLastError();
   }
 

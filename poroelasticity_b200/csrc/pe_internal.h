@@ -114,6 +114,7 @@ namespace pe
     int    one_lane       = 0;    // multi-GPU: no second stream + communicator for the pressure pipeline
     int    mg_fused_n     = -1;   // largest level handled by the single-CTA multigrid kernel (< 0: built-in)
     int    mg_dist_min_n  = 1024; // smallest grid level (cells per side) that is distributed over the ranks
+    int    esm_dfma       = 0;    // WG(Q2,Q2;RT[2]): the first, DFMA-only cell kernel instead of the DMMA one (A/B)
     int    reuse_operator = 1;    // keep the solver operator + preconditioner while the inputs of the matrix are unchanged
   };
 

@@ -22,6 +22,7 @@ namespace pe
     double         *values, *rhs;
     int             do_matrix;
     int             atomic_mode; // 1: matrix pre-zeroed, every contribution is a RED (cells in Morton order)
+    int             esm_variant; // WG(Q2,Q2;RT[2]) cell kernel: 0 = FP64 tensor-core (DMMA) version, 1 = first (DFMA) version
   };
 
   cudaError_t launch_scatter_offsets(int n_loc, int64_t n_asm, int64_t L, const int32_t *cdofs,

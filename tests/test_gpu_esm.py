@@ -32,18 +32,21 @@ def cg_identity(A, b, x0, tol, max_it):
     return x, it
 
 
-def make(nref, distort=0.0):
+def make(nref, distort=0.0, dfma=0):
+    """dfma = 0: the FP64 tensor-core (DMMA) cell kernel, the default; 1: the first, DFMA-only version"""
     o = EsmOracle(nref, distort=distort)
     b = pb.WGDarcyEquation()
+    b.set_tuning("esm_dfma", dfma)
     b.make_grid(nref, distort=distort)
     b.setup_system()
     b.set_case(pb.PE_CASE_DARCY_COSCOS)
     return o, b
 
 
+@pytest.mark.parametrize("dfma", [0, 1])
 @pytest.mark.parametrize("distort", [0.0, 0.2])
-def test_local_matrices(distort):
-    o, b = make(3, distort)
+def test_local_matrices(distort, dfma):
+    o, b = make(3, distort, dfma)
     k = np.exp(np.random.default_rng(1).normal(size=o.n_cells))
     o.set_kcell(k)
     b.set_material(1, 1, 1, 0, 1.0, k)
@@ -51,12 +54,18 @@ def test_local_matrices(distort):
     A_ref, b_ref, _ = o.local_matrices(0, o.n_cells)
     assert rel(A, A_ref) < 1e-12
     assert rel(rhs, b_ref) < 1e-12
+    # per cell, not only against the largest entry of the whole batch; exact symmetry of the tile-mirrored block
+    scale = np.abs(A_ref).reshape(o.n_cells, -1).max(axis=1)
+    assert (np.abs(A - A_ref).reshape(o.n_cells, -1).max(axis=1) / scale).max() < 1e-11
+    if dfma == 0:
+        assert np.array_equal(A, A.transpose(0, 2, 1))
 
 
+@pytest.mark.parametrize("dfma", [0, 1])
 @pytest.mark.parametrize("nref,distort", [(0, 0.0), (1, 0.0), (3, 0.0), (4, 0.2)])
-def test_assembled_system(nref, distort):
+def test_assembled_system(nref, distort, dfma):
     """system_matrix, system_rhs and solution after assemble_system (incl. apply_boundary_values, ESM:565-576)."""
-    o, b = make(nref, distort)
+    o, b = make(nref, distort, dfma)
     v_ref, r_ref, s_ref, _ = o.assemble()
     b.assemble_system()
     assert rel(b.system_matrix(), v_ref) < 1e-12
