@@ -2278,6 +2278,7 @@ extern "C"
     a.vy       = vy.p;
     a.cv       = cv.p;
     a.k_scalar = h->k_scalar;
+    a.esm_variant = h->tune.esm_dfma;
     if (h->k_lognormal)
       {
         PE_CUDA(kc.alloc((size_t)n));
@@ -2372,6 +2373,7 @@ extern "C"
     a.vy       = vy.p;
     a.cv       = cv.p;
     a.k_scalar = h->k_scalar;
+    a.esm_variant = h->tune.esm_dfma;
     if (h->k_lognormal)
       {
         PE_CUDA(kc.alloc((size_t)nc));

@@ -32,6 +32,9 @@ namespace pe
       double qx[kQ], qy[kQ], qw[kQ];
     };
     __constant__ EsmTables cT;
+    // the same tables in global memory: lane-dependent addresses serialise in the constant cache (one request per
+    // distinct address), which bounded BOTH cell kernels at 8.8e7 cells/s before the tensor-core version read them from here
+    EsmTables *dT = nullptr;
 
     void
     gauss4(double x[4], double w[4])
@@ -133,8 +136,12 @@ namespace pe
               for (int k = 0; k < kRt; ++k)
                 T.F[(3 * f + i) * kRt + k] += L[i] * (w[k][0] * nx + w[k][1] * ny) * gw[q];
           }
-      const cudaError_t e = cudaMemcpyToSymbol(cT, &T, sizeof(T));
-      tables_ready        = e == cudaSuccess;
+      cudaError_t e = cudaMemcpyToSymbol(cT, &T, sizeof(T));
+      if (e == cudaSuccess && !dT)
+        e = cudaMalloc(&dT, sizeof(T));
+      if (e == cudaSuccess)
+        e = cudaMemcpy(dT, &T, sizeof(T), cudaMemcpyHostToDevice);
+      tables_ready = e == cudaSuccess;
       return e;
     }
 
@@ -152,6 +159,7 @@ namespace pe
       double         *values, *rhs; // assembly mode
       double         *out, *rhs_out; // dense mode: out[n][21][21], rhs_out[n][21]
       int             case_id;
+      const EsmTables *tab;          // tables in global memory (tensor-core version)
     };
 
     // One warp per cell, everything but the final 21 x 21 block in REGISTERS: lane i holds row i of the Gram
@@ -373,15 +381,19 @@ namespace pe
     __global__ void __launch_bounds__(kWarps * 32, 4)
     k_esm_cell_mma(const EsmArgs a)
     {
-      __shared__ double sG[kWarps][kQ * 4];
+      __shared__ double sG[kWarps][kQ * 3];
       __shared__ __align__(16) double sM[kWarps][kRt * kMs];  // Gram matrix (stride 25), then L^T (stride 24), then A (21 x 21)
       __shared__ __align__(16) double sYs[kWarps][kRt * kYs]; // Y, columns 21..23 zero
-      __shared__ int64_t sRow[kWarps][kLoc];
-      __shared__ double  sFt[kRt * kLoc];
+      __shared__ int64_t sRow[DENSE ? 1 : kWarps][kLoc];
+      __shared__ double  sFt[kRt * kLoc], sPv[kQ * 9];
+      const EsmTables *__restrict__ T = a.tab;
       for (int e = threadIdx.x; e < kRt * kLoc; e += blockDim.x)
-        sFt[e] = cT.F[(e % kLoc) * kRt + e / kLoc]; // F^T (24 x 21)
+        sFt[(e % kRt) * kLoc + e / kRt] = T->F[e]; // F^T (24 x 21); coalesced read
+      for (int e = threadIdx.x; e < kQ * 9; e += blockDim.x)
+        sPv[e] = T->pv[e];
       const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, k4 = lane & 3;
-      // carrier values of this lane's fragment entries: cv[t][sq] = w_{8 t + g}(q = 4 sq + k4)
+      // per-lane constants, loaded once per (persistent) warp:
+      // carrier values of this lane's fragment entries cv[t][sq] = w_{8 t + g}(q = 4 sq + k4); its Gauss point
       double cv[3][4];
 #pragma unroll
       for (int t = 0; t < 3; ++t)
@@ -389,15 +401,16 @@ namespace pe
         for (int sq = 0; sq < 4; ++sq)
           {
             const int i = 8 * t + g, q = 4 * sq + k4;
-            cv[t][sq]   = i < 12 ? cT.px[q * 12 + i] : cT.py[q * 12 + i - 12];
+            cv[t][sq]   = i < 12 ? T->px[q * 12 + i] : T->py[q * 12 + i - 12];
           }
+      const double qx = T->qx[lane & (kQ - 1)], qy = T->qy[lane & (kQ - 1)], qw = T->qw[lane & (kQ - 1)];
       __syncthreads();
-      const int64_t t = (int64_t)blockIdx.x * kWarps + warp;
-      if (t >= a.n)
-        return;
       constexpr unsigned FULL = 0xffffffffu;
-      const int64_t      c    = a.first + t;
       double            *G    = sG[warp];
+      // persistent warps: the grid is a few CTAs per SM, every warp walks over the cells with the grid stride
+      for (int64_t t = (int64_t)blockIdx.x * kWarps + warp; t < a.n; t += (int64_t)gridDim.x * kWarps)
+      {
+      const int64_t c = a.first + t;
       double vx[4], vy[4];
 #pragma unroll
       for (int v = 0; v < 4; ++v)
@@ -412,16 +425,16 @@ namespace pe
       if (lane < kQ)
         {
           double j00, j01, j10, j11;
-          geo.jac(cT.qx[lane], cT.qy[lane], j00, j01, j10, j11);
-          const double det = j00 * j11 - j01 * j10, r = cT.qw[lane] / det;
-          G[lane * 4 + 0]  = r * (j00 * j00 + j10 * j10);
-          G[lane * 4 + 1]  = r * (j00 * j01 + j10 * j11);
-          G[lane * 4 + 2]  = r * (j01 * j01 + j11 * j11);
+          geo.jac(qx, qy, j00, j01, j10, j11);
+          const double det = j00 * j11 - j01 * j10, r = qw / det;
+          G[lane * 3 + 0]  = r * (j00 * j00 + j10 * j10);
+          G[lane * 3 + 1]  = r * (j00 * j01 + j10 * j11);
+          G[lane * 3 + 2]  = r * (j01 * j01 + j11 * j11);
           if (a.case_id == PE_CASE_DARCY_COSCOS)
             {
               double px, py;
-              geo.point(cT.qx[lane], cT.qy[lane], px, py);
-              fq = 2. * M_PI * M_PI * cospi(px) * cospi(py) * det * cT.qw[lane]; // RightHandSide, ESM:167
+              geo.point(qx, qy, px, py);
+              fq = 2. * M_PI * M_PI * cospi(px) * cospi(py) * det * qw; // RightHandSide, ESM:167
             }
         }
       if (!DENSE && lane < kLoc)
@@ -436,7 +449,7 @@ namespace pe
         for (int sq = 0; sq < 4; ++sq)
 #pragma unroll
           for (int e = 0; e < 3; ++e)
-            Gq[sq][e] = G[(4 * sq + k4) * 4 + e];
+            Gq[sq][e] = G[(4 * sq + k4) * 3 + e];
         // basis functions 0..11 carry the x component, 12..23 the y component: tile 0 all x, tile 1 mixed, tile 2 all y
         const bool isx[3] = {true, g < 4, false};
         // A fragments: U_i(q, b) for b = x (k-steps 0..3) and b = y (k-steps 4..7)
@@ -482,14 +495,19 @@ namespace pe
       __syncwarp();
       // Column k of L goes to shared memory as row k of L^T (the layout the substitution below wants) and comes back
       // as broadcast reads, two entries per LDS.128: 24 STS + 138 LDS instead of the 552 SHFL of the first version.
+      // The pivot travels on its own: every lane keeps d = M_ii - sum_{m<k} L_im^2 of its row, so that the next pivot
+      // only waits for rsqrt -> multiply -> one FMA and not for the shared-memory round trip of the column.
       double *Lt = Ms; // every lane holds its row of M in registers by now
       double  invd[kRt];
+      double  d = Ms[li * kMs + li];
+      __syncwarp();
 #pragma unroll
       for (int k = 0; k < kRt; ++k)
         {
-          const double dkk = __shfl_sync(FULL, M[k], k);
+          const double dkk = __shfl_sync(FULL, d, k);
           invd[k]          = rsqrt(dkk);
           const double lik = M[k] * invd[k]; // L_ik for lanes i > k, L_kk = sqrt(M_kk) on lane k
+          d -= lik * lik;
           if (lane < kRt)
             Lt[k * kRt + lane] = lik;
           __syncwarp();
@@ -575,7 +593,7 @@ namespace pe
         {
           const double f = __shfl_sync(FULL, fq, q);
           if (lane < 9)
-            bi += f * cT.pv[q * 9 + lane];
+            bi += f * sPv[q * 9 + lane];
         }
       __syncwarp();
       for (int e = lane; e < kLoc * kLoc; e += 32)
@@ -600,6 +618,8 @@ namespace pe
           if (bi != 0.)
             atomicAdd(a.rhs + r2, bi);
         }
+      __syncwarp(); // the next cell reuses this warp's shared-memory buffers
+      }
     }
 
     // ---- MatrixTools::apply_boundary_values (ESM:572-575), two passes ------------------------------------
@@ -844,6 +864,21 @@ namespace pe
     return cudaGetLastError();
   }
 
+  // persistent grid of the tensor-core kernel: 4 CTAs of 4 warps per SM (128 registers, 48 KB shared memory each)
+  static unsigned
+  mma_grid(const int64_t n_cells)
+  {
+    static int n_sm = 0;
+    if (n_sm == 0)
+      {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0)
+          n_sm = 148;
+      }
+    return (unsigned)std::min<int64_t>((n_cells + kWarps - 1) / kWarps, (int64_t)n_sm * 4);
+  }
+
   cudaError_t
   launch_esm_assemble(const AsmArgs &a, const int case_id, cudaStream_t s, int *n_launches)
   {
@@ -865,8 +900,9 @@ namespace pe
     x.values   = a.values;
     x.rhs      = a.rhs;
     x.case_id  = case_id;
+    x.tab = dT;
     if (a.esm_variant == 0)
-      k_esm_cell_mma<false><<<(unsigned)((x.n + kWarps - 1) / kWarps), kWarps * 32, 0, s>>>(x);
+      k_esm_cell_mma<false><<<mma_grid(x.n), kWarps * 32, 0, s>>>(x);
     else
       k_esm_cell<false><<<(unsigned)((x.n + kWarps - 1) / kWarps), kWarps * 32, 0, s>>>(x);
     ++*n_launches;
@@ -892,8 +928,9 @@ namespace pe
     x.out      = out;
     x.rhs_out  = rhs_out;
     x.case_id  = case_id;
+    x.tab = dT;
     if (a.esm_variant == 0)
-      k_esm_cell_mma<true><<<(unsigned)((n + kWarps - 1) / kWarps), kWarps * 32, 0, s>>>(x);
+      k_esm_cell_mma<true><<<mma_grid(n), kWarps * 32, 0, s>>>(x);
     else
       k_esm_cell<true><<<(unsigned)((n + kWarps - 1) / kWarps), kWarps * 32, 0, s>>>(x);
     return cudaGetLastError();
