@@ -58,7 +58,7 @@ enum {
 
 typedef struct pe_config {
   int32_t element;    /* pe_element */
-  int32_t dim;        /* 2; 3 = CGQ1-WG on hexahedra, cell loop only (pe_make_unit_cube, pe_set_mesh3, pe_local_matrices3) */
+  int32_t dim;        /* 2; 3 = CGQ1-WG on hexahedra: cell loop, numbering and sparsity (pe_make_unit_cube, pe_set_mesh3, pe_local_matrices3) */
   int32_t device;     /* CUDA device ordinal; -1 = current device */
   int32_t rank;       /* this process's rank in the mesh partition (0 if world_size == 1) */
   int32_t world_size; /* number of GPUs / processes the mesh is partitioned over */
@@ -115,8 +115,10 @@ int pe_set_mesh(pe_handle *h, int64_t n_vertices, const double *x, const double 
  * deal.II's 3-D Morton order, cell vertex v at offset (v & 1, (v >> 1) & 1, v >> 2)) and runs the CELL LOOP of
  * assemble_system (CGQ1:1165-1453): dense 31 x 31 local matrices out[n][31][31] and right-hand sides rhs_out[n][31]
  * for f = s = 0 (the sandwich problem), local dof order 3 v + c | 24 + face | 30 = p_int; cell_old = the 31 old-solution
- * values of every cell (may be NULL).  Numbering, scatter and solve in 3-D are not built yet: every other hot-path
- * call on a dim = 3 handle fails with PE_ERR_ARG. */
+ * values of every cell (may be NULL).  pe_distribute_dofs, pe_make_sparsity_pattern, pe_get_sizes, pe_get_dofs and
+ * pe_get_pattern work on a dim = 3 handle (host side: first-touch numbering of vertices x 3 | FE_FaceQ(0) quads | FE_DGQ(0)
+ * hex per cell + component_wise, full-coupling CSR; one rank).  Scatter, boundary values and the solve in 3-D are not
+ * built yet: pe_assemble_system / pe_solve_time_step on a dim = 3 handle fail with an error. */
 int pe_make_unit_cube(pe_handle *h, int n_refine, double distort, uint64_t seed);
 int pe_set_mesh3(pe_handle *h, int64_t n_vertices, const double *x, const double *y, const double *z, int64_t n_cells,
                  const uint32_t *cell_vertices);
@@ -200,7 +202,12 @@ int pe_set_solver_options(pe_handle *h, int use_multigrid, double theta, double 
  * Keys: "mg_omega2", "cmg_omega", "cmg_omega2", "face_omega" (smoother weights); "mg_fused_n" (largest level of the
  * single-CTA multigrid kernel); "asm_gather" (1: gather assembly instead of the RED scatter); multi-GPU: "mg_replicated",
  * "mg_whole_slabs", "one_lane" (1: the round-1 communication schemes, kept for A/B runs), "mg_dist_min_n" (smallest grid
- * level distributed over the ranks).  Structural keys rebuild the device tables before the next assembly. */
+ * level distributed over the ranks); "reuse_operator" (default 1: the solver operator and its preconditioner are rebuilt
+ * only when something that enters the matrix values changes -- material data, time step, permeability, boundary kinds,
+ * mesh / numbering; 0: rebuilt in every pe_solve_time_step.  The matrix itself is assembled by every
+ * pe_assemble_system and the true residual is taken on it either way); "esm_dfma" (1: the first, DFMA-only
+ * WG(Q2,Q2;RT[2]) cell kernel instead of the FP64 tensor-core one).  Structural keys rebuild the device tables before
+ * the next assembly. */
 int pe_set_tuning(pe_handle *h, const char *key, double value);
 /* Krylov method of pe_solve_time_step for the Biot elements on meshes with a refinement hierarchy:
  * method 1 (default) = restarted flexible GMRES(restart) on the row-signed three-field system with the block
