@@ -399,4 +399,39 @@ extern "C"
     if (colidx)
       std::copy(p.colidx.begin(), p.colidx.end(), colidx);
   }
+  // boundary data: face_kind[6 n_cells] (NULL: the shipped sandwich boundary, CGQ1:972-981) and the traction vector
+  void
+  orc3_set_boundary(void *h, const std::uint8_t *face_kind, const double *traction)
+  {
+    d3::Problem3 *P = (d3::Problem3 *)h;
+    if (!face_kind)
+      {
+        d3::set_sandwich_boundary(*P);
+        return;
+      }
+    P->face_kind.assign(face_kind, face_kind + 6 * (size_t)P->mesh.n_cells());
+    for (int k = 0; k < 3; ++k)
+      P->traction[k] = traction ? traction[k] : 0.;
+  }
+  void
+  orc3_get_boundary(void *h, std::uint8_t *face_kind, double *traction)
+  {
+    d3::Problem3 *P = (d3::Problem3 *)h;
+    std::copy(P->face_kind.begin(), P->face_kind.end(), face_kind);
+    std::copy(P->traction, P->traction + 3, traction);
+  }
+  // assemble_system in 3-D: values in the CSR order of orc3_dofs_pattern, rhs; old_solution may be NULL (zero)
+  void
+  orc3_assemble(void *h, const double *old_solution, double *values, double *rhs)
+  {
+    d3::Problem3       *P = (d3::Problem3 *)h;
+    const d3::Dofs3     d = d3::distribute_dofs3(P->mesh);
+    const Pattern       p = d3::make_sparsity_pattern3(d, P->mesh.n_cells());
+    std::vector<double> old, v, r;
+    if (old_solution)
+      old.assign(old_solution, old_solution + d.n());
+    d3::assemble_system3(*P, d, p, old, v, r);
+    std::copy(v.begin(), v.end(), values);
+    std::copy(r.begin(), r.end(), rhs);
+  }
 }

@@ -18,6 +18,7 @@
 // closed-form Darcy block of a cube, consistency with the 2-D oracle on an extruded cell).
 #pragma once
 #include "dealii_restated.hpp"
+#include "poro_oracle.hpp" // FK_* face kinds
 
 #include <array>
 #include <map>
@@ -97,7 +98,41 @@ namespace orc
       Mesh3               mesh;
       std::vector<double> kcell;
       double              lambda = 1, mu = 1, alpha = 1, capacity = 0, time_step = 1e-3;
+      // boundary data of assemble_system: per cell and face a bit set FK_DIR_U | FK_DIR_P | FK_NEU_U (0 on interior
+      // faces), one constant traction vector for the FK_NEU_U faces.  Dirichlet values are zero (BoundaryValues,
+      // CGQ1:697-725, returns 0 in all components).
+      std::vector<std::uint8_t> face_kind; // [n_cells][6]
+      double                    traction[3] = {0, 0, 0};
     };
+    // The shipped 3-D program (sandwich problem): boundary id 1 on faces with centre z = 1 (CGQ1:972-981) carries the
+    // face-pressure Dirichlet condition (interpolate_boundary_values(.., 1, .., face_pressure_mask), CGQ1:1663-1670) and the
+    // traction (0, 0, -1) (CGQ1:1563-1582); every other boundary face keeps id 0 = displacement Dirichlet (CGQ1:1673-1679).
+    inline void
+    set_sandwich_boundary(Problem3 &P)
+    {
+      const int nc = P.mesh.n_cells();
+      P.face_kind.assign((size_t)6 * nc, 0);
+      static const int face_v[6][4] = {{0, 2, 4, 6}, {1, 3, 5, 7}, {0, 1, 4, 5}, {2, 3, 6, 7}, {0, 1, 2, 3}, {4, 5, 6, 7}};
+      for (int c = 0; c < nc; ++c)
+        for (int f = 0; f < 6; ++f)
+          {
+            double ctr[3] = {0, 0, 0};
+            for (int k = 0; k < 4; ++k)
+              {
+                const std::uint32_t id = P.mesh.cell_vertices[8 * (size_t)c + face_v[f][k]];
+                ctr[0] += .25 * P.mesh.x[id];
+                ctr[1] += .25 * P.mesh.y[id];
+                ctr[2] += .25 * P.mesh.z[id];
+              }
+            const int  d  = f / 2;
+            const bool at = std::fabs(ctr[d] - ((f & 1) ? 1. : 0.)) < 1e-12; // unit cube: at_boundary()
+            if (!at)
+              continue;
+            P.face_kind[6 * (size_t)c + f] = std::fabs(ctr[2] - 1.) < 1e-12 ? (FK_DIR_P | FK_NEU_U) : FK_DIR_U;
+          }
+      P.traction[0] = P.traction[1] = 0;
+      P.traction[2] = -1;
+    }
 
     // trilinear map at a reference point: x, J = dx/dxi (rows x,y,z; columns xi,eta,zeta), det, J^-1
     struct Map3
@@ -444,6 +479,89 @@ namespace orc
         for (const dof_t c : rows[r])
           p.colidx.push_back((std::int32_t)c);
       return p;
+    }
+    // ------------------------------------------------------------------------------------------
+    // assemble_system (CGQ1:1165-1706) in 3-D: cell loop, traction term on the FK_NEU_U faces with QGauss<2>(3)
+    // (CGQ1:1563-1582), constraints of the whole mesh (interpolate_boundary_values is called on the dof_handler inside
+    // the cell loop, CGQ1:1662-1679: a cell sees every constrained dof it touches), distribute_local_to_global.
+    // ------------------------------------------------------------------------------------------
+    inline void
+    add_traction(const Problem3 &P, const int c, std::vector<double> &b)
+    {
+      double vx[8], vy[8], vz[8];
+      for (int v = 0; v < 8; ++v)
+        {
+          const std::uint32_t id = P.mesh.cell_vertices[8 * (size_t)c + v];
+          vx[v]                  = P.mesh.x[id];
+          vy[v]                  = P.mesh.y[id];
+          vz[v]                  = P.mesh.z[id];
+        }
+      static std::vector<double> gx, gw;
+      if (gx.empty())
+        qgauss_1d(3, gx, gw);
+      for (int f = 0; f < 6; ++f)
+        {
+          if (!(P.face_kind[6 * (size_t)c + f] & FK_NEU_U))
+            continue;
+          const int d = f / 2, a1 = (d + 1) % 3, a2 = (d + 2) % 3;
+          for (int q2 = 0; q2 < 3; ++q2)
+            for (int q1 = 0; q1 < 3; ++q1)
+              {
+                double r[3];
+                r[d]  = (f & 1) ? 1. : 0.;
+                r[a1] = gx[q1];
+                r[a2] = gx[q2];
+                const Map3   m     = map_at(vx, vy, vz, r);
+                const double t1[3] = {m.J[0][a1], m.J[1][a1], m.J[2][a1]}, t2[3] = {m.J[0][a2], m.J[1][a2], m.J[2][a2]};
+                const double cr[3] = {t1[1] * t2[2] - t1[2] * t2[1], t1[2] * t2[0] - t1[0] * t2[2], t1[0] * t2[1] - t1[1] * t2[0]};
+                const double JxW   = std::sqrt(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]) * gw[q1] * gw[q2];
+                Point3Tables ff;
+                fill_point(ff, m, r, f);
+                for (int i = 0; i < kNLoc; ++i)
+                  b[i] += (P.traction[0] * ff.uval[i][0] + P.traction[1] * ff.uval[i][1] + P.traction[2] * ff.uval[i][2]) * JxW;
+              }
+        }
+    }
+    inline AffineConstraints
+    boundary_constraints3(const Problem3 &P, const Dofs3 &dofs)
+    {
+      static const int  face_v[6][4] = {{0, 2, 4, 6}, {1, 3, 5, 7}, {0, 1, 4, 5}, {2, 3, 6, 7}, {0, 1, 2, 3}, {4, 5, 6, 7}};
+      AffineConstraints con;
+      for (int c = 0; c < P.mesh.n_cells(); ++c)
+        for (int f = 0; f < 6; ++f)
+          {
+            const std::uint8_t kind = P.face_kind.empty() ? 0 : P.face_kind[6 * (size_t)c + f];
+            const dof_t       *idx  = &dofs.cell_dofs[(size_t)c * kNLoc];
+            if (kind & FK_DIR_P)
+              con.set_inhomogeneity(idx[kPFace0 + f], 0.);
+            if (kind & FK_DIR_U)
+              for (int k = 0; k < 4; ++k)
+                for (int cc = 0; cc < 3; ++cc)
+                  con.set_inhomogeneity(idx[3 * face_v[f][k] + cc], 0.);
+          }
+      return con;
+    }
+    inline void
+    assemble_system3(const Problem3 &P, const Dofs3 &dofs, const Pattern &pat, const std::vector<double> &old_solution,
+                     std::vector<double> &values, std::vector<double> &rhs)
+    {
+      CsrMatrix mat;
+      mat.p = &pat;
+      mat.val.assign(pat.colidx.size(), 0.);
+      rhs.assign((size_t)dofs.n(), 0.);
+      const AffineConstraints con = boundary_constraints3(P, dofs);
+      std::vector<double>     A, b, cell_old(kNLoc);
+      for (int c = 0; c < P.mesh.n_cells(); ++c)
+        {
+          const dof_t *idx = &dofs.cell_dofs[(size_t)c * kNLoc];
+          for (int i = 0; i < kNLoc; ++i)
+            cell_old[i] = old_solution.empty() ? 0. : old_solution[idx[i]];
+          assemble_cell(P, c, cell_old, A, b);
+          if (!P.face_kind.empty())
+            add_traction(P, c, b);
+          distribute_local_to_global(con, A, b, idx, kNLoc, mat, rhs);
+        }
+      values.swap(mat.val);
     }
   } // namespace d3
 } // namespace orc

@@ -35,7 +35,7 @@ class pe_solve_stats(C.Structure):
 
 # every symbol include/poroelas_b200.h declares
 EXPORTS = [
-    "pe_create", "pe_destroy", "pe_last_error", "pe_version", "pe_make_unit_square", "pe_make_unit_cube", "pe_set_mesh3", "pe_get_mesh3", "pe_local_matrices3", "pe_set_mesh",
+    "pe_create", "pe_destroy", "pe_last_error", "pe_version", "pe_make_unit_square", "pe_make_unit_cube", "pe_set_mesh3", "pe_get_mesh3", "pe_local_matrices3", "pe_set_boundary3", "pe_set_mesh",
     "pe_distribute_dofs", "pe_set_dofs", "pe_make_sparsity_pattern", "pe_set_pattern", "pe_get_sizes", "pe_get_owned_ranges",
     "pe_get_mesh", "pe_get_dofs", "pe_get_pattern", "pe_get_dealii_block_order", "pe_set_material",
     "pe_set_lognormal_k", "pe_set_case", "pe_set_boundary", "pe_assemble_system", "pe_assemble_rhs_only",
@@ -72,6 +72,7 @@ def load():
         "pe_set_mesh3": [vp, i64, vp, vp, vp, i64, vp],
         "pe_get_mesh3": [vp, vp, vp, vp, vp, vp, vp],
         "pe_local_matrices3": [vp, i64, i64, dbl, vp, vp, vp],
+        "pe_set_boundary3": [vp, vp, vp],
         "pe_distribute_dofs": [vp],
         "pe_set_dofs": [vp, i64, i64, i64, vp],
         "pe_make_sparsity_pattern": [vp],

@@ -1420,6 +1420,46 @@ extern "C"
           m.cell_vertices[(size_t)8 * c + v] =
             (uint32_t)((((size_t)iz + (v >> 2)) * V + iy + ((v >> 1) & 1)) * V + ix + (v & 1));
       }
+    // boundary data of the shipped program (sandwich problem): faces with centre z = 1 carry boundary id 1 = face-pressure
+    // Dirichlet (CGQ1:972-981, 1663-1670) and the traction (0, 0, -1) (CGQ1:1563-1582); all other boundary faces keep
+    // id 0 = displacement Dirichlet (CGQ1:1673-1679)
+    m.face_kinds.assign((size_t)6 * m.n_cells, 0);
+    for (int64_t c = 0; c < m.n_cells; ++c)
+      {
+        const uint32_t v0 = m.cell_vertices[(size_t)8 * c];
+        const int      ix = (int)(v0 % V), iy = (int)((v0 / V) % V), iz = (int)(v0 / ((size_t)V * V));
+        const int      lo[3] = {ix, iy, iz};
+        for (int f = 0; f < 6; ++f)
+          {
+            const int d = f / 2;
+            if ((f & 1) ? lo[d] + 1 == N : lo[d] == 0)
+              m.face_kinds[(size_t)6 * c + f] = (f == 5) ? (PE_FACE_DIR_P | PE_FACE_NEU_U) : PE_FACE_DIR_U;
+          }
+      }
+    m.traction[0] = m.traction[1] = 0.;
+    m.traction[2] = -1.;
+    h->dev3.ready = false;
+    h->have_dofs = h->have_pattern = h->device_ready = h->matrix_valid = false;
+    return PE_OK;
+    PE_CATCH
+  }
+
+  int
+  pe_set_boundary3(pe_handle *h, const uint8_t *face_kinds, const double *traction)
+  {
+    if (!h || h->cfg.dim != 3 || h->mesh3.n_cells <= 0 || !face_kinds)
+      return fail(h, PE_ERR_ARG, "pe_set_boundary3: needs a dim = 3 handle with a mesh and face_kinds[n_cells][6]");
+    PE_TRY
+    auto &m = h->mesh3;
+    for (size_t e = 0; e < (size_t)6 * m.n_cells; ++e)
+      if (face_kinds[e] & ~7)
+        return fail(h, PE_ERR_ARG, "pe_set_boundary3: unknown face kind bits");
+    m.face_kinds.assign(face_kinds, face_kinds + (size_t)6 * m.n_cells);
+    for (int k = 0; k < 3; ++k)
+      m.traction[k] = traction ? traction[k] : 0.;
+    h->dev3.ready   = false;
+    h->matrix_valid = false;
+    ++h->data_epoch;
     return PE_OK;
     PE_CATCH
   }
@@ -1440,6 +1480,9 @@ extern "C"
       if ((int64_t)v >= n_vertices)
         return fail(h, PE_ERR_ARG, "pe_set_mesh3: vertex index out of range");
     m.n_cells = n_cells;
+    h->mesh3.face_kinds.clear(); // a user mesh carries no boundary data until pe_set_boundary3
+    h->dev3.ready = false;
+    h->have_dofs = h->have_pattern = h->device_ready = h->matrix_valid = false;
     return PE_OK;
     PE_CATCH
   }
@@ -1591,7 +1634,8 @@ extern "C"
         h->mesh.n_vertices = (int64_t)h->mesh3.x.size();
         h->mesh.n_refine   = -1;
         h->have_dofs       = true;
-        h->have_pattern = h->device_ready = false;
+        h->have_pattern = h->device_ready = h->matrix_valid = false;
+        h->dev3.ready   = false;
         ++h->dofs_epoch;
         return PE_OK;
         PE_CATCH
@@ -1655,6 +1699,7 @@ extern "C"
     make_sparsity_pattern(h->mesh, h->dofs, h->part, h->pat);
     h->have_pattern = true;
     h->device_ready = false;
+    h->dev3.ready   = false;
     return PE_OK;
     PE_CATCH
   }
@@ -1886,6 +1931,128 @@ extern "C"
     return PE_OK;
   }
 
+  // assemble_system on hexahedra (CGQ1:1165-1706 with dim = 3; one rank): dense blocks of k_local_matrices_3d in chunks,
+  // then constraints + traction + scatter with atomics into the pre-zeroed CSR values (k_scatter_3d).  Boundary values are
+  // homogeneous (BoundaryValues returns 0, CGQ1:697-725); old_solution = host vector of all dofs, NULL = zero.
+  static int
+  assemble3(pe_handle *h, const double time_step, const double *old_solution)
+  {
+    if (!h->have_dofs || !h->have_pattern)
+      return fail(h, PE_ERR_ARG, "pe_assemble_system (dim = 3): distribute dofs and build the sparsity pattern first");
+    if (h->device < 0)
+      return fail(h, PE_ERR_NO_DEVICE, "handle was created with PE_CFG_HOST_SETUP_ONLY: no hot path without a GPU");
+    cudaStream_t  s  = h->stream;
+    const auto   &m  = h->mesh3;
+    const int64_t nc = m.n_cells, n = h->dofs.n();
+    pe_handle::Dev3 &d = h->dev3;
+    if (!d.ready)
+      {
+        PE_CUDA(upload(d.x, m.x.data(), m.x.size(), s));
+        PE_CUDA(upload(d.y, m.y.data(), m.y.size(), s));
+        PE_CUDA(upload(d.z, m.z.data(), m.z.size(), s));
+        std::vector<uint32_t> cvh((size_t)8 * nc);
+        for (int64_t c = 0; c < nc; ++c)
+          for (int v = 0; v < 8; ++v)
+            cvh[(size_t)v * nc + c] = m.cell_vertices[(size_t)8 * c + v];
+        PE_CUDA(upload(d.cv, cvh.data(), cvh.size(), s));
+        std::vector<int32_t> cdh((size_t)31 * nc);
+        for (int64_t c = 0; c < nc; ++c)
+          for (int i = 0; i < 31; ++i)
+            cdh[(size_t)i * nc + c] = (int32_t)h->dofs.cell_dofs[(size_t)c * 31 + i];
+        PE_CUDA(upload(d.cdofs, cdh.data(), cdh.size(), s));
+        // constraints of the WHOLE mesh (interpolate_boundary_values runs on the dof_handler, CGQ1:1662-1679): a cell sees
+        // every constrained dof it touches, also through a vertex or an edge only
+        static const int     face_v[6][4] = {{0, 2, 4, 6}, {1, 3, 5, 7}, {0, 1, 4, 5}, {2, 3, 6, 7}, {0, 1, 2, 3}, {4, 5, 6, 7}};
+        std::vector<uint8_t> vflag(m.x.size(), 0);
+        const bool           have_bnd = !m.face_kinds.empty();
+        if (have_bnd)
+          for (int64_t c = 0; c < nc; ++c)
+            for (int f = 0; f < 6; ++f)
+              if (m.face_kinds[(size_t)6 * c + f] & PE_FACE_DIR_U)
+                for (int k = 0; k < 4; ++k)
+                  vflag[m.cell_vertices[(size_t)8 * c + face_v[f][k]]] = 1;
+        std::vector<uint32_t> mask((size_t)nc, 0u);
+        std::vector<uint8_t>  neu((size_t)nc, 0);
+        for (int64_t c = 0; c < nc; ++c)
+          {
+            uint32_t b = 0;
+            for (int v = 0; v < 8; ++v)
+              if (vflag[m.cell_vertices[(size_t)8 * c + v]])
+                b |= 7u << (3 * v);
+            if (have_bnd)
+              for (int f = 0; f < 6; ++f)
+                {
+                  const uint8_t kind = m.face_kinds[(size_t)6 * c + f];
+                  if (kind & PE_FACE_DIR_P)
+                    b |= 1u << (24 + f);
+                  if (kind & PE_FACE_NEU_U)
+                    neu[(size_t)c] |= (uint8_t)(1u << f);
+                }
+            mask[(size_t)c] = b;
+          }
+        PE_CUDA(upload(d.con_mask, mask.data(), mask.size(), s));
+        PE_CUDA(upload(d.neu_mask, neu.data(), neu.size(), s));
+        PE_CUDA(upload(h->d_rowptr, h->pat.rowptr.data(), h->pat.rowptr.size(), s));
+        PE_CUDA(upload(h->d_colidx, h->pat.colidx.data(), h->pat.colidx.size(), s));
+        h->L   = n;
+        h->H   = 0;
+        h->nnz = (int64_t)h->pat.colidx.size();
+        PE_CUDA(h->d_values.alloc((size_t)h->nnz));
+        PE_CUDA(h->d_rhs.alloc((size_t)n));
+        PE_CUDA(d.old.alloc((size_t)n));
+        PE_CUDA(d.err.alloc(1));
+        d.chunk = std::min<int64_t>(nc, 16384); // 16384 x 961 x 8 B = 126 MB of dense blocks per chunk
+        PE_CUDA(d.A.alloc((size_t)961 * d.chunk));
+        PE_CUDA(d.b.alloc((size_t)31 * d.chunk));
+        PE_CUDA(d.cell_old.alloc((size_t)31 * d.chunk));
+        PE_CUDA(cudaStreamSynchronize(s));
+        d.ready = true;
+      }
+    // permeability: per cell (pe_set_material) or the scalar
+    const double *kp = nullptr;
+    if (!h->k_cell.empty())
+      {
+        if ((int64_t)h->k_cell.size() != nc)
+          return fail(h, PE_ERR_ARG, "pe_assemble_system (dim = 3): k_cell was set for another mesh");
+        PE_CUDA(upload(d.kc, h->k_cell.data(), h->k_cell.size(), s));
+        kp = d.kc.p;
+      }
+    PE_CUDA(cudaEventRecord(h->ev[0], s));
+    if (old_solution)
+      PE_CUDA(cudaMemcpyAsync(d.old.p, old_solution, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s));
+    else
+      PE_CUDA(cudaMemsetAsync(d.old.p, 0, sizeof(double) * (size_t)n, s));
+    PE_CUDA(cudaMemsetAsync(h->d_values.p, 0, sizeof(double) * (size_t)h->nnz, s));
+    PE_CUDA(cudaMemsetAsync(h->d_rhs.p, 0, sizeof(double) * (size_t)n, s));
+    PE_CUDA(cudaMemsetAsync(d.err.p, 0, sizeof(int), s));
+    PE_CUDA(cudaEventRecord(h->ev[1], s));
+    for (int64_t first = 0; first < nc; first += d.chunk)
+      {
+        const int64_t cn = std::min(d.chunk, nc - first);
+        PE_CUDA(launch_gather_old_3d(nc, first, cn, d.cdofs.p, d.old.p, d.cell_old.p, s));
+        PE_CUDA(launch_local_matrices_3d(nc, first, cn, d.x.p, d.y.p, d.z.p, d.cv.p, kp, h->k_scalar, h->lambda, h->mu, h->alpha,
+                                         h->c0, time_step, d.cell_old.p, d.A.p, d.b.p, s));
+        PE_CUDA(launch_scatter_3d(nc, first, cn, d.x.p, d.y.p, d.z.p, d.cv.p, d.cdofs.p, d.con_mask.p, d.neu_mask.p, m.traction,
+                                  d.A.p, d.b.p, h->d_rowptr.p, h->d_colidx.p, h->d_values.p, h->d_rhs.p, d.err.p, s));
+        h->launches += 3;
+      }
+    PE_CUDA(cudaEventRecord(h->ev[2], s));
+    int bad = 0;
+    PE_CUDA(cudaMemcpyAsync(&bad, d.err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PE_CUDA(cudaEventSynchronize(h->ev[2]));
+    PE_CUDA(cudaStreamSynchronize(s));
+    if (bad)
+      return fail(h, PE_ERR_PATTERN, "pe_assemble_system (dim = 3): a local entry is not in the sparsity pattern");
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev[0], h->ev[2]);
+    h->assemble_ms = ms;
+    cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]);
+    h->assemble_kernel_ms = ms;
+    h->last_dt            = time_step;
+    h->matrix_valid       = true; // pe_get_matrix / pe_get_rhs read d_values / d_rhs (device_ready stays false: no 2-D tables)
+    return PE_OK;
+  }
+
   int
   pe_assemble_system(pe_handle *h, double t, double time_step, const double *old_solution)
   {
@@ -1894,6 +2061,8 @@ extern "C"
       return PE_ERR_ARG;
     PE_DEVICE(h);
     PE_TRY
+    if (h->cfg.dim == 3)
+      return assemble3(h, time_step, old_solution);
     return assemble_impl(h, t, time_step, old_solution, true);
     PE_CATCH
   }
@@ -1913,7 +2082,7 @@ extern "C"
   pe_get_matrix(const pe_handle *hc, double *values)
   {
     pe_handle *h = const_cast<pe_handle *>(hc);
-    if (!h || !values || !h->device_ready || !h->matrix_valid)
+    if (!h || !values || !(h->device_ready || (h->cfg.dim == 3 && h->dev3.ready)) || !h->matrix_valid)
       return fail(h, PE_ERR_ARG, "pe_get_matrix: nothing assembled");
     PE_DEVICE(h);
     PE_CUDA(cudaMemcpyAsync(values, h->d_values.p, sizeof(double) * (size_t)h->nnz, cudaMemcpyDeviceToHost, h->stream));
@@ -1925,7 +2094,7 @@ extern "C"
   pe_get_rhs(const pe_handle *hc, double *rhs)
   {
     pe_handle *h = const_cast<pe_handle *>(hc);
-    if (!h || !rhs || !h->device_ready)
+    if (!h || !rhs || !(h->device_ready || (h->cfg.dim == 3 && h->dev3.ready && h->matrix_valid)))
       return fail(h, PE_ERR_ARG, "pe_get_rhs: nothing assembled");
     PE_DEVICE(h);
     PE_CUDA(cudaMemcpyAsync(rhs, h->d_rhs.p, sizeof(double) * (size_t)h->L, cudaMemcpyDeviceToHost, h->stream));

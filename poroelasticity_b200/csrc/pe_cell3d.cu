@@ -246,7 +246,157 @@ namespace pe
           rhs_out[(size_t)30 * n + t] = c0 * pold * vol + alpha * dold * jc;
         }
     }
+
+    // ---- assemble_system in 3-D: old-solution gather, traction term, constraints, scatter ----------------------------
+    // cell_old[i][t] = old[cell_dofs[i][first + t]]
+    __global__ void
+    k_gather_old_3d(const int64_t n_cells, const int64_t first, const int64_t n, const int32_t *__restrict__ cdofs /* [31][n_cells] */,
+                    const double *__restrict__ old, double *__restrict__ cell_old /* [31][n] */)
+    {
+      const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      if (e >= n * NL3)
+        return;
+      const int64_t t = e % n;
+      const int     i = (int)(e / n);
+      cell_old[e]     = old[cdofs[(size_t)i * n_cells + first + t]];
+    }
+
+    // int_f N_v dS over face f of the hexahedron with QGauss<2>(3) (fe_face_values.JxW, CGQ1:1053, 1569-1580)
+    __device__ double
+    face_shape_integral(const Hex &H, const int f, const int v)
+    {
+      const int d = f >> 1, a1 = (d + 1) % 3, a2 = (d + 2) % 3;
+      double    sum = 0.;
+      for (int q2 = 0; q2 < 3; ++q2)
+        for (int q1 = 0; q1 < 3; ++q1)
+          {
+            double r[3];
+            r[d]  = (f & 1) ? 1. : 0.;
+            r[a1] = kG3x[q1];
+            r[a2] = kG3x[q2];
+            double J[3][3], dN[8][3];
+            H.jac(r[0], r[1], r[2], J, dN);
+            const double c0 = J[1][a1] * J[2][a2] - J[2][a1] * J[1][a2], c1 = J[2][a1] * J[0][a2] - J[0][a1] * J[2][a2],
+                         c2 = J[0][a1] * J[1][a2] - J[1][a1] * J[0][a2];
+            const double Nv = ((v & 1) ? r[0] : 1. - r[0]) * (((v >> 1) & 1) ? r[1] : 1. - r[1]) * ((v >> 2) ? r[2] : 1. - r[2]);
+            sum += Nv * sqrt(c0 * c0 + c1 * c1 + c2 * c2) * kG3w[q1] * kG3w[q2];
+          }
+      return sum;
+    }
+
+    // One thread per (cell, local row i), cells fastest (the dense blocks are entry-major: coalesced).
+    // AffineConstraints::distribute_local_to_global with homogeneous constraints (CGQ1:1697-1699; deal.II
+    // [deal.II-memory]): unconstrained row i receives its unconstrained columns and b_i; a constrained dof receives
+    // |A_ii| on the diagonal (the average of the |diagonal| of the block when A_ii = 0) and nothing else.
+    __global__ void
+    k_scatter_3d(const int64_t n_cells, const int64_t first, const int64_t n, const double *__restrict__ x, const double *__restrict__ y,
+                 const double *__restrict__ z, const uint32_t *__restrict__ cv, const int32_t *__restrict__ cdofs,
+                 const uint32_t *__restrict__ con_mask, const uint8_t *__restrict__ neu_mask, const double t0, const double t1,
+                 const double t2, const double *__restrict__ A /* [31*31][n] */, const double *__restrict__ b /* [31][n] */,
+                 const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx, double *__restrict__ values,
+                 double *__restrict__ rhs, int *__restrict__ err)
+    {
+      const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      if (e >= n * NL3)
+        return;
+      const int64_t  t = e % n, c = first + t;
+      const int      i = (int)(e / n);
+      const uint32_t m  = con_mask[c];
+      const int32_t  gi = cdofs[(size_t)i * n_cells + c];
+      const int64_t  r0 = rowptr[gi], r1 = rowptr[gi + 1];
+      auto           find = [&](const int32_t col) -> int64_t {
+        int64_t lo = r0, hi = r1;
+        while (lo < hi)
+          {
+            const int64_t mid = (lo + hi) >> 1;
+            if (colidx[mid] < col)
+              lo = mid + 1;
+            else
+              hi = mid;
+          }
+        return (lo < r1 && colidx[lo] == col) ? lo : -1;
+      };
+      if ((m >> i) & 1u)
+        {
+          double d = fabs(A[(size_t)(i * NL3 + i) * n + t]);
+          if (d == 0.)
+            {
+              for (int k = 0; k < NL3; ++k)
+                d += fabs(A[(size_t)(k * NL3 + k) * n + t]);
+              d /= NL3;
+            }
+          const int64_t pos = find(gi);
+          if (pos < 0)
+            atomicExch(err, 1);
+          else
+            atomicAdd(values + pos, d);
+          return;
+        }
+      for (int j = 0; j < NL3; ++j)
+        {
+          if ((m >> j) & 1u)
+            continue;
+          const double v = A[(size_t)(i * NL3 + j) * n + t];
+          const int64_t pos = find(cdofs[(size_t)j * n_cells + c]);
+          if (pos < 0)
+            atomicExch(err, 1);
+          else
+            atomicAdd(values + pos, v); // structural zeros are added as well: the reference adds every local entry
+        }
+      double bi = b[(size_t)i * n + t];
+      const uint8_t nm = neu_mask[c];
+      if (nm != 0 && i < 24)
+        {
+          // traction term: phi_i = N_v e_k, local_rhs(i) += t_k int_f N_v dS on the faces that contain vertex v
+          const int    v = i / 3, k = i % 3;
+          const double tk = k == 0 ? t0 : (k == 1 ? t1 : t2);
+          if (tk != 0.)
+            {
+              Hex H;
+              for (int w = 0; w < 8; ++w)
+                {
+                  const uint32_t id = cv[(size_t)w * n_cells + c];
+                  H.vx[w]           = x[id];
+                  H.vy[w]           = y[id];
+                  H.vz[w]           = z[id];
+                }
+              for (int f = 0; f < 6; ++f)
+                {
+                  const int  d  = f >> 1;
+                  const bool on = (((v >> d) & 1) == (f & 1));
+                  if (((nm >> f) & 1) && on)
+                    bi += tk * face_shape_integral(H, f, v);
+                }
+            }
+        }
+      if (bi != 0.)
+        atomicAdd(rhs + gi, bi);
+    }
   } // namespace
+
+  cudaError_t
+  launch_gather_old_3d(const int64_t n_cells, const int64_t first, const int64_t n, const int32_t *cdofs, const double *old,
+                       double *cell_old, cudaStream_t s)
+  {
+    if (n <= 0)
+      return cudaSuccess;
+    k_gather_old_3d<<<(unsigned)((n * NL3 + 255) / 256), 256, 0, s>>>(n_cells, first, n, cdofs, old, cell_old);
+    return cudaGetLastError();
+  }
+
+  cudaError_t
+  launch_scatter_3d(const int64_t n_cells, const int64_t first, const int64_t n, const double *x, const double *y, const double *z,
+                    const uint32_t *cv, const int32_t *cdofs, const uint32_t *con_mask, const uint8_t *neu_mask,
+                    const double traction[3], const double *A, const double *b, const int64_t *rowptr, const int32_t *colidx,
+                    double *values, double *rhs, int *err, cudaStream_t s)
+  {
+    if (n <= 0)
+      return cudaSuccess;
+    k_scatter_3d<<<(unsigned)((n * NL3 + 127) / 128), 128, 0, s>>>(n_cells, first, n, x, y, z, cv, cdofs, con_mask, neu_mask,
+                                                                  traction[0], traction[1], traction[2], A, b, rowptr, colidx,
+                                                                  values, rhs, err);
+    return cudaGetLastError();
+  }
 
   cudaError_t
   launch_local_matrices_3d(const int64_t n_cells, const int64_t first, const int64_t n, const double *x, const double *y,

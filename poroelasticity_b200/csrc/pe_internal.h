@@ -143,7 +143,20 @@ struct pe_handle
     std::vector<double>   x, y, z;
     std::vector<uint32_t> cell_vertices; // [n_cells][8]
     int64_t               n_cells = 0;
+    std::vector<uint8_t>  face_kinds;    // [n_cells][6], PE_FACE_* bits; empty = no boundary data
+    double                traction[3] = {0., 0., 0.};
   } mesh3;
+  // device side of assemble_system in 3-D (pe_api.cu: assemble3)
+  struct Dev3
+  {
+    pe::DevBuf<double>   x, y, z, kc, A, b, old, cell_old;
+    pe::DevBuf<uint32_t> cv, con_mask;
+    pe::DevBuf<uint8_t>  neu_mask;
+    pe::DevBuf<int32_t>  cdofs;
+    pe::DevBuf<int>      err;
+    int64_t          chunk = 0;
+    bool             ready = false;
+  } dev3;
   pe::HostMesh    mesh;
   pe::HostDofs    dofs;
   pe::Partition   part;

@@ -77,6 +77,14 @@ namespace pe
                                        double alpha, double c0, double dt, const double *cell_old, double *out, double *rhs_out,
                                        cudaStream_t s);
 
+  // assemble_system in 3-D: gather of the old solution per cell, constraints + traction + scatter of the dense blocks
+  cudaError_t launch_gather_old_3d(int64_t n_cells, int64_t first, int64_t n, const int32_t *cdofs, const double *old,
+                                   double *cell_old, cudaStream_t s);
+  cudaError_t launch_scatter_3d(int64_t n_cells, int64_t first, int64_t n, const double *x, const double *y, const double *z,
+                                const uint32_t *cv, const int32_t *cdofs, const uint32_t *con_mask, const uint8_t *neu_mask,
+                                const double traction[3], const double *A, const double *b, const int64_t *rowptr,
+                                const int32_t *colidx, double *values, double *rhs, int *err, cudaStream_t s);
+
   // ---- solver kernels (pe_solver.cu)
   cudaError_t launch_spmv(int64_t n_rows, const int64_t *rowptr, const int32_t *colidx, const double *values,
                           const double *x, double *y, cudaStream_t s);

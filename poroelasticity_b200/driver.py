@@ -344,6 +344,18 @@ class PoroElas_CGQ1_WG_3D(BiotSystem):
         self._ck(self.L.pe_get_mesh3(self.h, None, None, ptr(x), ptr(y), ptr(z), ptr(cv)))
         return x, y, z, cv
 
+    def setup_system(self):
+        """make_grid_and_dofs part 2 (CGQ1:902-943): distribute_dofs + component_wise, make_sparsity_pattern"""
+        self._ck(self.L.pe_distribute_dofs(self.h))
+        self._ck(self.L.pe_make_sparsity_pattern(self.h))
+        return self.sizes()
+
+    def set_boundary3(self, face_kinds, traction=None):
+        """face_kinds [n_cells][6] of PE_FACE_* bits; make_grid installs the shipped sandwich data"""
+        fk = np.ascontiguousarray(face_kinds, np.uint8)
+        tr = None if traction is None else np.ascontiguousarray(traction, np.float64)
+        self._ck(self.L.pe_set_boundary3(self.h, ptr(fk), ptr(tr)))
+
     def local_matrices3(self, first, n, cell_old=None, want_rhs=True):
         out = np.zeros((n, 31, 31))
         rhs = np.zeros((n, 31)) if want_rhs else None

@@ -291,6 +291,32 @@ class Oracle3D:
         self.L.orc3_dofs_pattern(self.h, _p(s), _p(cd), _p(rp), _p(ci))
         return tuple(int(v) for v in s[:3]), cd, rp, ci
 
+    def set_boundary(self, face_kind=None, traction=None):
+        """face_kind [n_cells][6] bits FK_DIR_U = 1 | FK_DIR_P = 2 | FK_NEU_U = 4; None = the shipped sandwich boundary"""
+        self.L.orc3_set_boundary.argtypes = [C.c_void_p] * 3
+        if face_kind is None:
+            self.L.orc3_set_boundary(self.h, None, None)
+            return
+        fk = np.ascontiguousarray(face_kind, np.uint8)
+        assert fk.size == 6 * self.n_cells
+        tr = np.ascontiguousarray(np.zeros(3) if traction is None else traction, np.float64)
+        self.L.orc3_set_boundary(self.h, _p(fk), _p(tr))
+
+    def boundary(self):
+        self.L.orc3_get_boundary.argtypes = [C.c_void_p] * 3
+        fk, tr = np.zeros((self.n_cells, 6), np.uint8), np.zeros(3)
+        self.L.orc3_get_boundary(self.h, _p(fk), _p(tr))
+        return fk, tr
+
+    def assemble(self, old_solution=None):
+        """(values in CSR order of dofs_pattern(), rhs) of assemble_system in 3-D"""
+        self.L.orc3_assemble.argtypes = [C.c_void_p] * 4
+        (n_u, n_pi, n_pf), cd, rp, ci = self.dofs_pattern()
+        v, r = np.zeros(ci.size), np.zeros(n_u + n_pi + n_pf)
+        o = None if old_solution is None else np.ascontiguousarray(old_solution, np.float64)
+        self.L.orc3_assemble(self.h, None if o is None else _p(o), _p(v), _p(r))
+        return v, r
+
     def local(self, cell, cell_old=None):
         o = np.zeros(31) if cell_old is None else np.ascontiguousarray(cell_old, np.float64)
         A, b = np.zeros((31, 31)), np.zeros(31)

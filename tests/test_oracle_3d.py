@@ -119,3 +119,52 @@ def test_dof_numbering_3d_shared_entities():
     (n_u, n_pint, n_pface), cd, rp, ci = o.dofs_pattern()
     r = cd[0, 25]
     assert rp[r + 1] - rp[r] == 31 + 31 - 13
+
+
+def test_assemble_system_3d_sandwich_boundary_by_hand():
+    """The shipped boundary data (CGQ1:972-981, 1563-1582, 1663-1679) on 4^3 cells: face kinds, total traction, and the
+    form distribute_local_to_global leaves constrained dofs in (a positive diagonal, nothing else in row and column)."""
+    import scipy.sparse as sp
+    o = Oracle3D(2)
+    o.set_material(3.0, 0.7, 0.93, 0.1, 1e-3)
+    o.set_boundary()
+    fk, tr = o.boundary()
+    assert list(tr) == [0.0, 0.0, -1.0]
+    assert (fk == 6).sum() == 16 and (fk == 1).sum() == 5 * 16 and (fk != 0).sum() == 6 * 16   # top: DIR_P | NEU_U
+    (n_u, n_pi, n_pf), cd, rp, ci = o.dofs_pattern()
+    v, r = o.assemble()
+    n = n_u + n_pi + n_pf
+    A = sp.csr_matrix((v, ci, rp), shape=(n, n)).toarray()
+    # traction (0, 0, -1) on z = 1: every free top vertex (the 3 x 3 interior ones) receives -h^2 in its z row
+    ru = r[:n_u].reshape(-1, 3)
+    assert np.allclose(ru[:, :2], 0) and np.isclose(ru[:, 2].sum(), -9 / 16) and np.count_nonzero(ru[:, 2]) == 9
+    assert np.allclose(r[n_u:], 0)          # f = s = 0 and old_solution = 0
+    # constrained dofs: all displacement dofs of boundary vertices except the 9 free top ones, and the 16 top face pressures
+    con = [i for i in range(n) if np.count_nonzero(A[i]) == 1 and np.count_nonzero(A[:, i]) == 1]
+    assert len(con) == 3 * (125 - 27 - 9) + 16 and all(A[i, i] > 0 for i in con)
+    # the reduced system is regular and the load pushes the free top vertices down
+    free = np.setdiff1d(np.arange(n), con)
+    x = np.linalg.solve(A[np.ix_(free, free)], r[free])
+    uz = np.zeros(n)
+    uz[free] = x
+    assert uz[:n_u].reshape(-1, 3)[:, 2].min() < 0 and uz[:n_u].reshape(-1, 3)[:, 2].max() <= 1e-14
+
+
+def test_assemble_system_3d_unconstrained_equals_sum_of_local_blocks():
+    """no boundary data: the global matrix is the plain sum of the local blocks, rhs carries the old-solution terms"""
+    o = Oracle3D(1, distort=0.2)
+    o.set_material(2.0, 0.9, 0.8, 0.05, 0.01)
+    o.set_boundary(np.zeros((o.n_cells, 6), np.uint8))
+    (n_u, n_pi, n_pf), cd, rp, ci = o.dofs_pattern()
+    n = n_u + n_pi + n_pf
+    rng = np.random.default_rng(5)
+    old = rng.normal(size=n)
+    v, r = o.assemble(old)
+    import scipy.sparse as sp
+    A = sp.csr_matrix((v, ci, rp), shape=(n, n)).toarray()
+    S, b = np.zeros((n, n)), np.zeros(n)
+    for c in range(o.n_cells):
+        Al, bl = o.local(c, old[cd[c]])
+        S[np.ix_(cd[c], cd[c])] += Al
+        b[cd[c]] += bl
+    assert np.abs(A - S).max() <= 1e-13 * np.abs(S).max() and np.abs(r - b).max() <= 1e-13 * np.abs(b).max()
