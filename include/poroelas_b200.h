@@ -117,8 +117,8 @@ int pe_set_mesh(pe_handle *h, int64_t n_vertices, const double *x, const double 
  * for f = s = 0 (the sandwich problem), local dof order 3 v + c | 24 + face | 30 = p_int; cell_old = the 31 old-solution
  * values of every cell (may be NULL).  pe_distribute_dofs, pe_make_sparsity_pattern, pe_get_sizes, pe_get_dofs and
  * pe_get_pattern work on a dim = 3 handle (host side: first-touch numbering of vertices x 3 | FE_FaceQ(0) quads | FE_DGQ(0)
- * hex per cell + component_wise, full-coupling CSR; one rank), and so does pe_assemble_system (below).  The solve in 3-D
- * is not built yet: pe_solve_time_step on a dim = 3 handle fails with an error. */
+ * hex per cell + component_wise, full-coupling CSR; one rank), and so do pe_assemble_system and pe_solve_time_step
+ * (below; first version of the 3-D solve).  Postprocessing, error norms and several GPUs in 3-D are not built. */
 int pe_make_unit_cube(pe_handle *h, int n_refine, double distort, uint64_t seed);
 int pe_set_mesh3(pe_handle *h, int64_t n_vertices, const double *x, const double *y, const double *z, int64_t n_cells,
                  const uint32_t *cell_vertices);
@@ -133,8 +133,12 @@ int pe_local_matrices3(pe_handle *h, int64_t first_cell, int64_t n, double time_
  * PE_FACE_DIR_U (CGQ1:1673-1679).  pe_set_mesh3 clears the boundary data.
  * pe_assemble_system on a dim = 3 handle (after pe_distribute_dofs + pe_make_sparsity_pattern; one GPU): cell loop,
  * traction term, constraints of the whole mesh, distribute_local_to_global (CGQ1:1165-1706); t is ignored (no
- * time-dependent data), old_solution = host vector of all dofs or NULL = zero; pe_get_matrix / pe_get_rhs return the
- * result in the CSR order of pe_get_pattern. */
+ * time-dependent data), old_solution = host vector of all dofs or NULL = the state resident on the device (zero after
+ * setup, the solution of the previous pe_solve_time_step afterwards); pe_get_matrix / pe_get_rhs return the result in
+ * the CSR order of pe_get_pattern.
+ * pe_solve_time_step on a dim = 3 handle (CGQ1:1712-1722): first version -- MINRES on the row-signed two-field system
+ * with a diagonal / Schur-diagonal preconditioner, warm start from old_solution, true residual <= rel_tol ||b||; no
+ * multigrid in 3-D yet (adequate for the shipped 8^3 mesh).  Constrained dofs come out as their boundary value 0. */
 int pe_set_boundary3(pe_handle *h, const uint8_t *face_kinds, const double *traction);
 
 /* ---- S2: DoFs.  distribute_dofs + DoFRenumbering::component_wise  BR1new:586-597 CGQ1:902-919 */

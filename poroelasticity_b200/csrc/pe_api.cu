@@ -1933,7 +1933,7 @@ extern "C"
 
   // assemble_system on hexahedra (CGQ1:1165-1706 with dim = 3; one rank): dense blocks of k_local_matrices_3d in chunks,
   // then constraints + traction + scatter with atomics into the pre-zeroed CSR values (k_scatter_3d).  Boundary values are
-  // homogeneous (BoundaryValues returns 0, CGQ1:697-725); old_solution = host vector of all dofs, NULL = zero.
+  // homogeneous (BoundaryValues returns 0, CGQ1:697-725).
   static int
   assemble3(pe_handle *h, const double time_step, const double *old_solution)
   {
@@ -2000,6 +2000,7 @@ extern "C"
         PE_CUDA(h->d_values.alloc((size_t)h->nnz));
         PE_CUDA(h->d_rhs.alloc((size_t)n));
         PE_CUDA(d.old.alloc((size_t)n));
+        PE_CUDA(cudaMemsetAsync(d.old.p, 0, sizeof(double) * (size_t)n, s)); // old_solution = 0 at the start of run()
         PE_CUDA(d.err.alloc(1));
         d.chunk = std::min<int64_t>(nc, 16384); // 16384 x 961 x 8 B = 126 MB of dense blocks per chunk
         PE_CUDA(d.A.alloc((size_t)961 * d.chunk));
@@ -2018,10 +2019,10 @@ extern "C"
         kp = d.kc.p;
       }
     PE_CUDA(cudaEventRecord(h->ev[0], s));
+    // old_solution: a host vector of all dofs, or NULL = the state resident on the device (zero after setup, the
+    // solution of the previous pe_solve_time_step afterwards: old_solution = solution, CGQ1:3011)
     if (old_solution)
       PE_CUDA(cudaMemcpyAsync(d.old.p, old_solution, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s));
-    else
-      PE_CUDA(cudaMemsetAsync(d.old.p, 0, sizeof(double) * (size_t)n, s));
     PE_CUDA(cudaMemsetAsync(h->d_values.p, 0, sizeof(double) * (size_t)h->nnz, s));
     PE_CUDA(cudaMemsetAsync(h->d_rhs.p, 0, sizeof(double) * (size_t)n, s));
     PE_CUDA(cudaMemsetAsync(d.err.p, 0, sizeof(int), s));
@@ -2050,6 +2051,63 @@ extern "C"
     h->assemble_kernel_ms = ms;
     h->last_dt            = time_step;
     h->matrix_valid       = true; // pe_get_matrix / pe_get_rhs read d_values / d_rhs (device_ready stays false: no 2-D tables)
+    return PE_OK;
+  }
+
+
+  // solve_time_step in 3-D (CGQ1:1712-1722: UMFPACK + constraints.distribute).  First version: MINRES on the row-signed
+  // two-field system (u rows kept, pressure rows negated: symmetric) with the diagonal preconditioner of the first 2-D
+  // solver -- |a_ii| on u and face-pressure rows, |a_ii| + sum_j b_ij^2 / |a_jj| (diagonal of the Schur complement) on
+  // the interior pressures --, warm start from old_solution, stopping rule ||b - A x|| <= rel_tol ||b|| on the assembled
+  // matrix.  No multigrid in 3-D yet: fine for the shipped 8^3 mesh, not a production solver.  The constrained dofs come
+  // out as their boundary value 0 (their rows are d x_i = 0), which is what constraints.distribute() enforces.
+  static int
+  solve3(pe_handle *h, const double rel_tol, const int max_iterations, double *solution, pe_solve_stats *stats)
+  {
+    pe_handle::Dev3 &d = h->dev3;
+    cudaStream_t     s = h->stream;
+    const size_t     n = (size_t)h->L;
+    for (int k = 0; k < 10; ++k)
+      if (h->d_w[k].n < n)
+        PE_CUDA(h->d_w[k].alloc(n));
+    if (h->d_scal.n < 64)
+      PE_CUDA(h->d_scal.alloc(64));
+    SolverCtx c;
+    c.L              = h->L;
+    c.H              = 0;
+    c.n_pos          = h->dofs.n_u;
+    c.pint_begin     = h->dofs.n_u;
+    c.pint_end       = h->dofs.n_u + h->dofs.n_pint;
+    c.rowptr         = h->d_rowptr.p;
+    c.colidx         = h->d_colidx.p;
+    c.values         = h->d_values.p;
+    c.stream         = s;
+    c.use_graphs     = h->use_graphs != 0;
+    c.launch_counter = &h->launches;
+    c.ev_ring        = h->ev_ring;
+    PE_CUDA(cudaEventRecord(h->ev[3], s));
+    double *diag = h->d_w[8].p, *pinv = h->d_w[9].p, *x = h->d_w[7].p;
+    if (build_preconditioner(c, diag, pinv) != 0)
+      return cuda_fail(h, cudaGetLastError(), "3-D diagonal preconditioner");
+    PE_CUDA(cudaMemcpyAsync(x, d.old.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+    double   *work[7] = {h->d_w[0].p, h->d_w[1].p, h->d_w[2].p, h->d_w[3].p, h->d_w[4].p, h->d_w[5].p, h->d_w[6].p};
+    const int rc      = minres_solve(c, h->d_rhs.p, x, pinv, work, (MinresState *)h->d_scal.p, h->h_scal, rel_tol, max_iterations, stats);
+    if (rc == -2)
+      return fail(h, PE_ERR_CUDA, "CUDA graph capture of the MINRES iteration failed (pe_set_solver_options bit 6 runs without graphs)");
+    PE_CUDA(cudaEventRecord(h->ev[4], s));
+    PE_CUDA(cudaEventSynchronize(h->ev[4]));
+    if (rc != 0)
+      return cuda_fail(h, cudaGetLastError(), "krylov solve (3-D)");
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]);
+    h->solve_ms    = ms;
+    stats->seconds = ms * 1e-3;
+    PE_CUDA(cudaMemcpyAsync(d.old.p, x, sizeof(double) * n, cudaMemcpyDeviceToDevice, s)); // old_solution = solution
+    if (solution)
+      PE_CUDA(cudaMemcpyAsync(solution, x, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    PE_CUDA(cudaStreamSynchronize(s));
+    if (!stats->converged)
+      return fail(h, PE_ERR_NOT_CONVERGED, "Krylov solver did not reach the requested residual");
     return PE_OK;
   }
 
@@ -2354,7 +2412,7 @@ extern "C"
   pe_solve_time_step(pe_handle *h, double rel_tol, int max_iterations, double *solution, pe_solve_stats *stats)
   {
     NvtxRange nvtx("pe_solve_time_step");
-    if (!h || !h->device_ready || !h->matrix_valid)
+    if (!h || !(h->device_ready || (h->cfg.dim == 3 && h->dev3.ready)) || !h->matrix_valid)
       return fail(h, PE_ERR_ARG, "pe_solve_time_step: assemble first");
     PE_DEVICE(h);
     PE_TRY
@@ -2362,6 +2420,8 @@ extern "C"
     if (!stats)
       stats = &local;
     std::memset(stats, 0, sizeof(*stats));
+    if (h->cfg.dim == 3)
+      return solve3(h, rel_tol, max_iterations, solution, stats);
     const size_t n = (size_t)(h->L + h->H);
     if (h->cfg.element == PE_WG_Q2RT2)
       for (int k = 0; k < 3; ++k)

@@ -350,6 +350,26 @@ class PoroElas_CGQ1_WG_3D(BiotSystem):
         self._ck(self.L.pe_make_sparsity_pattern(self.h))
         return self.sizes()
 
+    def run(self, n_refine=3, t_end=0.011, verbose=False):
+        """run() of the shipped program (CGQ1:2962-3011): hyper_cube + refine_global(3), sandwich permeability and
+        boundary data, `for (time = dt; time <= 0.011; time += dt)` (CGQ1:2929), old_solution = solution on the device.
+        Returns [(time, iterations, rel_residual)]."""
+        self.make_grid(n_refine)
+        x, y, z, cv = self.mesh3()
+        zc = z[cv].mean(axis=1)
+        self.set_material(k_cell=np.where((zc >= 0.25) & (zc <= 0.75), 1e-8, 1.0))   # Coefficient, CGQ1:176-189
+        self.setup_system()
+        hist, time, first = [], self.time_step, True
+        while time <= t_end:
+            if verbose:
+                print("Time step %d at t=%g" % (len(hist) + 1, time))
+            self.assemble_system(time, np.zeros(self.sizes().n_dofs) if first else None)
+            self.solve_time_step(want_solution=False)
+            hist.append((time, self.stats.iterations, self.stats.rel_residual))
+            time += self.time_step
+            first = False
+        return hist
+
     def set_boundary3(self, face_kinds, traction=None):
         """face_kinds [n_cells][6] of PE_FACE_* bits; make_grid installs the shipped sandwich data"""
         fk = np.ascontiguousarray(face_kinds, np.uint8)

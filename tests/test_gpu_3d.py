@@ -107,9 +107,68 @@ def test_assemble_system_3d(n_refine, distort, sandwich):
     assert np.abs(r - r_ref).max() <= 1e-12 * np.abs(r_ref).max()
     # a second assembly with the zero state reproduces the oracle as well (buffers are re-zeroed)
     v_ref0, r_ref0 = o.assemble()
-    g.assemble_system(0.0)
+    g.assemble_system(0.0, np.zeros_like(old))
     assert np.abs(g.system_matrix() - v_ref0).max() <= 1e-12 * np.abs(v_ref0).max()
     assert np.abs(g.system_rhs() - r_ref0).max() <= 1e-12 * max(np.abs(r_ref0).max(), 1e-300)
-    with pytest.raises(pb.PoroElasError):
-        g.solve_time_step()
+    g.close()
+
+
+def test_time_steps_3d_shipped_program():
+    """Three steps of the shipped 3-D program (CGQ1:859-866 data: lambda = mu = alpha = 1, c0 = 0, dt = 1/1000, 8^3 cells,
+    sandwich K and boundary): assemble + solve through the C ABI, old_solution resident on the device, against the sparse
+    LU solution of the oracle's system of the same step -- u and p within 1e-8 relative L2.
+    The system has condition number 5e11 (K = 1e-8 in the layer, dt = 1e-3): a plain SuperLU solve is only good to 1.6e-6
+    in p, so the comparison solution is computed on the symmetrically equilibrated matrix (condition 3e5) with one step
+    of iterative refinement (UMFPACK, which the reference uses, scales rows by default as well)."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+
+    def lu_equilibrated(A, b):
+        sc = 1.0 / np.sqrt(np.abs(A.diagonal()))
+        S = sp.diags(sc)
+        Ah = (S @ A @ S).tocsc()
+        lu = spla.splu(Ah)
+        y = lu.solve(sc * b)
+        y += lu.solve(sc * b - Ah @ y)
+        return sc * y
+
+    o = Oracle3D(3)
+    g = pb.PoroElas_CGQ1_WG_3D()
+    g.make_grid(3)
+    k = sandwich_k(o)
+    dt = 1e-3
+    o.set_material(1.0, 1.0, 1.0, 0.0, dt)
+    o.set_kcell(k)
+    o.set_boundary()
+    g.set_material(1.0, 1.0, 1.0, 0.0, k_cell=k)
+    g.time_step = dt
+    g.setup_system()
+    g.rel_tol, g.max_iterations = 1e-11, 20000
+    (n_u, n_pi, n_pf), cd, rp, ci = o.dofs_pattern()
+    n = n_u + n_pi + n_pf
+    old = np.zeros(n)
+    for step in range(3):
+        v_ref, r_ref = o.assemble(old)
+        x_ref = lu_equilibrated(sp.csr_matrix((v_ref, ci, rp), shape=(n, n)), r_ref)
+        g.assemble_system((step + 1) * dt, old if step == 0 else None)
+        if step > 0:   # the resident state is the previous device solution: the rhs agrees to solver accuracy only
+            assert rel(g.system_rhs(), r_ref) < 1e-7
+        else:
+            assert rel(g.system_matrix(), v_ref) < 1e-12 and rel(g.system_rhs(), r_ref) < 1e-12
+        x = g.solve_time_step()
+        assert g.stats.converged >= 1 and g.stats.rel_residual <= 1e-11 * (1 + 1e-9) or g.stats.converged == 2
+        eu = np.linalg.norm(x[:n_u] - x_ref[:n_u]) / np.linalg.norm(x_ref[:n_u])
+        ep = np.linalg.norm(x[n_u:] - x_ref[n_u:]) / np.linalg.norm(x_ref[n_u:])
+        assert eu < 1e-8 and ep < 1e-8, (step, eu, ep, g.stats.iterations)
+        old = x_ref
+    # the load pushes the top down
+    assert x[:n_u].reshape(-1, 3)[:, 2].min() < 0
+    g.close()
+
+
+def test_run_3d():
+    g = pb.PoroElas_CGQ1_WG_3D()
+    g.rel_tol, g.max_iterations = 1e-10, 20000
+    hist = g.run(n_refine=2)
+    assert len(hist) in (10, 11) and all(h[2] <= 1e-10 * (1 + 1e-9) for h in hist)
     g.close()
