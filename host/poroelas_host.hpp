@@ -36,7 +36,7 @@ namespace poroelas
       , alpha(alpha_)
       , capacity(capacity_)
     {
-      static_assert(dim == 2, "3-D is SURVEY 8(f) 'next'");
+      static_assert(dim == 2 || dim == 3, "dim = 2 or 3");
       pe_config cfg{};
       cfg.element    = element;
       cfg.dim        = dim;
@@ -63,12 +63,16 @@ namespace poroelas
     {
       std::cout << "Solving problem in " << dim << " space dimensions." << std::endl;
       make_grid_and_dofs();
-      // old_solution = 0 (BR1new:2163): the device solution starts at zero
-      for (timestep_number = 1, time = time_step; time <= total_time; time += time_step, ++timestep_number)
+      // old_solution = 0 (BR1new:2163): the device solution starts at zero.
+      // The 3-D program hard-codes its loop bound: `time <= 0.011` (CGQ1:2929, total_time = 1/100).
+      const double t_end = dim == 3 ? 0.011 : total_time;
+      for (timestep_number = 1, time = time_step; time <= t_end; time += time_step, ++timestep_number)
         {
           std::cout << "Time step " << timestep_number << " at t=" << time << " time_step " << time_step << std::endl;
           assemble_system(time);
           solve_time_step();
+          if (dim == 3)
+            continue; // postprocess / error norms / velocity output are not built in 3-D
           postprocess();
           if (with_errors)
             postprocess_errors(time, timestep_number);
@@ -86,6 +90,15 @@ namespace poroelas
     const std::vector<double> &dilation() const { return div_displacement; }
     const std::vector<double> &magnitude() const { return displacement_magnitude; }
 
+    // 3-D: the solution of the last step (pe_solve_time_step hands it out; there is no pe_get_solution in 3-D yet)
+    const std::vector<double> &solution3() const { return last_solution; }
+    int64_t
+    n_u() const
+    {
+      pe_sizes s;
+      pe_get_sizes(h, &s);
+      return s.n_u;
+    }
     const pe_solve_stats &last_solve() const { return stats; }
     pe_handle            *handle() { return h; }
     std::vector<double>
@@ -99,9 +112,42 @@ namespace poroelas
     }
 
   protected:
+    // 3-D: hyper_cube + refine_global (CGQ1:886-887), boundary ids of the sandwich problem (CGQ1:972-981, installed by
+    // pe_make_unit_cube), Coefficient = 1e-8 for 1/4 <= z <= 3/4 (CGQ1:176-189) evaluated at the cell centre
+    void
+    make_grid_and_dofs3()
+    {
+      check(pe_make_unit_cube(h, refinement, 0., 0), "pe_make_unit_cube");
+      int64_t nv = 0, nc = 0;
+      check(pe_get_mesh3(h, &nv, &nc, nullptr, nullptr, nullptr, nullptr), "pe_get_mesh3");
+      std::vector<double>   x((size_t)nv), y((size_t)nv), z((size_t)nv), k((size_t)nc);
+      std::vector<uint32_t> cv((size_t)8 * nc);
+      check(pe_get_mesh3(h, nullptr, nullptr, x.data(), y.data(), z.data(), cv.data()), "pe_get_mesh3");
+      for (int64_t c = 0; c < nc; ++c)
+        {
+          double zc = 0.;
+          for (int v = 0; v < 8; ++v)
+            zc += z[cv[(size_t)8 * c + v]] / 8.;
+          k[(size_t)c] = (zc >= 0.25 && zc <= 0.75) ? 1e-8 : 1.;
+        }
+      check(pe_distribute_dofs(h), "pe_distribute_dofs");
+      check(pe_make_sparsity_pattern(h), "pe_make_sparsity_pattern");
+      pe_sizes s;
+      pe_get_sizes(h, &s);
+      std::cout << "Number of active cells: " << s.n_cells << std::endl
+                << "Number of degrees of freedom: " << s.n_dofs << " (" << s.n_u << '+' << s.n_pint << '+' << s.n_pface
+                << ')' << std::endl
+                << std::endl;
+      check(pe_set_material(h, lambda, mu, alpha, capacity, 1.0, k.data()), "pe_set_material");
+    }
     void
     make_grid_and_dofs()
     {
+      if (dim == 3)
+        {
+          make_grid_and_dofs3();
+          return;
+        }
       check(pe_make_unit_square(h, refinement, 0., 0, cantilever ? 0 : boundary_kinds), "pe_make_unit_square");
       check(pe_distribute_dofs(h), "pe_distribute_dofs");
       check(pe_make_sparsity_pattern(h), "pe_make_sparsity_pattern");
@@ -156,7 +202,14 @@ namespace poroelas
     void
     solve_time_step()
     {
-      check(pe_solve_time_step(h, rel_tol, max_iterations, nullptr, &stats), "pe_solve_time_step");
+      if (dim == 3)
+        {
+          pe_sizes s;
+          pe_get_sizes(h, &s);
+          last_solution.resize((size_t)s.n_dofs);
+        }
+      check(pe_solve_time_step(h, rel_tol, max_iterations, dim == 3 ? last_solution.data() : nullptr, &stats),
+            "pe_solve_time_step");
     }
     // postprocess()  BR1new:1189-1246 / CGQ1:1744-1879: cell averages of div u_h and |u_h|
     void
@@ -201,7 +254,7 @@ namespace poroelas
 
     pe_handle     *h = nullptr;
     pe_solve_stats stats{};
-    std::vector<double> div_displacement, displacement_magnitude;
+    std::vector<double> div_displacement, displacement_magnitude, last_solution;
     double              err_acc[3] = {0., 0., 0.};
     double         total_time, time = 0., time_step;
     unsigned int   number_timestep, timestep_number;
@@ -219,7 +272,8 @@ namespace poroelas
       : BiotProgram<dim>(PE_BR1_WG, T, dt, lambda, mu, alpha, c0)
     {}
   };
-  // PoroElas_CGQ1_WG<2>: "general case" constructor block CGQ1:824-831
+  // PoroElas_CGQ1_WG<2>: "general case" constructor block CGQ1:824-831; PoroElas_CGQ1_WG<3>(1./100, 1./1000, 1, 1, 1, 0) with
+  // refinement = 3 is the program the file ships (CGQ1:859-866, 3029)
   template <int dim>
   struct PoroElas_CGQ1_WG : BiotProgram<dim>
   {

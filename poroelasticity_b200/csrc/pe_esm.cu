@@ -34,7 +34,10 @@ namespace pe
     __constant__ EsmTables cT;
     // the same tables in global memory: lane-dependent addresses serialise in the constant cache (one request per
     // distinct address), which bounded BOTH cell kernels at 8.8e7 cells/s before the tensor-core version read them from here
-    EsmTables *dT = nullptr;
+    // (constant memory and allocations belong to one device: both copies are kept per device, a process may hold
+    //  handles on several GPUs)
+    constexpr int kMaxDev = 64;
+    EsmTables    *dT[kMaxDev] = {};
 
     void
     gauss4(double x[4], double w[4])
@@ -86,11 +89,19 @@ namespace pe
           dv[12 + k]   = Px[k % 3] * dPy[k / 3];
         }
     }
-    bool tables_ready = false;
+    bool tables_ready[kMaxDev] = {};
+    int
+    current_device()
+    {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      return dev >= 0 && dev < kMaxDev ? dev : 0;
+    }
     cudaError_t
     upload_tables()
     {
-      if (tables_ready)
+      const int dev = current_device();
+      if (tables_ready[dev])
         return cudaSuccess;
       static EsmTables T;
       double           gx[4], gw[4];
@@ -137,11 +148,11 @@ namespace pe
                 T.F[(3 * f + i) * kRt + k] += L[i] * (w[k][0] * nx + w[k][1] * ny) * gw[q];
           }
       cudaError_t e = cudaMemcpyToSymbol(cT, &T, sizeof(T));
-      if (e == cudaSuccess && !dT)
-        e = cudaMalloc(&dT, sizeof(T));
+      if (e == cudaSuccess && !dT[dev])
+        e = cudaMalloc(&dT[dev], sizeof(T));
       if (e == cudaSuccess)
-        e = cudaMemcpy(dT, &T, sizeof(T), cudaMemcpyHostToDevice);
-      tables_ready = e == cudaSuccess;
+        e = cudaMemcpy(dT[dev], &T, sizeof(T), cudaMemcpyHostToDevice);
+      tables_ready[dev] = e == cudaSuccess;
       return e;
     }
 
@@ -900,7 +911,7 @@ namespace pe
     x.values   = a.values;
     x.rhs      = a.rhs;
     x.case_id  = case_id;
-    x.tab = dT;
+    x.tab = dT[current_device()];
     if (a.esm_variant == 0)
       k_esm_cell_mma<false><<<mma_grid(x.n), kWarps * 32, 0, s>>>(x);
     else
@@ -928,7 +939,7 @@ namespace pe
     x.out      = out;
     x.rhs_out  = rhs_out;
     x.case_id  = case_id;
-    x.tab = dT;
+    x.tab = dT[current_device()];
     if (a.esm_variant == 0)
       k_esm_cell_mma<true><<<mma_grid(n), kWarps * 32, 0, s>>>(x);
     else

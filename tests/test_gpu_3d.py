@@ -172,3 +172,22 @@ def test_run_3d():
     hist = g.run(n_refine=2)
     assert len(hist) in (10, 11) and all(h[2] <= 1e-10 * (1 + 1e-9) for h in hist)
     g.close()
+
+
+def test_cpp_host_driver_runs_the_shipped_3d_program():
+    """host/poroelas_cgq1wg 3d: PoroElas_CGQ1_WG<3>(1/100, 1/1000, 1, 1, 1, 0).run() of the C++ mirror (CGQ1:859-866,
+    2929, 3029) on 4^3 cells: the reference's stdout lines, every step converged, the top settles."""
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "host", "poroelas_cgq1wg")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(root, "host")])
+    out = subprocess.run([exe, "3d", "2"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "Solving problem in 3 space dimensions." in out.stdout
+    assert "Number of degrees of freedom: 679 (375+64+240)" in out.stdout
+    assert out.stdout.count("Time step") in (10, 11)
+    m = re.search(r"largest settlement: u_z = (-[\d.e+-]+)", out.stdout)
+    assert m and float(m.group(1)) < 0
