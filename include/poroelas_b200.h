@@ -216,10 +216,11 @@ int pe_set_solver_options(pe_handle *h, int use_multigrid, double theta, double 
  * Keys: "mg_omega2", "cmg_omega", "cmg_omega2", "face_omega" (smoother weights); "mg_fused_n" (largest level of the
  * single-CTA multigrid kernel); "asm_gather" (1: gather assembly instead of the RED scatter); multi-GPU: "mg_replicated",
  * "mg_whole_slabs", "one_lane" (1: the round-1 communication schemes, kept for A/B runs), "mg_dist_min_n" (smallest grid
- * level distributed over the ranks); "reuse_operator" (default 1: the solver operator and its preconditioner are rebuilt
- * only when something that enters the matrix values changes -- material data, time step, permeability, boundary kinds,
- * mesh / numbering; 0: rebuilt in every pe_solve_time_step.  The matrix itself is assembled by every
- * pe_assemble_system and the true residual is taken on it either way); "esm_dfma" (1: the first, DFMA-only
+ * level distributed over the ranks); "reuse_operator" (CACHED MODE, default 0 = the solver operator and its
+ * preconditioner are rebuilt in every pe_solve_time_step, as the reference refactorises in every step; 1 = they are
+ * rebuilt only when something that enters the matrix values changes -- material data, time step, permeability,
+ * boundary kinds, mesh / numbering.  The matrix itself is assembled by every pe_assemble_system and the true residual is
+ * taken on it either way); "esm_dfma" (1: the first, DFMA-only
  * WG(Q2,Q2;RT[2]) cell kernel instead of the FP64 tensor-core one).  Structural keys rebuild the device tables before
  * the next assembly. */
 int pe_set_tuning(pe_handle *h, const char *key, double value);

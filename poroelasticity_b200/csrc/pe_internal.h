@@ -115,7 +115,8 @@ namespace pe
     int    mg_fused_n     = -1;   // largest level handled by the single-CTA multigrid kernel (< 0: built-in)
     int    mg_dist_min_n  = 1024; // smallest grid level (cells per side) that is distributed over the ranks
     int    esm_dfma       = 0;    // WG(Q2,Q2;RT[2]): the first, DFMA-only cell kernel instead of the DMMA one (A/B)
-    int    reuse_operator = 1;    // keep the solver operator + preconditioner while the inputs of the matrix are unchanged
+    int    reuse_operator = 0;    // 1 = cached mode: keep the solver operator + preconditioner while the inputs of the
+                                  // matrix are unchanged (default 0: rebuilt by every solve, as the reference refactorises)
   };
 
   struct HaloPeer
