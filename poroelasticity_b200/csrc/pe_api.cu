@@ -2130,6 +2130,8 @@ extern "C"
   {
     if (!h)
       return PE_ERR_ARG;
+    if (h->cfg.dim == 3)
+      return fail(h, PE_ERR_ARG, "pe_assemble_rhs_only: not built for dim = 3 yet");
     PE_DEVICE(h);
     PE_TRY
     return assemble_impl(h, t, time_step, old_solution, false);
@@ -2193,6 +2195,8 @@ extern "C"
   {
     if (!h || !solution)
       return PE_ERR_ARG;
+    if (h->cfg.dim == 3)
+      return fail(h, PE_ERR_ARG, "pe_set_solution: not built for dim = 3 yet");
     PE_DEVICE(h);
     PE_TRY
     const int rc = ensure_device(h);
@@ -2658,6 +2662,8 @@ extern "C"
   {
     if (!h || !e)
       return PE_ERR_ARG;
+    if (h->cfg.dim == 3)
+      return fail(h, PE_ERR_ARG, "pe_step_errors: not built for dim = 3 yet");
     if (h->cfg.element != PE_BR1_WG && h->cfg.element != PE_CGQ1_WG)
       return fail(h, PE_ERR_ARG, "pe_step_errors: element not implemented yet");
     PE_DEVICE(h);
@@ -2687,6 +2693,8 @@ extern "C"
   {
     if (!h)
       return PE_ERR_ARG;
+    if (h->cfg.dim == 3)
+      return fail(h, PE_ERR_ARG, "pe_postprocess: not built for dim = 3 yet");
     if (h->cfg.element != PE_BR1_WG && h->cfg.element != PE_CGQ1_WG)
       return fail(h, PE_ERR_ARG, "pe_postprocess: Biot elements only (the Darcy element has pe_darcy_errors)");
     PE_DEVICE(h);

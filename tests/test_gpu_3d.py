@@ -60,11 +60,15 @@ def test_local_matrices_3d(distort):
     b.close()
 
 
-def test_other_hot_path_calls_say_not_built_in_3d():
+def test_calls_out_of_order_or_not_built_in_3d_are_refused():
     b = pb.PoroElas_CGQ1_WG_3D()
     b.make_grid(1)
     with pytest.raises(pb.PoroElasError):
-        b.assemble_system(0.1)
+        b.assemble_system(0.1)            # before distribute_dofs / make_sparsity_pattern
+    with pytest.raises(pb.PoroElasError):
+        b.solve_time_step()               # nothing assembled
+    with pytest.raises(pb.PoroElasError):
+        b.postprocess()                   # not built for dim = 3
     b.close()
 
 

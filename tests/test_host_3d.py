@@ -50,3 +50,18 @@ def test_hot_path_in_3d_is_refused_not_faked():
     with pytest.raises(PoroElasError):
         g.assemble_system(0.0)
     g.close()
+
+
+def test_calls_out_of_order_or_not_built_in_3d_are_refused():
+    """the same refusals tests/test_gpu_3d.py checks on the GPU box are decided before any device access"""
+    b = PoroElas_CGQ1_WG_3D(host_setup_only=True)
+    b.make_grid(1)
+    with pytest.raises(PoroElasError):
+        b.assemble_system(0.1)            # before distribute_dofs / make_sparsity_pattern
+    with pytest.raises(PoroElasError):
+        b.solve_time_step()               # nothing assembled
+    with pytest.raises(PoroElasError):
+        b.postprocess()                   # not built for dim = 3
+    with pytest.raises(PoroElasError):
+        b.set_solution(np.zeros(10))
+    b.close()
